@@ -1,0 +1,48 @@
+"""Shared test helpers: golden loading, oracle runs, tolerance rule (SURVEY.md 8(c) ladder)."""
+import os
+import types
+
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_golden(name):
+    return torch.load(os.path.join(GOLDEN, name + ".pt"), map_location="cpu", weights_only=False)
+
+
+def cfg_of(gold):
+    return types.SimpleNamespace(**gold["config"])
+
+
+def batch_of(gold):
+    from pamnet_b200.data import Batch
+    return Batch(**gold["batch"])
+
+
+def rel_err(a, b):
+    """max |a-b| / max |b| (tensor-level relative error used throughout the parity tests)."""
+    a, b = a.double().cpu(), b.double().cpu()
+    denom = b.abs().max().clamp(min=1e-30)
+    return float((a - b).abs().max() / denom)
+
+
+def oracle_step(sd, cfg, batch, simple=False, loss="l1", dtype=torch.float32):
+    """forward + loss + backward of the oracle; returns (out, loss, grads-by-key)."""
+    from oracle import pamnet_oracle as O
+    leaves = {k: v.detach().to(dtype).clone().requires_grad_(True) for k, v in sd.items()}
+    out = O.forward(leaves, cfg, batch, simple=simple)
+    y = batch.y.to(dtype)
+    l = (out - y).abs().mean() if loss == "l1" else ((out - y) ** 2).mean()
+    l.backward()
+    return out.detach(), l.detach(), {k: v.grad for k, v in leaves.items()}
+
+
+def ladder_ok(new, ref32, ref64, tol=1e-5):
+    """SURVEY.md 8(c) precision ladder: fp64 is truth; accept err_new <= max(tol, 2*err_ref),
+    both measured against fp64 relative to max|fp64|.  Returns (ok, err_new, err_ref)."""
+    ref64 = ref64.double().cpu()
+    scale = float(ref64.abs().max().clamp(min=1e-30))
+    err_new = float((new.double().cpu() - ref64).abs().max()) / scale
+    err_ref = float((ref32.double().cpu() - ref64).abs().max()) / scale
+    return err_new <= max(tol, 2 * err_ref), err_new, err_ref
