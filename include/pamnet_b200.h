@@ -1,0 +1,177 @@
+/*
+ * pamnet_b200.h -- C ABI of libpamnet_sm100.so: the PAMNet message-passing hot path on B200 (sm_100a).
+ *
+ * The reference (XieResearchGroup/Physics-aware-Multiplex-GNN) is pure Python and has no FFI; the operator
+ * boundary this library sits under is the set of torch / third-party calls its nn.Modules make.  Each entry
+ * point below names the reference interface it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every buffer (inputs, outputs, plan, workspace) is owned by the caller
+ *    and lives in device memory unless a parameter says "host"; the library never allocates, frees or
+ *    retains a pointer, and keeps no global state besides the thread-local error string;
+ *  - every function enqueues on `stream` (a cudaStream_t passed as void*) and returns without synchronising;
+ *  - return 0 = OK, < 0 = argument / shape error, > 0 = cudaError_t; text via pamnet_last_error();
+ *  - API-visible index tensors are int64 (as torch LongTensor); floating point is fp32;
+ *  - variable-length results use count -> (caller reads the count, allocates) -> fill.
+ */
+#ifndef PAMNET_B200_H
+#define PAMNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PAMNET_ABI_VERSION 1
+
+enum { PAMNET_QM9 = 0, PAMNET_PDBBIND = 1, PAMNET_RNA = 2 };          /* models.py:104,117,138 */
+enum { PAMNET_SOURCE_TO_TARGET = 0, PAMNET_TARGET_TO_SOURCE = 1 };    /* models.py:13 `flow`   */
+
+/* Config(dataset, dim, n_layer, cutoff_l, cutoff_g, flow) -- models.py:12-19; PAMNet vs PAMNet_s -- :21,:227 */
+typedef struct pamnet_config {
+    int32_t dataset;      /* PAMNET_QM9 | PAMNET_PDBBIND | PAMNET_RNA */
+    int32_t dim;          /* 16, 32, 64 or 128 */
+    int32_t n_layer;
+    int32_t flow;
+    int32_t simple;       /* 1 = PAMNet_s (one-hop only, models.py:227-353) */
+    float cutoff_l;
+    float cutoff_g;
+} pamnet_config_t;
+
+/* Spherical-basis constants, utils/sbf.py:13-26 (zeros, stored fp32 there) and :41-49 (normalisers);
+ * index l*6+m, l < 7, m < 6.  Passed by the caller (host memory, copied into kernel arguments). */
+typedef struct pamnet_sbf_consts {
+    double zeros[42];
+    double norm[42];
+} pamnet_sbf_consts_t;
+
+int pamnet_abi_version(void);
+const char* pamnet_last_error(void);
+
+/* ---- parameters -------------------------------------------------------------------------------------
+ * One flat fp32 buffer holding every tensor of the reference module's state_dict, in state_dict order
+ * (models.py:22-56, global_message_passing.py:9-31, local_message_passing.py:9-34).
+ * pamnet_param_count returns the number of tensors, pamnet_param_total the number of floats;
+ * pamnet_param_offsets fills offsets[count] (in floats) and numel[count].  Gradients use the same layout. */
+int pamnet_param_count(const pamnet_config_t* cfg);
+int64_t pamnet_param_total(const pamnet_config_t* cfg);
+int pamnet_param_offsets(const pamnet_config_t* cfg, int64_t* offsets, int64_t* numel);
+
+/* ---- graph construction -----------------------------------------------------------------------------
+ * torch_cluster.radius(x, x, r, batch, batch, max_num_neighbors) as called at models.py:110,128,301,
+ * canonical semantics of oracle/graph_ops.py:radius_pairs; `batch` non-decreasing.
+ * count: deg[n] (int32 [n_nodes], neighbours kept for query n after the optional self-loop drop of
+ *        models.py:63), ptr[n_nodes+1] exclusive scan, *total_dev = ptr[n_nodes] (device int64).
+ * fill : edge_index[2*total] int64 (row = query, col = neighbour; ordered by (query, neighbour)). */
+int pamnet_radius_count(const float* pos, const int64_t* batch, int64_t n_nodes, float r,
+                        int32_t max_num_neighbors, int32_t drop_self, int32_t* deg, int32_t* ptr,
+                        int64_t* total_dev, void* stream);
+int pamnet_radius_fill(const float* pos, const int64_t* batch, int64_t n_nodes, float r,
+                       int32_t max_num_neighbors, int32_t drop_self, const int32_t* ptr, int64_t total,
+                       int64_t* edge_index, void* stream);
+
+/* torch_cluster.knn(x, x, k, batch, batch) at models.py:143 (oracle/graph_ops.py:knn_pairs): per query the k
+ * nearest points of its own graph (itself included), ascending distance, ties to the lower index.
+ * nbr[n_nodes*k] int32 (-1 padded when the graph has fewer than k points), d2[n_nodes*k] fp32. */
+int pamnet_knn(const float* pos, const int64_t* batch, int64_t n_nodes, int32_t k, int32_t* nbr, float* d2,
+               void* stream);
+/* models.py:144-157: drop self, keep dist <= cutoff; count then fill like the radius pair. */
+int pamnet_knn_edges_count(const int32_t* nbr, const float* pos, int64_t n_nodes, int32_t k, float cutoff,
+                           int32_t* deg, int32_t* ptr, int64_t* total_dev, void* stream);
+int pamnet_knn_edges_fill(const int32_t* nbr, const float* pos, int64_t n_nodes, int32_t k, float cutoff,
+                          const int32_t* ptr, int64_t total, int64_t* edge_index, void* stream);
+
+/* torch_geometric.utils.remove_self_loops (models.py:63) / boolean edge masks (models.py:131-136):
+ * order-preserving compaction of edge_index[2*n_edges] by (row != col) and, when pos != NULL,
+ * |pos[col]-pos[row]| <= cutoff.  count writes keep[n_edges] (int32 0/1), ptr[n_edges+1], *total_dev. */
+int pamnet_edge_filter_count(const int64_t* edge_index, int64_t n_edges, const float* pos, float cutoff,
+                             int32_t* keep, int32_t* ptr, int64_t* total_dev, void* stream);
+int pamnet_edge_filter_fill(const int64_t* edge_index, int64_t n_edges, const int32_t* keep, const int32_t* ptr,
+                            int64_t total, int64_t* edge_index_out, void* stream);
+
+/* PAMNet.indices (models.py:68-98): triplet (two-hop) and pair (one-hop) index vectors of a local graph.
+ * count: needs scratch of pamnet_triplet_scratch_bytes(); writes counts_dev[2] = {T2, T1} (device int64).
+ * fill : the ten int64 vectors in the reference's order; two-hop ones have T2 entries, pair ones T1. */
+size_t pamnet_triplet_scratch_bytes(int64_t n_nodes, int64_t n_edges);
+int pamnet_triplet_count(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, void* scratch,
+                         int64_t* counts_dev, void* stream);
+int pamnet_triplet_fill(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, const void* scratch,
+                        int64_t t2, int64_t t1,
+                        int64_t* idx_i, int64_t* idx_j, int64_t* idx_k, int64_t* idx_kj, int64_t* idx_ji,
+                        int64_t* idx_i_pair, int64_t* idx_j1_pair, int64_t* idx_j2_pair,
+                        int64_t* idx_jj_pair, int64_t* idx_ji_pair, void* stream);
+
+/* ---- execution plan ---------------------------------------------------------------------------------
+ * Internal, destination-sorted (CSR) form of the two edge lists and of the triplet lists, built once per
+ * batch and reused by every layer (everything graph-structural is layer-invariant: models.py:104-188).
+ * The plan is two opaque caller-owned device blobs: `plan_base` (sized from N, G, E_g, E_l; needed by
+ * plan_count) and `plan_trip` (sized from T2 + T1, allocated once the counts are known).
+ * plan_count : builds the CSR part, counts triplets -> counts_dev[2] = {T2, T1} (for PAMNet_s T2 = 0);
+ * plan_fill  : fills the triplet part, edge lengths and the reverse (gather-keyed) triplet lists. */
+typedef struct pamnet_sizes {
+    int64_t n_nodes, n_graphs, n_edges_g, n_edges_l, n_t2, n_t1;
+} pamnet_sizes_t;
+
+int pamnet_plan_bytes(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, size_t* base_bytes, size_t* trip_bytes);
+int pamnet_plan_count(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, const int64_t* edge_index_g,
+                      const int64_t* edge_index_l, const int64_t* batch, void* plan_base, int64_t* counts_dev,
+                      void* stream);
+int pamnet_plan_fill(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, const float* pos, void* plan_base,
+                     void* plan_trip, void* stream);
+
+/* ---- the hot path: PAMNet.forward / autograd backward (models.py:100-224, main_qm9.py:107-110) -----
+ * node_in : QM9 / RNA: atom-type id per node as fp32 [n_nodes] (models.py:107,140);
+ *           PDBbind  : 18 features per node [n_nodes,18] (models.py:119).
+ * sign    : PDBbind only, +-1 per node (models.py:122-125), else NULL.
+ * out     : [n_graphs].  workspace keeps what backward needs; it must stay untouched between the calls.
+ * backward: grad_out [n_graphs] -> grad_params (flat, same layout as params; fully overwritten). */
+size_t pamnet_workspace_bytes(const pamnet_config_t* cfg, const pamnet_sizes_t* sz);
+int pamnet_model_forward(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, const pamnet_sbf_consts_t* sbf,
+                         const float* params, const float* node_in, const float* sign, const float* pos,
+                         void* plan_base, void* plan_trip, void* workspace, size_t workspace_bytes,
+                         int32_t save_for_backward, float* out, void* stream);
+int pamnet_model_backward(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, const pamnet_sbf_consts_t* sbf,
+                          const float* params, const float* node_in, const float* sign, const float* pos,
+                          void* plan_base, void* plan_trip, void* workspace, size_t workspace_bytes,
+                          const float* grad_out, float* grad_params, void* stream);
+
+/* L1 / MSE loss + its gradient w.r.t. the prediction in one launch (main_qm9.py:108 F.l1_loss,
+ * main_pdbbind.py MSE): loss_dev[0] = mean(|out-y|) or mean((out-y)^2); grad_out[g] = d loss / d out[g]. */
+int pamnet_loss(const float* out, const float* y, int64_t n, int32_t kind /*0 = L1, 1 = MSE*/, float* loss_dev,
+                float* grad_out, void* stream);
+
+/* ---- operator surface, also the unit-test hooks ----------------------------------
+ * torch_scatter.scatter(src, index, dim=0, dim_size, 'add') (local_message_passing.py:50,54) for a
+ * non-decreasing or arbitrary index: out[dim_size, width] zero-initialised then summed in index order per row
+ * group when sorted, by atomics otherwise. */
+int pamnet_scatter_add(const float* src, const int64_t* index, int64_t n_rows, int64_t width, int64_t dim_size,
+                       float* out, void* stream);
+/* BesselBasisLayer.forward (layers/basic.py:74-76): rbf[n_edges,16]. */
+int pamnet_bessel_rbf(const float* dist, int64_t n_edges, const float* freq, float cutoff, float* rbf,
+                      void* stream);
+/* SphericalBasisLayer.forward (layers/basic.py:107-116) in two steps: the per-edge radial part
+ * radial[n_edges,42] = u(x) N_lm j_l(z_lm x) (evaluated in double, rounded once), then
+ * out[n_trip,42] = radial[gather[t]] * Y_l0(angle[t]) with gather = idx_kj / idx_jj_pair. */
+int pamnet_sbf_radial(const pamnet_sbf_consts_t* sbf, const float* dist, int64_t n_edges, float cutoff,
+                      float* radial, void* stream);
+int pamnet_spherical_basis(const pamnet_sbf_consts_t* sbf, const float* radial, const float* angle,
+                           const int64_t* gather, int64_t n_trip, float* out, void* stream);
+/* y = act(x W^T + b): nn.Linear (+ SiLU, layers/basic.py:11-22); W [n_out, n_in] row-major. */
+int pamnet_linear(const float* x, int64_t n_rows, int32_t n_in, int32_t n_out, const float* w, const float* b,
+                  int32_t silu, float* y, void* stream);
+
+/* Plain fp32 GEMM hook used by the unit tests: mode 0: C = A B^T, 1: C = A B, 2: C = A^T B (+ column sums of A
+ * into dbias when non-null); ksplit > 1 accumulates into a zero-initialised C with atomics. */
+int pamnet_gemm(int32_t mode, const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc,
+                int32_t M, int32_t N, int32_t K, int32_t ksplit, float* dbias, void* stream);
+
+/* Test / debugging aids: byte offsets of named buffers inside the caller-owned workspace and plan blobs. */
+int64_t pamnet_debug_ws_offset(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, const char* name, int32_t half);
+int64_t pamnet_debug_plan_offset(const pamnet_sizes_t* sz, int32_t which, int32_t* in_trip);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAMNET_B200_H */

@@ -262,14 +262,14 @@ def forward(sd, cfg, data, simple=False, consts=None, return_parts=False):
         sbf2 = spherical_basis(g.dist_l, g.angle2, g.idx_kj, cfg.cutoff_l, consts)
         s1, s2 = _mlp(sd, "mlp_sbf1", sbf1, 1), _mlp(sd, "mlp_sbf2", sbf2, 1)
 
-    outs_g, outs_l, atts_g, atts_l = [], [], [], []
+    outs_g, outs_l, atts_g, atts_l, x_halves = [], [], [], [], []
     for l in range(cfg.n_layer):
         x, o, a = global_layer(sd, f"global_layer.{l}", x, e_g, g.edge_index_g,
                                getattr(cfg, "flow", "source_to_target"))
-        outs_g.append(o), atts_g.append(a)
+        outs_g.append(o), atts_g.append(a), x_halves.append(x)
         x, o, a = local_layer(sd, f"local_layer.{l}", x, e_l, s2, s1, g.idx_kj, g.idx_ji,
                               g.idx_jj_pair, g.idx_ji_pair, g.edge_index_l, two_hop=not simple)
-        outs_l.append(o), atts_l.append(a)
+        outs_l.append(o), atts_l.append(a), x_halves.append(x)
 
     # fusion (models.py:206-213): softmax over the {global, local} pair of every layer
     att = torch.stack((torch.stack(atts_g), torch.stack(atts_l)), -1).squeeze(2)   # [L, N, 2]
@@ -285,7 +285,7 @@ def forward(sd, cfg, data, simple=False, consts=None, return_parts=False):
         pooled = pooled / cnt
     if return_parts:
         return pooled, dict(graph=g, rbf_l=rbf_l, rbf_g=rbf_g, sbf1=sbf1, e_g=e_g, e_l=e_l, s1=s1, s2=s2,
-                            x_last=x)
+                            x_last=x, x_halves=x_halves, att=att, out=out)
     return pooled
 
 

@@ -1,2 +1,9 @@
-"""pamnet_b200 -- B200-native PAMNet message-passing hot path behind the reference's API."""
+"""pamnet_b200 -- B200-native PAMNet message-passing hot path behind the reference's module API.
+
+    from pamnet_b200 import Config, PAMNet, PAMNet_s          # == reference models.py
+    from pamnet_b200 import ops                               # radius / knn / scatter / bases on CUDA
+"""
 from .data import Batch, synthetic_qm9_batch, synthetic_rna_batch  # noqa: F401
+from .models import Config, PAMNet, PAMNet_s  # noqa: F401
+from . import layers, ops  # noqa: F401
+from ._lib import PamnetError  # noqa: F401

@@ -1,0 +1,219 @@
+// extern "C" surface of libpamnet_sm100.so (declared in include/pamnet_b200.h).
+#include <stdarg.h>
+
+#include "basis.cuh"
+#include "gemm.cuh"
+#include "graph.cuh"
+#include "message.cuh"
+#include "model.cuh"
+#include "readout.cuh"
+
+namespace pamnet {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_err; }
+}  // namespace pamnet
+
+using namespace pamnet;
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define REQUIRE(p) PAMNET_CHECK_ARG((p) != nullptr, "null pointer: %s", #p)
+
+extern "C" {
+
+int pamnet_abi_version(void) { return PAMNET_ABI_VERSION; }
+const char* pamnet_last_error(void) { return get_error(); }
+
+int pamnet_param_count(const pamnet_config_t* cfg) {
+    ModelP mp;
+    if (!cfg || build_param_layout(*cfg, &mp) != 0) return -1;
+    return (int)mp.offsets.size();
+}
+int64_t pamnet_param_total(const pamnet_config_t* cfg) {
+    ModelP mp;
+    if (!cfg || build_param_layout(*cfg, &mp) != 0) return -1;
+    return mp.total;
+}
+int pamnet_param_offsets(const pamnet_config_t* cfg, int64_t* offsets, int64_t* numel) {
+    REQUIRE(cfg); REQUIRE(offsets); REQUIRE(numel);
+    ModelP mp;
+    PAMNET_TRY(build_param_layout(*cfg, &mp));
+    for (size_t i = 0; i < mp.offsets.size(); ++i) { offsets[i] = mp.offsets[i]; numel[i] = mp.numel[i]; }
+    return 0;
+}
+
+int pamnet_radius_count(const float* pos, const int64_t* batch, int64_t n_nodes, float r, int32_t max_nb,
+                        int32_t drop_self, int32_t* deg, int32_t* ptr, int64_t* total_dev, void* stream) {
+    REQUIRE(pos); REQUIRE(batch); REQUIRE(deg); REQUIRE(ptr); REQUIRE(total_dev);
+    PAMNET_CHECK_ARG(n_nodes >= 0 && max_nb > 0, "radius: n_nodes=%lld max=%d", (long long)n_nodes, max_nb);
+    return radius_count(pos, batch, n_nodes, r, max_nb, drop_self, deg, ptr, total_dev, ST(stream));
+}
+int pamnet_radius_fill(const float* pos, const int64_t* batch, int64_t n_nodes, float r, int32_t max_nb,
+                       int32_t drop_self, const int32_t* ptr, int64_t total, int64_t* edge_index, void* stream) {
+    REQUIRE(pos); REQUIRE(batch); REQUIRE(ptr);
+    PAMNET_CHECK_ARG(total == 0 || edge_index, "radius_fill: null edge_index");
+    return radius_fill(pos, batch, n_nodes, r, max_nb, drop_self, ptr, total, edge_index, ST(stream));
+}
+int pamnet_knn(const float* pos, const int64_t* batch, int64_t n_nodes, int32_t k, int32_t* nbr, float* d2,
+               void* stream) {
+    REQUIRE(pos); REQUIRE(batch); REQUIRE(nbr); REQUIRE(d2);
+    PAMNET_CHECK_ARG(k > 0, "knn: k=%d", k);
+    return knn(pos, batch, n_nodes, k, nbr, d2, ST(stream));
+}
+int pamnet_knn_edges_count(const int32_t* nbr, const float* pos, int64_t n_nodes, int32_t k, float cutoff,
+                           int32_t* deg, int32_t* ptr, int64_t* total_dev, void* stream) {
+    REQUIRE(nbr); REQUIRE(pos); REQUIRE(deg); REQUIRE(ptr); REQUIRE(total_dev);
+    return knn_edges_count(nbr, pos, n_nodes, k, cutoff, deg, ptr, total_dev, ST(stream));
+}
+int pamnet_knn_edges_fill(const int32_t* nbr, const float* pos, int64_t n_nodes, int32_t k, float cutoff,
+                          const int32_t* ptr, int64_t total, int64_t* edge_index, void* stream) {
+    REQUIRE(nbr); REQUIRE(pos); REQUIRE(ptr);
+    return knn_edges_fill(nbr, pos, n_nodes, k, cutoff, ptr, total, edge_index, ST(stream));
+}
+int pamnet_edge_filter_count(const int64_t* edge_index, int64_t n_edges, const float* pos, float cutoff,
+                             int32_t* keep, int32_t* ptr, int64_t* total_dev, void* stream) {
+    REQUIRE(keep); REQUIRE(ptr); REQUIRE(total_dev);
+    PAMNET_CHECK_ARG(n_edges == 0 || edge_index, "edge_filter: null edge_index");
+    return edge_filter_count(edge_index, n_edges, pos, cutoff, keep, ptr, total_dev, ST(stream));
+}
+int pamnet_edge_filter_fill(const int64_t* edge_index, int64_t n_edges, const int32_t* keep, const int32_t* ptr,
+                            int64_t total, int64_t* edge_index_out, void* stream) {
+    REQUIRE(keep); REQUIRE(ptr);
+    return edge_filter_fill(edge_index, n_edges, keep, ptr, total, edge_index_out, ST(stream));
+}
+
+size_t pamnet_triplet_scratch_bytes(int64_t n_nodes, int64_t n_edges) { return triplet_scratch_bytes(n_nodes, n_edges); }
+int pamnet_triplet_count(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, void* scratch,
+                         int64_t* counts_dev, void* stream) {
+    REQUIRE(scratch); REQUIRE(counts_dev);
+    return triplet_count(edge_index, n_edges, n_nodes, scratch, counts_dev, ST(stream));
+}
+int pamnet_triplet_fill(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, const void* scratch,
+                        int64_t t2, int64_t t1, int64_t* idx_i, int64_t* idx_j, int64_t* idx_k, int64_t* idx_kj,
+                        int64_t* idx_ji, int64_t* idx_i_pair, int64_t* idx_j1_pair, int64_t* idx_j2_pair,
+                        int64_t* idx_jj_pair, int64_t* idx_ji_pair, void* stream) {
+    REQUIRE(scratch);
+    (void)t2; (void)t1;
+    int64_t* out[10] = {idx_i, idx_j, idx_k, idx_kj, idx_ji, idx_i_pair, idx_j1_pair, idx_j2_pair, idx_jj_pair, idx_ji_pair};
+    return triplet_fill(edge_index, n_edges, n_nodes, scratch, out, ST(stream));
+}
+
+int pamnet_plan_bytes(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, size_t* base_bytes, size_t* trip_bytes) {
+    REQUIRE(cfg); REQUIRE(sz);
+    plan_layout(*sz, nullptr, nullptr, nullptr, base_bytes, trip_bytes);
+    return 0;
+}
+int pamnet_plan_count(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, const int64_t* edge_index_g,
+                      const int64_t* edge_index_l, const int64_t* batch, void* plan_base, int64_t* counts_dev,
+                      void* stream) {
+    REQUIRE(cfg); REQUIRE(sz); REQUIRE(batch); REQUIRE(plan_base); REQUIRE(counts_dev);
+    return plan_count(*cfg, *sz, edge_index_g, edge_index_l, batch, plan_base, counts_dev, ST(stream));
+}
+int pamnet_plan_fill(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, const float* pos, void* plan_base,
+                     void* plan_trip, void* stream) {
+    REQUIRE(cfg); REQUIRE(sz); REQUIRE(pos); REQUIRE(plan_base); REQUIRE(plan_trip);
+    return plan_fill(*cfg, *sz, pos, plan_base, plan_trip, ST(stream));
+}
+
+size_t pamnet_workspace_bytes(const pamnet_config_t* cfg, const pamnet_sizes_t* sz) {
+    if (!cfg || !sz) return 0;
+    return workspace_bytes(*cfg, *sz);
+}
+int pamnet_model_forward(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, const pamnet_sbf_consts_t* sbf,
+                         const float* params, const float* node_in, const float* sign, const float* pos,
+                         void* plan_base, void* plan_trip, void* workspace, size_t workspace_bytes,
+                         int32_t save_for_backward, float* out, void* stream) {
+    REQUIRE(cfg); REQUIRE(sz); REQUIRE(sbf); REQUIRE(params); REQUIRE(node_in); REQUIRE(pos); REQUIRE(plan_base);
+    REQUIRE(plan_trip); REQUIRE(workspace); REQUIRE(out);
+    (void)save_for_backward;
+    return model_forward(*cfg, *sz, *sbf, params, node_in, sign, pos, plan_base, plan_trip, workspace,
+                         workspace_bytes, out, ST(stream));
+}
+int pamnet_model_backward(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, const pamnet_sbf_consts_t* sbf,
+                          const float* params, const float* node_in, const float* sign, const float* pos,
+                          void* plan_base, void* plan_trip, void* workspace, size_t workspace_bytes,
+                          const float* grad_out, float* grad_params, void* stream) {
+    REQUIRE(cfg); REQUIRE(sz); REQUIRE(sbf); REQUIRE(params); REQUIRE(node_in); REQUIRE(pos); REQUIRE(plan_base);
+    REQUIRE(plan_trip); REQUIRE(workspace); REQUIRE(grad_out); REQUIRE(grad_params);
+    return model_backward(*cfg, *sz, *sbf, params, node_in, sign, pos, plan_base, plan_trip, workspace,
+                          workspace_bytes, grad_out, grad_params, ST(stream));
+}
+
+int64_t pamnet_debug_ws_offset(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, const char* name, int32_t half) {
+    if (!cfg || !sz || !name) return -1;
+    return debug_ws_offset(*cfg, *sz, name, half);
+}
+// plan arrays for tests: which = 0 g_ptr, 1 g_src, 2 g_eid, 3 l_ptr, 4 l_src, 5 l_dst, 6 l_eid, 7 t_ptr, 8 t_gather,
+// 9 t_owner, 10 t_split, 11 dist_g, 12 dist_l, 13 t_angle; returns the byte offset inside base (0..12) or trip blob
+int64_t pamnet_debug_plan_offset(const pamnet_sizes_t* sz, int32_t which, int32_t* in_trip) {
+    if (!sz) return -1;
+    Plan p;
+    char* b = reinterpret_cast<char*>(0x1000);
+    char* t = reinterpret_cast<char*>(0x1000);
+    plan_layout(*sz, b, t, &p, nullptr, nullptr);
+    const void* tab[] = {p.g_ptr, p.g_src, p.g_eid, p.l_ptr, p.l_src, p.l_dst, p.l_eid, p.t_ptr, p.t_gather,
+                         p.t_owner, p.t_split, p.dist_g, p.dist_l, p.t_angle};
+    if (which < 0 || which > 13) return -1;
+    const bool trip = (which == 8 || which == 9 || which == 13);
+    if (in_trip) *in_trip = trip;
+    return (int64_t)(reinterpret_cast<const char*>(tab[which]) - (trip ? t : b));
+}
+
+int pamnet_loss(const float* out, const float* y, int64_t n, int32_t kind, float* loss_dev, float* grad_out,
+                void* stream) {
+    REQUIRE(out); REQUIRE(y); REQUIRE(loss_dev); REQUIRE(grad_out);
+    return loss_forward_backward(out, y, n, kind, loss_dev, grad_out, ST(stream));
+}
+
+int pamnet_scatter_add(const float* src, const int64_t* index, int64_t n_rows, int64_t width, int64_t dim_size,
+                       float* out, void* stream) {
+    REQUIRE(out);
+    return scatter_add_rows(src, index, n_rows, width, dim_size, out, ST(stream));
+}
+int pamnet_bessel_rbf(const float* dist, int64_t n_edges, const float* freq, float cutoff, float* rbf,
+                      void* stream) {
+    REQUIRE(freq);
+    return rbf_forward(dist, n_edges, freq, cutoff, rbf, ST(stream));
+}
+int pamnet_sbf_radial(const pamnet_sbf_consts_t* sbf, const float* dist, int64_t n_edges, float cutoff,
+                      float* radial, void* stream) {
+    REQUIRE(sbf);
+    SbfTables tab;
+    make_sbf_tables(*sbf, &tab);
+    return sbf_radial(tab, dist, n_edges, cutoff, radial, ST(stream));
+}
+int pamnet_spherical_basis(const pamnet_sbf_consts_t* sbf, const float* radial, const float* angle,
+                           const int64_t* gather, int64_t n_trip, float* out, void* stream) {
+    REQUIRE(sbf);
+    SbfTables tab;
+    make_sbf_tables(*sbf, &tab);
+    return sbf_combine(tab, radial, angle, gather, n_trip, out, ST(stream));
+}
+int pamnet_linear(const float* x, int64_t n_rows, int32_t n_in, int32_t n_out, const float* w, const float* b,
+                  int32_t act, float* y, void* stream) {
+    REQUIRE(w); REQUIRE(y);
+    GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.mode = GEMM_NT; a.epi = act ? EPI_BIAS_SILU : EPI_BIAS; a.M = (int)n_rows; a.N = n_out; a.K = n_in;
+    a.ksplit = 1; a.nslots = 1;
+    a.slot[0].A = x; a.slot[0].lda = n_in; a.slot[0].B = w; a.slot[0].ldb = n_in; a.slot[0].bias = b;
+    a.slot[0].C = y; a.slot[0].ldc = n_out;
+    return gemm_launch(a, ST(stream));
+}
+// Generic fp32 GEMM hook (unit tests of the NT / NN / TN paths): C[M,N] (+)= op(A) op(B)
+int pamnet_gemm(int32_t mode, const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc,
+                int32_t M, int32_t N, int32_t K, int32_t ksplit, float* dbias, void* stream) {
+    GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.mode = mode; a.epi = EPI_NONE; a.M = M; a.N = N; a.K = K; a.ksplit = ksplit; a.nslots = 1;
+    a.slot[0].A = A; a.slot[0].lda = lda; a.slot[0].B = B; a.slot[0].ldb = ldb; a.slot[0].C = C; a.slot[0].ldc = ldc;
+    a.slot[0].C2 = dbias;
+    return gemm_launch(a, ST(stream));
+}
+
+}  // extern "C"

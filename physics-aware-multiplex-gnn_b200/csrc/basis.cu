@@ -1,0 +1,337 @@
+// Basis / embedding kernels (see basis.cuh).
+#include "basis.cuh"
+
+namespace pamnet {
+
+void make_sbf_tables(const pamnet_sbf_consts_t& c, SbfTables* t) {
+    for (int i = 0; i < kNumSbf; ++i) {
+        t->zeros[i] = c.zeros[i];
+        t->norm[i] = c.norm[i];
+    }
+    // Legendre recurrence (utils/sbf.py:69-79) scaled by sqrt((2l+1)/4pi) (utils/sbf.py:62-66)
+    double leg[kNumSph][kNumSph] = {};
+    leg[0][0] = 1.0;
+    leg[1][1] = 1.0;
+    for (int j = 2; j < kNumSph; ++j)
+        for (int p = 0; p <= j; ++p) {
+            double v = 0.0;
+            if (p >= 1) v += (2 * j - 1) * leg[j - 1][p - 1];
+            v -= (j - 1) * leg[j - 2][p];
+            leg[j][p] = v / j;
+        }
+    const double four_pi = 12.566370614359172;
+    for (int l = 0; l < kNumSph; ++l)
+        for (int p = 0; p < kNumSph; ++p) t->ycoef[l][p] = sqrt((2 * l + 1) / four_pi) * leg[l][p];
+}
+
+// Envelope u(x), exponent p = 5 (layers/basic.py:36-51; note x^p, not x^(p-1))
+__device__ __forceinline__ float envelope_f(float x) {
+    if (!(x < 1.0f)) return 0.0f;
+    const float x5 = x * x * x * x * x;
+    return 1.0f / x + (-21.0f) * x5 + 35.0f * x5 * x + (-15.0f) * x5 * x * x;
+}
+__device__ __forceinline__ double envelope_d(double x) {
+    if (!(x < 1.0)) return 0.0;
+    const double x5 = x * x * x * x * x;
+    return 1.0 / x - 21.0 * x5 + 35.0 * x5 * x - 15.0 * x5 * x * x;
+}
+
+__global__ void rbf_kernel(const float* __restrict__ dist, int64_t n_edges, const float* __restrict__ freq,
+                           float cutoff, float* __restrict__ rbf) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_edges * kNumRbf) return;
+    const int64_t e = i / kNumRbf;
+    const int n = (int)(i % kNumRbf);
+    const float x = dist[e] / cutoff;
+    rbf[i] = envelope_f(x) * sinf(freq[n] * x);
+}
+
+int rbf_forward(const float* dist, int64_t n_edges, const float* freq, float cutoff, float* rbf, cudaStream_t st) {
+    if (n_edges == 0) return 0;
+    rbf_kernel<<<ceil_div(n_edges * kNumRbf, 256), 256, 0, st>>>(dist, n_edges, freq, cutoff, rbf);
+    PAMNET_LAUNCH_CHECK();
+    return 0;
+}
+
+// 16 columns x 16 row-lanes per block; fixed-order tree inside the block, one atomicAdd per block and column
+__global__ void __launch_bounds__(256) rbf_freq_bwd_kernel(const float* __restrict__ dist, int64_t n_edges,
+                                                           const float* __restrict__ freq, float cutoff,
+                                                           const float* __restrict__ g_rbf, int64_t rows_per_block,
+                                                           float* __restrict__ g_freq) {
+    __shared__ float red[16][17];
+    const int n = threadIdx.x & 15, rl = threadIdx.x >> 4;
+    const int64_t e0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t e1 = min(n_edges, e0 + rows_per_block);
+    const float f = freq[n];
+    float s = 0.f;
+    for (int64_t e = e0 + rl; e < e1; e += 16) {
+        const float x = dist[e] / cutoff;
+        s += g_rbf[e * kNumRbf + n] * envelope_f(x) * x * cosf(f * x);
+    }
+    red[rl][n] = s;
+    __syncthreads();
+    if (rl == 0) {
+        float tot = 0.f;
+        for (int r = 0; r < 16; ++r) tot += red[r][n];
+        atomicAdd(&g_freq[n], tot);
+    }
+}
+
+int rbf_freq_backward(const float* dist, int64_t n_edges, const float* freq, float cutoff, const float* g_rbf,
+                      float* g_freq, cudaStream_t st) {
+    if (n_edges == 0) return 0;
+    const int64_t rpb = 512;
+    rbf_freq_bwd_kernel<<<ceil_div(n_edges, rpb), 256, 0, st>>>(dist, n_edges, freq, cutoff, g_rbf, rpb, g_freq);
+    PAMNET_LAUNCH_CHECK();
+    return 0;
+}
+
+// j_0..j_6 by upward recurrence in double (equivalent to the closed forms utils/sbf.py:29-38 generates; the
+// reference evaluates those in fp32, where they lose up to 4 digits to cancellation -- SURVEY.md fact 5)
+__global__ void sbf_radial_kernel(const SbfTables tab, const float* __restrict__ dist, int64_t n_edges, float cutoff,
+                                  float* __restrict__ radial) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_edges * kNumRad) return;
+    const int64_t e = i / kNumRad;
+    const int m = (int)(i % kNumRad);
+    const double x = (double)dist[e] / (double)cutoff;
+    const double env = envelope_d(x);
+#pragma unroll
+    for (int l = 0; l < kNumSph; ++l) {
+        const double a = tab.zeros[l * kNumRad + m] * x;
+        double s, c;
+        sincos(a, &s, &c);
+        double jm = s / a, j = (s / a - c) / a;   // j_0, j_1
+        double val = jm;
+        if (l >= 1) val = j;
+        for (int q = 1; q < l; ++q) {
+            const double jn = (2 * q + 1) / a * j - jm;
+            jm = j;
+            j = jn;
+            val = j;
+        }
+        radial[e * kNumSbf + l * kNumRad + m] = (float)(env * tab.norm[l * kNumRad + m] * val);
+    }
+}
+
+int sbf_radial(const SbfTables& tab, const float* dist, int64_t n_edges, float cutoff, float* radial,
+               cudaStream_t st) {
+    if (n_edges == 0) return 0;
+    sbf_radial_kernel<<<ceil_div(n_edges * kNumRad, 128), 128, 0, st>>>(tab, dist, n_edges, cutoff, radial);
+    PAMNET_LAUNCH_CHECK();
+    return 0;
+}
+
+__device__ __forceinline__ void zonal(const SbfTables& tab, double ct, float* out7) {
+#pragma unroll
+    for (int l = 0; l < kNumSph; ++l) {
+        double v = 0.0;
+#pragma unroll
+        for (int p = kNumSph - 1; p >= 0; --p) v = v * ct + tab.ycoef[l][p];
+        out7[l] = (float)v;
+    }
+}
+
+__global__ void sbf_combine_kernel(const SbfTables tab, const float* __restrict__ radial,
+                                   const float* __restrict__ angle, const int64_t* __restrict__ gather, int64_t n_trip,
+                                   float* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_trip) return;
+    float y[kNumSph];
+    zonal(tab, cos((double)angle[t]), y);
+    const float* r = radial + gather[t] * kNumSbf;
+    for (int c = 0; c < kNumSbf; ++c) out[t * kNumSbf + c] = r[c] * y[c / kNumRad];
+}
+
+int sbf_combine(const SbfTables& tab, const float* radial, const float* angle, const int64_t* gather, int64_t n_trip,
+                float* out, cudaStream_t st) {
+    if (n_trip == 0) return 0;
+    sbf_combine_kernel<<<ceil_div(n_trip, 128), 128, 0, st>>>(tab, radial, angle, gather, n_trip, out);
+    PAMNET_LAUNCH_CHECK();
+    return 0;
+}
+
+// cos of the angle between u = p_b - p_a and v = p_c - p_b (models.py:165-177 take atan2(|u x v|, u.v) first)
+__device__ __forceinline__ double cos_angle(const float* __restrict__ pos, int a, int b, int c) {
+    const double ux = (double)pos[3 * b] - pos[3 * a], uy = (double)pos[3 * b + 1] - pos[3 * a + 1],
+                 uz = (double)pos[3 * b + 2] - pos[3 * a + 2];
+    const double vx = (double)pos[3 * c] - pos[3 * b], vy = (double)pos[3 * c + 1] - pos[3 * b + 1],
+                 vz = (double)pos[3 * c + 2] - pos[3 * b + 2];
+    const double dot = ux * vx + uy * vy + uz * vz;
+    const double cx = uy * vz - uz * vy, cy = uz * vx - ux * vz, cz = ux * vy - uy * vx;
+    const double cr = sqrt(cx * cx + cy * cy + cz * cz);
+    const double h = sqrt(dot * dot + cr * cr);
+    return h > 0.0 ? dot / h : 1.0;   // atan2(0, 0) = 0
+}
+
+// one warp per triplet row: lanes cover the 88 columns
+__global__ void __launch_bounds__(128) sbf_ext_kernel(const SbfTables tab, const int32_t* __restrict__ l_src,
+                                                      const int32_t* __restrict__ l_dst,
+                                                      const int32_t* __restrict__ t_ptr,
+                                                      const int32_t* __restrict__ t_split,
+                                                      const int32_t* __restrict__ t_gather,
+                                                      const int32_t* __restrict__ t_owner, int64_t n_trip,
+                                                      const float* __restrict__ pos, const float* __restrict__ radial,
+                                                      float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t t = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (t >= n_trip) return;
+    const int k = t_owner[t], p = t_gather[t];
+    const int i = l_dst[k], j = l_src[k], o = l_src[p];
+    const bool two_hop = (t - t_ptr[k]) < t_split[k];
+    // two-hop: (idx_i, idx_j, idx_k) = (i, j, o); one-hop: (idx_i_pair, idx_j1_pair, idx_j2_pair) = (j, i, o)
+    const double ct = two_hop ? cos_angle(pos, i, j, o) : cos_angle(pos, j, i, o);
+    float y[kNumSph];
+    zonal(tab, ct, y);
+    const float* r = radial + (size_t)p * kNumSbf;
+    float* row = out + t * kSbfExt;
+    for (int c = lane; c < kSbfExt; c += 32) {
+        float v = 0.f;
+        if (c < 2 * kNumSbf) {
+            const int cc = c < kNumSbf ? c : c - kNumSbf;
+            if ((c < kNumSbf) == two_hop) v = r[cc] * y[cc / kNumRad];
+        } else if (c == 2 * kNumSbf) {
+            v = two_hop ? 1.f : 0.f;
+        } else if (c == 2 * kNumSbf + 1) {
+            v = two_hop ? 0.f : 1.f;
+        }
+        row[c] = v;
+    }
+}
+
+int sbf_ext_forward(const SbfTables& tab, const Plan& plan, int64_t n_edges, int64_t n_trip, const float* pos,
+                    const float* radial, float* sbf_ext, cudaStream_t st) {
+    (void)n_edges;
+    if (n_trip == 0) return 0;
+    sbf_ext_kernel<<<ceil_div(n_trip, 4), 128, 0, st>>>(tab, plan.l_src, plan.l_dst, plan.t_ptr, plan.t_split,
+                                                        plan.t_gather, plan.t_owner, n_trip, pos, radial, sbf_ext);
+    PAMNET_LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void sbf_pack_kernel(int dim, const float* __restrict__ w2, const float* __restrict__ b2,
+                                const float* __restrict__ w1, const float* __restrict__ b1, float* __restrict__ w_ext) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dim * kSbfExt) return;
+    const int o = i / kSbfExt, c = i % kSbfExt;
+    float v = 0.f;
+    if (c < kNumSbf) v = w2 ? w2[o * kNumSbf + c] : 0.f;
+    else if (c < 2 * kNumSbf) v = w1[o * kNumSbf + c - kNumSbf];
+    else if (c == 2 * kNumSbf) v = b2 ? b2[o] : 0.f;
+    else if (c == 2 * kNumSbf + 1) v = b1[o];
+    w_ext[i] = v;
+}
+
+int sbf_weight_pack(int dim, const float* w2, const float* b2, const float* w1, const float* b1, float* w_ext,
+                    cudaStream_t st) {
+    sbf_pack_kernel<<<ceil_div(dim * kSbfExt, 256), 256, 0, st>>>(dim, w2, b2, w1, b1, w_ext);
+    PAMNET_LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void sbf_unpack_kernel(int dim, const float* __restrict__ g_ext, float* __restrict__ gw2,
+                                  float* __restrict__ gb2, float* __restrict__ gw1, float* __restrict__ gb1) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dim * kSbfExt) return;
+    const int o = i / kSbfExt, c = i % kSbfExt;
+    const float v = g_ext[i];
+    if (c < kNumSbf) { if (gw2) gw2[o * kNumSbf + c] = v; }
+    else if (c < 2 * kNumSbf) gw1[o * kNumSbf + c - kNumSbf] = v;
+    else if (c == 2 * kNumSbf) { if (gb2) gb2[o] = v; }
+    else if (c == 2 * kNumSbf + 1) gb1[o] = v;
+}
+
+int sbf_weight_unpack_grad(int dim, const float* g_ext, float* gw2, float* gb2, float* gw1, float* gb1,
+                           cudaStream_t st) {
+    sbf_unpack_kernel<<<ceil_div(dim * kSbfExt, 256), 256, 0, st>>>(dim, g_ext, gw2, gb2, gw1, gb1);
+    PAMNET_LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void embed_fwd_kernel(const float* __restrict__ type_f, int64_t n_nodes, const float* __restrict__ emb,
+                                 int n_embed, int dim, float* __restrict__ x) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes * dim) return;
+    const int64_t n = i / dim;
+    int ty = (int)type_f[n];                       // x_raw.long() (models.py:107,140)
+    ty = ty < 0 ? 0 : (ty >= n_embed ? n_embed - 1 : ty);
+    x[i] = emb[(size_t)ty * dim + i % dim];
+}
+
+int embed_forward(const float* type_f, int64_t n_nodes, const float* emb, int n_embed, int dim, float* x,
+                  cudaStream_t st) {
+    if (n_nodes == 0) return 0;
+    embed_fwd_kernel<<<ceil_div(n_nodes * dim, 256), 256, 0, st>>>(type_f, n_nodes, emb, n_embed, dim, x);
+    PAMNET_LAUNCH_CHECK();
+    return 0;
+}
+
+// one block per (type, column tile): fixed-order sum over the nodes of that type -> deterministic
+__global__ void embed_bwd_kernel(const float* __restrict__ type_f, int64_t n_nodes, const float* __restrict__ g_x,
+                                 int dim, float* __restrict__ g_emb) {
+    const int ty = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= dim) return;
+    float s = 0.f;
+    for (int64_t n = 0; n < n_nodes; ++n)
+        if ((int)type_f[n] == ty) s += g_x[n * dim + c];
+    g_emb[(size_t)ty * dim + c] = s;
+}
+
+int embed_backward(const float* type_f, int64_t n_nodes, const float* g_x, int n_embed, int dim, float* g_emb,
+                   cudaStream_t st) {
+    dim3 grid(ceil_div(dim, 32), n_embed);
+    embed_bwd_kernel<<<grid, 32, 0, st>>>(type_f, n_nodes, g_x, dim, g_emb);
+    PAMNET_LAUNCH_CHECK();
+    return 0;
+}
+
+constexpr int kTransJobs = 128;
+struct TransposeArgs {
+    int n_jobs;
+    int src_off[kTransJobs], dst_off[kTransJobs];
+    short rows[kTransJobs], cols[kTransJobs];
+    int ld[kTransJobs];
+};
+
+// 32x32 tiles through shared memory; grid.y = job
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ src_base, float* __restrict__ dst_base,
+                                                        const TransposeArgs a) {
+    __shared__ float tile[32][33];
+    const int job = blockIdx.y;
+    const int rows = a.rows[job], cols = a.cols[job], ld = a.ld[job];
+    const float* src = src_base + a.src_off[job];
+    float* dst = dst_base + a.dst_off[job];
+    const int tiles_c = (cols + 31) / 32, tiles_r = (rows + 31) / 32;
+    for (int tile_id = blockIdx.x; tile_id < tiles_r * tiles_c; tile_id += gridDim.x) {
+        const int r0 = (tile_id / tiles_c) * 32, c0 = (tile_id % tiles_c) * 32;
+        const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+        for (int r = ty; r < 32; r += 8)
+            if (r0 + r < rows && c0 + tx < cols) tile[r][tx] = src[(size_t)(r0 + r) * ld + c0 + tx];
+        __syncthreads();
+        for (int c = ty; c < 32; c += 8)
+            if (c0 + c < cols && r0 + tx < rows) dst[(size_t)(c0 + c) * rows + r0 + tx] = tile[tx][c];
+        __syncthreads();
+    }
+}
+
+int transpose_batch(const float* src_base, float* dst_base, const TransposeJob* jobs, int n_jobs, cudaStream_t st) {
+    for (int j0 = 0; j0 < n_jobs; j0 += kTransJobs) {
+        TransposeArgs a;
+        a.n_jobs = (n_jobs - j0 < kTransJobs) ? n_jobs - j0 : kTransJobs;
+        int max_tiles = 1;
+        for (int j = 0; j < a.n_jobs; ++j) {
+            const TransposeJob& jb = jobs[j0 + j];
+            a.src_off[j] = (int)jb.src_off; a.dst_off[j] = (int)jb.dst_off;
+            a.rows[j] = (short)jb.rows; a.cols[j] = (short)jb.cols; a.ld[j] = jb.ld;
+            const int tiles = ceil_div(jb.rows, 32) * ceil_div(jb.cols, 32);
+            if (tiles > max_tiles) max_tiles = tiles;
+        }
+        dim3 grid(max_tiles > 16 ? 16 : max_tiles, a.n_jobs);
+        transpose_kernel<<<grid, 256, 0, st>>>(src_base, dst_base, a);
+        PAMNET_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+}  // namespace pamnet

@@ -1,0 +1,48 @@
+// Row-local chains of D x D Linear(+SiLU)(+residual) stages fused into one kernel.
+//
+// Everything a PAMNet layer does to node features between two message-passing steps is row-local
+// (global_message_passing.py:35,39-48; local_message_passing.py:43,55-64): mlp_x2, three Res blocks, mlp_out,
+// the two readout heads, then the next layer's mlp_x1 and the per-node halves of its edge-MLP
+// (W [x_i ; x_j ; e] = W_i x_i + W_j x_j + W_e e).  A CTA owns R rows, keeps the activations in shared
+// memory and streams the weights; the reference issues one cuBLAS + two elementwise launches per stage.
+// The same interpreter runs the data-gradient chain in reverse (stage prologue multiplies by SiLU').
+#pragma once
+#include "common.cuh"
+
+namespace pamnet {
+
+enum ChainOp : int { CH_LOAD = 0, CH_GEMM = 1, CH_DOT2 = 2, CH_HEADS_BWD = 3 };
+
+constexpr int kChainMaxStages = 26;
+constexpr int kChainSlots = 3;      // D-wide slots 0..2; slot 3 is the wide (4D) staging slot
+constexpr int kChainWide = 3;
+
+struct ChainStage {
+    int op;
+    int src, src_off;   // GEMM / DOT2 input slot and column offset inside it
+    int psrc;           // GEMM: slot that receives src * silu'(zmul) (== src: in place; -1: no prologue)
+    int dst;            // output slot, -1 = none
+    int add_slot;       // slot added to the output after the activation, -1 = none
+    int act;            // 1 = SiLU
+    int width;          // LOAD: columns
+    int ldw, ld_out, ld_add, ld_g;
+    const float* W;     // GEMM: [D(k)][D(n)] k-major (transposed weight in forward, weight itself in backward)
+    const float* bias;
+    const float* zmul;
+    float* save_src;    // prologue result written to global (grad wrt pre-activation, for weight gradients)
+    float* out_z;       // pre-activation written to global
+    float* out_a;       // final value written to global
+    const float* add_g; // global tensor added to the output after the activation
+    const float* g0;    // LOAD: source; HEADS_BWD: grad_att [N]; DOT2: pointer to W_out.bias
+    const float* g1;    // LOAD: optional second addend; HEADS_BWD: grad_out [N]
+};
+
+struct ChainArgs {
+    int n_rows;
+    int n_stages;
+    ChainStage st[kChainMaxStages];
+};
+
+int chain_launch(int dim, const ChainArgs& args, cudaStream_t st);
+
+}  // namespace pamnet

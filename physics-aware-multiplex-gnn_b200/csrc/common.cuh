@@ -1,0 +1,127 @@
+// Shared device/host helpers for libpamnet_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/pamnet_b200.h"
+
+namespace pamnet {
+
+constexpr int kNumRbf = 16;        // models.py:37-38
+constexpr int kNumSph = 7;         // models.py:22 num_spherical
+constexpr int kNumRad = 6;         // models.py:22 num_radial
+constexpr int kNumSbf = kNumSph * kNumRad;
+constexpr int kFeatPdb = 18;       // models.py:35 init_linear in-features
+constexpr int kNumSM = 148;        // B200
+
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define PAMNET_CHECK_ARG(cond, ...)                     \
+    do {                                                \
+        if (!(cond)) {                                  \
+            ::pamnet::set_error(__VA_ARGS__);           \
+            return -1;                                  \
+        }                                               \
+    } while (0)
+
+#define PAMNET_CUDA(expr)                                                                   \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            ::pamnet::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),     \
+                                __FILE__, __LINE__);                                        \
+            return (int)_e;                                                                 \
+        }                                                                                   \
+    } while (0)
+
+#define PAMNET_LAUNCH_CHECK() PAMNET_CUDA(cudaGetLastError())
+
+#define PAMNET_TRY(expr)            \
+    do {                            \
+        int _r = (expr);            \
+        if (_r != 0) return _r;     \
+    } while (0)
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------
+// device math
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// SiLU and its derivative (layers/basic.py:11-16): s(z)*(1 + z*(1-s(z)))
+__device__ __forceinline__ float silu(float z) { return z * sigmoidf_(z); }
+__device__ __forceinline__ float dsilu(float z) {
+    float s = sigmoidf_(z);
+    return s * (1.0f + z * (1.0f - s));
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 operator+(float4 a, float4 b) {
+    return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ float4 operator*(float4 a, float4 b) {
+    return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+}
+__device__ __forceinline__ float4 silu4(float4 z) { return make_float4(silu(z.x), silu(z.y), silu(z.z), silu(z.w)); }
+__device__ __forceinline__ float4 dsilu4(float4 z) {
+    return make_float4(dsilu(z.x), dsilu(z.y), dsilu(z.z), dsilu(z.w));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row vector held by one warp: D floats, lane owns VPL = D/32 consecutive-by-stride chunks.
+// D = 128 -> one float4 per lane (a 512 B row is one fully coalesced request); D = 64 -> float2;
+// D = 32 -> float; D = 16 -> float on the lower half-warp.
+// ---------------------------------------------------------------------------------------------
+template <int D>
+struct RowVec {
+    static constexpr int V = (D >= 128) ? 4 : (D >= 64 ? 2 : 1);   // floats per lane per chunk
+    static constexpr int C = (D + 32 * V - 1) / (32 * V);           // chunks per lane
+    float v[C * V];
+
+    __device__ __forceinline__ static bool active(int lane) { return D >= 32 || lane < D; }
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int i = 0; i < C * V; ++i) v[i] = 0.f;
+    }
+    __device__ __forceinline__ void load(const float* __restrict__ row, int lane) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float* p = row + (c * 32 + lane) * V;
+            if (V == 4) {
+                float4 t = ld4(p);
+                v[c * 4 + 0] = t.x; v[c * 4 + 1] = t.y; v[c * 4 + 2] = t.z; v[c * 4 + 3] = t.w;
+            } else if (V == 2) {
+                float2 t = *reinterpret_cast<const float2*>(p);
+                v[c * 2 + 0] = t.x; v[c * 2 + 1] = t.y;
+            } else {
+                v[c] = active(lane) ? *p : 0.f;
+            }
+        }
+    }
+    __device__ __forceinline__ void store(float* __restrict__ row, int lane) const {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            float* p = row + (c * 32 + lane) * V;
+            if (V == 4) {
+                st4(p, make_float4(v[c * 4 + 0], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]));
+            } else if (V == 2) {
+                *reinterpret_cast<float2*>(p) = make_float2(v[c * 2 + 0], v[c * 2 + 1]);
+            } else {
+                if (active(lane)) *p = v[c];
+            }
+        }
+    }
+};
+
+}  // namespace pamnet

@@ -1,0 +1,209 @@
+// fp32 FFMA GEMM, 64x64x16 tiles, 256 threads, 4x4 register micro-tile, register-prefetch double buffering.
+// Results are plain IEEE fp32 sums (no tensor-core rounding), which is what holds the 1e-5 parity bar of the
+// reference's nn.Linear layers (layers/basic.py:19-22).
+#include "gemm.cuh"
+
+namespace pamnet {
+
+constexpr int BM = 64, BN = 64, BK = 16, GT = 256;
+constexpr int PAD = 4;
+
+__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// Load 4 consecutive elements along the contiguous axis with range guards.
+__device__ __forceinline__ float4 load4_guard(const float* __restrict__ p, int valid, bool vec_ok) {
+    if (valid >= 4 && vec_ok) return ld4(p);
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid > 0) r.x = p[0];
+    if (valid > 1) r.y = p[1];
+    if (valid > 2) r.z = p[2];
+    if (valid > 3) r.w = p[3];
+    return r;
+}
+
+__global__ void __launch_bounds__(GT) gemm_kernel(const GemmArgs args) {
+    __shared__ __align__(16) float As[2][BK][BM + PAD];
+    __shared__ __align__(16) float Bs[2][BK][BN + PAD];
+
+    const GemmSlot& sl = args.slot[blockIdx.z];
+    const int M = args.M, N = args.N, K = args.K, mode = args.mode;
+    const int tiles_n = (N + BN - 1) / BN;
+    const int m0 = (blockIdx.x / tiles_n) * BM, n0 = (blockIdx.x % tiles_n) * BN;
+    const int t = threadIdx.x;
+
+    // K range of this split
+    int k_begin = 0, k_end = K;
+    if (args.ksplit > 1) {
+        const int chunk = ((K + args.ksplit - 1) / args.ksplit + BK - 1) / BK * BK;
+        k_begin = blockIdx.y * chunk;
+        k_end = min(K, k_begin + chunk);
+        if (k_begin >= k_end) return;
+    }
+
+    const bool a_kcontig = (mode != GEMM_TN);
+    const bool b_kcontig = (mode == GEMM_NT);
+    const bool a_vec = aligned16(sl.A) && (sl.lda % 4 == 0);
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    float4 ra, rb;
+    // thread -> load coordinates
+    const int lk_row = t >> 2, lk_k = (t & 3) * 4;      // k-contiguous: 64 rows x 16 k
+    const int lm_k = t >> 4, lm_m = (t & 15) * 4;       // m/n-contiguous: 16 k x 64 m
+
+    auto fetch = [&](int k0) {
+        if (a_kcontig) {
+            const int m = m0 + lk_row, k = k0 + lk_k;
+            ra = (m < M) ? load4_guard(sl.A + (size_t)m * sl.lda + k, k_end - k, a_vec) : make_float4(0, 0, 0, 0);
+        } else {
+            const int k = k0 + lm_k, m = m0 + lm_m;
+            ra = (k < k_end) ? load4_guard(sl.A + (size_t)k * sl.lda + m, M - m, a_vec) : make_float4(0, 0, 0, 0);
+        }
+        const float* Bp = sl.B;
+        int ldb = sl.ldb, kb = k0;
+        if (args.nseg > 0) {
+            const int s = k0 / args.seg_len;
+            Bp = args.seg_B[s];
+            ldb = args.seg_ldb[s];
+            kb = k0 - s * args.seg_len;
+        }
+        const bool b_vec = aligned16(Bp) && (ldb % 4 == 0);
+        if (b_kcontig) {
+            const int n = n0 + lk_row, k = kb + lk_k;
+            rb = (n < N) ? load4_guard(Bp + (size_t)n * ldb + k, k_end - (k0 + lk_k), b_vec) : make_float4(0, 0, 0, 0);
+        } else {
+            const int k = kb + lm_k, n = n0 + lm_m;
+            rb = (k0 + lm_k < k_end) ? load4_guard(Bp + (size_t)k * ldb + n, N - n, b_vec) : make_float4(0, 0, 0, 0);
+        }
+    };
+    auto stash = [&](int buf) {
+        if (a_kcontig) {
+            As[buf][lk_k + 0][lk_row] = ra.x; As[buf][lk_k + 1][lk_row] = ra.y;
+            As[buf][lk_k + 2][lk_row] = ra.z; As[buf][lk_k + 3][lk_row] = ra.w;
+        } else {
+            *reinterpret_cast<float4*>(&As[buf][lm_k][lm_m]) = ra;
+        }
+        if (b_kcontig) {
+            Bs[buf][lk_k + 0][lk_row] = rb.x; Bs[buf][lk_k + 1][lk_row] = rb.y;
+            Bs[buf][lk_k + 2][lk_row] = rb.z; Bs[buf][lk_k + 3][lk_row] = rb.w;
+        } else {
+            *reinterpret_cast<float4*>(&Bs[buf][lm_k][lm_m]) = rb;
+        }
+    };
+
+    const int ty = t >> 4, tx = t & 15;
+    // weight-gradient mode: column sums of A (= bias gradient) ride along on the first column tile
+    const bool do_bias = (mode == GEMM_TN) && sl.C2 != nullptr && n0 == 0 && tx == 0;
+    float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+    fetch(k_begin);
+    stash(0);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+        const bool more = (k0 + BK < k_end);
+        if (more) fetch(k0 + BK);
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+            const float bv[4] = {b.x, b.y, b.z, b.w};
+            if (do_bias) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) bsum[i] += av[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (more) {
+            stash(buf ^ 1);
+            __syncthreads();
+            buf ^= 1;
+        }
+    }
+
+    // epilogue
+    if (do_bias) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int m = m0 + ty * 4 + i;
+            if (m >= M) continue;
+            if (args.ksplit > 1) atomicAdd(&sl.C2[m], bsum[i]); else sl.C2[m] = bsum[i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            float v = acc[i][j];
+            const size_t ci = (size_t)m * sl.ldc + n;
+            if (args.ksplit > 1) {
+                atomicAdd(&sl.C[ci], v);
+                continue;
+            }
+            switch (args.epi) {
+                case EPI_BIAS:
+                    if (sl.bias) v += sl.bias[n];
+                    break;
+                case EPI_BIAS_SILU: {
+                    if (sl.bias) v += sl.bias[n];
+                    if (sl.C2) sl.C2[ci] = v;
+                    v = silu(v);   // (C2 here is the pre-activation, NT mode only)
+                    break;
+                }
+                case EPI_MUL_DSILU:
+                    v *= dsilu(sl.Z[(size_t)m * sl.ldz + n]);
+                    break;
+                default:
+                    break;
+            }
+            if (sl.C) sl.C[ci] = args.accumulate ? sl.C[ci] + v : v;
+        }
+    }
+}
+
+int gemm_launch(const GemmArgs& a, cudaStream_t st) {
+    PAMNET_CHECK_ARG(a.nslots >= 1 && a.nslots <= kGemmMaxSlots, "gemm: nslots=%d", a.nslots);
+    PAMNET_CHECK_ARG(a.nseg <= kGemmMaxSeg, "gemm: nseg=%d", a.nseg);
+    PAMNET_CHECK_ARG(a.nseg == 0 || (a.mode == GEMM_NN && a.seg_len % BK == 0 && a.nseg * a.seg_len == a.K),
+                     "gemm: bad K segmentation");
+    PAMNET_CHECK_ARG(a.ksplit <= 1 || (a.epi == EPI_NONE && !a.accumulate), "gemm: split-K needs EPI_NONE");
+    if (a.M <= 0 || a.N <= 0) return 0;
+    if (a.K <= 0) return 0;   // callers zero-fill outputs themselves when K == 0 matters
+    dim3 grid(ceil_div(a.M, BM) * ceil_div(a.N, BN), a.ksplit > 1 ? a.ksplit : 1, a.nslots);
+    gemm_kernel<<<grid, GT, 0, st>>>(a);
+    PAMNET_LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void colsum_kernel(const float* __restrict__ X, int64_t rows, int cols, int ld, int64_t rows_per_block,
+                              float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+    const int64_t r1 = min(rows, r0 + rows_per_block);
+    float s = 0.f;
+    for (int64_t r = r0; r < r1; ++r) s += X[r * ld + c];
+    atomicAdd(&out[c], s);
+}
+
+int colsum_launch(const float* X, int64_t rows, int cols, int ld, float* out, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return 0;
+    const int64_t rpb = 256;
+    dim3 grid(ceil_div(cols, 128), ceil_div(rows, rpb));
+    colsum_kernel<<<grid, 128, 0, st>>>(X, rows, cols, ld, rpb, out);
+    PAMNET_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace pamnet

@@ -1,0 +1,53 @@
+// fp32 (FFMA) batched GEMM used for the x-independent dense contractions of the hot path:
+// edge / triplet embeddings, per-layer edge projections for all layers at once, and their backward
+// (data-grad with K segmented over layers, weight-grad with split-K over edges).
+#pragma once
+#include "common.cuh"
+
+namespace pamnet {
+
+enum GemmMode : int {
+    GEMM_NT = 0,   // C[M,N] = A[M,K] * B[N,K]^T      forward of nn.Linear (B = weight [out,in])
+    GEMM_NN = 1,   // C[M,N] = A[M,K] * B[K,N]        data gradient      (B = weight [out,in], K = out)
+    GEMM_TN = 2,   // C[M,N] = A[K,M]^T * B[K,N]      weight gradient    (A = grad_z [rows,out], B = input [rows,in])
+};
+
+enum GemmEpi : int {
+    EPI_NONE = 0,
+    EPI_BIAS = 1,        // + bias[n]
+    EPI_BIAS_SILU = 2,   // z = acc + bias[n] (bias may be null); C2 = z (if C2); C = silu(z) (if C)
+    EPI_MUL_DSILU = 3,   // C = acc * silu'(Z[m,n])
+};
+
+constexpr int kGemmMaxSlots = 32;
+constexpr int kGemmMaxSeg = 32;
+
+struct GemmSlot {
+    const float* A;
+    const float* B;
+    const float* bias;
+    const float* Z;
+    float* C;
+    float* C2;
+    int lda, ldb, ldc, ldz;
+};
+
+struct GemmArgs {
+    int M, N, K;
+    int mode, epi;
+    int accumulate;       // C += (plain read-modify-write; slots/tiles never overlap)
+    int ksplit;           // > 1: split K across blockIdx.y, results combined with atomicAdd into C (EPI_NONE only)
+    int nslots;           // blockIdx.z
+    // K segmentation (GEMM_NN only): K = nseg*seg_len, segment s multiplies B = seg_B[s] (leading dim seg_ldb[s])
+    int nseg, seg_len;
+    GemmSlot slot[kGemmMaxSlots];
+    const float* seg_B[kGemmMaxSeg];
+    int seg_ldb[kGemmMaxSeg];
+};
+
+int gemm_launch(const GemmArgs& args, cudaStream_t st);
+
+// out[c] += sum_r X[r*ld + c]  (bias gradients); out must be zero-initialised by the caller
+int colsum_launch(const float* X, int64_t rows, int cols, int ld, float* out, cudaStream_t st);
+
+}  // namespace pamnet

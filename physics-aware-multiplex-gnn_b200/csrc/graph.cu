@@ -1,0 +1,642 @@
+// Graph construction on the device: radius / kNN neighbour search, edge filtering, destination-sorted CSR,
+// triplet (two-hop) and pair (one-hop) enumeration, and the execution plan the layer kernels consume.
+//
+// Reference behaviour restated (no reference code exists for these -- they are third-party calls):
+//   torch_cluster.radius / knn        models.py:110,128,143,301     -> radius_*, knn_*
+//   remove_self_loops + dist masks    models.py:62-66,131-136,148-157 -> edge_filter_*, knn_edges_*
+//   SparseTensor row gathers          models.py:68-98               -> incoming CSR walks (triplet_*, plan_*)
+// Canonical ordering and tie rules: oracle/graph_ops.py.
+#include "graph.cuh"
+
+namespace pamnet {
+
+// ---------------------------------------------------------------------------------------------
+// single-block exclusive scan (n up to a few million; graph sizes here are << that)
+// ---------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 4;
+
+__global__ void __launch_bounds__(kScanThreads) scan_exclusive_kernel(const int32_t* __restrict__ in,
+                                                                      int32_t* __restrict__ out, int64_t n,
+                                                                      int64_t* __restrict__ total64) {
+    __shared__ int32_t warp_tot[32];
+    __shared__ int32_t carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n; base += (int64_t)kScanThreads * kScanItems) {
+        int32_t v[kScanItems];
+        int32_t local = 0;
+        const int64_t i0 = base + (int64_t)tid * kScanItems;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            v[k] = (i0 + k < n) ? in[i0 + k] : 0;
+            local += v[k];
+        }
+        int32_t incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_tot[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            int32_t w = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int32_t t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += t;
+            }
+            warp_tot[lane] = w;   // inclusive over warps
+        }
+        __syncthreads();
+        const int32_t carry = carry_s;
+        int32_t excl = carry + incl - local + (wid > 0 ? warp_tot[wid - 1] : 0);
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            if (i0 + k < n) out[i0 + k] = excl;
+            excl += v[k];
+        }
+        __syncthreads();
+        if (tid == kScanThreads - 1) carry_s = carry + warp_tot[31];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        out[n] = carry_s;
+        if (total64) *total64 = carry_s;
+    }
+}
+
+int scan_exclusive(const int32_t* in, int32_t* out, int64_t n, int64_t* total64, cudaStream_t st) {
+    scan_exclusive_kernel<<<1, kScanThreads, 0, st>>>(in, out, n, total64);
+    PAMNET_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// graph segments from a non-decreasing batch vector
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t lower_bound_i64(const int64_t* __restrict__ a, int64_t n, int64_t key) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// canonical squared distance: ((dx*dx)+(dy*dy))+(dz*dz), no FMA contraction (oracle/graph_ops.py:_d2_block)
+__device__ __forceinline__ float canon_d2(float ax, float ay, float az, float bx, float by, float bz) {
+    float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// One thread per query; the scan over the query's own graph reads pos[n] warp-uniformly for small molecules.
+template <bool FILL>
+__global__ void radius_kernel(const float* __restrict__ pos, const int64_t* __restrict__ batch, int64_t n_nodes,
+                              float r2, int max_nb, int drop_self, int32_t* __restrict__ deg,
+                              const int32_t* __restrict__ ptr, int64_t total, int64_t* __restrict__ edge_index) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_nodes) return;
+    const int64_t g = batch[q];
+    const int64_t s = lower_bound_i64(batch, n_nodes, g);
+    const float qx = pos[3 * q], qy = pos[3 * q + 1], qz = pos[3 * q + 2];
+    int found = 0, kept = 0;
+    int64_t w = FILL ? ptr[q] : 0;
+    for (int64_t n = s; n < n_nodes && batch[n] == g && found < max_nb; ++n) {
+        float d2 = canon_d2(qx, qy, qz, pos[3 * n], pos[3 * n + 1], pos[3 * n + 2]);
+        if (d2 <= r2) {
+            ++found;
+            if (!(drop_self && n == q)) {
+                if (FILL) {
+                    edge_index[w] = q;
+                    edge_index[total + w] = n;
+                    ++w;
+                }
+                ++kept;
+            }
+        }
+    }
+    if (!FILL) deg[q] = kept;
+}
+
+int radius_count(const float* pos, const int64_t* batch, int64_t n_nodes, float r, int max_nb, int drop_self,
+                 int32_t* deg, int32_t* ptr, int64_t* total_dev, cudaStream_t st) {
+    if (n_nodes > 0) {
+        radius_kernel<false><<<ceil_div(n_nodes, 128), 128, 0, st>>>(pos, batch, n_nodes, r * r, max_nb, drop_self,
+                                                                     deg, nullptr, 0, nullptr);
+        PAMNET_LAUNCH_CHECK();
+    }
+    return scan_exclusive(deg, ptr, n_nodes, total_dev, st);
+}
+
+int radius_fill(const float* pos, const int64_t* batch, int64_t n_nodes, float r, int max_nb, int drop_self,
+                const int32_t* ptr, int64_t total, int64_t* edge_index, cudaStream_t st) {
+    if (n_nodes == 0 || total == 0) return 0;
+    radius_kernel<true><<<ceil_div(n_nodes, 128), 128, 0, st>>>(pos, batch, n_nodes, r * r, max_nb, drop_self,
+                                                                nullptr, ptr, total, edge_index);
+    PAMNET_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kNN: one thread per query, sorted candidate list in shared memory ([slot][thread] layout).
+// ---------------------------------------------------------------------------------------------
+constexpr int kKnnThreads = 64;
+
+__global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restrict__ pos,
+                                                          const int64_t* __restrict__ batch, int64_t n_nodes, int k,
+                                                          int32_t* __restrict__ nbr, float* __restrict__ d2out) {
+    extern __shared__ unsigned char smem_raw[];
+    float* sd = reinterpret_cast<float*>(smem_raw);                 // [k][kKnnThreads]
+    int32_t* si = reinterpret_cast<int32_t*>(sd + (size_t)k * kKnnThreads);
+    const int t = threadIdx.x;
+    const int64_t q = (int64_t)blockIdx.x * kKnnThreads + t;
+    if (q >= n_nodes) return;
+    const int64_t g = batch[q];
+    const int64_t s = lower_bound_i64(batch, n_nodes, g);
+    const float qx = pos[3 * q], qy = pos[3 * q + 1], qz = pos[3 * q + 2];
+    int cnt = 0;
+    for (int64_t n = s; n < n_nodes && batch[n] == g; ++n) {
+        float d2 = canon_d2(qx, qy, qz, pos[3 * n], pos[3 * n + 1], pos[3 * n + 2]);
+        if (cnt == k && !(d2 < sd[(k - 1) * kKnnThreads + t])) continue;   // ties keep the earlier (lower) index
+        int p = (cnt < k) ? cnt : k - 1;
+        while (p > 0 && sd[(p - 1) * kKnnThreads + t] > d2) {
+            sd[p * kKnnThreads + t] = sd[(p - 1) * kKnnThreads + t];
+            si[p * kKnnThreads + t] = si[(p - 1) * kKnnThreads + t];
+            --p;
+        }
+        sd[p * kKnnThreads + t] = d2;
+        si[p * kKnnThreads + t] = (int32_t)n;
+        if (cnt < k) ++cnt;
+    }
+    for (int p = 0; p < k; ++p) {
+        nbr[q * k + p] = (p < cnt) ? si[p * kKnnThreads + t] : -1;
+        d2out[q * k + p] = (p < cnt) ? sd[p * kKnnThreads + t] : 0.f;
+    }
+}
+
+int knn(const float* pos, const int64_t* batch, int64_t n_nodes, int k, int32_t* nbr, float* d2, cudaStream_t st) {
+    if (n_nodes == 0) return 0;
+    size_t smem = (size_t)k * kKnnThreads * 8;
+    PAMNET_CHECK_ARG(smem <= 200 * 1024, "knn: k=%d too large", k);
+    PAMNET_CUDA(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    knn_kernel<<<ceil_div(n_nodes, kKnnThreads), kKnnThreads, smem, st>>>(pos, batch, n_nodes, k, nbr, d2);
+    PAMNET_LAUNCH_CHECK();
+    return 0;
+}
+
+// edge length exactly as models.py:64-65 evaluates it on the API tensors: sqrt(sum((pos[i]-pos[j])^2))
+__device__ __forceinline__ float edge_len(const float* __restrict__ pos, int64_t a, int64_t b) {
+    float dx = pos[3 * a] - pos[3 * b], dy = pos[3 * a + 1] - pos[3 * b + 1], dz = pos[3 * a + 2] - pos[3 * b + 2];
+    return sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+}
+
+template <bool FILL>
+__global__ void knn_edges_kernel(const int32_t* __restrict__ nbr, const float* __restrict__ pos, int64_t n_nodes,
+                                 int k, float cutoff, int32_t* __restrict__ deg, const int32_t* __restrict__ ptr,
+                                 int64_t total, int64_t* __restrict__ edge_index) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_nodes) return;
+    int kept = 0;
+    int64_t w = FILL ? ptr[q] : 0;
+    for (int p = 0; p < k; ++p) {
+        const int n = nbr[q * k + p];
+        if (n < 0 || n == q) continue;
+        if (edge_len(pos, n, q) <= cutoff) {
+            if (FILL) {
+                edge_index[w] = q;
+                edge_index[total + w] = n;
+                ++w;
+            }
+            ++kept;
+        }
+    }
+    if (!FILL) deg[q] = kept;
+}
+
+int knn_edges_count(const int32_t* nbr, const float* pos, int64_t n_nodes, int k, float cutoff, int32_t* deg,
+                    int32_t* ptr, int64_t* total_dev, cudaStream_t st) {
+    if (n_nodes > 0) {
+        knn_edges_kernel<false><<<ceil_div(n_nodes, 128), 128, 0, st>>>(nbr, pos, n_nodes, k, cutoff, deg, nullptr, 0,
+                                                                        nullptr);
+        PAMNET_LAUNCH_CHECK();
+    }
+    return scan_exclusive(deg, ptr, n_nodes, total_dev, st);
+}
+
+int knn_edges_fill(const int32_t* nbr, const float* pos, int64_t n_nodes, int k, float cutoff, const int32_t* ptr,
+                   int64_t total, int64_t* edge_index, cudaStream_t st) {
+    if (n_nodes == 0 || total == 0) return 0;
+    knn_edges_kernel<true><<<ceil_div(n_nodes, 128), 128, 0, st>>>(nbr, pos, n_nodes, k, cutoff, nullptr, ptr, total,
+                                                                   edge_index);
+    PAMNET_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// order-preserving edge compaction
+// ---------------------------------------------------------------------------------------------
+__global__ void edge_keep_kernel(const int64_t* __restrict__ ei, int64_t n_edges, const float* __restrict__ pos,
+                                 float cutoff, int32_t* __restrict__ keep) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_edges) return;
+    const int64_t a = ei[e], b = ei[n_edges + e];
+    int k = (a != b);
+    if (k && pos) k = edge_len(pos, b, a) <= cutoff;
+    keep[e] = k;
+}
+
+__global__ void edge_compact_kernel(const int64_t* __restrict__ ei, int64_t n_edges, const int32_t* __restrict__ keep,
+                                    const int32_t* __restrict__ ptr, int64_t total, int64_t* __restrict__ out) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_edges || !keep[e]) return;
+    out[ptr[e]] = ei[e];
+    out[total + ptr[e]] = ei[n_edges + e];
+}
+
+int edge_filter_count(const int64_t* ei, int64_t n_edges, const float* pos, float cutoff, int32_t* keep, int32_t* ptr,
+                      int64_t* total_dev, cudaStream_t st) {
+    if (n_edges > 0) {
+        edge_keep_kernel<<<ceil_div(n_edges, 256), 256, 0, st>>>(ei, n_edges, pos, cutoff, keep);
+        PAMNET_LAUNCH_CHECK();
+    }
+    return scan_exclusive(keep, ptr, n_edges, total_dev, st);
+}
+
+int edge_filter_fill(const int64_t* ei, int64_t n_edges, const int32_t* keep, const int32_t* ptr, int64_t total,
+                     int64_t* out, cudaStream_t st) {
+    if (n_edges == 0 || total == 0) return 0;
+    edge_compact_kernel<<<ceil_div(n_edges, 256), 256, 0, st>>>(ei, n_edges, keep, ptr, total, out);
+    PAMNET_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// bucketed CSR: histogram -> scan -> unordered fill -> per-bucket insertion sort (buckets are node degrees)
+// ---------------------------------------------------------------------------------------------
+__global__ void split_edges_kernel(const int64_t* __restrict__ ei, int64_t n_edges, int dst_row,
+                                   int32_t* __restrict__ dst, int32_t* __restrict__ src) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_edges) return;
+    dst[e] = (int32_t)ei[(int64_t)dst_row * n_edges + e];
+    src[e] = (int32_t)ei[(int64_t)(1 - dst_row) * n_edges + e];
+}
+
+__global__ void hist_kernel(const int32_t* __restrict__ keys, int64_t n, int32_t* __restrict__ cnt) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&cnt[keys[i]], 1);
+}
+
+__global__ void bucket_fill_kernel(const int32_t* __restrict__ keys, int64_t n, const int32_t* __restrict__ ptr,
+                                   int32_t* __restrict__ cursor, int32_t* __restrict__ items) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int k = keys[i];
+    items[ptr[k] + atomicAdd(&cursor[k], 1)] = (int32_t)i;
+}
+
+// sort each bucket by (key2[item], item); key2 may be null (sort by item only)
+__global__ void bucket_sort_kernel(const int32_t* __restrict__ ptr, int64_t n_buckets, int32_t* __restrict__ items,
+                                   const int32_t* __restrict__ key2) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_buckets) return;
+    const int s = ptr[b], e = ptr[b + 1];
+    for (int i = s + 1; i < e; ++i) {
+        const int it = items[i];
+        const int k2 = key2 ? key2[it] : 0;
+        int p = i;
+        while (p > s) {
+            const int jt = items[p - 1];
+            const int j2 = key2 ? key2[jt] : 0;
+            if (j2 > k2 || (j2 == k2 && jt > it)) {
+                items[p] = jt;
+                --p;
+            } else {
+                break;
+            }
+        }
+        items[p] = it;
+    }
+}
+
+// ptr[n_buckets+1], items[n]: items of bucket b sorted by (key2, item)
+int build_buckets(const int32_t* keys, int64_t n, int64_t n_buckets, const int32_t* key2, int32_t* cnt_scratch,
+                  int32_t* ptr, int32_t* items, cudaStream_t st) {
+    PAMNET_CUDA(cudaMemsetAsync(cnt_scratch, 0, sizeof(int32_t) * (n_buckets + 1), st));
+    if (n > 0) {
+        hist_kernel<<<ceil_div(n, 256), 256, 0, st>>>(keys, n, cnt_scratch);
+        PAMNET_LAUNCH_CHECK();
+    }
+    PAMNET_TRY(scan_exclusive(cnt_scratch, ptr, n_buckets, nullptr, st));
+    if (n > 0) {
+        PAMNET_CUDA(cudaMemsetAsync(cnt_scratch, 0, sizeof(int32_t) * (n_buckets + 1), st));
+        bucket_fill_kernel<<<ceil_div(n, 256), 256, 0, st>>>(keys, n, ptr, cnt_scratch, items);
+        PAMNET_LAUNCH_CHECK();
+        bucket_sort_kernel<<<ceil_div(n_buckets, 128), 128, 0, st>>>(ptr, n_buckets, items, key2);
+        PAMNET_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+__global__ void gather_i32_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ idx, int64_t n,
+                                  int32_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[idx[i]];
+}
+
+__global__ void invert_perm_kernel(const int32_t* __restrict__ perm, int64_t n, int32_t* __restrict__ inv) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) inv[perm[i]] = (int32_t)i;
+}
+
+// incoming CSR keyed by destination: ptr, eid (API edge id per slot), src/dst per slot.
+// Slot order inside a destination = (source id, edge id): SparseTensor's sort at models.py:72.
+int build_in_csr(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, int dst_row, int32_t* dst_api,
+                 int32_t* src_api, int32_t* cnt_scratch, int32_t* ptr, int32_t* eid, int32_t* src_csr,
+                 int32_t* dst_csr, cudaStream_t st) {
+    if (n_edges > 0) {
+        split_edges_kernel<<<ceil_div(n_edges, 256), 256, 0, st>>>(edge_index, n_edges, dst_row, dst_api, src_api);
+        PAMNET_LAUNCH_CHECK();
+    }
+    PAMNET_TRY(build_buckets(dst_api, n_edges, n_nodes, src_api, cnt_scratch, ptr, eid, st));
+    if (n_edges > 0) {
+        gather_i32_kernel<<<ceil_div(n_edges, 256), 256, 0, st>>>(src_api, eid, n_edges, src_csr);
+        PAMNET_LAUNCH_CHECK();
+        if (dst_csr) {
+            gather_i32_kernel<<<ceil_div(n_edges, 256), 256, 0, st>>>(dst_api, eid, n_edges, dst_csr);
+            PAMNET_LAUNCH_CHECK();
+        }
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// triplets in the reference's (API) order -- PAMNet.indices, models.py:68-98
+// ---------------------------------------------------------------------------------------------
+// per API edge e = (j -> i):  two-hop count = |{p in in(j): src[p] != i}|, one-hop = |{p in in(i): src[p] != i}|
+__global__ void triplet_count_kernel(const int32_t* __restrict__ dst_api, const int32_t* __restrict__ src_api,
+                                     int64_t n_edges, const int32_t* __restrict__ ptr,
+                                     const int32_t* __restrict__ src_csr, int32_t* __restrict__ c2,
+                                     int32_t* __restrict__ c1) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_edges) return;
+    const int j = src_api[e], i = dst_api[e];
+    int n2 = 0, n1 = 0;
+    for (int p = ptr[j]; p < ptr[j + 1]; ++p) n2 += (src_csr[p] != i);
+    for (int p = ptr[i]; p < ptr[i + 1]; ++p) n1 += (src_csr[p] != i);
+    c2[e] = n2;
+    c1[e] = n1;
+}
+
+__global__ void triplet_fill_kernel(const int32_t* __restrict__ dst_api, const int32_t* __restrict__ src_api,
+                                    int64_t n_edges, const int32_t* __restrict__ ptr,
+                                    const int32_t* __restrict__ src_csr, const int32_t* __restrict__ eid,
+                                    const int32_t* __restrict__ off2, const int32_t* __restrict__ off1,
+                                    int64_t* __restrict__ idx_i, int64_t* __restrict__ idx_j,
+                                    int64_t* __restrict__ idx_k, int64_t* __restrict__ idx_kj,
+                                    int64_t* __restrict__ idx_ji, int64_t* __restrict__ idx_i_pair,
+                                    int64_t* __restrict__ idx_j1_pair, int64_t* __restrict__ idx_j2_pair,
+                                    int64_t* __restrict__ idx_jj_pair, int64_t* __restrict__ idx_ji_pair) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_edges) return;
+    const int j = src_api[e], i = dst_api[e];
+    int w = off2[e];
+    for (int p = ptr[j]; p < ptr[j + 1]; ++p) {
+        const int k = src_csr[p];
+        if (k == i) continue;
+        idx_i[w] = i; idx_j[w] = j; idx_k[w] = k; idx_kj[w] = eid[p]; idx_ji[w] = e;
+        ++w;
+    }
+    w = off1[e];
+    for (int p = ptr[i]; p < ptr[i + 1]; ++p) {
+        const int j2 = src_csr[p];
+        if (j2 == i) continue;
+        idx_i_pair[w] = j; idx_j1_pair[w] = i; idx_j2_pair[w] = j2; idx_jj_pair[w] = eid[p]; idx_ji_pair[w] = e;
+        ++w;
+    }
+}
+
+struct TripletScratch {
+    int32_t *dst_api, *src_api, *cnt, *ptr, *eid, *src_csr, *c2, *c1, *off2, *off1;
+};
+
+static size_t triplet_scratch_layout(int64_t n_nodes, int64_t n_edges, void* base, TripletScratch* s) {
+    size_t off = 0;
+    auto take = [&](int64_t n) {
+        int32_t* p = base ? reinterpret_cast<int32_t*>(static_cast<char*>(base) + off) : nullptr;
+        off += align_up(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+        return p;
+    };
+    TripletScratch t;
+    t.dst_api = take(n_edges); t.src_api = take(n_edges); t.cnt = take(n_nodes + 1); t.ptr = take(n_nodes + 1);
+    t.eid = take(n_edges); t.src_csr = take(n_edges); t.c2 = take(n_edges); t.c1 = take(n_edges);
+    t.off2 = take(n_edges + 1); t.off1 = take(n_edges + 1);
+    if (s) *s = t;
+    return off;
+}
+
+size_t triplet_scratch_bytes(int64_t n_nodes, int64_t n_edges) {
+    return triplet_scratch_layout(n_nodes, n_edges, nullptr, nullptr);
+}
+
+int triplet_count(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, void* scratch, int64_t* counts_dev,
+                  cudaStream_t st) {
+    TripletScratch s;
+    triplet_scratch_layout(n_nodes, n_edges, scratch, &s);
+    PAMNET_TRY(build_in_csr(edge_index, n_edges, n_nodes, 1, s.dst_api, s.src_api, s.cnt, s.ptr, s.eid, s.src_csr,
+                            nullptr, st));
+    if (n_edges > 0) {
+        triplet_count_kernel<<<ceil_div(n_edges, 128), 128, 0, st>>>(s.dst_api, s.src_api, n_edges, s.ptr, s.src_csr,
+                                                                     s.c2, s.c1);
+        PAMNET_LAUNCH_CHECK();
+    }
+    PAMNET_TRY(scan_exclusive(s.c2, s.off2, n_edges, counts_dev, st));
+    PAMNET_TRY(scan_exclusive(s.c1, s.off1, n_edges, counts_dev + 1, st));
+    return 0;
+}
+
+int triplet_fill(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, const void* scratch, int64_t* const* out,
+                 cudaStream_t st) {
+    (void)edge_index;
+    TripletScratch s;
+    triplet_scratch_layout(n_nodes, n_edges, const_cast<void*>(scratch), &s);
+    if (n_edges == 0) return 0;
+    triplet_fill_kernel<<<ceil_div(n_edges, 128), 128, 0, st>>>(s.dst_api, s.src_api, n_edges, s.ptr, s.src_csr, s.eid,
+                                                                s.off2, s.off1, out[0], out[1], out[2], out[3], out[4],
+                                                                out[5], out[6], out[7], out[8], out[9]);
+    PAMNET_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// execution plan
+// ---------------------------------------------------------------------------------------------
+// Two blobs: `base` holds everything whose size is known before the triplet count (so plan_count can run),
+// `trip` holds the T-sized arrays and is allocated by the caller once {T2, T1} are known.
+void plan_layout(const pamnet_sizes_t& sz, void* base, void* trip, Plan* out, size_t* base_bytes,
+                 size_t* trip_bytes) {
+    size_t off = 0;
+    char* cur = static_cast<char*>(base);
+    auto take_i = [&](int64_t n) {
+        int32_t* p = cur ? reinterpret_cast<int32_t*>(cur + off) : nullptr;
+        off += align_up(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+        return p;
+    };
+    auto take_f = [&](int64_t n) { return reinterpret_cast<float*>(take_i(n)); };
+    const int64_t N = sz.n_nodes, G = sz.n_graphs, Eg = sz.n_edges_g, El = sz.n_edges_l, T = sz.n_t2 + sz.n_t1;
+    const int64_t Emax = Eg > El ? Eg : El;
+    Plan p;
+    p.n2g = take_i(N); p.gptr = take_i(G + 1);
+    p.g_ptr = take_i(N + 1); p.g_src = take_i(Eg); p.g_eid = take_i(Eg); p.g_optr = take_i(N + 1); p.g_opos = take_i(Eg);
+    p.l_ptr = take_i(N + 1); p.l_src = take_i(El); p.l_dst = take_i(El); p.l_eid = take_i(El);
+    p.l_optr = take_i(N + 1); p.l_opos = take_i(El);
+    p.t_split = take_i(El); p.t_cnt = take_i(El); p.t_ptr = take_i(El + 1); p.tt_ptr = take_i(El + 1);
+    p.dist_g = take_f(Eg); p.dist_l = take_f(El);
+    p.tmp_a = take_i(Emax); p.tmp_b = take_i(Emax);
+    p.cnt = take_i((N > El ? N : El) + 2);
+    if (base_bytes) *base_bytes = off;
+    off = 0;
+    cur = static_cast<char*>(trip);
+    p.t_gather = take_i(T); p.t_owner = take_i(T); p.tt_t = take_i(T); p.t_angle = take_f(T);
+    if (trip_bytes) *trip_bytes = off;
+    if (out) *out = p;
+}
+
+__global__ void n2g_kernel(const int64_t* __restrict__ batch, int64_t n, int64_t n_graphs, int32_t* __restrict__ n2g,
+                           int32_t* __restrict__ gptr) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) n2g[i] = (int32_t)batch[i];
+    if (i <= n_graphs) gptr[i] = (int32_t)lower_bound_i64(batch, n, i);
+}
+
+// per local CSR slot k (edge j -> i): two-hop and one-hop counts (same rule as triplet_count_kernel)
+__global__ void plan_tcount_kernel(const int32_t* __restrict__ l_ptr, const int32_t* __restrict__ l_src,
+                                   const int32_t* __restrict__ l_dst, int64_t n_edges, int two_hop,
+                                   int32_t* __restrict__ t_split, int32_t* __restrict__ t_cnt,
+                                   unsigned long long* __restrict__ totals) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int n2 = 0, n1 = 0;
+    if (k < n_edges) {
+        const int j = l_src[k], i = l_dst[k];
+        if (two_hop)
+            for (int p = l_ptr[j]; p < l_ptr[j + 1]; ++p) n2 += (l_src[p] != i);
+        for (int p = l_ptr[i]; p < l_ptr[i + 1]; ++p) n1 += (l_src[p] != i);
+        t_split[k] = n2;
+        t_cnt[k] = n2 + n1;
+    }
+    // block totals -> {T2, T1}
+    __shared__ int s2[32], s1[32];
+    int w2 = n2, w1 = n1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        w2 += __shfl_xor_sync(0xffffffffu, w2, o);
+        w1 += __shfl_xor_sync(0xffffffffu, w1, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s2[threadIdx.x >> 5] = w2; s1[threadIdx.x >> 5] = w1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int a = 0, b = 0;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) { a += s2[w]; b += s1[w]; }
+        atomicAdd(&totals[0], (unsigned long long)a);
+        atomicAdd(&totals[1], (unsigned long long)b);
+    }
+}
+
+__device__ __forceinline__ float bond_angle(const float* __restrict__ pos, int a, int b, int c) {
+    // models.py:165-177: u = pos[b]-pos[a], v = pos[c]-pos[b]; atan2(|u x v|, u.v)
+    const float ux = pos[3 * b] - pos[3 * a], uy = pos[3 * b + 1] - pos[3 * a + 1], uz = pos[3 * b + 2] - pos[3 * a + 2];
+    const float vx = pos[3 * c] - pos[3 * b], vy = pos[3 * c + 1] - pos[3 * b + 1], vz = pos[3 * c + 2] - pos[3 * b + 2];
+    const float dot = ux * vx + uy * vy + uz * vz;
+    const float cx = uy * vz - uz * vy, cy = uz * vx - ux * vz, cz = ux * vy - uy * vx;
+    return atan2f(sqrtf(cx * cx + cy * cy + cz * cz), dot);
+}
+
+// segment of slot k: first its two-hop entries (edges into the source j, minus the back edge), then its
+// one-hop entries (edges into the target i) -- the order the reference's cat() gives (local_message_passing.py:38-40)
+__global__ void plan_tfill_kernel(const int32_t* __restrict__ l_ptr, const int32_t* __restrict__ l_src,
+                                  const int32_t* __restrict__ l_dst, int64_t n_edges, int two_hop,
+                                  const int32_t* __restrict__ t_ptr, const float* __restrict__ pos,
+                                  int32_t* __restrict__ t_gather, int32_t* __restrict__ t_owner,
+                                  float* __restrict__ t_angle) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_edges) return;
+    const int j = l_src[k], i = l_dst[k];
+    int w = t_ptr[k];
+    if (two_hop) {
+        for (int p = l_ptr[j]; p < l_ptr[j + 1]; ++p) {
+            const int kk = l_src[p];
+            if (kk == i) continue;
+            t_gather[w] = p; t_owner[w] = (int32_t)k;
+            t_angle[w] = bond_angle(pos, i, j, kk);       // (idx_i, idx_j, idx_k)
+            ++w;
+        }
+    }
+    for (int p = l_ptr[i]; p < l_ptr[i + 1]; ++p) {
+        const int j2 = l_src[p];
+        if (j2 == i) continue;
+        t_gather[w] = p; t_owner[w] = (int32_t)k;
+        t_angle[w] = bond_angle(pos, j, i, j2);           // (idx_i_pair, idx_j1_pair, idx_j2_pair)
+        ++w;
+    }
+}
+
+__global__ void csr_dist_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ src, int64_t n_nodes,
+                                const float* __restrict__ pos, float* __restrict__ dist) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_nodes) return;
+    for (int p = ptr[n]; p < ptr[n + 1]; ++p) dist[p] = edge_len(pos, n, src[p]);
+}
+
+int plan_count(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const int64_t* edge_index_g,
+               const int64_t* edge_index_l, const int64_t* batch, void* plan_base, int64_t* counts_dev,
+               cudaStream_t st) {
+    Plan p;
+    plan_layout(sz, plan_base, nullptr, &p, nullptr, nullptr);
+    const int64_t N = sz.n_nodes, Eg = sz.n_edges_g, El = sz.n_edges_l;
+    {
+        const int64_t n = (N > sz.n_graphs + 1 ? N : sz.n_graphs + 1);
+        n2g_kernel<<<ceil_div(n, 256), 256, 0, st>>>(batch, N, sz.n_graphs, p.n2g, p.gptr);
+        PAMNET_LAUNCH_CHECK();
+    }
+    // global graph: x_i = x[edge_index[dst_row]] is also the aggregation target (PyG propagate)
+    const int g_dst_row = (cfg.flow == PAMNET_TARGET_TO_SOURCE) ? 0 : 1;
+    PAMNET_TRY(build_in_csr(edge_index_g, Eg, N, g_dst_row, p.tmp_a, p.tmp_b, p.cnt, p.g_ptr, p.g_eid, p.g_src,
+                            nullptr, st));
+    PAMNET_TRY(build_buckets(p.g_src, Eg, N, nullptr, p.cnt, p.g_optr, p.g_opos, st));
+    // local graph: i = edge_index[1] always (local_message_passing.py:37)
+    PAMNET_TRY(build_in_csr(edge_index_l, El, N, 1, p.tmp_a, p.tmp_b, p.cnt, p.l_ptr, p.l_eid, p.l_src, p.l_dst, st));
+    PAMNET_TRY(build_buckets(p.l_src, El, N, nullptr, p.cnt, p.l_optr, p.l_opos, st));
+    PAMNET_CUDA(cudaMemsetAsync(counts_dev, 0, 2 * sizeof(int64_t), st));
+    if (El > 0) {
+        plan_tcount_kernel<<<ceil_div(El, 128), 128, 0, st>>>(p.l_ptr, p.l_src, p.l_dst, El, cfg.simple ? 0 : 1,
+                                                              p.t_split, p.t_cnt,
+                                                              reinterpret_cast<unsigned long long*>(counts_dev));
+        PAMNET_LAUNCH_CHECK();
+    }
+    PAMNET_TRY(scan_exclusive(p.t_cnt, p.t_ptr, El, nullptr, st));
+    return 0;
+}
+
+int plan_fill(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const float* pos, void* plan_base,
+              void* plan_trip, cudaStream_t st) {
+    Plan p;
+    plan_layout(sz, plan_base, plan_trip, &p, nullptr, nullptr);
+    const int64_t N = sz.n_nodes, El = sz.n_edges_l, T = sz.n_t2 + sz.n_t1;
+    if (El > 0 && T > 0) {
+        plan_tfill_kernel<<<ceil_div(El, 128), 128, 0, st>>>(p.l_ptr, p.l_src, p.l_dst, El, cfg.simple ? 0 : 1, p.t_ptr,
+                                                             pos, p.t_gather, p.t_owner, p.t_angle);
+        PAMNET_LAUNCH_CHECK();
+    }
+    PAMNET_TRY(build_buckets(p.t_gather, T, El, nullptr, p.cnt, p.tt_ptr, p.tt_t, st));
+    if (N > 0) {
+        csr_dist_kernel<<<ceil_div(N, 128), 128, 0, st>>>(p.g_ptr, p.g_src, N, pos, p.dist_g);
+        PAMNET_LAUNCH_CHECK();
+        csr_dist_kernel<<<ceil_div(N, 128), 128, 0, st>>>(p.l_ptr, p.l_src, N, pos, p.dist_l);
+        PAMNET_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+}  // namespace pamnet

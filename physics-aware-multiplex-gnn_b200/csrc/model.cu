@@ -1,0 +1,747 @@
+// Forward / backward drivers for PAMNet.forward (models.py:100-224) and its autograd backward
+// (main_qm9.py:110), composed from the kernels in graph/basis/gemm/chain/message/readout.
+//
+// Structure (DESIGN.md "Execution schedule"):
+//   phase A  x-independent dense work, once per step and for ALL layers at once: basis -> edge/triplet
+//            embeddings (models.py:180-188) -> per-layer edge projections Q|Tt (global), Qji|Qkj|R|Rout (local)
+//            and the triplet gate MLP (local_message_passing.py:17,49);
+//   phase B  the sequential layer loop (models.py:196-204): per layer two message kernels + two node chains;
+//   readout  models.py:206-224.
+// Backward mirrors it: phase B reversed (data gradients, per-edge gradients written once), then phase A'
+// turns the accumulated per-edge / per-triplet gradients into weight gradients with a few large GEMMs.
+#include "model.cuh"
+
+#include "basis.cuh"
+#include "chain.cuh"
+#include "gemm.cuh"
+#include "graph.cuh"
+#include "message.cuh"
+#include "readout.cuh"
+
+namespace pamnet {
+
+// ---------------------------------------------------------------------------------------------
+// parameter layout == reference state_dict order, every tensor 128 B aligned
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct LayoutBuilder {
+    ModelP* mp;
+    int64_t cur = 0;
+    int64_t take(int64_t n) {
+        const int64_t off = cur;
+        mp->offsets.push_back(off);
+        mp->numel.push_back(n);
+        cur = (cur + n + kParamAlign - 1) / kParamAlign * kParamAlign;
+        return off;
+    }
+    Lin lin(int64_t out, int64_t in, bool bias = true) {
+        Lin l;
+        l.w = take(out * in);
+        if (bias) l.b = take(out);
+        return l;
+    }
+};
+}  // namespace
+
+int build_param_layout(const pamnet_config_t& cfg, ModelP* mp) {
+    PAMNET_CHECK_ARG(cfg.dim == 16 || cfg.dim == 32 || cfg.dim == 64 || cfg.dim == 128,
+                     "dim=%d unsupported (16, 32, 64, 128)", cfg.dim);
+    PAMNET_CHECK_ARG(cfg.n_layer >= 1 && cfg.n_layer <= kMaxLayers, "n_layer=%d unsupported (1..%d)", cfg.n_layer,
+                     kMaxLayers);
+    PAMNET_CHECK_ARG(cfg.dataset >= PAMNET_QM9 && cfg.dataset <= PAMNET_RNA, "bad dataset id %d", cfg.dataset);
+    PAMNET_CHECK_ARG(!cfg.simple || cfg.dataset == PAMNET_QM9, "PAMNet_s is QM9-only (models.py:286-287)");
+    const int64_t D = cfg.dim;
+    *mp = ModelP();
+    LayoutBuilder b{mp};
+    const bool rna = cfg.dataset == PAMNET_RNA;
+    mp->n_embed = rna ? 3 : 5;                                   // models.py:31-34
+    mp->emb = b.take(mp->n_embed * D);
+    if (!rna && !cfg.simple) mp->init_linear = b.take(D * kFeatPdb);   // models.py:35
+    mp->freq_g = b.take(kNumRbf);
+    mp->freq_l = b.take(kNumRbf);
+    mp->rbf_g = b.lin(D, kNumRbf);
+    mp->rbf_l = b.lin(D, kNumRbf);
+    mp->sbf1 = b.lin(D, kNumSbf);
+    if (!cfg.simple) mp->sbf2 = b.lin(D, kNumSbf);
+    auto res_and = [&](HalfP& h) {
+        for (int r = 0; r < 3; ++r)
+            for (int s = 0; s < 2; ++s) h.res[r][s] = b.lin(D, D);
+    };
+    auto heads = [&](HalfP& h) {
+        for (int s = 0; s < 3; ++s) h.out[s] = b.lin(D, D);
+        h.W_out = b.lin(1, D);
+    };
+    for (int l = 0; l < cfg.n_layer; ++l) {                      // global_message_passing.py:13-26
+        HalfP& h = mp->g[l];
+        h.W = b.take(D);
+        h.x1 = b.lin(D, D);
+        h.x2 = b.lin(D, D);
+        res_and(h);
+        h.m = b.lin(D, 3 * D);
+        h.We = b.lin(D, D, false);
+        heads(h);
+    }
+    for (int l = 0; l < cfg.n_layer; ++l) {                      // local_message_passing.py:13-29
+        HalfP& h = mp->l[l];
+        h.W = b.take(D);
+        h.x1 = b.lin(D, D);
+        h.m_ji = b.lin(D, 3 * D);
+        h.m_kj = b.lin(D, 3 * D);
+        h.sbf[0] = b.lin(D, D);
+        h.sbf[1] = b.lin(D, D);
+        h.lin_rbf = b.lin(D, D, false);
+        res_and(h);
+        h.lin_rbf_out = b.lin(D, D, false);
+        h.x2 = b.lin(D, D);
+        heads(h);
+    }
+    mp->total = b.cur;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct HalfWs {
+    // transposed weights (k-major) for the forward chain; offsets into Ws::wt
+    float *x1T, *x2T, *resT[3][2], *outT[3], *projT;
+    // saved activations, each [N, D] unless noted
+    float *P;                               // [N, nP*D]
+    float *z_x1, *x1, *h, *z_x2, *a_x2;
+    float *z_A[3], *a_A[3], *z_B[3], *r[3];
+    float *z_o[3], *a_o[3];
+    float *m_nb, *msum;                     // local only, [El, D]
+    // backward
+    float *gz_x1, *gz_x2, *gz_A[3], *gz_B[3], *gz_o[3];
+};
+
+struct Ws {
+    float* wt;
+    float *x0, *rbf_g, *rbf_l, *radial, *sbf_ext, *w_ext, *gw_ext;
+    float *z_eg, *e_g, *z_el, *e_l, *z_s, *s;
+    float *QT, *QR, *zq1, *aq1, *zq2;
+    float *att, *out, *node_val;
+    HalfWs half[2 * kMaxLayers];
+    // backward
+    float *g_att, *g_out, *g_h, *g_resx, *g_P, *g_s, *g_x0;
+    float *gQT, *gQR, *gzq2, *gzq1, *gz_s, *gz_eg, *gz_el, *g_rbf_g, *g_rbf_l;
+};
+
+// half index hh = 2*l (global layer l) or 2*l+1 (local layer l)
+inline bool is_local(int hh) { return hh & 1; }
+inline int nP_of(int hh) { return is_local(hh) ? 4 : 2; }
+
+size_t ws_layout(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, void* base, Ws* out) {
+    size_t off = 0;
+    auto take = [&](int64_t n) {
+        float* p = base ? reinterpret_cast<float*>(static_cast<char*>(base) + off) : nullptr;
+        off += align_up(sizeof(float) * (size_t)(n > 0 ? n : 1));
+        return p;
+    };
+    const int64_t N = sz.n_nodes, Eg = sz.n_edges_g, El = sz.n_edges_l, T = sz.n_t2 + sz.n_t1;
+    const int64_t D = cfg.dim, L = cfg.n_layer, H = 2 * L;
+    Ws w;
+    memset(&w, 0, sizeof(w));
+    w.wt = nullptr;
+    for (int hh = 0; hh < H; ++hh) {      // transposed weights first: their offsets stay small
+        HalfWs& h = w.half[hh];
+        h.x1T = take(D * D); h.x2T = take(D * D);
+        for (int r = 0; r < 3; ++r) for (int s = 0; s < 2; ++s) h.resT[r][s] = take(D * D);
+        for (int s = 0; s < 3; ++s) h.outT[s] = take(D * D);
+        h.projT = take(nP_of(hh) * D * D);
+    }
+    w.x0 = take(N * D);
+    w.rbf_g = take(Eg * kNumRbf); w.rbf_l = take(El * kNumRbf); w.radial = take(El * kNumSbf);
+    w.sbf_ext = take(T * kSbfExt); w.w_ext = take(D * kSbfExt); w.gw_ext = take(D * kSbfExt);
+    w.z_eg = take(Eg * D); w.e_g = take(Eg * D); w.z_el = take(El * D); w.e_l = take(El * D);
+    w.z_s = take(T * D); w.s = take(T * D);
+    w.QT = take(Eg * L * 2 * D); w.QR = take(El * L * 4 * D);
+    w.zq1 = take(T * L * D); w.aq1 = take(T * L * D); w.zq2 = take(T * L * D);
+    w.att = take(H * N); w.out = take(H * N); w.node_val = take(N);
+    for (int hh = 0; hh < H; ++hh) {
+        HalfWs& h = w.half[hh];
+        h.P = take(N * nP_of(hh) * D);
+        h.z_x1 = take(N * D); h.x1 = take(N * D); h.h = take(N * D); h.z_x2 = take(N * D); h.a_x2 = take(N * D);
+        for (int r = 0; r < 3; ++r) {
+            h.z_A[r] = take(N * D); h.a_A[r] = take(N * D); h.z_B[r] = take(N * D); h.r[r] = take(N * D);
+        }
+        for (int s = 0; s < 3; ++s) { h.z_o[s] = take(N * D); h.a_o[s] = take(N * D); }
+        if (is_local(hh)) { h.m_nb = take(El * D); h.msum = take(El * D); }
+        h.gz_x1 = take(N * D); h.gz_x2 = take(N * D);
+        for (int r = 0; r < 3; ++r) { h.gz_A[r] = take(N * D); h.gz_B[r] = take(N * D); }
+        for (int s = 0; s < 3; ++s) h.gz_o[s] = take(N * D);
+    }
+    w.g_att = take(H * N); w.g_out = take(H * N);
+    w.g_h = take(N * D); w.g_resx = take(N * D); w.g_P = take(N * 4 * D); w.g_s = take(El * D); w.g_x0 = take(N * D);
+    w.gQT = take(Eg * L * 2 * D); w.gQR = take(El * L * 4 * D);
+    w.gzq2 = take(T * L * D); w.gzq1 = take(T * L * D); w.gz_s = take(T * D);
+    w.gz_eg = take(Eg * D); w.gz_el = take(El * D); w.g_rbf_g = take(Eg * kNumRbf); w.g_rbf_l = take(El * kNumRbf);
+    if (out) *out = w;
+    return off;
+}
+
+const HalfP& half_params(const ModelP& mp, int hh) { return is_local(hh) ? mp.l[hh >> 1] : mp.g[hh >> 1]; }
+
+// ---- small builders ---------------------------------------------------------------------------
+ChainStage stage_zero() {
+    ChainStage s;
+    memset(&s, 0, sizeof(s));
+    s.psrc = -1; s.dst = -1; s.add_slot = -1;
+    return s;
+}
+ChainStage st_load(int dst, const float* g0, int ld_g, int width, const float* g1 = nullptr) {
+    ChainStage s = stage_zero();
+    s.op = CH_LOAD; s.dst = dst; s.g0 = g0; s.g1 = g1; s.ld_g = ld_g; s.width = width;
+    return s;
+}
+ChainStage st_gemm(int src, int dst, const float* W, int ldw, const float* bias, int act) {
+    ChainStage s = stage_zero();
+    s.op = CH_GEMM; s.src = src; s.dst = dst; s.W = W; s.ldw = ldw; s.bias = bias; s.act = act;
+    return s;
+}
+
+struct Prog {
+    ChainArgs a;
+    Prog(int n_rows) { memset(&a, 0, sizeof(a)); a.n_rows = n_rows; }
+    ChainStage& add(const ChainStage& s) { a.st[a.n_stages] = s; return a.st[a.n_stages++]; }
+};
+
+// forward: x1 = SiLU(mlp_x1(x)) (global_message_passing.py:35 / local_message_passing.py:43) and the per-node
+// halves of the edge MLPs.  `src` holds x; uses slot (src+2)%3 for x1.
+void add_pre_fwd(Prog& p, const float* params, const HalfP& hp, const HalfWs& hw, int hh, int D, int src) {
+    const int x1s = (src + 2) % 3;
+    ChainStage& a = p.add(st_gemm(src, x1s, hw.x1T, D, params + hp.x1.b, 1));
+    a.out_z = hw.z_x1; a.out_a = hw.x1; a.ld_out = D;
+    const int nP = nP_of(hh);
+    for (int c = 0; c < nP; ++c) {
+        ChainStage& g = p.add(st_gemm(x1s, -1, hw.projT + (size_t)c * D * D, D, nullptr, 0));
+        g.out_a = hw.P + c * D; g.ld_out = nP * D;
+    }
+}
+
+// forward update block + heads (global_message_passing.py:39-48); leaves x_out in slot 1
+void add_post_fwd(Prog& p, const float* params, const HalfP& hp, const HalfWs& hw, int D, const float* res_x,
+                  float* att, float* out) {
+    p.add(st_load(0, hw.h, D, D));
+    { ChainStage& s = p.add(st_gemm(0, 1, hw.x2T, D, params + hp.x2.b, 1)); s.out_z = hw.z_x2; s.out_a = hw.a_x2; s.ld_out = D; }
+    int cur = 1;                                    // slot holding the Res input
+    for (int r = 0; r < 3; ++r) {
+        const int tmp = (cur + 2) % 3, nxt = (cur + 1) % 3;
+        { ChainStage& s = p.add(st_gemm(cur, tmp, hw.resT[r][0], D, params + hp.res[r][0].b, 1));
+          s.out_z = hw.z_A[r]; s.out_a = hw.a_A[r]; s.ld_out = D; }
+        { ChainStage& s = p.add(st_gemm(tmp, nxt, hw.resT[r][1], D, params + hp.res[r][1].b, 1));
+          s.add_slot = cur; s.out_z = hw.z_B[r]; s.out_a = hw.r[r]; s.ld_out = D;
+          if (r == 0) { s.add_g = res_x; s.ld_add = D; } }
+        cur = nxt;
+    }
+    // cur == 1 after three rotations (1 -> 2 -> 0 -> 1); heads read mlp_out(x)
+    const int xs = cur;
+    int a = xs;
+    for (int s3 = 0; s3 < 3; ++s3) {
+        int d = (a + 1) % 3;
+        if (d == xs) d = (d + 1) % 3;
+        ChainStage& s = p.add(st_gemm(a, d, hw.outT[s3], D, params + hp.out[s3].b, 1));
+        s.out_z = hw.z_o[s3]; s.out_a = hw.a_o[s3]; s.ld_out = D;
+        a = d;
+    }
+    ChainStage d2 = stage_zero();
+    d2.op = CH_DOT2; d2.src = a; d2.W = params + hp.W; d2.bias = params + hp.W_out.w; d2.g0 = params + hp.W_out.b;
+    d2.out_z = att; d2.out_a = out;
+    p.add(d2);
+}
+
+// backward of add_pre_fwd for half hh: g_x1 = g_h + g_P . W_proj ; g_x = (g_x1 * SiLU'(z_x1)) . W_x1 + g_resx
+// result in slot 2 (and in `g_x_out` if non-null)
+void add_pre_bwd(Prog& p, const float* params, const HalfP& hp, const HalfWs& hw, int hh, int D, const Ws& w,
+                 float* g_x_out) {
+    const int nP = nP_of(hh);
+    p.add(st_load(kChainWide, w.g_P, nP * D, nP * D));
+    p.add(st_load(0, w.g_h, D, D));
+    int cur = 0;
+    for (int c = 0; c < nP; ++c) {
+        const float* Wc;
+        if (!is_local(hh)) Wc = params + hp.m.w + c * D;
+        else Wc = params + (c < 2 ? hp.m_ji.w : hp.m_kj.w) + (c & 1) * D;
+        ChainStage& s = p.add(st_gemm(kChainWide, cur ^ 1, Wc, 3 * D, nullptr, 0));
+        s.src_off = c * D; s.add_slot = cur;
+        cur ^= 1;
+    }
+    // nP is even -> cur == 0 holds g_x1
+    ChainStage& s = p.add(st_gemm(cur, 2, params + hp.x1.w, D, nullptr, 0));
+    s.psrc = cur; s.zmul = hw.z_x1; s.save_src = hw.gz_x1; s.add_g = w.g_resx; s.ld_add = D;
+    s.out_a = g_x_out; s.ld_out = D;
+}
+
+// backward of add_post_fwd; expects grad wrt x_out in slot 2 when has_gx; writes g_h and g_resx
+void add_post_bwd(Prog& p, const float* params, const HalfP& hp, const HalfWs& hw, int D, const Ws& w,
+                  const float* g_att, const float* g_out, bool has_gx) {
+    ChainStage hb = stage_zero();
+    hb.op = CH_HEADS_BWD; hb.dst = 0; hb.g0 = g_att; hb.g1 = g_out; hb.W = params + hp.W; hb.bias = params + hp.W_out.w;
+    p.add(hb);
+    auto bwd = [&](int src, int psrc, int dst, const float* z, float* save, const float* W, int add_slot) -> ChainStage& {
+        ChainStage& s = p.add(st_gemm(src, dst, W, D, nullptr, 0));
+        s.psrc = psrc; s.zmul = z; s.save_src = save; s.add_slot = add_slot;
+        return s;
+    };
+    bwd(0, 0, 1, hw.z_o[2], hw.gz_o[2], params + hp.out[2].w, -1);
+    bwd(1, 1, 0, hw.z_o[1], hw.gz_o[1], params + hp.out[1].w, -1);
+    bwd(0, 0, 1, hw.z_o[0], hw.gz_o[0], params + hp.out[0].w, has_gx ? 2 : -1);      // slot1 = g_r3
+    bwd(1, 0, 2, hw.z_B[2], hw.gz_B[2], params + hp.res[2][1].w, -1);
+    bwd(2, 2, 0, hw.z_A[2], hw.gz_A[2], params + hp.res[2][0].w, 1);                 // slot0 = g_r2
+    bwd(0, 1, 2, hw.z_B[1], hw.gz_B[1], params + hp.res[1][1].w, -1);
+    { ChainStage& s = bwd(2, 2, 1, hw.z_A[1], hw.gz_A[1], params + hp.res[1][0].w, 0);    // slot1 = g_r1
+      s.out_a = w.g_resx; s.ld_out = D; }
+    bwd(1, 0, 2, hw.z_B[0], hw.gz_B[0], params + hp.res[0][1].w, -1);
+    bwd(2, 2, 0, hw.z_A[0], hw.gz_A[0], params + hp.res[0][0].w, 1);                 // slot0 = g_x2
+    { ChainStage& s = bwd(0, 0, 1, hw.z_x2, hw.gz_x2, params + hp.x2.w, -1);
+      s.out_a = w.g_h; s.ld_out = D; }
+}
+
+GemmArgs gemm_zero(int mode, int epi, int M, int N, int K) {
+    GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.mode = mode; a.epi = epi; a.M = M; a.N = N; a.K = K; a.ksplit = 1;
+    return a;
+}
+GemmSlot slot(const float* A, int lda, const float* B, int ldb, float* C, int ldc, const float* bias = nullptr,
+              float* C2 = nullptr, const float* Z = nullptr, int ldz = 0) {
+    GemmSlot s;
+    s.A = A; s.B = B; s.bias = bias; s.Z = Z; s.C = C; s.C2 = C2; s.lda = lda; s.ldb = ldb; s.ldc = ldc; s.ldz = ldz;
+    return s;
+}
+int pick_ksplit(int64_t K) {
+    int64_t s = K / 1024;
+    return (int)(s < 1 ? 1 : (s > 32 ? 32 : s));
+}
+
+// launch a list of slots sharing one GemmArgs header, 32 at a time
+int gemm_multi(GemmArgs a, const std::vector<GemmSlot>& slots, cudaStream_t st) {
+    for (size_t i = 0; i < slots.size(); i += kGemmMaxSlots) {
+        const size_t n = slots.size() - i < (size_t)kGemmMaxSlots ? slots.size() - i : kGemmMaxSlots;
+        a.nslots = (int)n;
+        for (size_t j = 0; j < n; ++j) a.slot[j] = slots[i + j];
+        PAMNET_TRY(gemm_launch(a, st));
+    }
+    return 0;
+}
+
+struct Ctx {
+    pamnet_config_t cfg;
+    pamnet_sizes_t sz;
+    ModelP mp;
+    Plan plan;
+    Ws w;
+    SbfTables tab;
+    int D, L, H;
+    int64_t N, G, Eg, El, T;
+};
+
+int make_ctx(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pamnet_sbf_consts_t& sbf, void* plan_base,
+             void* plan_trip, void* workspace, size_t ws_bytes, Ctx* c) {
+    PAMNET_TRY(build_param_layout(cfg, &c->mp));
+    c->cfg = cfg; c->sz = sz;
+    c->D = cfg.dim; c->L = cfg.n_layer; c->H = 2 * cfg.n_layer;
+    c->N = sz.n_nodes; c->G = sz.n_graphs; c->Eg = sz.n_edges_g; c->El = sz.n_edges_l; c->T = sz.n_t2 + sz.n_t1;
+    PAMNET_CHECK_ARG(c->N > 0 && c->G > 0, "empty batch (n_nodes=%lld, n_graphs=%lld)", (long long)c->N, (long long)c->G);
+    PAMNET_CHECK_ARG(c->N < (1 << 30) && c->Eg * (int64_t)c->L * 2 * c->D < (1ll << 40), "batch too large");
+    const size_t need = ws_layout(cfg, sz, workspace, &c->w);
+    PAMNET_CHECK_ARG(ws_bytes >= need, "workspace too small: %zu < %zu", ws_bytes, need);
+    plan_layout(sz, plan_base, plan_trip, &c->plan, nullptr, nullptr);
+    make_sbf_tables(sbf, &c->tab);
+    return 0;
+}
+
+}  // namespace
+
+size_t workspace_bytes(const pamnet_config_t& cfg, const pamnet_sizes_t& sz) { return ws_layout(cfg, sz, nullptr, nullptr); }
+
+// byte offset of a named workspace buffer (test / debugging aid; -1 = unknown name)
+int64_t debug_ws_offset(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const char* name, int half) {
+    Ws w;
+    char* base = reinterpret_cast<char*>(0x1000);   // fake non-null base; only differences are used
+    ws_layout(cfg, sz, base, &w);
+    const HalfWs& h = w.half[half < 0 ? 0 : half];
+    struct { const char* n; const float* p; } tab[] = {
+        {"x0", w.x0}, {"rbf_g", w.rbf_g}, {"rbf_l", w.rbf_l}, {"radial", w.radial}, {"sbf_ext", w.sbf_ext},
+        {"e_g", w.e_g}, {"e_l", w.e_l}, {"s", w.s}, {"QT", w.QT}, {"QR", w.QR}, {"zq1", w.zq1}, {"aq1", w.aq1},
+        {"zq2", w.zq2}, {"att", w.att}, {"out", w.out}, {"node_val", w.node_val},
+        {"P", h.P}, {"x1", h.x1}, {"h", h.h}, {"a_x2", h.a_x2}, {"r0", h.r[0]}, {"r1", h.r[1]}, {"r2", h.r[2]},
+        {"a_o2", h.a_o[2]}, {"m_nb", h.m_nb}, {"msum", h.msum}, {"x1T", h.x1T},
+        {"g_att", w.g_att}, {"g_out", w.g_out}, {"g_h", w.g_h}, {"g_P", w.g_P}, {"g_x0", w.g_x0},
+        {"gQT", w.gQT}, {"gQR", w.gQR}, {"gzq2", w.gzq2}, {"gz_s", w.gz_s}, {"gz_eg", w.gz_eg}, {"gz_el", w.gz_el},
+        {"gz_x1", h.gz_x1}, {"gz_x2", h.gz_x2}, {"gz_o2", h.gz_o[2]},
+    };
+    for (auto& e : tab)
+        if (strcmp(e.n, name) == 0) return e.p ? (int64_t)(reinterpret_cast<const char*>(e.p) - base) : -1;
+    return -1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pamnet_sbf_consts_t& sbf,
+                  const float* params, const float* node_in, const float* sign, const float* pos, void* plan_base,
+                  void* plan_trip, void* workspace, size_t ws_bytes, float* out, cudaStream_t st) {
+    Ctx c;
+    PAMNET_TRY(make_ctx(cfg, sz, sbf, plan_base, plan_trip, workspace, ws_bytes, &c));
+    const int D = c.D, L = c.L, H = c.H;
+    const int64_t N = c.N, Eg = c.Eg, El = c.El, T = c.T;
+    const ModelP& mp = c.mp;
+    Ws& w = c.w;
+    const Plan& pl = c.plan;
+
+    // ---- transposed (k-major) copies of the chain weights -------------------------------------------
+    {
+        std::vector<TransposeJob> jobs;
+        const float* ws_base = reinterpret_cast<const float*>(workspace);
+        auto job = [&](int64_t src_off, int rows, int cols, int ld, float* dst) {
+            jobs.push_back(TransposeJob{src_off, (int64_t)(dst - ws_base), rows, cols, ld});
+        };
+        for (int hh = 0; hh < H; ++hh) {
+            const HalfP& hp = half_params(mp, hh);
+            const HalfWs& hw = w.half[hh];
+            job(hp.x1.w, D, D, D, hw.x1T);
+            job(hp.x2.w, D, D, D, hw.x2T);
+            for (int r = 0; r < 3; ++r) for (int s = 0; s < 2; ++s) job(hp.res[r][s].w, D, D, D, hw.resT[r][s]);
+            for (int s = 0; s < 3; ++s) job(hp.out[s].w, D, D, D, hw.outT[s]);
+            if (!is_local(hh)) {
+                job(hp.m.w, D, 2 * D, 3 * D, hw.projT);                       // -> [2D, D]
+            } else {
+                job(hp.m_ji.w, D, 2 * D, 3 * D, hw.projT);
+                job(hp.m_kj.w, D, 2 * D, 3 * D, hw.projT + (size_t)2 * D * D);
+            }
+        }
+        PAMNET_TRY(transpose_batch(params, reinterpret_cast<float*>(workspace), jobs.data(), (int)jobs.size(), st));
+    }
+
+    // ---- node input (models.py:107,119,140) ----------------------------------------------------------
+    if (cfg.dataset == PAMNET_PDBBIND) {
+        GemmArgs a = gemm_zero(GEMM_NT, EPI_NONE, (int)N, D, kFeatPdb);
+        a.nslots = 1;
+        a.slot[0] = slot(node_in, kFeatPdb, params + mp.init_linear, kFeatPdb, w.x0, D);
+        PAMNET_TRY(gemm_launch(a, st));
+    } else {
+        PAMNET_TRY(embed_forward(node_in, N, params + mp.emb, mp.n_embed, D, w.x0, st));
+    }
+
+    // ---- phase A: bases and embeddings (models.py:180-188) ------------------------------------------
+    PAMNET_TRY(rbf_forward(pl.dist_g, Eg, params + mp.freq_g, cfg.cutoff_g, w.rbf_g, st));
+    PAMNET_TRY(rbf_forward(pl.dist_l, El, params + mp.freq_l, cfg.cutoff_l, w.rbf_l, st));
+    PAMNET_TRY(sbf_radial(c.tab, pl.dist_l, El, cfg.cutoff_l, w.radial, st));
+    PAMNET_TRY(sbf_ext_forward(c.tab, pl, El, T, pos, w.radial, w.sbf_ext, st));
+    PAMNET_TRY(sbf_weight_pack(D, cfg.simple ? nullptr : params + mp.sbf2.w, cfg.simple ? nullptr : params + mp.sbf2.b,
+                               params + mp.sbf1.w, params + mp.sbf1.b, w.w_ext, st));
+    {
+        GemmArgs a = gemm_zero(GEMM_NT, EPI_BIAS_SILU, (int)Eg, D, kNumRbf);
+        a.nslots = 1;
+        a.slot[0] = slot(w.rbf_g, kNumRbf, params + mp.rbf_g.w, kNumRbf, w.e_g, D, params + mp.rbf_g.b, w.z_eg);
+        PAMNET_TRY(gemm_launch(a, st));
+        a.M = (int)El;
+        a.slot[0] = slot(w.rbf_l, kNumRbf, params + mp.rbf_l.w, kNumRbf, w.e_l, D, params + mp.rbf_l.b, w.z_el);
+        PAMNET_TRY(gemm_launch(a, st));
+        a.M = (int)T; a.K = kSbfExt;
+        a.slot[0] = slot(w.sbf_ext, kSbfExt, w.w_ext, kSbfExt, w.s, D, nullptr, w.z_s);
+        PAMNET_TRY(gemm_launch(a, st));
+    }
+    // ---- phase A: per-layer edge / triplet projections for all layers --------------------------------
+    {
+        std::vector<GemmSlot> sl;
+        const int ldq = L * 2 * D;
+        for (int l = 0; l < L; ++l) {
+            const HalfP& hp = mp.g[l];
+            sl.push_back(slot(w.e_g, D, params + hp.m.w + 2 * D, 3 * D, w.QT + l * 2 * D, ldq, params + hp.m.b));
+            sl.push_back(slot(w.e_g, D, params + hp.We.w, D, w.QT + l * 2 * D + D, ldq));
+        }
+        PAMNET_TRY(gemm_multi(gemm_zero(GEMM_NT, EPI_BIAS, (int)Eg, D, D), sl, st));
+    }
+    {
+        std::vector<GemmSlot> sl;
+        const int ldq = L * 4 * D;
+        for (int l = 0; l < L; ++l) {
+            const HalfP& hp = mp.l[l];
+            float* base = w.QR + l * 4 * D;
+            sl.push_back(slot(w.e_l, D, params + hp.m_ji.w + 2 * D, 3 * D, base, ldq, params + hp.m_ji.b));
+            sl.push_back(slot(w.e_l, D, params + hp.m_kj.w + 2 * D, 3 * D, base + D, ldq, params + hp.m_kj.b));
+            sl.push_back(slot(w.e_l, D, params + hp.lin_rbf.w, D, base + 2 * D, ldq));
+            sl.push_back(slot(w.e_l, D, params + hp.lin_rbf_out.w, D, base + 3 * D, ldq));
+        }
+        PAMNET_TRY(gemm_multi(gemm_zero(GEMM_NT, EPI_BIAS, (int)El, D, D), sl, st));
+    }
+    {
+        const int ldt = L * D;
+        std::vector<GemmSlot> s1, s2;
+        for (int l = 0; l < L; ++l) {
+            const HalfP& hp = mp.l[l];
+            s1.push_back(slot(w.s, D, params + hp.sbf[0].w, D, w.aq1 + l * D, ldt, params + hp.sbf[0].b, w.zq1 + l * D));
+            s2.push_back(slot(w.aq1 + l * D, ldt, params + hp.sbf[1].w, D, w.zq2 + l * D, ldt, params + hp.sbf[1].b));
+        }
+        PAMNET_TRY(gemm_multi(gemm_zero(GEMM_NT, EPI_BIAS_SILU, (int)T, D, D), s1, st));
+        PAMNET_TRY(gemm_multi(gemm_zero(GEMM_NT, EPI_BIAS, (int)T, D, D), s2, st));
+    }
+
+    // ---- phase B: the layer loop (models.py:196-204) -------------------------------------------------
+    {
+        Prog p((int)N);
+        p.add(st_load(2, w.x0, D, D));
+        add_pre_fwd(p, params, half_params(mp, 0), w.half[0], 0, D, 2);
+        PAMNET_TRY(chain_launch(D, p.a, st));
+    }
+    for (int hh = 0; hh < H; ++hh) {
+        const HalfWs& hw = w.half[hh];
+        const int l = hh >> 1;
+        if (!is_local(hh)) {
+            GlobalMsgArgs a;
+            memset(&a, 0, sizeof(a));
+            a.n_nodes = (int)N; a.ptr = pl.g_ptr; a.src = pl.g_src; a.P = hw.P;
+            a.QT = w.QT + l * 2 * D; a.ldq = L * 2 * D; a.x1 = hw.x1; a.h = hw.h;
+            PAMNET_TRY(global_msg_fwd(D, a, st));
+        } else {
+            LocalMsgArgs a;
+            memset(&a, 0, sizeof(a));
+            a.n_nodes = (int)N; a.n_edges = (int)El; a.ptr = pl.l_ptr; a.src = pl.l_src; a.dst = pl.l_dst;
+            a.t_ptr = pl.t_ptr; a.t_gather = pl.t_gather; a.P = hw.P;
+            a.QR = w.QR + l * 4 * D; a.ldq = L * 4 * D; a.zq = w.zq2 + l * D; a.ldt = L * D;
+            a.x1 = hw.x1; a.m_nb = hw.m_nb; a.msum = hw.msum; a.h = hw.h;
+            PAMNET_TRY(local_edge_fwd(D, a, st));
+            PAMNET_TRY(local_msg_fwd(D, a, st));
+        }
+        Prog p((int)N);
+        const float* res_x = hh == 0 ? w.x0 : w.half[hh - 1].r[2];
+        add_post_fwd(p, params, half_params(mp, hh), hw, D, res_x, w.att + (size_t)hh * N, w.out + (size_t)hh * N);
+        if (hh + 1 < H) add_pre_fwd(p, params, half_params(mp, hh + 1), w.half[hh + 1], hh + 1, D, 1);
+        PAMNET_TRY(chain_launch(D, p.a, st));
+    }
+
+    // ---- readout (models.py:206-224) ------------------------------------------------------------------
+    ReadoutArgs r;
+    memset(&r, 0, sizeof(r));
+    r.n_nodes = (int)N; r.n_graphs = (int)c.G; r.n_layer = L; r.pool_mean = cfg.dataset == PAMNET_RNA;
+    r.sign = cfg.dataset == PAMNET_PDBBIND ? sign : nullptr;
+    r.gptr = pl.gptr; r.n2g = pl.n2g; r.att = w.att; r.out = w.out; r.node_val = w.node_val; r.pooled = out;
+    PAMNET_TRY(readout_forward(r, st));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pamnet_sbf_consts_t& sbf,
+                   const float* params, const float* node_in, const float* sign, const float* pos, void* plan_base,
+                   void* plan_trip, void* workspace, size_t ws_bytes, const float* grad_out, float* gp,
+                   cudaStream_t st) {
+    (void)pos;
+    Ctx c;
+    PAMNET_TRY(make_ctx(cfg, sz, sbf, plan_base, plan_trip, workspace, ws_bytes, &c));
+    const int D = c.D, L = c.L, H = c.H;
+    const int64_t N = c.N, Eg = c.Eg, El = c.El, T = c.T;
+    const ModelP& mp = c.mp;
+    Ws& w = c.w;
+    const Plan& pl = c.plan;
+
+    PAMNET_CUDA(cudaMemsetAsync(gp, 0, sizeof(float) * mp.total, st));
+
+    ReadoutArgs r;
+    memset(&r, 0, sizeof(r));
+    r.n_nodes = (int)N; r.n_graphs = (int)c.G; r.n_layer = L; r.pool_mean = cfg.dataset == PAMNET_RNA;
+    r.sign = cfg.dataset == PAMNET_PDBBIND ? sign : nullptr;
+    r.gptr = pl.gptr; r.n2g = pl.n2g; r.att = w.att; r.out = w.out; r.g_pooled = grad_out; r.g_att = w.g_att; r.g_out = w.g_out;
+    PAMNET_TRY(readout_backward(r, st));
+
+    const int ks_n = pick_ksplit(N);
+    // ---- phase B reversed -----------------------------------------------------------------------------
+    for (int hh = H - 1; hh >= 0; --hh) {
+        const HalfWs& hw = w.half[hh];
+        const HalfP& hp = half_params(mp, hh);
+        const int l = hh >> 1;
+        {
+            Prog p((int)N);
+            const bool has_gx = hh + 1 < H;   // the last layer's x output is unused (models.py:201-204)
+            if (has_gx) add_pre_bwd(p, params, half_params(mp, hh + 1), w.half[hh + 1], hh + 1, D, w, nullptr);
+            add_post_bwd(p, params, hp, hw, D, w, w.g_att + (size_t)hh * N, w.g_out + (size_t)hh * N, has_gx);
+            PAMNET_TRY(chain_launch(D, p.a, st));
+        }
+        const int nP = nP_of(hh);
+        NodeGatherArgs ng;
+        memset(&ng, 0, sizeof(ng));
+        ng.n_nodes = (int)N; ng.g_P = w.g_P;
+        if (!is_local(hh)) {
+            GlobalMsgArgs a;
+            memset(&a, 0, sizeof(a));
+            a.n_nodes = (int)N; a.ptr = pl.g_ptr; a.src = pl.g_src; a.P = hw.P;
+            a.QT = w.QT + l * 2 * D; a.ldq = L * 2 * D; a.g_h = w.g_h; a.gQT = w.gQT + l * 2 * D;
+            PAMNET_TRY(global_msg_bwd(D, a, st));
+            ng.n_blocks = 1; ng.ptr = pl.g_ptr; ng.optr = pl.g_optr; ng.opos = pl.g_opos;
+            ng.gz = w.gQT + l * 2 * D; ng.ldq = L * 2 * D;
+        } else {
+            LocalMsgArgs a;
+            memset(&a, 0, sizeof(a));
+            a.n_nodes = (int)N; a.n_edges = (int)El; a.ptr = pl.l_ptr; a.src = pl.l_src; a.dst = pl.l_dst;
+            a.t_ptr = pl.t_ptr; a.t_gather = pl.t_gather; a.tt_ptr = pl.tt_ptr; a.tt_t = pl.tt_t; a.t_owner = pl.t_owner;
+            a.P = hw.P; a.QR = w.QR + l * 4 * D; a.ldq = L * 4 * D; a.zq = w.zq2 + l * D; a.ldt = L * D;
+            a.m_nb = hw.m_nb; a.msum = hw.msum; a.g_h = w.g_h; a.g_s = w.g_s;
+            a.gQR = w.gQR + l * 4 * D; a.gzq = w.gzq2 + l * D;
+            PAMNET_TRY(local_msg_bwd(D, a, st));
+            PAMNET_TRY(local_trip_bwd(D, a, st));
+            ng.n_blocks = 2; ng.ptr = pl.l_ptr; ng.optr = pl.l_optr; ng.opos = pl.l_opos;
+            ng.gz = w.gQR + l * 4 * D; ng.ldq = L * 4 * D;
+        }
+        PAMNET_TRY(node_grad_gather(D, ng, st));
+        // weight gradients of the per-node halves of the edge MLPs: dW[:, cD:(c+1)D] = g_P_c^T x1
+        {
+            std::vector<GemmSlot> sl;
+            for (int cblk = 0; cblk < nP; ++cblk) {
+                int64_t woff;
+                if (!is_local(hh)) woff = hp.m.w + cblk * D;
+                else woff = (cblk < 2 ? hp.m_ji.w : hp.m_kj.w) + (cblk & 1) * D;
+                sl.push_back(slot(w.g_P + cblk * D, nP * D, hw.x1, D, gp + woff, 3 * D));
+            }
+            GemmArgs a = gemm_zero(GEMM_TN, EPI_NONE, D, D, (int)N);
+            a.ksplit = ks_n;
+            PAMNET_TRY(gemm_multi(a, sl, st));
+        }
+    }
+    {   // into the node input
+        Prog p((int)N);
+        add_pre_bwd(p, params, half_params(mp, 0), w.half[0], 0, D, w, w.g_x0);
+        // half 0 has no res_x contribution from a previous layer: g_resx currently holds half 0's own skip grad
+        PAMNET_TRY(chain_launch(D, p.a, st));
+    }
+    if (cfg.dataset == PAMNET_PDBBIND) {
+        GemmArgs a = gemm_zero(GEMM_TN, EPI_NONE, D, kFeatPdb, (int)N);
+        a.nslots = 1; a.ksplit = ks_n;
+        a.slot[0] = slot(w.g_x0, D, node_in, kFeatPdb, gp + mp.init_linear, kFeatPdb);
+        PAMNET_TRY(gemm_launch(a, st));
+    } else {
+        PAMNET_TRY(embed_backward(node_in, N, w.g_x0, mp.n_embed, D, gp + mp.emb, st));
+    }
+
+    // ---- weight gradients of the node chains (all halves batched) ------------------------------------
+    {
+        std::vector<GemmSlot> sl, heads;
+        for (int hh = 0; hh < H; ++hh) {
+            const HalfWs& hw = w.half[hh];
+            const HalfP& hp = half_params(mp, hh);
+            const float* x_in = hh == 0 ? w.x0 : w.half[hh - 1].r[2];
+            auto lin = [&](const float* gz, const float* a_in, const Lin& p) {
+                sl.push_back(slot(gz, D, a_in, D, gp + p.w, D, nullptr, gp + p.b));
+            };
+            lin(hw.gz_x1, x_in, hp.x1);
+            lin(hw.gz_x2, hw.h, hp.x2);
+            for (int rr = 0; rr < 3; ++rr) {
+                lin(hw.gz_A[rr], rr == 0 ? hw.a_x2 : hw.r[rr - 1], hp.res[rr][0]);
+                lin(hw.gz_B[rr], hw.a_A[rr], hp.res[rr][1]);
+            }
+            lin(hw.gz_o[0], hw.r[2], hp.out[0]);
+            lin(hw.gz_o[1], hw.a_o[0], hp.out[1]);
+            lin(hw.gz_o[2], hw.a_o[1], hp.out[2]);
+            // heads: dW = o3^T g_att, dW_out = o3^T g_out (+ bias)
+            heads.push_back(slot(w.g_att + (size_t)hh * N, 1, hw.a_o[2], D, gp + hp.W, D));
+            heads.push_back(slot(w.g_out + (size_t)hh * N, 1, hw.a_o[2], D, gp + hp.W_out.w, D, nullptr, gp + hp.W_out.b));
+        }
+        GemmArgs a = gemm_zero(GEMM_TN, EPI_NONE, D, D, (int)N);
+        a.ksplit = ks_n;
+        PAMNET_TRY(gemm_multi(a, sl, st));
+        a.M = 1;
+        PAMNET_TRY(gemm_multi(a, heads, st));
+    }
+
+    // ---- phase A': per-edge / per-triplet gradients -> weights -----------------------------------------
+    {   // global edges
+        const int ldq = L * 2 * D;
+        std::vector<GemmSlot> sl;
+        for (int l = 0; l < L; ++l) {
+            const HalfP& hp = mp.g[l];
+            sl.push_back(slot(w.gQT + l * 2 * D, ldq, w.e_g, D, gp + hp.m.w + 2 * D, 3 * D, nullptr, gp + hp.m.b));
+            sl.push_back(slot(w.gQT + l * 2 * D + D, ldq, w.e_g, D, gp + hp.We.w, D));
+        }
+        GemmArgs a = gemm_zero(GEMM_TN, EPI_NONE, D, D, (int)Eg);
+        a.ksplit = pick_ksplit(Eg);
+        PAMNET_TRY(gemm_multi(a, sl, st));
+        // grad e_g = sum_l [gQ_l | gTt_l] . [W_m,e ; W_e]_l, then through SiLU of the embedding
+        GemmArgs b = gemm_zero(GEMM_NN, EPI_MUL_DSILU, (int)Eg, D, L * 2 * D);
+        b.nslots = 1; b.nseg = 2 * L; b.seg_len = D;
+        for (int l = 0; l < L; ++l) {
+            b.seg_B[2 * l] = params + mp.g[l].m.w + 2 * D; b.seg_ldb[2 * l] = 3 * D;
+            b.seg_B[2 * l + 1] = params + mp.g[l].We.w; b.seg_ldb[2 * l + 1] = D;
+        }
+        b.slot[0] = slot(w.gQT, ldq, nullptr, 0, w.gz_eg, D, nullptr, nullptr, w.z_eg, D);
+        PAMNET_TRY(gemm_launch(b, st));
+        GemmArgs cw = gemm_zero(GEMM_TN, EPI_NONE, D, kNumRbf, (int)Eg);
+        cw.nslots = 1; cw.ksplit = pick_ksplit(Eg);
+        cw.slot[0] = slot(w.gz_eg, D, w.rbf_g, kNumRbf, gp + mp.rbf_g.w, kNumRbf, nullptr, gp + mp.rbf_g.b);
+        PAMNET_TRY(gemm_launch(cw, st));
+        GemmArgs d = gemm_zero(GEMM_NN, EPI_NONE, (int)Eg, kNumRbf, D);
+        d.nslots = 1;
+        d.slot[0] = slot(w.gz_eg, D, params + mp.rbf_g.w, kNumRbf, w.g_rbf_g, kNumRbf);
+        PAMNET_TRY(gemm_launch(d, st));
+        PAMNET_TRY(rbf_freq_backward(pl.dist_g, Eg, params + mp.freq_g, cfg.cutoff_g, w.g_rbf_g, gp + mp.freq_g, st));
+    }
+    {   // local edges
+        const int ldq = L * 4 * D;
+        std::vector<GemmSlot> sl;
+        for (int l = 0; l < L; ++l) {
+            const HalfP& hp = mp.l[l];
+            const float* base = w.gQR + l * 4 * D;
+            sl.push_back(slot(base, ldq, w.e_l, D, gp + hp.m_ji.w + 2 * D, 3 * D, nullptr, gp + hp.m_ji.b));
+            sl.push_back(slot(base + D, ldq, w.e_l, D, gp + hp.m_kj.w + 2 * D, 3 * D, nullptr, gp + hp.m_kj.b));
+            sl.push_back(slot(base + 2 * D, ldq, w.e_l, D, gp + hp.lin_rbf.w, D));
+            sl.push_back(slot(base + 3 * D, ldq, w.e_l, D, gp + hp.lin_rbf_out.w, D));
+        }
+        GemmArgs a = gemm_zero(GEMM_TN, EPI_NONE, D, D, (int)El);
+        a.ksplit = pick_ksplit(El);
+        PAMNET_TRY(gemm_multi(a, sl, st));
+        GemmArgs b = gemm_zero(GEMM_NN, EPI_MUL_DSILU, (int)El, D, L * 4 * D);
+        b.nslots = 1; b.nseg = 4 * L; b.seg_len = D;
+        for (int l = 0; l < L; ++l) {
+            const HalfP& hp = mp.l[l];
+            b.seg_B[4 * l] = params + hp.m_ji.w + 2 * D; b.seg_ldb[4 * l] = 3 * D;
+            b.seg_B[4 * l + 1] = params + hp.m_kj.w + 2 * D; b.seg_ldb[4 * l + 1] = 3 * D;
+            b.seg_B[4 * l + 2] = params + hp.lin_rbf.w; b.seg_ldb[4 * l + 2] = D;
+            b.seg_B[4 * l + 3] = params + hp.lin_rbf_out.w; b.seg_ldb[4 * l + 3] = D;
+        }
+        b.slot[0] = slot(w.gQR, ldq, nullptr, 0, w.gz_el, D, nullptr, nullptr, w.z_el, D);
+        PAMNET_TRY(gemm_launch(b, st));
+        GemmArgs cw = gemm_zero(GEMM_TN, EPI_NONE, D, kNumRbf, (int)El);
+        cw.nslots = 1; cw.ksplit = pick_ksplit(El);
+        cw.slot[0] = slot(w.gz_el, D, w.rbf_l, kNumRbf, gp + mp.rbf_l.w, kNumRbf, nullptr, gp + mp.rbf_l.b);
+        PAMNET_TRY(gemm_launch(cw, st));
+        GemmArgs d = gemm_zero(GEMM_NN, EPI_NONE, (int)El, kNumRbf, D);
+        d.nslots = 1;
+        d.slot[0] = slot(w.gz_el, D, params + mp.rbf_l.w, kNumRbf, w.g_rbf_l, kNumRbf);
+        PAMNET_TRY(gemm_launch(d, st));
+        PAMNET_TRY(rbf_freq_backward(pl.dist_l, El, params + mp.freq_l, cfg.cutoff_l, w.g_rbf_l, gp + mp.freq_l, st));
+    }
+    {   // triplet gate MLP (local_message_passing.py:17,49) and the SBF embeddings (models.py:187-188)
+        const int ldt = L * D;
+        std::vector<GemmSlot> w2, dg, w1;
+        for (int l = 0; l < L; ++l) {
+            const HalfP& hp = mp.l[l];
+            w2.push_back(slot(w.gzq2 + l * D, ldt, w.aq1 + l * D, ldt, gp + hp.sbf[1].w, D, nullptr, gp + hp.sbf[1].b));
+            dg.push_back(slot(w.gzq2 + l * D, ldt, params + hp.sbf[1].w, D, w.gzq1 + l * D, ldt, nullptr, nullptr,
+                              w.zq1 + l * D, ldt));
+            w1.push_back(slot(w.gzq1 + l * D, ldt, w.s, D, gp + hp.sbf[0].w, D, nullptr, gp + hp.sbf[0].b));
+        }
+        GemmArgs a = gemm_zero(GEMM_TN, EPI_NONE, D, D, (int)T);
+        a.ksplit = pick_ksplit(T);
+        PAMNET_TRY(gemm_multi(a, w2, st));
+        PAMNET_TRY(gemm_multi(gemm_zero(GEMM_NN, EPI_MUL_DSILU, (int)T, D, D), dg, st));
+        PAMNET_TRY(gemm_multi(a, w1, st));
+        GemmArgs b = gemm_zero(GEMM_NN, EPI_MUL_DSILU, (int)T, D, L * D);
+        b.nslots = 1; b.nseg = L; b.seg_len = D;
+        for (int l = 0; l < L; ++l) { b.seg_B[l] = params + mp.l[l].sbf[0].w; b.seg_ldb[l] = D; }
+        b.slot[0] = slot(w.gzq1, ldt, nullptr, 0, w.gz_s, D, nullptr, nullptr, w.z_s, D);
+        PAMNET_TRY(gemm_launch(b, st));
+        PAMNET_CUDA(cudaMemsetAsync(w.gw_ext, 0, sizeof(float) * D * kSbfExt, st));
+        GemmArgs cw = gemm_zero(GEMM_TN, EPI_NONE, D, kSbfExt, (int)T);
+        cw.nslots = 1; cw.ksplit = pick_ksplit(T);
+        cw.slot[0] = slot(w.gz_s, D, w.sbf_ext, kSbfExt, w.gw_ext, kSbfExt);
+        PAMNET_TRY(gemm_launch(cw, st));
+        PAMNET_TRY(sbf_weight_unpack_grad(D, w.gw_ext, cfg.simple ? nullptr : gp + mp.sbf2.w,
+                                          cfg.simple ? nullptr : gp + mp.sbf2.b, gp + mp.sbf1.w, gp + mp.sbf1.b, st));
+    }
+    return 0;
+}
+
+}  // namespace pamnet

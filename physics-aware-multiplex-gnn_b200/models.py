@@ -1,0 +1,271 @@
+"""``Config`` / ``PAMNet`` / ``PAMNet_s`` with the reference's constructor signatures, module tree and
+state_dict keys (models.py:12-56, :227-258), executing on libpamnet_sm100.so.
+
+Drop-in for ``from models import PAMNet, PAMNet_s, Config`` (main_qm9.py:13): ``model(data)`` returns
+Tensor[num_graphs] on the data's device, differentiable w.r.t. every parameter (one autograd node whose
+backward is the hand-written CUDA backward).  CUDA only; there is no CPU / eager fallback.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from .basis import sbf_consts_struct
+from .layers import (MLP, BesselBasisLayer, Global_MessagePassing, Local_MessagePassing,
+                     Local_MessagePassing_s, SphericalBasisLayer)
+
+_DATASET_IDS = {"QM9": 0, "PDBbind": 1}
+
+
+class Config(object):
+    def __init__(self, dataset, dim, n_layer, cutoff_l, cutoff_g, flow='source_to_target'):
+        self.dataset = dataset
+        self.dim = dim
+        self.n_layer = n_layer
+        self.cutoff_l = cutoff_l
+        self.cutoff_g = cutoff_g
+        self.flow = flow
+
+
+def _dataset_kind(name):
+    if name[:3].lower() == "rna":
+        return 2
+    return _DATASET_IDS.get(name, -1)
+
+
+class GraphPlan:
+    """Per-batch execution plan (device blobs + sizes); layer-invariant (models.py:104-188)."""
+
+    def __init__(self, sizes, base, trip, edge_index_g, edge_index_l):
+        self.sizes, self.base, self.trip = sizes, base, trip
+        self.edge_index_g, self.edge_index_l = edge_index_g, edge_index_l
+
+
+class _PAMNetFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod, plan, node_in, sign, pos, *params):
+        lib = _lib.load()
+        dev = pos.device
+        cfg, sz = mod._ccfg, plan.sizes
+        ws_bytes = lib.pamnet_workspace_bytes(cfg, sz)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        out = torch.empty(sz.n_graphs, dtype=torch.float32, device=dev)
+        need_grad = any(ctx.needs_input_grad[5:])
+        _lib.check(lib.pamnet_model_forward(cfg, sz, sbf_consts_struct(), mod._flat.data_ptr(), node_in.data_ptr(),
+                                            _lib.ptr(sign), pos.data_ptr(), plan.base.data_ptr(),
+                                            plan.trip.data_ptr(), ws.data_ptr(), ws_bytes, int(need_grad),
+                                            out.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                   "model_forward")
+        if need_grad:
+            ctx.mod, ctx.plan, ctx.ws, ctx.ws_bytes = mod, plan, ws, ws_bytes
+            ctx.node_in, ctx.sign, ctx.pos = node_in, sign, pos
+            ctx.flat_version = mod._flat._version
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        mod, plan = ctx.mod, ctx.plan
+        if mod._flat._version != ctx.flat_version:
+            raise RuntimeError("PAMNet parameters were modified in place between forward and backward")
+        grad_out = grad_out.contiguous().float()
+        gflat = torch.empty(mod._flat.numel(), dtype=torch.float32, device=grad_out.device)
+        _lib.check(lib.pamnet_model_backward(mod._ccfg, plan.sizes, sbf_consts_struct(), mod._flat.data_ptr(),
+                                             ctx.node_in.data_ptr(), _lib.ptr(ctx.sign), ctx.pos.data_ptr(),
+                                             plan.base.data_ptr(), plan.trip.data_ptr(), ctx.ws.data_ptr(),
+                                             ctx.ws_bytes, grad_out.data_ptr(), gflat.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream), "model_backward")
+        ctx.ws = None
+        grads = []
+        for (name, p), off, used in zip(mod._param_list, mod._offsets, mod._param_used):
+            grads.append(gflat[off:off + p.numel()].view(p.shape) if used else None)
+        return (None, None, None, None, None, *grads)
+
+
+class _PAMNetBase(nn.Module):
+    _simple = False
+
+    # ---- flat parameter storage ---------------------------------------------------------------------
+    def _setup_flat(self, config):
+        kind = _dataset_kind(config.dataset)
+        flow = 1 if getattr(config, "flow", "source_to_target") == "target_to_source" else 0
+        self._ccfg = _lib.Config(max(kind, 0), int(config.dim), int(config.n_layer), flow, int(self._simple),
+                                 float(config.cutoff_l), float(config.cutoff_g))
+        lib = _lib.load()
+        n = lib.pamnet_param_count(self._ccfg)
+        if n < 0:
+            raise ValueError(lib.pamnet_last_error().decode())
+        offs = (_lib.c_i64 * n)()
+        numel = (_lib.c_i64 * n)()
+        _lib.check(lib.pamnet_param_offsets(self._ccfg, offs, numel), "param_offsets")
+        self._param_list = list(self.named_parameters())
+        if len(self._param_list) != n or any(p.numel() != m for (_, p), m in zip(self._param_list, numel)):
+            raise RuntimeError("module tree does not match the C parameter layout (state_dict order)")
+        self._offsets = list(offs)
+        self._total = int(lib.pamnet_param_total(self._ccfg))
+        # init_linear exists but is unused outside PDBbind (models.py:35,119): its grad stays None there
+        self._param_used = [not (name == "init_linear.weight" and kind != 1) for name, _ in self._param_list]
+        self._flat = None
+        self._flatten()
+
+    def _flatten(self):
+        """(Re)pack all parameters into one flat buffer; parameters become views of it."""
+        ps = [p for _, p in self._param_list]
+        dev = ps[0].device
+        if any(p.dtype != torch.float32 for p in ps):
+            raise TypeError("pamnet_b200 computes in fp32 only (the reference's precision)")
+        flat = torch.zeros(self._total, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p, off in zip(ps, self._offsets):
+                flat[off:off + p.numel()].copy_(p.detach().reshape(-1))
+                p.data = flat[off:off + p.numel()].view(p.shape)
+        self._flat = flat
+
+    def _aliased(self):
+        base = self._flat.data_ptr()
+        return all(p.data_ptr() == base + 4 * off for (_, p), off in zip(self._param_list, self._offsets))
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        if getattr(self, "_param_list", None):
+            self._flatten()
+        return out
+
+    # ---- graph construction ---------------------------------------------------------------------------
+    def _build_plan(self, pos, batch, n_graphs, edge_index_l_in, max_nb):
+        lib = _lib.load()
+        cfg, dev = self._ccfg, pos.device
+        n = pos.shape[0]
+        c = ops.Counts(dev)
+        kind = cfg.dataset
+        if kind == 2:       # rna: kNN-50 then two cutoff masks (models.py:143-157)
+            nbr, _ = ops.knn_lists(pos, batch, 50)
+            pg = ops.knn_edges_count(nbr, pos, self.cutoff_g, c, 0)
+            plc = ops.knn_edges_count(nbr, pos, self.cutoff_l, c, 1)
+            eg_n, el_n = c.read()[:2]
+            eg = ops.knn_edges_fill(nbr, pos, self.cutoff_g, pg, eg_n)
+            el = ops.knn_edges_fill(nbr, pos, self.cutoff_l, plc, el_n)
+        else:
+            pg = ops.radius_count(pos, batch, self.cutoff_g, max_nb, True, c, 0)
+            if kind == 0:   # QM9: local graph = chemical bonds (models.py:115)
+                el_in = edge_index_l_in.to(torch.int64).contiguous()
+                keep, pk = ops.edge_filter_count(el_in, None, None, c, 1)
+                eg_n, el_n = c.read()[:2]
+                eg = ops.radius_fill(pos, batch, self.cutoff_g, max_nb, True, pg, eg_n)
+                el = ops.edge_filter_fill(el_in, keep, pk, el_n)
+            else:           # PDBbind: local = global edges within cutoff_l (models.py:131-136)
+                eg_n = c.read()[0]
+                eg = ops.radius_fill(pos, batch, self.cutoff_g, max_nb, True, pg, eg_n)
+                el = ops.filter_edges(eg, pos, self.cutoff_l)
+        sz = _lib.Sizes(n, n_graphs, eg.shape[1], el.shape[1], 0, 0)
+        base_b, trip_b = _lib.c_sz(), _lib.c_sz()
+        _lib.check(lib.pamnet_plan_bytes(cfg, sz, base_b, trip_b), "plan_bytes")
+        base = torch.empty(base_b.value, dtype=torch.uint8, device=dev)
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.pamnet_plan_count(cfg, sz, eg.data_ptr(), el.data_ptr(), batch.data_ptr(), base.data_ptr(),
+                                         c.ptr(2), stream), "plan_count")
+        t2, t1 = c.read()[2:4]
+        sz.n_t2, sz.n_t1 = t2, t1
+        _lib.check(lib.pamnet_plan_bytes(cfg, sz, base_b, trip_b), "plan_bytes")
+        trip = torch.empty(trip_b.value, dtype=torch.uint8, device=dev)
+        _lib.check(lib.pamnet_plan_fill(cfg, sz, pos.data_ptr(), base.data_ptr(), trip.data_ptr(), stream), "plan_fill")
+        return GraphPlan(sz, base, trip, eg, el)
+
+    def _run(self, data, max_nb):
+        x_raw, batch = data.x, data.batch
+        if not x_raw.is_cuda:
+            raise _lib.PamnetError("pamnet_b200 runs on CUDA tensors only: move the model and the batch to a GPU "
+                                   "(there is no CPU fallback)")
+        if self._flat.device != x_raw.device:
+            raise RuntimeError("model and data are on different devices")
+        if not self._aliased():      # e.g. EMA.assign swapped param.data (utils/ema.py:27)
+            self._flatten()
+        kind = self._ccfg.dataset
+        batch = batch.to(torch.int64).contiguous()
+        n_graphs = getattr(data, "num_graphs", None)
+        if n_graphs is None:
+            n_graphs = int(batch.max()) + 1
+        sign, el_in = None, None
+        if kind == 0:
+            pos = data.pos.to(torch.float32).contiguous()
+            node_in = x_raw.to(torch.float32).contiguous().view(-1)
+            el_in = data.edge_index
+        else:
+            xr = x_raw.unsqueeze(-1) if x_raw.dim() == 1 else x_raw
+            xr = xr.to(torch.float32)
+            pos = xr[:, :3].contiguous()
+            if kind == 1:
+                node_in = xr[:, 3:].contiguous()
+                sign = torch.where(pos[:, 0] > 40.0, -1.0, 1.0).to(torch.float32).contiguous()   # models.py:122-125
+            else:
+                node_in = xr[:, -1].contiguous()
+        plan = self._build_plan(pos, batch, int(n_graphs), el_in, max_nb)
+        self.last_plan = plan
+        return _PAMNetFunction.apply(self, plan, node_in, sign, pos, *[p for _, p in self._param_list])
+
+    def _init_embeddings(self):
+        stdv = math.sqrt(3)
+        self.embeddings.data.uniform_(-stdv, stdv)
+
+
+class PAMNet(_PAMNetBase):
+    def __init__(self, config: Config, num_spherical=7, num_radial=6, envelope_exponent=5):
+        super(PAMNet, self).__init__()
+        self.dataset = config.dataset
+        self.dim = config.dim
+        self.n_layer = config.n_layer
+        self.cutoff_l = config.cutoff_l
+        self.cutoff_g = config.cutoff_g
+        rna = self.dataset[:3].lower() == "rna"
+        self.embeddings = nn.Parameter(torch.ones((3 if rna else 5, self.dim)))
+        if not rna:
+            self.init_linear = nn.Linear(18, self.dim, bias=False)
+        self.rbf_g = BesselBasisLayer(16, self.cutoff_g, envelope_exponent)
+        self.rbf_l = BesselBasisLayer(16, self.cutoff_l, envelope_exponent)
+        self.sbf = SphericalBasisLayer(num_spherical, num_radial, self.cutoff_l, envelope_exponent)
+        self.mlp_rbf_g = MLP([16, self.dim])
+        self.mlp_rbf_l = MLP([16, self.dim])
+        self.mlp_sbf1 = MLP([num_spherical * num_radial, self.dim])
+        self.mlp_sbf2 = MLP([num_spherical * num_radial, self.dim])
+        self.global_layer = nn.ModuleList(Global_MessagePassing(config) for _ in range(config.n_layer))
+        self.local_layer = nn.ModuleList(Local_MessagePassing(config) for _ in range(config.n_layer))
+        self.softmax = nn.Softmax(dim=-1)
+        self._init_embeddings()
+        self._setup_flat(config)
+
+    def forward(self, data):
+        if _dataset_kind(self.dataset) < 0:
+            raise ValueError("Invalid dataset. If you are using any dataset related to RNA 3D structure prediction, "
+                             "be sure to use 'rna' as the first 3 characters of the dataset name.")
+        return self._run(data, max_nb=1000)
+
+
+class PAMNet_s(_PAMNetBase):
+    _simple = True
+
+    def __init__(self, config: Config, num_spherical=7, num_radial=6, envelope_exponent=5):
+        super(PAMNet_s, self).__init__()
+        self.dataset = config.dataset
+        self.dim = config.dim
+        self.n_layer = config.n_layer
+        self.cutoff_l = config.cutoff_l
+        self.cutoff_g = config.cutoff_g
+        self.embeddings = nn.Parameter(torch.ones((5, self.dim)))
+        self.rbf_g = BesselBasisLayer(16, self.cutoff_g, envelope_exponent)
+        self.rbf_l = BesselBasisLayer(16, self.cutoff_l, envelope_exponent)
+        self.sbf = SphericalBasisLayer(num_spherical, num_radial, self.cutoff_l, envelope_exponent)
+        self.mlp_rbf_g = MLP([16, self.dim])
+        self.mlp_rbf_l = MLP([16, self.dim])
+        self.mlp_sbf = MLP([num_spherical * num_radial, self.dim])
+        self.global_layer = nn.ModuleList(Global_MessagePassing(config) for _ in range(config.n_layer))
+        self.local_layer = nn.ModuleList(Local_MessagePassing_s(config) for _ in range(config.n_layer))
+        self.softmax = nn.Softmax(dim=-1)
+        self._init_embeddings()
+        if self.dataset == "QM9":
+            self._setup_flat(config)
+
+    def forward(self, data):
+        if self.dataset != "QM9":
+            raise ValueError("Invalid dataset. The current PAMNet_s is only for QM9 experiments.")
+        return self._run(data, max_nb=500)

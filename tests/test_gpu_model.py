@@ -1,0 +1,151 @@
+"""GPU: the fused CUDA model path (C ABI behind pamnet_b200.PAMNet) against the golden vectors produced by
+the verbatim reference and against the oracle at BASELINE.json's full size.
+
+Tolerance (SURVEY.md 8(c) ladder): fp64 golden / oracle is truth; accept err <= max(1e-5 rel, 2 * err of the
+fp32 reference), per tensor, relative to max|truth|.  Integer outputs bit-exact."""
+import pytest
+import torch
+
+from tests.helpers import load_golden, cfg_of, batch_of, rel_err, ladder_ok, oracle_step
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(gold, simple=False):
+    from pamnet_b200 import Config, PAMNet, PAMNet_s
+    m = (PAMNet_s if simple else PAMNet)(Config(**gold["config"]))
+    m.load_state_dict(gold["state_dict"])
+    return m.cuda()
+
+
+def _step(model, batch, loss="l1"):
+    b = batch.to("cuda")
+    model.zero_grad()
+    out = model(b)
+    l = (out - b.y).abs().mean() if loss == "l1" else ((out - b.y) ** 2).mean()
+    l.backward()
+    torch.cuda.synchronize()
+    return out.detach().cpu(), l.detach().cpu(), {k: (p.grad.cpu() if p.grad is not None else None)
+                                                   for k, p in model.named_parameters()}
+
+
+@pytest.mark.parametrize("name,simple,loss", [("qm9_small_pamnet", False, "l1"), ("qm9_small_pamnet_s", True, "l1"),
+                                              ("pdbbind_small", False, "mse"), ("rna_native", False, "l1")])
+def test_golden_forward_backward(name, simple, loss):
+    gold = load_golden(name)
+    model = _model(gold, simple)
+    out, l, grads = _step(model, batch_of(gold), loss)
+    ok, e_new, e_ref = ladder_ok(out, gold["out_f32"], gold["out_f64"])
+    assert ok, ("out", e_new, e_ref)
+    assert rel_err(out, gold["out_f32"]) < 1e-5
+    bad = []
+    for k, ref64 in gold["grads_f64"].items():
+        if ref64 is None:
+            assert grads[k] is None, k
+            continue
+        ok, e_new, e_ref = ladder_ok(grads[k], gold["grads_f32"][k], ref64)
+        if not ok:
+            bad.append((k, e_new, e_ref))
+    assert not bad, bad[:10]
+
+
+def test_golden_graph_is_bit_exact():
+    gold = load_golden("qm9_small_pamnet")
+    model = _model(gold)
+    with torch.no_grad():
+        model(batch_of(gold).to("cuda"))
+    plan = model.last_plan
+    assert torch.equal(plan.edge_index_g.cpu(), gold["graph"]["edge_index_g"])
+    assert torch.equal(plan.edge_index_l.cpu(), gold["graph"]["edge_index_l"])
+    assert plan.sizes.n_t2 == gold["graph"]["idx_kj"].numel() and plan.sizes.n_t1 == gold["graph"]["idx_jj_pair"].numel()
+
+
+def test_rna_native_scores():
+    """Shipped checkpoint x shipped native structures -> the reference's scores (README.md:107-109 workflow)."""
+    gold = load_golden("rna_native")
+    model = _model(gold).eval()
+    from pamnet_b200.data import Batch
+    for g in gold["shipped"]:
+        x = gold["inputs"][g].cuda()
+        b = Batch(x=x, batch=torch.zeros(x.shape[0], dtype=torch.long, device="cuda"), y=torch.zeros(1, device="cuda"))
+        with torch.no_grad():
+            out = model(b)
+        assert rel_err(out, gold["scores_f64"][g:g + 1]) < 1e-5
+
+
+@pytest.mark.parametrize("n_graphs,dim,n_layer", [(32, 128, 6), (5, 64, 1), (3, 16, 2)])
+def test_full_size_vs_oracle(n_graphs, dim, n_layer):
+    """BASELINE.json configs[1] (QM9 dim=128 L=6 bs=32) and smaller shapes: CUDA vs oracle (fp32 and fp64)."""
+    import types
+    from pamnet_b200 import Config, PAMNet
+    from pamnet_b200.data import synthetic_qm9_batch
+    from oracle import pamnet_oracle as O
+    cfg = types.SimpleNamespace(dataset="QM9", dim=dim, n_layer=n_layer, cutoff_l=5.0, cutoff_g=5.0,
+                                flow="source_to_target")
+    sd = O.init_state_dict(cfg, seed=0)
+    b = synthetic_qm9_batch(n_graphs, seed=0)
+    model = PAMNet(Config(**vars(cfg)))
+    model.load_state_dict(sd)
+    out, l, grads = _step(model.cuda(), b)
+    o32, _, g32 = oracle_step(sd, cfg, b, dtype=torch.float32)
+    o64, _, g64 = oracle_step(sd, cfg, b, dtype=torch.float64)
+    ok, e_new, e_ref = ladder_ok(out, o32, o64)
+    assert ok, (e_new, e_ref)
+    bad = []
+    for k, ref64 in g64.items():
+        if ref64 is None:
+            continue
+        ok, e_new, e_ref = ladder_ok(grads[k], g32[k], ref64)
+        if not ok:
+            bad.append((k, e_new, e_ref))
+    assert not bad, bad[:10]
+
+
+def test_edge_cases_isolated_atoms_and_single_atom_graph():
+    """A graph with one atom (no edges at all) and an atom with no bonds inside a molecule."""
+    import types
+    from pamnet_b200 import Config, PAMNet
+    from pamnet_b200.data import synthetic_qm9_batch, Batch
+    from oracle import pamnet_oracle as O
+    b = synthetic_qm9_batch(2, seed=4)
+    n = b.pos.shape[0]
+    keep = (b.edge_index[0] != 1) & (b.edge_index[1] != 1)          # atom 1 loses its bonds
+    x = torch.cat([b.x, torch.tensor([2.0])])
+    pos = torch.cat([b.pos, torch.tensor([[50.0, 50.0, 50.0]])])
+    batch = torch.cat([b.batch, torch.tensor([2])])
+    bb = Batch(x=x, pos=pos, edge_index=b.edge_index[:, keep], batch=batch, y=torch.tensor([0.1, -0.2, 0.3]))
+    cfg = types.SimpleNamespace(dataset="QM9", dim=32, n_layer=2, cutoff_l=5.0, cutoff_g=5.0, flow="source_to_target")
+    sd = O.init_state_dict(cfg, seed=1)
+    model = PAMNet(Config(**vars(cfg)))
+    model.load_state_dict(sd)
+    out, l, grads = _step(model.cuda(), bb)
+    o64, _, g64 = oracle_step(sd, cfg, bb, dtype=torch.float64)
+    assert rel_err(out, o64) < 1e-5
+    for k, ref in g64.items():
+        if ref is not None:
+            assert rel_err(grads[k], ref) < 2e-5, k
+
+
+def test_accumulates_like_autograd_and_is_deterministic():
+    gold = load_golden("qm9_small_pamnet")
+    model = _model(gold)
+    b = batch_of(gold).to("cuda")
+    model.zero_grad()
+    (model(b) - b.y).abs().mean().backward()
+    g1 = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+    (model(b) - b.y).abs().mean().backward()                       # no zero_grad: grads must double
+    for k, p in model.named_parameters():
+        if p.grad is not None:
+            assert rel_err(p.grad, 2 * g1[k]) < 1e-6, k
+    model.zero_grad()
+    (model(b) - b.y).abs().mean().backward()
+    same = all(torch.equal(p.grad, g1[k]) for k, p in model.named_parameters() if p.grad is not None)
+    assert same or max(rel_err(p.grad, g1[k]) for k, p in model.named_parameters() if p.grad is not None) < 1e-6
+
+
+def test_cpu_input_fails_loudly():
+    from pamnet_b200 import PamnetError
+    gold = load_golden("qm9_small_pamnet")
+    model = _model(gold)
+    with pytest.raises((PamnetError, RuntimeError)):
+        model(batch_of(gold))
