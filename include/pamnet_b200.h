@@ -170,6 +170,13 @@ int pamnet_gemm(int32_t mode, const float* A, int32_t lda, const float* B, int32
 /* Test / debugging aids: byte offsets of named buffers inside the caller-owned workspace and plan blobs. */
 int64_t pamnet_debug_ws_offset(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, const char* name, int32_t half);
 int64_t pamnet_debug_plan_offset(const pamnet_sizes_t* sz, int32_t which, int32_t* in_trip);
+/* Kernel launches issued by this library in this process so far (bench.py "gpu_launches"). */
+int64_t pamnet_debug_launch_count(void);
+/* Optional per-kernel-class CUDA-event timing on the launching stream (bench.py roofline): begin arms it,
+ * end synchronises and fills ms / launches / algorithmic bytes per class (13 classes, order of KernelClass in
+ * csrc/common.cuh); returns the class count.  Not thread-safe; off by default. */
+void pamnet_debug_profile_begin(void);
+int pamnet_debug_profile_end(double* ms, int64_t* launches, double* bytes);
 
 #ifdef __cplusplus
 }

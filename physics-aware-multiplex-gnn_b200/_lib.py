@@ -60,6 +60,9 @@ SIGNATURES = {
     "pamnet_gemm": (c_i32, [c_i32, c_vp, c_i32, c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "pamnet_debug_ws_offset": (c_i64, [_PC, _PS, C.c_char_p, c_i32]),
     "pamnet_debug_plan_offset": (c_i64, [_PS, c_i32, C.POINTER(c_i32)]),
+    "pamnet_debug_launch_count": (c_i64, []),
+    "pamnet_debug_profile_begin": (None, []),
+    "pamnet_debug_profile_end": (c_i32, [c_vp, c_vp, c_vp]),
 }
 
 _lib = None
@@ -86,6 +89,27 @@ def load():
         raise PamnetError("libpamnet_sm100.so ABI version mismatch")
     _lib = lib
     return lib
+
+
+KERNEL_CLASSES = ("gemm_f32", "node_chain", "global_msg_fwd", "global_msg_bwd", "local_edge_fwd", "local_msg_fwd",
+                  "local_msg_bwd", "local_trip_bwd", "node_grad_gather", "basis", "graph", "readout", "misc")
+
+
+def launch_count():
+    return int(load().pamnet_debug_launch_count())
+
+
+def profile_begin():
+    load().pamnet_debug_profile_begin()
+
+
+def profile_end():
+    """-> {class: (ms, launches, algorithmic_bytes)} accumulated since profile_begin()."""
+    n = len(KERNEL_CLASSES)
+    ms, cnt, byt = (C.c_double * n)(), (c_i64 * n)(), (C.c_double * n)()
+    got = load().pamnet_debug_profile_end(ms, cnt, byt)
+    assert got == n, "kernel class table out of sync with csrc/common.cuh"
+    return {k: (ms[i], int(cnt[i]), byt[i]) for i, k in enumerate(KERNEL_CLASSES)}
 
 
 def check(rc, what=""):

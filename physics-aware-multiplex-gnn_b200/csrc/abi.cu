@@ -1,6 +1,9 @@
 // extern "C" surface of libpamnet_sm100.so (declared in include/pamnet_b200.h).
 #include <stdarg.h>
 
+#include <atomic>
+#include <vector>
+
 #include "basis.cuh"
 #include "gemm.cuh"
 #include "graph.cuh"
@@ -17,6 +20,34 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 const char* get_error() { return g_err; }
+
+// ---- launch counter + event profiler (single-threaded use: bench / tests) --------------------------
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct ProfRec { int cls; double bytes; cudaEvent_t e0, e1; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<cudaEvent_t> g_prof_pool;
+static size_t g_prof_used = 0;
+static cudaEvent_t prof_event() {
+    if (g_prof_used == g_prof_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        g_prof_pool.push_back(e);
+    }
+    return g_prof_pool[g_prof_used++];
+}
+void prof_begin(int cls, double bytes, cudaStream_t st) {
+    if (!g_prof_on) return;
+    ProfRec r{cls, bytes, prof_event(), prof_event()};
+    cudaEventRecord(r.e0, st);
+    g_prof_recs.push_back(r);
+}
+void prof_end(cudaStream_t st) {
+    if (!g_prof_on || g_prof_recs.empty()) return;
+    cudaEventRecord(g_prof_recs.back().e1, st);
+}
 }  // namespace pamnet
 
 using namespace pamnet;
@@ -162,6 +193,27 @@ int64_t pamnet_debug_plan_offset(const pamnet_sizes_t* sz, int32_t which, int32_
     const bool trip = (which == 8 || which == 9 || which == 13);
     if (in_trip) *in_trip = trip;
     return (int64_t)(reinterpret_cast<const char*>(tab[which]) - (trip ? t : b));
+}
+
+int64_t pamnet_debug_launch_count(void) { return g_launches.load(); }
+void pamnet_debug_profile_begin(void) {
+    g_prof_recs.clear();
+    g_prof_used = 0;
+    g_prof_on = true;
+}
+// ms[KC_COUNT], launches[KC_COUNT], bytes[KC_COUNT]; synchronises the device
+int pamnet_debug_profile_end(double* ms, int64_t* launches, double* bytes) {
+    g_prof_on = false;
+    PAMNET_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < KC_COUNT; ++i) { ms[i] = 0; launches[i] = 0; bytes[i] = 0; }
+    for (auto& r : g_prof_recs) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess) continue;
+        ms[r.cls] += t; launches[r.cls] += 1; bytes[r.cls] += r.bytes;
+    }
+    g_prof_recs.clear();
+    g_prof_used = 0;
+    return KC_COUNT;
 }
 
 int pamnet_loss(const float* out, const float* y, int64_t n, int32_t kind, float* loss_dev, float* grad_out,

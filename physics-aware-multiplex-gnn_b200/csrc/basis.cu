@@ -48,7 +48,9 @@ __global__ void rbf_kernel(const float* __restrict__ dist, int64_t n_edges, cons
 
 int rbf_forward(const float* dist, int64_t n_edges, const float* freq, float cutoff, float* rbf, cudaStream_t st) {
     if (n_edges == 0) return 0;
+    prof_begin(KC_BASIS, 0.0, st);
     rbf_kernel<<<ceil_div(n_edges * kNumRbf, 256), 256, 0, st>>>(dist, n_edges, freq, cutoff, rbf);
+    prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;
 }
@@ -81,7 +83,9 @@ int rbf_freq_backward(const float* dist, int64_t n_edges, const float* freq, flo
                       float* g_freq, cudaStream_t st) {
     if (n_edges == 0) return 0;
     const int64_t rpb = 512;
+    prof_begin(KC_BASIS, 0.0, st);
     rbf_freq_bwd_kernel<<<ceil_div(n_edges, rpb), 256, 0, st>>>(dist, n_edges, freq, cutoff, g_rbf, rpb, g_freq);
+    prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;
 }
@@ -117,7 +121,9 @@ __global__ void sbf_radial_kernel(const SbfTables tab, const float* __restrict__
 int sbf_radial(const SbfTables& tab, const float* dist, int64_t n_edges, float cutoff, float* radial,
                cudaStream_t st) {
     if (n_edges == 0) return 0;
+    prof_begin(KC_BASIS, 0.0, st);
     sbf_radial_kernel<<<ceil_div(n_edges * kNumRad, 128), 128, 0, st>>>(tab, dist, n_edges, cutoff, radial);
+    prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;
 }
@@ -146,7 +152,9 @@ __global__ void sbf_combine_kernel(const SbfTables tab, const float* __restrict_
 int sbf_combine(const SbfTables& tab, const float* radial, const float* angle, const int64_t* gather, int64_t n_trip,
                 float* out, cudaStream_t st) {
     if (n_trip == 0) return 0;
+    prof_begin(KC_BASIS, 0.0, st);
     sbf_combine_kernel<<<ceil_div(n_trip, 128), 128, 0, st>>>(tab, radial, angle, gather, n_trip, out);
+    prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;
 }
@@ -203,8 +211,10 @@ int sbf_ext_forward(const SbfTables& tab, const Plan& plan, int64_t n_edges, int
                     const float* radial, float* sbf_ext, cudaStream_t st) {
     (void)n_edges;
     if (n_trip == 0) return 0;
+    prof_begin(KC_BASIS, 0.0, st);
     sbf_ext_kernel<<<ceil_div(n_trip, 4), 128, 0, st>>>(tab, plan.l_src, plan.l_dst, plan.t_ptr, plan.t_split,
                                                         plan.t_gather, plan.t_owner, n_trip, pos, radial, sbf_ext);
+    prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;
 }
@@ -224,7 +234,9 @@ __global__ void sbf_pack_kernel(int dim, const float* __restrict__ w2, const flo
 
 int sbf_weight_pack(int dim, const float* w2, const float* b2, const float* w1, const float* b1, float* w_ext,
                     cudaStream_t st) {
+    prof_begin(KC_BASIS, 0.0, st);
     sbf_pack_kernel<<<ceil_div(dim * kSbfExt, 256), 256, 0, st>>>(dim, w2, b2, w1, b1, w_ext);
+    prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;
 }
@@ -243,7 +255,9 @@ __global__ void sbf_unpack_kernel(int dim, const float* __restrict__ g_ext, floa
 
 int sbf_weight_unpack_grad(int dim, const float* g_ext, float* gw2, float* gb2, float* gw1, float* gb1,
                            cudaStream_t st) {
+    prof_begin(KC_BASIS, 0.0, st);
     sbf_unpack_kernel<<<ceil_div(dim * kSbfExt, 256), 256, 0, st>>>(dim, g_ext, gw2, gb2, gw1, gb1);
+    prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;
 }
@@ -261,7 +275,9 @@ __global__ void embed_fwd_kernel(const float* __restrict__ type_f, int64_t n_nod
 int embed_forward(const float* type_f, int64_t n_nodes, const float* emb, int n_embed, int dim, float* x,
                   cudaStream_t st) {
     if (n_nodes == 0) return 0;
+    prof_begin(KC_BASIS, 0.0, st);
     embed_fwd_kernel<<<ceil_div(n_nodes * dim, 256), 256, 0, st>>>(type_f, n_nodes, emb, n_embed, dim, x);
+    prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;
 }
@@ -281,7 +297,9 @@ __global__ void embed_bwd_kernel(const float* __restrict__ type_f, int64_t n_nod
 int embed_backward(const float* type_f, int64_t n_nodes, const float* g_x, int n_embed, int dim, float* g_emb,
                    cudaStream_t st) {
     dim3 grid(ceil_div(dim, 32), n_embed);
+    prof_begin(KC_BASIS, 0.0, st);
     embed_bwd_kernel<<<grid, 32, 0, st>>>(type_f, n_nodes, g_x, dim, g_emb);
+    prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;
 }
@@ -328,7 +346,9 @@ int transpose_batch(const float* src_base, float* dst_base, const TransposeJob* 
             if (tiles > max_tiles) max_tiles = tiles;
         }
         dim3 grid(max_tiles > 16 ? 16 : max_tiles, a.n_jobs);
+        prof_begin(KC_BASIS, 0.0, st);
         transpose_kernel<<<grid, 256, 0, st>>>(src_base, dst_base, a);
+        prof_end(st);
         PAMNET_LAUNCH_CHECK();
     }
     return 0;

@@ -184,7 +184,19 @@ static int chain_launch_t(const ChainArgs& args, cudaStream_t st) {
         PAMNET_CUDA(cudaFuncSetAttribute(chain_kernel<D, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
+    double bytes = 0.0;
+    for (int i = 0; i < args.n_stages; ++i) {
+        const ChainStage& s = args.st[i];
+        const double row = 4.0 * args.n_rows * D;
+        if (s.op == CH_LOAD) bytes += 4.0 * args.n_rows * s.width * ((s.g1 ? 2 : 1) + (s.out_a ? 1 : 0));
+        if (s.op == CH_GEMM)
+            bytes += 4.0 * D * D + row * ((s.zmul ? 1 : 0) + (s.save_src ? 1 : 0) + (s.out_z ? 1 : 0) +
+                                          (s.out_a ? 1 : 0) + (s.add_g ? 1 : 0));
+        if (s.op == CH_DOT2 || s.op == CH_HEADS_BWD) bytes += 8.0 * args.n_rows + 8.0 * D;
+    }
+    prof_begin(KC_CHAIN, bytes, st);
     chain_kernel<D, RPT><<<ceil_div(args.n_rows, C::R), kChainThreads, smem, st>>>(args);
+    prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;
 }

@@ -37,7 +37,20 @@ const char* get_error();
         }                                                                                   \
     } while (0)
 
-#define PAMNET_LAUNCH_CHECK() PAMNET_CUDA(cudaGetLastError())
+// ---- launch accounting / optional per-kernel-class event timing (bench.py roofline; off by default) ----
+enum KernelClass : int {
+    KC_GEMM = 0, KC_CHAIN, KC_GLOBAL_MSG_FWD, KC_GLOBAL_MSG_BWD, KC_LOCAL_EDGE_FWD, KC_LOCAL_MSG_FWD,
+    KC_LOCAL_MSG_BWD, KC_LOCAL_TRIP_BWD, KC_NODE_GATHER, KC_BASIS, KC_GRAPH, KC_READOUT, KC_MISC, KC_COUNT
+};
+void prof_begin(int cls, double alg_bytes, cudaStream_t st);   // call right before a kernel launch
+void prof_end(cudaStream_t st);                                // call right after it
+void count_launch();
+
+#define PAMNET_LAUNCH_CHECK()                 \
+    do {                                      \
+        ::pamnet::count_launch();             \
+        PAMNET_CUDA(cudaGetLastError());      \
+    } while (0)
 
 #define PAMNET_TRY(expr)            \
     do {                            \

@@ -181,7 +181,11 @@ int gemm_launch(const GemmArgs& a, cudaStream_t st) {
     if (a.M <= 0 || a.N <= 0) return 0;
     if (a.K <= 0) return 0;   // callers zero-fill outputs themselves when K == 0 matters
     dim3 grid(ceil_div(a.M, BM) * ceil_div(a.N, BN), a.ksplit > 1 ? a.ksplit : 1, a.nslots);
+    double bytes = 4.0 * a.nslots * ((double)a.M * a.K + (double)a.K * a.N + (double)a.M * a.N);
+    if (a.epi == EPI_MUL_DSILU || (a.epi == EPI_BIAS_SILU && a.slot[0].C2)) bytes += 4.0 * a.nslots * (double)a.M * a.N;
+    prof_begin(KC_GEMM, bytes, st);
     gemm_kernel<<<grid, GT, 0, st>>>(a);
+    prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;
 }

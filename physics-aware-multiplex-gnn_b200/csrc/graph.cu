@@ -69,7 +69,9 @@ __global__ void __launch_bounds__(kScanThreads) scan_exclusive_kernel(const int3
 }
 
 int scan_exclusive(const int32_t* in, int32_t* out, int64_t n, int64_t* total64, cudaStream_t st) {
+    prof_begin(KC_GRAPH, 0.0, st);
     scan_exclusive_kernel<<<1, kScanThreads, 0, st>>>(in, out, n, total64);
+    prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;
 }
@@ -124,8 +126,10 @@ __global__ void radius_kernel(const float* __restrict__ pos, const int64_t* __re
 int radius_count(const float* pos, const int64_t* batch, int64_t n_nodes, float r, int max_nb, int drop_self,
                  int32_t* deg, int32_t* ptr, int64_t* total_dev, cudaStream_t st) {
     if (n_nodes > 0) {
+        prof_begin(KC_GRAPH, 0.0, st);
         radius_kernel<false><<<ceil_div(n_nodes, 128), 128, 0, st>>>(pos, batch, n_nodes, r * r, max_nb, drop_self,
                                                                      deg, nullptr, 0, nullptr);
+        prof_end(st);
         PAMNET_LAUNCH_CHECK();
     }
     return scan_exclusive(deg, ptr, n_nodes, total_dev, st);
@@ -134,8 +138,10 @@ int radius_count(const float* pos, const int64_t* batch, int64_t n_nodes, float 
 int radius_fill(const float* pos, const int64_t* batch, int64_t n_nodes, float r, int max_nb, int drop_self,
                 const int32_t* ptr, int64_t total, int64_t* edge_index, cudaStream_t st) {
     if (n_nodes == 0 || total == 0) return 0;
+    prof_begin(KC_GRAPH, 0.0, st);
     radius_kernel<true><<<ceil_div(n_nodes, 128), 128, 0, st>>>(pos, batch, n_nodes, r * r, max_nb, drop_self,
                                                                 nullptr, ptr, total, edge_index);
+    prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;
 }
@@ -182,7 +188,9 @@ int knn(const float* pos, const int64_t* batch, int64_t n_nodes, int k, int32_t*
     size_t smem = (size_t)k * kKnnThreads * 8;
     PAMNET_CHECK_ARG(smem <= 200 * 1024, "knn: k=%d too large", k);
     PAMNET_CUDA(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prof_begin(KC_GRAPH, 0.0, st);
     knn_kernel<<<ceil_div(n_nodes, kKnnThreads), kKnnThreads, smem, st>>>(pos, batch, n_nodes, k, nbr, d2);
+    prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;
 }
@@ -219,8 +227,10 @@ __global__ void knn_edges_kernel(const int32_t* __restrict__ nbr, const float* _
 int knn_edges_count(const int32_t* nbr, const float* pos, int64_t n_nodes, int k, float cutoff, int32_t* deg,
                     int32_t* ptr, int64_t* total_dev, cudaStream_t st) {
     if (n_nodes > 0) {
+        prof_begin(KC_GRAPH, 0.0, st);
         knn_edges_kernel<false><<<ceil_div(n_nodes, 128), 128, 0, st>>>(nbr, pos, n_nodes, k, cutoff, deg, nullptr, 0,
                                                                         nullptr);
+        prof_end(st);
         PAMNET_LAUNCH_CHECK();
     }
     return scan_exclusive(deg, ptr, n_nodes, total_dev, st);
@@ -229,8 +239,10 @@ int knn_edges_count(const int32_t* nbr, const float* pos, int64_t n_nodes, int k
 int knn_edges_fill(const int32_t* nbr, const float* pos, int64_t n_nodes, int k, float cutoff, const int32_t* ptr,
                    int64_t total, int64_t* edge_index, cudaStream_t st) {
     if (n_nodes == 0 || total == 0) return 0;
+    prof_begin(KC_GRAPH, 0.0, st);
     knn_edges_kernel<true><<<ceil_div(n_nodes, 128), 128, 0, st>>>(nbr, pos, n_nodes, k, cutoff, nullptr, ptr, total,
                                                                    edge_index);
+    prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;
 }
@@ -259,7 +271,9 @@ __global__ void edge_compact_kernel(const int64_t* __restrict__ ei, int64_t n_ed
 int edge_filter_count(const int64_t* ei, int64_t n_edges, const float* pos, float cutoff, int32_t* keep, int32_t* ptr,
                       int64_t* total_dev, cudaStream_t st) {
     if (n_edges > 0) {
+        prof_begin(KC_GRAPH, 0.0, st);
         edge_keep_kernel<<<ceil_div(n_edges, 256), 256, 0, st>>>(ei, n_edges, pos, cutoff, keep);
+        prof_end(st);
         PAMNET_LAUNCH_CHECK();
     }
     return scan_exclusive(keep, ptr, n_edges, total_dev, st);
@@ -268,7 +282,9 @@ int edge_filter_count(const int64_t* ei, int64_t n_edges, const float* pos, floa
 int edge_filter_fill(const int64_t* ei, int64_t n_edges, const int32_t* keep, const int32_t* ptr, int64_t total,
                      int64_t* out, cudaStream_t st) {
     if (n_edges == 0 || total == 0) return 0;
+    prof_begin(KC_GRAPH, 0.0, st);
     edge_compact_kernel<<<ceil_div(n_edges, 256), 256, 0, st>>>(ei, n_edges, keep, ptr, total, out);
+    prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;
 }
@@ -326,15 +342,21 @@ int build_buckets(const int32_t* keys, int64_t n, int64_t n_buckets, const int32
                   int32_t* ptr, int32_t* items, cudaStream_t st) {
     PAMNET_CUDA(cudaMemsetAsync(cnt_scratch, 0, sizeof(int32_t) * (n_buckets + 1), st));
     if (n > 0) {
+        prof_begin(KC_GRAPH, 0.0, st);
         hist_kernel<<<ceil_div(n, 256), 256, 0, st>>>(keys, n, cnt_scratch);
+        prof_end(st);
         PAMNET_LAUNCH_CHECK();
     }
     PAMNET_TRY(scan_exclusive(cnt_scratch, ptr, n_buckets, nullptr, st));
     if (n > 0) {
         PAMNET_CUDA(cudaMemsetAsync(cnt_scratch, 0, sizeof(int32_t) * (n_buckets + 1), st));
+        prof_begin(KC_GRAPH, 0.0, st);
         bucket_fill_kernel<<<ceil_div(n, 256), 256, 0, st>>>(keys, n, ptr, cnt_scratch, items);
+        prof_end(st);
         PAMNET_LAUNCH_CHECK();
+        prof_begin(KC_GRAPH, 0.0, st);
         bucket_sort_kernel<<<ceil_div(n_buckets, 128), 128, 0, st>>>(ptr, n_buckets, items, key2);
+        prof_end(st);
         PAMNET_LAUNCH_CHECK();
     }
     return 0;
@@ -357,15 +379,21 @@ int build_in_csr(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, in
                  int32_t* src_api, int32_t* cnt_scratch, int32_t* ptr, int32_t* eid, int32_t* src_csr,
                  int32_t* dst_csr, cudaStream_t st) {
     if (n_edges > 0) {
+        prof_begin(KC_GRAPH, 0.0, st);
         split_edges_kernel<<<ceil_div(n_edges, 256), 256, 0, st>>>(edge_index, n_edges, dst_row, dst_api, src_api);
+        prof_end(st);
         PAMNET_LAUNCH_CHECK();
     }
     PAMNET_TRY(build_buckets(dst_api, n_edges, n_nodes, src_api, cnt_scratch, ptr, eid, st));
     if (n_edges > 0) {
+        prof_begin(KC_GRAPH, 0.0, st);
         gather_i32_kernel<<<ceil_div(n_edges, 256), 256, 0, st>>>(src_api, eid, n_edges, src_csr);
+        prof_end(st);
         PAMNET_LAUNCH_CHECK();
         if (dst_csr) {
+            prof_begin(KC_GRAPH, 0.0, st);
             gather_i32_kernel<<<ceil_div(n_edges, 256), 256, 0, st>>>(dst_api, eid, n_edges, dst_csr);
+            prof_end(st);
             PAMNET_LAUNCH_CHECK();
         }
     }
@@ -448,8 +476,10 @@ int triplet_count(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, v
     PAMNET_TRY(build_in_csr(edge_index, n_edges, n_nodes, 1, s.dst_api, s.src_api, s.cnt, s.ptr, s.eid, s.src_csr,
                             nullptr, st));
     if (n_edges > 0) {
+        prof_begin(KC_GRAPH, 0.0, st);
         triplet_count_kernel<<<ceil_div(n_edges, 128), 128, 0, st>>>(s.dst_api, s.src_api, n_edges, s.ptr, s.src_csr,
                                                                      s.c2, s.c1);
+        prof_end(st);
         PAMNET_LAUNCH_CHECK();
     }
     PAMNET_TRY(scan_exclusive(s.c2, s.off2, n_edges, counts_dev, st));
@@ -463,9 +493,11 @@ int triplet_fill(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, co
     TripletScratch s;
     triplet_scratch_layout(n_nodes, n_edges, const_cast<void*>(scratch), &s);
     if (n_edges == 0) return 0;
+    prof_begin(KC_GRAPH, 0.0, st);
     triplet_fill_kernel<<<ceil_div(n_edges, 128), 128, 0, st>>>(s.dst_api, s.src_api, n_edges, s.ptr, s.src_csr, s.eid,
                                                                 s.off2, s.off1, out[0], out[1], out[2], out[3], out[4],
                                                                 out[5], out[6], out[7], out[8], out[9]);
+    prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;
 }
@@ -597,7 +629,9 @@ int plan_count(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const int64
     const int64_t N = sz.n_nodes, Eg = sz.n_edges_g, El = sz.n_edges_l;
     {
         const int64_t n = (N > sz.n_graphs + 1 ? N : sz.n_graphs + 1);
+        prof_begin(KC_GRAPH, 0.0, st);
         n2g_kernel<<<ceil_div(n, 256), 256, 0, st>>>(batch, N, sz.n_graphs, p.n2g, p.gptr);
+        prof_end(st);
         PAMNET_LAUNCH_CHECK();
     }
     // global graph: x_i = x[edge_index[dst_row]] is also the aggregation target (PyG propagate)
@@ -610,9 +644,11 @@ int plan_count(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const int64
     PAMNET_TRY(build_buckets(p.l_src, El, N, nullptr, p.cnt, p.l_optr, p.l_opos, st));
     PAMNET_CUDA(cudaMemsetAsync(counts_dev, 0, 2 * sizeof(int64_t), st));
     if (El > 0) {
+        prof_begin(KC_GRAPH, 0.0, st);
         plan_tcount_kernel<<<ceil_div(El, 128), 128, 0, st>>>(p.l_ptr, p.l_src, p.l_dst, El, cfg.simple ? 0 : 1,
                                                               p.t_split, p.t_cnt,
                                                               reinterpret_cast<unsigned long long*>(counts_dev));
+        prof_end(st);
         PAMNET_LAUNCH_CHECK();
     }
     PAMNET_TRY(scan_exclusive(p.t_cnt, p.t_ptr, El, nullptr, st));
@@ -625,15 +661,21 @@ int plan_fill(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const float*
     plan_layout(sz, plan_base, plan_trip, &p, nullptr, nullptr);
     const int64_t N = sz.n_nodes, El = sz.n_edges_l, T = sz.n_t2 + sz.n_t1;
     if (El > 0 && T > 0) {
+        prof_begin(KC_GRAPH, 0.0, st);
         plan_tfill_kernel<<<ceil_div(El, 128), 128, 0, st>>>(p.l_ptr, p.l_src, p.l_dst, El, cfg.simple ? 0 : 1, p.t_ptr,
                                                              pos, p.t_gather, p.t_owner, p.t_angle);
+        prof_end(st);
         PAMNET_LAUNCH_CHECK();
     }
     PAMNET_TRY(build_buckets(p.t_gather, T, El, nullptr, p.cnt, p.tt_ptr, p.tt_t, st));
     if (N > 0) {
+        prof_begin(KC_GRAPH, 0.0, st);
         csr_dist_kernel<<<ceil_div(N, 128), 128, 0, st>>>(p.g_ptr, p.g_src, N, pos, p.dist_g);
+        prof_end(st);
         PAMNET_LAUNCH_CHECK();
+        prof_begin(KC_GRAPH, 0.0, st);
         csr_dist_kernel<<<ceil_div(N, 128), 128, 0, st>>>(p.l_ptr, p.l_src, N, pos, p.dist_l);
+        prof_end(st);
         PAMNET_LAUNCH_CHECK();
     }
     return 0;

@@ -207,10 +207,11 @@ __global__ void __launch_bounds__(kMsgThreads) node_grad_gather_kernel(const Nod
     }
 }
 
-#define DISPATCH_DIM(dim, KERNEL, rows, args)                                                         \
+#define DISPATCH_DIM(dim, KERNEL, rows, args, CLS, BYTES)                                             \
     do {                                                                                              \
         if ((rows) <= 0) return 0;                                                                    \
         const int grid = ceil_div((rows), kMsgThreads / 32);                                          \
+        prof_begin(CLS, BYTES, st);                                                                   \
         switch (dim) {                                                                                \
             case 128: KERNEL<128><<<grid, kMsgThreads, 0, st>>>(args); break;                         \
             case 64:  KERNEL<64><<<grid, kMsgThreads, 0, st>>>(args); break;                          \
@@ -218,17 +219,44 @@ __global__ void __launch_bounds__(kMsgThreads) node_grad_gather_kernel(const Nod
             case 16:  KERNEL<16><<<grid, kMsgThreads, 0, st>>>(args); break;                          \
             default: set_error("unsupported dim %d (16, 32, 64, 128)", dim); return -1;               \
         }                                                                                             \
+        prof_end(st);                                                                                 \
         PAMNET_LAUNCH_CHECK();                                                                        \
         return 0;                                                                                     \
     } while (0)
 
-int global_msg_fwd(int dim, const GlobalMsgArgs& a, cudaStream_t st) { DISPATCH_DIM(dim, global_msg_fwd_kernel, a.n_nodes, a); }
-int global_msg_bwd(int dim, const GlobalMsgArgs& a, cudaStream_t st) { DISPATCH_DIM(dim, global_msg_bwd_kernel, a.n_nodes, a); }
-int local_edge_fwd(int dim, const LocalMsgArgs& a, cudaStream_t st) { DISPATCH_DIM(dim, local_edge_fwd_kernel, a.n_edges, a); }
-int local_msg_fwd(int dim, const LocalMsgArgs& a, cudaStream_t st) { DISPATCH_DIM(dim, local_msg_fwd_kernel, a.n_nodes, a); }
-int local_msg_bwd(int dim, const LocalMsgArgs& a, cudaStream_t st) { DISPATCH_DIM(dim, local_msg_bwd_kernel, a.n_nodes, a); }
-int local_trip_bwd(int dim, const LocalMsgArgs& a, cudaStream_t st) { DISPATCH_DIM(dim, local_trip_bwd_kernel, a.n_edges, a); }
-int node_grad_gather(int dim, const NodeGatherArgs& a, cudaStream_t st) { DISPATCH_DIM(dim, node_grad_gather_kernel, a.n_nodes, a); }
+// algorithmic bytes: every operand row touched once (row = 4*D bytes), index arrays as int32
+static double nbytes(int dim, double node_rows, double edge_rows, double trip_rows, double idx) {
+    return 4.0 * dim * (node_rows + edge_rows + trip_rows) + 4.0 * idx;
+}
+
+int global_msg_fwd(int dim, const GlobalMsgArgs& a, int n_edges, cudaStream_t st) {
+    DISPATCH_DIM(dim, global_msg_fwd_kernel, a.n_nodes, a, KC_GLOBAL_MSG_FWD,
+                 nbytes(dim, 3.0 * a.n_nodes, 3.0 * n_edges, 0, a.n_nodes + n_edges));
+}
+int global_msg_bwd(int dim, const GlobalMsgArgs& a, int n_edges, cudaStream_t st) {
+    DISPATCH_DIM(dim, global_msg_bwd_kernel, a.n_nodes, a, KC_GLOBAL_MSG_BWD,
+                 nbytes(dim, 2.0 * a.n_nodes, 5.0 * n_edges, 0, a.n_nodes + n_edges));
+}
+int local_edge_fwd(int dim, const LocalMsgArgs& a, cudaStream_t st) {
+    DISPATCH_DIM(dim, local_edge_fwd_kernel, a.n_edges, a, KC_LOCAL_EDGE_FWD,
+                 nbytes(dim, 0, 5.0 * a.n_edges, 0, 2.0 * a.n_edges));
+}
+int local_msg_fwd(int dim, const LocalMsgArgs& a, int n_trip, cudaStream_t st) {
+    DISPATCH_DIM(dim, local_msg_fwd_kernel, a.n_nodes, a, KC_LOCAL_MSG_FWD,
+                 nbytes(dim, 3.0 * a.n_nodes, 4.0 * a.n_edges, 2.0 * n_trip, a.n_nodes + 2.0 * a.n_edges + n_trip));
+}
+int local_msg_bwd(int dim, const LocalMsgArgs& a, int n_trip, cudaStream_t st) {
+    DISPATCH_DIM(dim, local_msg_bwd_kernel, a.n_nodes, a, KC_LOCAL_MSG_BWD,
+                 nbytes(dim, 2.0 * a.n_nodes, 7.0 * a.n_edges, 3.0 * n_trip, a.n_nodes + 2.0 * a.n_edges + n_trip));
+}
+int local_trip_bwd(int dim, const LocalMsgArgs& a, int n_trip, cudaStream_t st) {
+    DISPATCH_DIM(dim, local_trip_bwd_kernel, a.n_edges, a, KC_LOCAL_TRIP_BWD,
+                 nbytes(dim, 0, 6.0 * a.n_edges, 2.0 * n_trip, 3.0 * a.n_edges + 2.0 * n_trip));
+}
+int node_grad_gather(int dim, const NodeGatherArgs& a, int n_edges, cudaStream_t st) {
+    DISPATCH_DIM(dim, node_grad_gather_kernel, a.n_nodes, a, KC_NODE_GATHER,
+                 nbytes(dim, 2.0 * a.n_blocks * a.n_nodes, 2.0 * a.n_blocks * n_edges, 0, 2.0 * a.n_nodes + n_edges));
+}
 
 // ---------------------------------------------------------------------------------------------
 // generic scatter-add (operator surface; index arbitrary -> atomics)

@@ -25,8 +25,8 @@ struct GlobalMsgArgs {
     const float* g_h;                // [N, D]
     float* gQT;                      // [E, ldq] at this layer's block: grad Q (= grad z) | grad Tt
 };
-int global_msg_fwd(int dim, const GlobalMsgArgs& a, cudaStream_t st);
-int global_msg_bwd(int dim, const GlobalMsgArgs& a, cudaStream_t st);
+int global_msg_fwd(int dim, const GlobalMsgArgs& a, int n_edges, cudaStream_t st);
+int global_msg_bwd(int dim, const GlobalMsgArgs& a, int n_edges, cudaStream_t st);
 
 struct LocalMsgArgs {
     int n_nodes, n_edges;
@@ -49,9 +49,9 @@ struct LocalMsgArgs {
     float* gzq;                      // [T, ldt] at this layer's block: grad of zq
 };
 int local_edge_fwd(int dim, const LocalMsgArgs& a, cudaStream_t st);
-int local_msg_fwd(int dim, const LocalMsgArgs& a, cudaStream_t st);
-int local_msg_bwd(int dim, const LocalMsgArgs& a, cudaStream_t st);
-int local_trip_bwd(int dim, const LocalMsgArgs& a, cudaStream_t st);
+int local_msg_fwd(int dim, const LocalMsgArgs& a, int n_trip, cudaStream_t st);
+int local_msg_bwd(int dim, const LocalMsgArgs& a, int n_trip, cudaStream_t st);
+int local_trip_bwd(int dim, const LocalMsgArgs& a, int n_trip, cudaStream_t st);
 
 // g_P[n, (2b)D..] = sum over incoming slots of gz_b ; g_P[n, (2b+1)D..] = sum over outgoing slots of gz_b
 struct NodeGatherArgs {
@@ -61,7 +61,7 @@ struct NodeGatherArgs {
     int ldq;
     float* g_P;                      // [N, 2*n_blocks*D]
 };
-int node_grad_gather(int dim, const NodeGatherArgs& a, cudaStream_t st);
+int node_grad_gather(int dim, const NodeGatherArgs& a, int n_edges, cudaStream_t st);
 
 // generic torch_scatter.scatter(src, index, dim=0, reduce='add') for the operator surface
 int scatter_add_rows(const float* src, const int64_t* index, int64_t n_rows, int64_t width, int64_t dim_size,

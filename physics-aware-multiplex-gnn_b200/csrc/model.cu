@@ -496,7 +496,7 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
             memset(&a, 0, sizeof(a));
             a.n_nodes = (int)N; a.ptr = pl.g_ptr; a.src = pl.g_src; a.P = hw.P;
             a.QT = w.QT + l * 2 * D; a.ldq = L * 2 * D; a.x1 = hw.x1; a.h = hw.h;
-            PAMNET_TRY(global_msg_fwd(D, a, st));
+            PAMNET_TRY(global_msg_fwd(D, a, (int)Eg, st));
         } else {
             LocalMsgArgs a;
             memset(&a, 0, sizeof(a));
@@ -505,7 +505,7 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
             a.QR = w.QR + l * 4 * D; a.ldq = L * 4 * D; a.zq = w.zq2 + l * D; a.ldt = L * D;
             a.x1 = hw.x1; a.m_nb = hw.m_nb; a.msum = hw.msum; a.h = hw.h;
             PAMNET_TRY(local_edge_fwd(D, a, st));
-            PAMNET_TRY(local_msg_fwd(D, a, st));
+            PAMNET_TRY(local_msg_fwd(D, a, (int)T, st));
         }
         Prog p((int)N);
         const float* res_x = hh == 0 ? w.x0 : w.half[hh - 1].r[2];
@@ -571,7 +571,7 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
             memset(&a, 0, sizeof(a));
             a.n_nodes = (int)N; a.ptr = pl.g_ptr; a.src = pl.g_src; a.P = hw.P;
             a.QT = w.QT + l * 2 * D; a.ldq = L * 2 * D; a.g_h = w.g_h; a.gQT = w.gQT + l * 2 * D;
-            PAMNET_TRY(global_msg_bwd(D, a, st));
+            PAMNET_TRY(global_msg_bwd(D, a, (int)Eg, st));
             ng.n_blocks = 1; ng.ptr = pl.g_ptr; ng.optr = pl.g_optr; ng.opos = pl.g_opos;
             ng.gz = w.gQT + l * 2 * D; ng.ldq = L * 2 * D;
         } else {
@@ -582,12 +582,12 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
             a.P = hw.P; a.QR = w.QR + l * 4 * D; a.ldq = L * 4 * D; a.zq = w.zq2 + l * D; a.ldt = L * D;
             a.m_nb = hw.m_nb; a.msum = hw.msum; a.g_h = w.g_h; a.g_s = w.g_s;
             a.gQR = w.gQR + l * 4 * D; a.gzq = w.gzq2 + l * D;
-            PAMNET_TRY(local_msg_bwd(D, a, st));
-            PAMNET_TRY(local_trip_bwd(D, a, st));
+            PAMNET_TRY(local_msg_bwd(D, a, (int)T, st));
+            PAMNET_TRY(local_trip_bwd(D, a, (int)T, st));
             ng.n_blocks = 2; ng.ptr = pl.l_ptr; ng.optr = pl.l_optr; ng.opos = pl.l_opos;
             ng.gz = w.gQR + l * 4 * D; ng.ldq = L * 4 * D;
         }
-        PAMNET_TRY(node_grad_gather(D, ng, st));
+        PAMNET_TRY(node_grad_gather(D, ng, is_local(hh) ? (int)El : (int)Eg, st));
         // weight gradients of the per-node halves of the edge MLPs: dW[:, cD:(c+1)D] = g_P_c^T x1
         {
             std::vector<GemmSlot> sl;

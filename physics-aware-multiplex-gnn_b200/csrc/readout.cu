@@ -36,11 +36,15 @@ __global__ void readout_pool_kernel(const ReadoutArgs a) {
 
 int readout_forward(const ReadoutArgs& a, cudaStream_t st) {
     if (a.n_nodes > 0) {
+        prof_begin(KC_READOUT, 0.0, st);
         readout_node_kernel<<<ceil_div(a.n_nodes, 128), 128, 0, st>>>(a);
+        prof_end(st);
         PAMNET_LAUNCH_CHECK();
     }
     if (a.n_graphs > 0) {
+        prof_begin(KC_READOUT, 0.0, st);
         readout_pool_kernel<<<ceil_div(a.n_graphs, 4), 128, 0, st>>>(a);
+        prof_end(st);
         PAMNET_LAUNCH_CHECK();
     }
     return 0;
@@ -74,7 +78,9 @@ __global__ void readout_bwd_kernel(const ReadoutArgs a) {
 
 int readout_backward(const ReadoutArgs& a, cudaStream_t st) {
     if (a.n_nodes == 0) return 0;
+    prof_begin(KC_READOUT, 0.0, st);
     readout_bwd_kernel<<<ceil_div(a.n_nodes, 128), 128, 0, st>>>(a);
+    prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;
 }
@@ -108,7 +114,9 @@ __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ out
 int loss_forward_backward(const float* out, const float* y, int64_t n, int kind, float* loss, float* grad_out,
                           cudaStream_t st) {
     PAMNET_CHECK_ARG(n > 0, "loss: empty batch");
+    prof_begin(KC_READOUT, 0.0, st);
     loss_kernel<<<1, 256, 0, st>>>(out, y, n, kind, loss, grad_out);
+    prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;
 }

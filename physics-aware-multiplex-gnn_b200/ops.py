@@ -198,7 +198,10 @@ def scatter(src, index, dim=0, dim_size=None, reduce="add"):
         raise NotImplementedError("hot path uses scatter(src, index, dim=0, reduce='add') only")
     _require_cuda(src, index)
     lib = _lib.load()
-    src2 = _f32(src).reshape(src.shape[0], -1)
+    width = 1
+    for d in src.shape[1:]:
+        width *= d
+    src2 = _f32(src).reshape(src.shape[0], width)
     index = _i64(index)
     if dim_size is None:
         dim_size = int(index.max()) + 1 if index.numel() else 0

@@ -1,0 +1,54 @@
+"""Molecule-sharded data parallelism: one process per GPU, full parameter replica, each rank
+runs its own batch; the only collective is ONE NCCL all-reduce over the flat gradient buffer per step.
+
+The reference has no distributed code at all (single process, main_qm9.py:56-58); its loss is a mean over the
+local batch (main_qm9.py:108), so gradients are averaged over ranks.
+"""
+import torch
+import torch.distributed as dist
+
+
+def flat_grad(model):
+    """The flat gradient buffer if every p.grad is a view into one (the layout our backward produces), else None."""
+    ps = [p for (_, p), used in zip(model._param_list, model._param_used) if used]
+    if any(p.grad is None for p in ps):
+        return None
+    first = ps[0].grad
+    base = first._base if first._base is not None else first
+    if base.dim() != 1 or base.numel() != model._total:
+        return None
+    start = base.data_ptr()
+    offs = [off for off, used in zip(model._offsets, model._param_used) if used]
+    if all(p.grad.data_ptr() == start + 4 * off for p, off in zip(ps, offs)):
+        return base
+    return None
+
+
+def allreduce_gradients(model, group=None, average=True):
+    """All-reduce (mean) the gradients of `model` across the process group: one collective on the flat buffer
+    when the grads alias it, otherwise a pack / all-reduce / unpack."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    world = dist.get_world_size(group)
+    buf = flat_grad(model)
+    if buf is not None:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            buf.mul_(1.0 / world)
+        return
+    grads = [p.grad for p in model.parameters() if p.grad is not None]
+    packed = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        packed.mul_(1.0 / world)
+    off = 0
+    for g in grads:
+        g.copy_(packed[off:off + g.numel()].view_as(g))
+        off += g.numel()
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous shard [lo, hi) of n_items for `rank` (molecule sharding of a global batch)."""
+    per, rem = divmod(n_items, world)
+    lo = rank * per + min(rank, rem)
+    return lo, lo + per + (1 if rank < rem else 0)

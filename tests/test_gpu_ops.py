@@ -156,10 +156,15 @@ def test_linear(ops, n_in, n_out, rows):
 def test_gemm_modes(ops, m, n, k, ksplit):
     g = torch.Generator().manual_seed(3)
     a, b = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g)
-    assert rel_err(ops.gemm(0, a.cuda(), b.cuda(), m, n, k), a.double() @ b.double().T) < 2e-6
+    # fp32 running sums over k terms of magnitude ~1: error ~ sqrt(k) * eps, independent of the result's size
+    tol = 4e-7 * k ** 0.5
+
+    def err(x, ref):
+        return float((x.double().cpu() - ref).abs().max())
+    assert err(ops.gemm(0, a.cuda(), b.cuda(), m, n, k), a.double() @ b.double().T) < tol
     bt = b.T.contiguous()
-    assert rel_err(ops.gemm(1, a.cuda(), bt.cuda(), m, n, k), a.double() @ bt.double()) < 2e-6
+    assert err(ops.gemm(1, a.cuda(), bt.cuda(), m, n, k), a.double() @ bt.double()) < tol
     at = a.T.contiguous()
     c, db = ops.gemm(2, at.cuda(), bt.cuda(), m, n, k, ksplit=ksplit, want_dbias=True)
-    assert rel_err(c, at.double().T @ bt.double()) < 2e-6
-    assert rel_err(db, at.double().sum(0)) < 2e-6
+    assert err(c, at.double().T @ bt.double()) < tol
+    assert err(db, at.double().sum(0)) < tol
