@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256) rbf_freq_bwd_kernel(const float* __restri
 int rbf_freq_backward(const float* dist, int64_t n_edges, const float* freq, float cutoff, const float* g_rbf,
                       float* g_freq, cudaStream_t st) {
     if (n_edges == 0) return 0;
-    const int64_t rpb = 512;
+    const int64_t rpb = 128;
     prof_begin(KC_BASIS, 0.0, st);
     rbf_freq_bwd_kernel<<<ceil_div(n_edges, rpb), 256, 0, st>>>(dist, n_edges, freq, cutoff, g_rbf, rpb, g_freq);
     prof_end(st);
@@ -282,23 +282,32 @@ int embed_forward(const float* type_f, int64_t n_nodes, const float* emb, int n_
     return 0;
 }
 
-// one block per (type, column tile): fixed-order sum over the nodes of that type -> deterministic
-__global__ void embed_bwd_kernel(const float* __restrict__ type_f, int64_t n_nodes, const float* __restrict__ g_x,
-                                 int dim, float* __restrict__ g_emb) {
+// one block per (type, 32-column tile): 8 node-strided partial sums per column, combined in fixed order
+__global__ void __launch_bounds__(256) embed_bwd_kernel(const float* __restrict__ type_f, int64_t n_nodes,
+                                                        const float* __restrict__ g_x, int dim,
+                                                        float* __restrict__ g_emb) {
+    __shared__ float red[8][33];
     const int ty = blockIdx.y;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= dim) return;
+    const int cl = threadIdx.x & 31, part = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
     float s = 0.f;
-    for (int64_t n = 0; n < n_nodes; ++n)
-        if ((int)type_f[n] == ty) s += g_x[n * dim + c];
-    g_emb[(size_t)ty * dim + c] = s;
+    if (c < dim)
+        for (int64_t n = part; n < n_nodes; n += 8)
+            if ((int)type_f[n] == ty) s += g_x[n * dim + c];
+    red[part][cl] = s;
+    __syncthreads();
+    if (part == 0 && c < dim) {
+        float tot = 0.f;
+        for (int p = 0; p < 8; ++p) tot += red[p][cl];
+        g_emb[(size_t)ty * dim + c] = tot;
+    }
 }
 
 int embed_backward(const float* type_f, int64_t n_nodes, const float* g_x, int n_embed, int dim, float* g_emb,
                    cudaStream_t st) {
     dim3 grid(ceil_div(dim, 32), n_embed);
     prof_begin(KC_BASIS, 0.0, st);
-    embed_bwd_kernel<<<grid, 32, 0, st>>>(type_f, n_nodes, g_x, dim, g_emb);
+    embed_bwd_kernel<<<grid, 256, 0, st>>>(type_f, n_nodes, g_x, dim, g_emb);
     prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;

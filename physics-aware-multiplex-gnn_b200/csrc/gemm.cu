@@ -1,11 +1,12 @@
-// fp32 FFMA GEMM, 64x64x16 tiles, 256 threads, 4x4 register micro-tile, register-prefetch double buffering.
+// fp32 FFMA GEMM: BM x BN x 16 tiles, 256 threads, TM x TN register micro-tile (128x128 / 8x8 for the large
+// edge/triplet contractions, 64x64 / 4x4 for small or skinny ones), register-prefetch double buffering.
 // Results are plain IEEE fp32 sums (no tensor-core rounding), which is what holds the 1e-5 parity bar of the
 // reference's nn.Linear layers (layers/basic.py:19-22).
 #include "gemm.cuh"
 
 namespace pamnet {
 
-constexpr int BM = 64, BN = 64, BK = 16, GT = 256;
+constexpr int BK = 16, GT = 256;
 constexpr int PAD = 4;
 
 __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -21,7 +22,14 @@ __device__ __forceinline__ float4 load4_guard(const float* __restrict__ p, int v
     return r;
 }
 
+// Micro-tile rows: TM/4 groups of 4 consecutive rows, group g at offset g * (BM / (TM/4)) + ty*4 (same for
+// columns): keeps every shared-memory read a conflict-free / broadcast 128-bit access.
+template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__(GT) gemm_kernel(const GemmArgs args) {
+    static_assert((BM / TM) * (BN / TN) == GT, "256 threads");
+    constexpr int GM = TM / 4, GN = TN / 4;          // 4-wide groups per thread
+    constexpr int SM_ = BM / GM, SN_ = BN / GN;      // group stride
+    constexpr int LA = BM / 64, LB = BN / 64;        // float4 loads per thread per k-tile
     __shared__ __align__(16) float As[2][BK][BM + PAD];
     __shared__ __align__(16) float Bs[2][BK][BN + PAD];
 
@@ -31,7 +39,6 @@ __global__ void __launch_bounds__(GT) gemm_kernel(const GemmArgs args) {
     const int m0 = (blockIdx.x / tiles_n) * BM, n0 = (blockIdx.x % tiles_n) * BN;
     const int t = threadIdx.x;
 
-    // K range of this split
     int k_begin = 0, k_end = K;
     if (args.ksplit > 1) {
         const int chunk = ((K + args.ksplit - 1) / args.ksplit + BK - 1) / BK * BK;
@@ -44,24 +51,27 @@ __global__ void __launch_bounds__(GT) gemm_kernel(const GemmArgs args) {
     const bool b_kcontig = (mode == GEMM_NT);
     const bool a_vec = aligned16(sl.A) && (sl.lda % 4 == 0);
 
-    float acc[4][4];
+    float acc[TM][TN];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-    float4 ra, rb;
-    // thread -> load coordinates
-    const int lk_row = t >> 2, lk_k = (t & 3) * 4;      // k-contiguous: 64 rows x 16 k
-    const int lm_k = t >> 4, lm_m = (t & 15) * 4;       // m/n-contiguous: 16 k x 64 m
+    float4 ra[LA], rb[LB];
+    // k-contiguous operand: 64 rows x (4 float4 along k) per pass; m/n-contiguous: 16 k x (16 float4) per pass
+    const int lk_row = t >> 2, lk_k = (t & 3) * 4;
+    const int lm_k = t >> 4, lm_m = (t & 15) * 4;
 
     auto fetch = [&](int k0) {
-        if (a_kcontig) {
-            const int m = m0 + lk_row, k = k0 + lk_k;
-            ra = (m < M) ? load4_guard(sl.A + (size_t)m * sl.lda + k, k_end - k, a_vec) : make_float4(0, 0, 0, 0);
-        } else {
-            const int k = k0 + lm_k, m = m0 + lm_m;
-            ra = (k < k_end) ? load4_guard(sl.A + (size_t)k * sl.lda + m, M - m, a_vec) : make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int p = 0; p < LA; ++p) {
+            if (a_kcontig) {
+                const int m = m0 + lk_row + 64 * p, k = k0 + lk_k;
+                ra[p] = (m < M) ? load4_guard(sl.A + (size_t)m * sl.lda + k, k_end - k, a_vec) : make_float4(0, 0, 0, 0);
+            } else {
+                const int k = k0 + lm_k, m = m0 + lm_m + 64 * p;
+                ra[p] = (k < k_end) ? load4_guard(sl.A + (size_t)k * sl.lda + m, M - m, a_vec) : make_float4(0, 0, 0, 0);
+            }
         }
         const float* Bp = sl.B;
         int ldb = sl.ldb, kb = k0;
@@ -72,33 +82,47 @@ __global__ void __launch_bounds__(GT) gemm_kernel(const GemmArgs args) {
             kb = k0 - s * args.seg_len;
         }
         const bool b_vec = aligned16(Bp) && (ldb % 4 == 0);
-        if (b_kcontig) {
-            const int n = n0 + lk_row, k = kb + lk_k;
-            rb = (n < N) ? load4_guard(Bp + (size_t)n * ldb + k, k_end - (k0 + lk_k), b_vec) : make_float4(0, 0, 0, 0);
-        } else {
-            const int k = kb + lm_k, n = n0 + lm_m;
-            rb = (k0 + lm_k < k_end) ? load4_guard(Bp + (size_t)k * ldb + n, N - n, b_vec) : make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int p = 0; p < LB; ++p) {
+            if (b_kcontig) {
+                const int n = n0 + lk_row + 64 * p, k = kb + lk_k;
+                rb[p] = (n < N) ? load4_guard(Bp + (size_t)n * ldb + k, k_end - (k0 + lk_k), b_vec) : make_float4(0, 0, 0, 0);
+            } else {
+                const int k = kb + lm_k, n = n0 + lm_m + 64 * p;
+                rb[p] = (k0 + lm_k < k_end) ? load4_guard(Bp + (size_t)k * ldb + n, N - n, b_vec) : make_float4(0, 0, 0, 0);
+            }
         }
     };
     auto stash = [&](int buf) {
-        if (a_kcontig) {
-            As[buf][lk_k + 0][lk_row] = ra.x; As[buf][lk_k + 1][lk_row] = ra.y;
-            As[buf][lk_k + 2][lk_row] = ra.z; As[buf][lk_k + 3][lk_row] = ra.w;
-        } else {
-            *reinterpret_cast<float4*>(&As[buf][lm_k][lm_m]) = ra;
+#pragma unroll
+        for (int p = 0; p < LA; ++p) {
+            if (a_kcontig) {
+                const int r = lk_row + 64 * p;
+                As[buf][lk_k + 0][r] = ra[p].x; As[buf][lk_k + 1][r] = ra[p].y;
+                As[buf][lk_k + 2][r] = ra[p].z; As[buf][lk_k + 3][r] = ra[p].w;
+            } else {
+                *reinterpret_cast<float4*>(&As[buf][lm_k][lm_m + 64 * p]) = ra[p];
+            }
         }
-        if (b_kcontig) {
-            Bs[buf][lk_k + 0][lk_row] = rb.x; Bs[buf][lk_k + 1][lk_row] = rb.y;
-            Bs[buf][lk_k + 2][lk_row] = rb.z; Bs[buf][lk_k + 3][lk_row] = rb.w;
-        } else {
-            *reinterpret_cast<float4*>(&Bs[buf][lm_k][lm_m]) = rb;
+#pragma unroll
+        for (int p = 0; p < LB; ++p) {
+            if (b_kcontig) {
+                const int r = lk_row + 64 * p;
+                Bs[buf][lk_k + 0][r] = rb[p].x; Bs[buf][lk_k + 1][r] = rb[p].y;
+                Bs[buf][lk_k + 2][r] = rb[p].z; Bs[buf][lk_k + 3][r] = rb[p].w;
+            } else {
+                *reinterpret_cast<float4*>(&Bs[buf][lm_k][lm_m + 64 * p]) = rb[p];
+            }
         }
     };
 
     const int ty = t >> 4, tx = t & 15;
     // weight-gradient mode: column sums of A (= bias gradient) ride along on the first column tile
     const bool do_bias = (mode == GEMM_TN) && sl.C2 != nullptr && n0 == 0 && tx == 0;
-    float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+    float bsum[TM];
+#pragma unroll
+    for (int i = 0; i < TM; ++i) bsum[i] = 0.f;
+
     fetch(k_begin);
     stash(0);
     __syncthreads();
@@ -108,18 +132,25 @@ __global__ void __launch_bounds__(GT) gemm_kernel(const GemmArgs args) {
         if (more) fetch(k0 + BK);
 #pragma unroll
         for (int kk = 0; kk < BK; ++kk) {
-            const float4 a = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
-            const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w};
-            const float bv[4] = {b.x, b.y, b.z, b.w};
-            if (do_bias) {
+            float av[TM], bv[TN];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) bsum[i] += av[i];
+            for (int g = 0; g < GM; ++g) {
+                const float4 a = *reinterpret_cast<const float4*>(&As[buf][kk][g * SM_ + ty * 4]);
+                av[g * 4 + 0] = a.x; av[g * 4 + 1] = a.y; av[g * 4 + 2] = a.z; av[g * 4 + 3] = a.w;
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int g = 0; g < GN; ++g) {
+                const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][kk][g * SN_ + tx * 4]);
+                bv[g * 4 + 0] = b.x; bv[g * 4 + 1] = b.y; bv[g * 4 + 2] = b.z; bv[g * 4 + 3] = b.w;
+            }
+            if (do_bias) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+                for (int i = 0; i < TM; ++i) bsum[i] += av[i];
+            }
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
         if (more) {
             stash(buf ^ 1);
@@ -129,21 +160,16 @@ __global__ void __launch_bounds__(GT) gemm_kernel(const GemmArgs args) {
     }
 
     // epilogue
-    if (do_bias) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int m = m0 + ty * 4 + i;
-            if (m >= M) continue;
+    for (int i = 0; i < TM; ++i) {
+        const int m = m0 + (i / 4) * SM_ + ty * 4 + (i & 3);
+        if (m >= M) continue;
+        if (do_bias) {
             if (args.ksplit > 1) atomicAdd(&sl.C2[m], bsum[i]); else sl.C2[m] = bsum[i];
         }
-    }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + ty * 4 + i;
-        if (m >= M) continue;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int n = n0 + tx * 4 + j;
+        for (int j = 0; j < TN; ++j) {
+            const int n = n0 + (j / 4) * SN_ + tx * 4 + (j & 3);
             if (n >= N) continue;
             float v = acc[i][j];
             const size_t ci = (size_t)m * sl.ldc + n;
@@ -157,8 +183,8 @@ __global__ void __launch_bounds__(GT) gemm_kernel(const GemmArgs args) {
                     break;
                 case EPI_BIAS_SILU: {
                     if (sl.bias) v += sl.bias[n];
-                    if (sl.C2) sl.C2[ci] = v;
-                    v = silu(v);   // (C2 here is the pre-activation, NT mode only)
+                    if (sl.C2) sl.C2[ci] = v;   // pre-activation (NT mode only)
+                    v = silu(v);
                     break;
                 }
                 case EPI_MUL_DSILU:
@@ -180,11 +206,20 @@ int gemm_launch(const GemmArgs& a, cudaStream_t st) {
     PAMNET_CHECK_ARG(a.ksplit <= 1 || (a.epi == EPI_NONE && !a.accumulate), "gemm: split-K needs EPI_NONE");
     if (a.M <= 0 || a.N <= 0) return 0;
     if (a.K <= 0) return 0;   // callers zero-fill outputs themselves when K == 0 matters
-    dim3 grid(ceil_div(a.M, BM) * ceil_div(a.N, BN), a.ksplit > 1 ? a.ksplit : 1, a.nslots);
     double bytes = 4.0 * a.nslots * ((double)a.M * a.K + (double)a.K * a.N + (double)a.M * a.N);
     if (a.epi == EPI_MUL_DSILU || (a.epi == EPI_BIAS_SILU && a.slot[0].C2)) bytes += 4.0 * a.nslots * (double)a.M * a.N;
+    const int ks = a.ksplit > 1 ? a.ksplit : 1;
+    // big tiles only when they still give >= 2 waves of CTAs on 148 SMs
+    const long big_ctas = (long)ceil_div(a.M, 128) * ceil_div(a.N, 128) * ks * a.nslots;
+    const bool big = a.M >= 128 && a.N >= 128 && big_ctas >= 2 * kNumSM;
     prof_begin(KC_GEMM, bytes, st);
-    gemm_kernel<<<grid, GT, 0, st>>>(a);
+    if (big) {
+        dim3 grid(ceil_div(a.M, 128) * ceil_div(a.N, 128), ks, a.nslots);
+        gemm_kernel<128, 128, 8, 8><<<grid, GT, 0, st>>>(a);
+    } else {
+        dim3 grid(ceil_div(a.M, 64) * ceil_div(a.N, 64), ks, a.nslots);
+        gemm_kernel<64, 64, 4, 4><<<grid, GT, 0, st>>>(a);
+    }
     prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;

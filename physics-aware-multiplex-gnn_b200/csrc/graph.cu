@@ -313,33 +313,32 @@ __global__ void bucket_fill_kernel(const int32_t* __restrict__ keys, int64_t n, 
     items[ptr[k] + atomicAdd(&cursor[k], 1)] = (int32_t)i;
 }
 
-// sort each bucket by (key2[item], item); key2 may be null (sort by item only)
-__global__ void bucket_sort_kernel(const int32_t* __restrict__ ptr, int64_t n_buckets, int32_t* __restrict__ items,
-                                   const int32_t* __restrict__ key2) {
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// order each bucket by (key2[item], item); key2 may be null (order by item only).  One warp per bucket: every
+// lane ranks its items against the whole bucket (buckets are node degrees, ~20 for QM9, 49 for RNA kNN).
+__global__ void __launch_bounds__(128) bucket_sort_kernel(const int32_t* __restrict__ ptr, int64_t n_buckets,
+                                                          const int32_t* __restrict__ items_in,
+                                                          int32_t* __restrict__ items_out,
+                                                          const int32_t* __restrict__ key2) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (b >= n_buckets) return;
     const int s = ptr[b], e = ptr[b + 1];
-    for (int i = s + 1; i < e; ++i) {
-        const int it = items[i];
+    for (int i = s + lane; i < e; i += 32) {
+        const int it = items_in[i];
         const int k2 = key2 ? key2[it] : 0;
-        int p = i;
-        while (p > s) {
-            const int jt = items[p - 1];
+        int rank = 0;
+        for (int j = s; j < e; ++j) {
+            const int jt = items_in[j];
             const int j2 = key2 ? key2[jt] : 0;
-            if (j2 > k2 || (j2 == k2 && jt > it)) {
-                items[p] = jt;
-                --p;
-            } else {
-                break;
-            }
+            rank += (j2 < k2) || (j2 == k2 && jt < it);
         }
-        items[p] = it;
+        items_out[s + rank] = it;
     }
 }
 
 // ptr[n_buckets+1], items[n]: items of bucket b sorted by (key2, item)
 int build_buckets(const int32_t* keys, int64_t n, int64_t n_buckets, const int32_t* key2, int32_t* cnt_scratch,
-                  int32_t* ptr, int32_t* items, cudaStream_t st) {
+                  int32_t* ptr, int32_t* items, int32_t* items_tmp, cudaStream_t st) {
     PAMNET_CUDA(cudaMemsetAsync(cnt_scratch, 0, sizeof(int32_t) * (n_buckets + 1), st));
     if (n > 0) {
         prof_begin(KC_GRAPH, 0.0, st);
@@ -351,11 +350,11 @@ int build_buckets(const int32_t* keys, int64_t n, int64_t n_buckets, const int32
     if (n > 0) {
         PAMNET_CUDA(cudaMemsetAsync(cnt_scratch, 0, sizeof(int32_t) * (n_buckets + 1), st));
         prof_begin(KC_GRAPH, 0.0, st);
-        bucket_fill_kernel<<<ceil_div(n, 256), 256, 0, st>>>(keys, n, ptr, cnt_scratch, items);
+        bucket_fill_kernel<<<ceil_div(n, 256), 256, 0, st>>>(keys, n, ptr, cnt_scratch, items_tmp);
         prof_end(st);
         PAMNET_LAUNCH_CHECK();
         prof_begin(KC_GRAPH, 0.0, st);
-        bucket_sort_kernel<<<ceil_div(n_buckets, 128), 128, 0, st>>>(ptr, n_buckets, items, key2);
+        bucket_sort_kernel<<<ceil_div(n_buckets, 4), 128, 0, st>>>(ptr, n_buckets, items_tmp, items, key2);
         prof_end(st);
         PAMNET_LAUNCH_CHECK();
     }
@@ -376,7 +375,7 @@ __global__ void invert_perm_kernel(const int32_t* __restrict__ perm, int64_t n, 
 // incoming CSR keyed by destination: ptr, eid (API edge id per slot), src/dst per slot.
 // Slot order inside a destination = (source id, edge id): SparseTensor's sort at models.py:72.
 int build_in_csr(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, int dst_row, int32_t* dst_api,
-                 int32_t* src_api, int32_t* cnt_scratch, int32_t* ptr, int32_t* eid, int32_t* src_csr,
+                 int32_t* src_api, int32_t* cnt_scratch, int32_t* tmp, int32_t* ptr, int32_t* eid, int32_t* src_csr,
                  int32_t* dst_csr, cudaStream_t st) {
     if (n_edges > 0) {
         prof_begin(KC_GRAPH, 0.0, st);
@@ -384,7 +383,7 @@ int build_in_csr(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, in
         prof_end(st);
         PAMNET_LAUNCH_CHECK();
     }
-    PAMNET_TRY(build_buckets(dst_api, n_edges, n_nodes, src_api, cnt_scratch, ptr, eid, st));
+    PAMNET_TRY(build_buckets(dst_api, n_edges, n_nodes, src_api, cnt_scratch, ptr, eid, tmp, st));
     if (n_edges > 0) {
         prof_begin(KC_GRAPH, 0.0, st);
         gather_i32_kernel<<<ceil_div(n_edges, 256), 256, 0, st>>>(src_api, eid, n_edges, src_csr);
@@ -447,7 +446,7 @@ __global__ void triplet_fill_kernel(const int32_t* __restrict__ dst_api, const i
 }
 
 struct TripletScratch {
-    int32_t *dst_api, *src_api, *cnt, *ptr, *eid, *src_csr, *c2, *c1, *off2, *off1;
+    int32_t *dst_api, *src_api, *cnt, *ptr, *eid, *src_csr, *c2, *c1, *off2, *off1, *tmp;
 };
 
 static size_t triplet_scratch_layout(int64_t n_nodes, int64_t n_edges, void* base, TripletScratch* s) {
@@ -460,7 +459,7 @@ static size_t triplet_scratch_layout(int64_t n_nodes, int64_t n_edges, void* bas
     TripletScratch t;
     t.dst_api = take(n_edges); t.src_api = take(n_edges); t.cnt = take(n_nodes + 1); t.ptr = take(n_nodes + 1);
     t.eid = take(n_edges); t.src_csr = take(n_edges); t.c2 = take(n_edges); t.c1 = take(n_edges);
-    t.off2 = take(n_edges + 1); t.off1 = take(n_edges + 1);
+    t.off2 = take(n_edges + 1); t.off1 = take(n_edges + 1); t.tmp = take(n_edges);
     if (s) *s = t;
     return off;
 }
@@ -473,8 +472,8 @@ int triplet_count(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, v
                   cudaStream_t st) {
     TripletScratch s;
     triplet_scratch_layout(n_nodes, n_edges, scratch, &s);
-    PAMNET_TRY(build_in_csr(edge_index, n_edges, n_nodes, 1, s.dst_api, s.src_api, s.cnt, s.ptr, s.eid, s.src_csr,
-                            nullptr, st));
+    PAMNET_TRY(build_in_csr(edge_index, n_edges, n_nodes, 1, s.dst_api, s.src_api, s.cnt, s.tmp, s.ptr, s.eid,
+                            s.src_csr, nullptr, st));
     if (n_edges > 0) {
         prof_begin(KC_GRAPH, 0.0, st);
         triplet_count_kernel<<<ceil_div(n_edges, 128), 128, 0, st>>>(s.dst_api, s.src_api, n_edges, s.ptr, s.src_csr,
@@ -526,12 +525,12 @@ void plan_layout(const pamnet_sizes_t& sz, void* base, void* trip, Plan* out, si
     p.l_optr = take_i(N + 1); p.l_opos = take_i(El);
     p.t_split = take_i(El); p.t_cnt = take_i(El); p.t_ptr = take_i(El + 1); p.tt_ptr = take_i(El + 1);
     p.dist_g = take_f(Eg); p.dist_l = take_f(El);
-    p.tmp_a = take_i(Emax); p.tmp_b = take_i(Emax);
+    p.tmp_a = take_i(Emax); p.tmp_b = take_i(Emax); p.tmp_c = take_i(Emax);
     p.cnt = take_i((N > El ? N : El) + 2);
     if (base_bytes) *base_bytes = off;
     off = 0;
     cur = static_cast<char*>(trip);
-    p.t_gather = take_i(T); p.t_owner = take_i(T); p.tt_t = take_i(T); p.t_angle = take_f(T);
+    p.t_gather = take_i(T); p.t_owner = take_i(T); p.tt_t = take_i(T); p.t_tmp = take_i(T); p.t_angle = take_f(T);
     if (trip_bytes) *trip_bytes = off;
     if (out) *out = p;
 }
@@ -636,12 +635,13 @@ int plan_count(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const int64
     }
     // global graph: x_i = x[edge_index[dst_row]] is also the aggregation target (PyG propagate)
     const int g_dst_row = (cfg.flow == PAMNET_TARGET_TO_SOURCE) ? 0 : 1;
-    PAMNET_TRY(build_in_csr(edge_index_g, Eg, N, g_dst_row, p.tmp_a, p.tmp_b, p.cnt, p.g_ptr, p.g_eid, p.g_src,
-                            nullptr, st));
-    PAMNET_TRY(build_buckets(p.g_src, Eg, N, nullptr, p.cnt, p.g_optr, p.g_opos, st));
+    PAMNET_TRY(build_in_csr(edge_index_g, Eg, N, g_dst_row, p.tmp_a, p.tmp_b, p.cnt, p.tmp_c, p.g_ptr, p.g_eid,
+                            p.g_src, nullptr, st));
+    PAMNET_TRY(build_buckets(p.g_src, Eg, N, nullptr, p.cnt, p.g_optr, p.g_opos, p.tmp_c, st));
     // local graph: i = edge_index[1] always (local_message_passing.py:37)
-    PAMNET_TRY(build_in_csr(edge_index_l, El, N, 1, p.tmp_a, p.tmp_b, p.cnt, p.l_ptr, p.l_eid, p.l_src, p.l_dst, st));
-    PAMNET_TRY(build_buckets(p.l_src, El, N, nullptr, p.cnt, p.l_optr, p.l_opos, st));
+    PAMNET_TRY(build_in_csr(edge_index_l, El, N, 1, p.tmp_a, p.tmp_b, p.cnt, p.tmp_c, p.l_ptr, p.l_eid, p.l_src,
+                            p.l_dst, st));
+    PAMNET_TRY(build_buckets(p.l_src, El, N, nullptr, p.cnt, p.l_optr, p.l_opos, p.tmp_c, st));
     PAMNET_CUDA(cudaMemsetAsync(counts_dev, 0, 2 * sizeof(int64_t), st));
     if (El > 0) {
         prof_begin(KC_GRAPH, 0.0, st);
@@ -667,7 +667,7 @@ int plan_fill(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const float*
         prof_end(st);
         PAMNET_LAUNCH_CHECK();
     }
-    PAMNET_TRY(build_buckets(p.t_gather, T, El, nullptr, p.cnt, p.tt_ptr, p.tt_t, st));
+    PAMNET_TRY(build_buckets(p.t_gather, T, El, nullptr, p.cnt, p.tt_ptr, p.tt_t, p.t_tmp, st));
     if (N > 0) {
         prof_begin(KC_GRAPH, 0.0, st);
         csr_dist_kernel<<<ceil_div(N, 128), 128, 0, st>>>(p.g_ptr, p.g_src, N, pos, p.dist_g);

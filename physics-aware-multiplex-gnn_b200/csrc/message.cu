@@ -5,7 +5,8 @@
 
 namespace pamnet {
 
-constexpr int kMsgThreads = 128;   // 4 warps per CTA -> N/4 CTAs; QM9 bs=32 (N~600) gives ~150 CTAs on 148 SMs
+constexpr int kMsgThreads = 128;
+constexpr int kUnroll = 4;       // independent row loads kept in flight per warp (L2 latency ~1 us per dependent trip)   // 4 warps per CTA -> N/4 CTAs; QM9 bs=32 (N~600) gives ~150 CTAs on 148 SMs
 
 #define ROW_FOR(i) _Pragma("unroll") for (int i = 0; i < RowVec<D>::C * RowVec<D>::V; ++i)
 
@@ -21,13 +22,23 @@ __global__ void __launch_bounds__(kMsgThreads) global_msg_fwd_kernel(const Globa
     pi.load(a.P + (size_t)n * 2 * D, lane);
     acc.zero();
     const int e0 = a.ptr[n], e1 = a.ptr[n + 1];
-    for (int k = e0; k < e1; ++k) {
-        const int s = a.src[k];
-        RowVec<D> pj, q, tt;
-        pj.load(a.P + (size_t)s * 2 * D + D, lane);
-        q.load(a.QT + (size_t)k * a.ldq, lane);
-        tt.load(a.QT + (size_t)k * a.ldq + D, lane);
-        ROW_FOR(i) acc.v[i] += silu(pi.v[i] + pj.v[i] + q.v[i]) * tt.v[i];
+    for (int k = e0; k < e1; k += kUnroll) {          // kUnroll edges in flight; summed in edge order
+        RowVec<D> pj[kUnroll], q[kUnroll], tt[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (k + u < e1) {
+                const int s = a.src[k + u];
+                pj[u].load(a.P + (size_t)s * 2 * D + D, lane);
+                q[u].load(a.QT + (size_t)(k + u) * a.ldq, lane);
+                tt[u].load(a.QT + (size_t)(k + u) * a.ldq + D, lane);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (k + u < e1) {
+                ROW_FOR(i) acc.v[i] += silu(pi.v[i] + pj[u].v[i] + q[u].v[i]) * tt[u].v[i];
+            }
+        }
     }
     RowVec<D> x;
     x.load(a.x1 + (size_t)n * D, lane);
@@ -44,20 +55,31 @@ __global__ void __launch_bounds__(kMsgThreads) global_msg_bwd_kernel(const Globa
     pi.load(a.P + (size_t)n * 2 * D, lane);
     g.load(a.g_h + (size_t)n * D, lane);
     const int e0 = a.ptr[n], e1 = a.ptr[n + 1];
-    for (int k = e0; k < e1; ++k) {
-        const int s = a.src[k];
-        RowVec<D> pj, q, tt, gz, gt;
-        pj.load(a.P + (size_t)s * 2 * D + D, lane);
-        q.load(a.QT + (size_t)k * a.ldq, lane);
-        tt.load(a.QT + (size_t)k * a.ldq + D, lane);
-        ROW_FOR(i) {
-            const float z = pi.v[i] + pj.v[i] + q.v[i];
-            const float sg = sigmoidf_(z);
-            gt.v[i] = g.v[i] * (z * sg);                                     // grad Tt = g * SiLU(z)
-            gz.v[i] = g.v[i] * tt.v[i] * (sg * (1.0f + z * (1.0f - sg)));   // grad z  = g * Tt * SiLU'(z)
+    for (int k = e0; k < e1; k += kUnroll) {
+        RowVec<D> pj[kUnroll], q[kUnroll], tt[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (k + u < e1) {
+                const int s = a.src[k + u];
+                pj[u].load(a.P + (size_t)s * 2 * D + D, lane);
+                q[u].load(a.QT + (size_t)(k + u) * a.ldq, lane);
+                tt[u].load(a.QT + (size_t)(k + u) * a.ldq + D, lane);
+            }
         }
-        gz.store(a.gQT + (size_t)k * a.ldq, lane);
-        gt.store(a.gQT + (size_t)k * a.ldq + D, lane);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (k + u < e1) {
+                RowVec<D> gz, gt;
+                ROW_FOR(i) {
+                    const float z = pi.v[i] + pj[u].v[i] + q[u].v[i];
+                    const float sg = sigmoidf_(z);
+                    gt.v[i] = g.v[i] * (z * sg);                                        // grad Tt = g * SiLU(z)
+                    gz.v[i] = g.v[i] * tt[u].v[i] * (sg * (1.0f + z * (1.0f - sg)));   // grad z  = g * Tt * SiLU'(z)
+                }
+                gz.store(a.gQT + (size_t)(k + u) * a.ldq, lane);
+                gt.store(a.gQT + (size_t)(k + u) * a.ldq + D, lane);
+            }
+        }
     }
 }
 
@@ -95,11 +117,21 @@ __global__ void __launch_bounds__(kMsgThreads) local_msg_fwd_kernel(const LocalM
         q.load(a.QR + (size_t)k * a.ldq, lane);
         ROW_FOR(c) ms.v[c] = silu(pi.v[c] + pj.v[c] + q.v[c]);          // m_ji
         const int t0 = a.t_ptr[k], t1 = a.t_ptr[k + 1];
-        for (int t = t0; t < t1; ++t) {                                    // + m_other, in the reference's order
-            RowVec<D> mn, zq;
-            mn.load(a.m_nb + (size_t)a.t_gather[t] * D, lane);
-            zq.load(a.zq + (size_t)t * a.ldt, lane);
-            ROW_FOR(c) ms.v[c] += mn.v[c] * silu(zq.v[c]);
+        for (int t = t0; t < t1; t += kUnroll) {                           // + m_other, in the reference's order
+            RowVec<D> mn[kUnroll], zq[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                if (t + u < t1) {
+                    mn[u].load(a.m_nb + (size_t)a.t_gather[t + u] * D, lane);
+                    zq[u].load(a.zq + (size_t)(t + u) * a.ldt, lane);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                if (t + u < t1) {
+                    ROW_FOR(c) ms.v[c] += mn[u].v[c] * silu(zq[u].v[c]);
+                }
+            }
         }
         ms.store(a.msum + (size_t)k * D, lane);
         RowVec<D> ro;
@@ -139,12 +171,22 @@ __global__ void __launch_bounds__(kMsgThreads) local_msg_bwd_kernel(const LocalM
         ROW_FOR(c) gz.v[c] = gs.v[c] * dsilu(pi.v[c] + pj.v[c] + q.v[c]);
         gz.store(a.gQR + (size_t)k * a.ldq, lane);
         const int t0 = a.t_ptr[k], t1 = a.t_ptr[k + 1];
-        for (int t = t0; t < t1; ++t) {
-            RowVec<D> mn, zq;
-            mn.load(a.m_nb + (size_t)a.t_gather[t] * D, lane);
-            zq.load(a.zq + (size_t)t * a.ldt, lane);
-            ROW_FOR(c) zq.v[c] = gs.v[c] * mn.v[c] * dsilu(zq.v[c]);      // grad zq = g_s * m_nb * SiLU'(zq)
-            zq.store(a.gzq + (size_t)t * a.ldt, lane);
+        for (int t = t0; t < t1; t += kUnroll) {
+            RowVec<D> mn[kUnroll], zq[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                if (t + u < t1) {
+                    mn[u].load(a.m_nb + (size_t)a.t_gather[t + u] * D, lane);
+                    zq[u].load(a.zq + (size_t)(t + u) * a.ldt, lane);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                if (t + u < t1) {
+                    ROW_FOR(c) zq[u].v[c] = gs.v[c] * mn[u].v[c] * dsilu(zq[u].v[c]);   // grad zq = g_s m_nb SiLU'(zq)
+                    zq[u].store(a.gzq + (size_t)(t + u) * a.ldt, lane);
+                }
+            }
         }
     }
 }
@@ -159,12 +201,22 @@ __global__ void __launch_bounds__(kMsgThreads) local_trip_bwd_kernel(const Local
     RowVec<D> gm;
     gm.zero();
     const int u0 = a.tt_ptr[k], u1 = a.tt_ptr[k + 1];
-    for (int u = u0; u < u1; ++u) {
-        const int t = a.tt_t[u];
-        RowVec<D> gs, zq;
-        gs.load(a.g_s + (size_t)a.t_owner[t] * D, lane);
-        zq.load(a.zq + (size_t)t * a.ldt, lane);
-        ROW_FOR(c) gm.v[c] += gs.v[c] * silu(zq.v[c]);
+    for (int u = u0; u < u1; u += kUnroll) {
+        RowVec<D> gs[kUnroll], zq[kUnroll];
+#pragma unroll
+        for (int w = 0; w < kUnroll; ++w) {
+            if (u + w < u1) {
+                const int t = a.tt_t[u + w];
+                gs[w].load(a.g_s + (size_t)a.t_owner[t] * D, lane);
+                zq[w].load(a.zq + (size_t)t * a.ldt, lane);
+            }
+        }
+#pragma unroll
+        for (int w = 0; w < kUnroll; ++w) {
+            if (u + w < u1) {
+                ROW_FOR(c) gm.v[c] += gs[w].v[c] * silu(zq[w].v[c]);
+            }
+        }
     }
     const int i = a.dst[k], j = a.src[k];
     RowVec<D> pi, pj, q, r, gz, gr;
@@ -191,17 +243,25 @@ __global__ void __launch_bounds__(kMsgThreads) node_grad_gather_kernel(const Nod
     for (int b = 0; b < a.n_blocks; ++b) {
         RowVec<D> s;
         s.zero();
-        for (int k = a.ptr[n]; k < a.ptr[n + 1]; ++k) {
-            RowVec<D> v;
-            v.load(a.gz + (size_t)k * a.ldq + b * D, lane);
-            ROW_FOR(c) s.v[c] += v.v[c];
+        for (int k = a.ptr[n], k1 = a.ptr[n + 1]; k < k1; k += kUnroll) {
+            RowVec<D> v[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u)
+                if (k + u < k1) v[u].load(a.gz + (size_t)(k + u) * a.ldq + b * D, lane);
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u)
+                if (k + u < k1) { ROW_FOR(c) s.v[c] += v[u].v[c]; }
         }
         s.store(a.g_P + (size_t)n * w + (2 * b) * D, lane);
         s.zero();
-        for (int u = a.optr[n]; u < a.optr[n + 1]; ++u) {
-            RowVec<D> v;
-            v.load(a.gz + (size_t)a.opos[u] * a.ldq + b * D, lane);
-            ROW_FOR(c) s.v[c] += v.v[c];
+        for (int k = a.optr[n], k1 = a.optr[n + 1]; k < k1; k += kUnroll) {
+            RowVec<D> v[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u)
+                if (k + u < k1) v[u].load(a.gz + (size_t)a.opos[k + u] * a.ldq + b * D, lane);
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u)
+                if (k + u < k1) { ROW_FOR(c) s.v[c] += v[u].v[c]; }
         }
         s.store(a.g_P + (size_t)n * w + (2 * b + 1) * D, lane);
     }

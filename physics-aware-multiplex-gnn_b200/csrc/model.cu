@@ -311,9 +311,11 @@ GemmSlot slot(const float* A, int lda, const float* B, int ldb, float* C, int ld
     s.A = A; s.B = B; s.bias = bias; s.Z = Z; s.C = C; s.C2 = C2; s.lda = lda; s.ldb = ldb; s.ldc = ldc; s.ldz = ldz;
     return s;
 }
+// split-K factor of the weight-gradient GEMMs: ~128 reduction rows per CTA keeps the dependent k-loop short
+// (one tile fetch is ~1 us of L2 latency) and gives the small [D, D] outputs enough CTAs to fill the GPU
 int pick_ksplit(int64_t K) {
-    int64_t s = K / 1024;
-    return (int)(s < 1 ? 1 : (s > 32 ? 32 : s));
+    int64_t s = (K + 127) / 128;
+    return (int)(s < 1 ? 1 : (s > 64 ? 64 : s));
 }
 
 // launch a list of slots sharing one GemmArgs header, 32 at a time

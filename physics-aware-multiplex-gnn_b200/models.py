@@ -105,7 +105,9 @@ class _PAMNetBase(nn.Module):
         self._offsets = list(offs)
         self._total = int(lib.pamnet_param_total(self._ccfg))
         # init_linear exists but is unused outside PDBbind (models.py:35,119): its grad stays None there
-        self._param_used = [not (name == "init_linear.weight" and kind != 1) for name, _ in self._param_list]
+        # and the atom-type embedding table is unused on PDBbind (models.py:119)
+        self._param_used = [not ((name == "init_linear.weight" and kind != 1) or (name == "embeddings" and kind == 1))
+                            for name, _ in self._param_list]
         self._flat = None
         self._flatten()
 

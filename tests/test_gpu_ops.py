@@ -156,8 +156,8 @@ def test_linear(ops, n_in, n_out, rows):
 def test_gemm_modes(ops, m, n, k, ksplit):
     g = torch.Generator().manual_seed(3)
     a, b = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g)
-    # fp32 running sums over k terms of magnitude ~1: error ~ sqrt(k) * eps, independent of the result's size
-    tol = 4e-7 * k ** 0.5
+    # fp32 running sums of k unit-variance terms: rounding error grows ~ eps * k / sqrt(2) in absolute terms
+    tol = 2e-7 * k
 
     def err(x, ref):
         return float((x.double().cpu() - ref).abs().max())
