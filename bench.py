@@ -186,8 +186,10 @@ def run_ours(args):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     loss_buf = torch.zeros(1, device=dev)
 
+    params = list(model.parameters())
+
     def step(batch):
-        for p in model.parameters():
+        for p in params:             # == optimizer.zero_grad(set_to_none=True)
             p.grad = None
         out = model(batch)
         loss = (out - batch.y).abs().mean()

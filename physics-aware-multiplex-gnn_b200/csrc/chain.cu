@@ -1,10 +1,12 @@
-// Stage interpreter for row-local node chains (see chain.cuh).  One CTA = R rows; activations live in
-// shared memory across all stages; D x D weights are streamed k-major through a cp.async double buffer.
+// Stage interpreter for row-local node chains (see chain.cuh).  One CTA = 8 rows; activations live (transposed)
+// in shared memory across all stages; whole D x D weight matrices are streamed k-major through a cp.async
+// double buffer, the next stage's matrix in flight while the current one multiplies.
 #include "chain.cuh"
 
 namespace pamnet {
 
-constexpr int kChainThreads = 256;
+constexpr int kChainRows = 8;     // rows per CTA
+constexpr int kChainKS = 4;       // k-slices: a CTA has kChainKS * D threads
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -14,39 +16,41 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// Thread (c, g): output column c = tid % D, row group g = tid / D owning RT consecutive rows.  Per k the warp
-// reads 32 consecutive weights (one conflict-free 128 B request) and RT activations by broadcast, so a weight
-// element leaves shared memory once per row group instead of once per row.
-template <int D, int RT>
+// Thread (c, ks): output column c = tid % D, k-slice ks = tid / D.  It accumulates all 8 rows of its column over
+// its quarter of K: per k one conflict-free 128 B weight request per warp plus two broadcast 128-bit loads of
+// the 8 row values (activations are kept TRANSPOSED in shared memory, [k][8]).  The four partial sums meet in
+// shared memory and thread (c, ks) finishes rows 2ks, 2ks+1.  4*D threads per CTA = 16 warps at D = 128, which
+// is what hides the shared-memory latency that a 2-warp-per-scheduler version could not (ncu: short_scoreboard).
+template <int D>
 struct ChainCfg {
-    static constexpr int G = kChainThreads / D;          // row groups
-    static constexpr int R = G * RT;                     // rows per CTA
-    static constexpr int LD = D + 4;                     // slot row stride (floats)
-    static constexpr int LDW = 4 * D + 4;                // wide slot row stride
-    static constexpr size_t smem_floats = (size_t)kChainSlots * R * LD + (size_t)R * LDW + 2 * (size_t)D * D;
+    static constexpr int R = kChainRows;
+    static constexpr int T = kChainKS * D;               // threads
+    static constexpr int KL = D / kChainKS;              // k per slice
+    static constexpr size_t smem_floats = 2 * (size_t)D * D + (size_t)kChainSlots * D * R + 4 * (size_t)D * R +
+                                          (size_t)kChainKS * R * D;
 };
 
-template <int D, int RT>
-__global__ void __launch_bounds__(kChainThreads) chain_kernel(const ChainArgs args) {
-    using C = ChainCfg<D, RT>;
+template <int D>
+__global__ void __launch_bounds__(kChainKS * D) chain_kernel(const ChainArgs args) {
+    using C = ChainCfg<D>;
+    constexpr int R = C::R, NT = C::T, KL = C::KL;
     extern __shared__ __align__(16) float smem[];
     float* wbuf = smem;                                   // [2][D][D]: this stage's weights + the next GEMM stage's
-    float* slots = smem + 2 * D * D;                      // [3][R][LD] then wide [R][LDW]
-    auto slot_ptr = [&](int s) -> float* {
-        return s == kChainWide ? slots + kChainSlots * C::R * C::LD : slots + s * C::R * C::LD;
-    };
-    auto slot_ld = [&](int s) -> int { return s == kChainWide ? C::LDW : C::LD; };
+    float* slots = wbuf + 2 * D * D;                      // 3 x [D][R] transposed activations, then wide [4D][R]
+    float* red = slots + (kChainSlots + 4) * D * R;       // [KS][R][D] partial sums
+    auto slot_ptr = [&](int s) -> float* { return slots + s * D * R; };   // wide slot = index 3 (4x larger)
 
     const int t = threadIdx.x;
-    const int c = t % D, r0 = (t / D) * RT;
-    const int row0 = blockIdx.x * C::R;
+    const int c = t % D, ks = t / D;
+    const int row0 = blockIdx.x * R;
     const int n_rows = args.n_rows;
+    // element-wise stages walk (r, c4) with r fastest so that a warp touches 8 rows x 64 contiguous bytes
+    const int er = t & (R - 1), ec = t / R;
 
-    // whole D x D weight matrix of GEMM stage `si` -> wbuf[buf]; one commit group per matrix
     auto issue_weights = [&](int si, int buf) {
         const ChainStage& st = args.st[si];
         float* dstw = wbuf + buf * D * D;
-        for (int f = t; f < D * (D / 4); f += kChainThreads) {
+        for (int f = t; f < D * (D / 4); f += NT) {
             const int r = f / (D / 4), cc = (f % (D / 4)) * 4;
             cp_async16(dstw + r * D + cc, st.W + (size_t)r * st.ldw + cc);
         }
@@ -57,7 +61,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(const ChainArgs ar
             if (args.st[i].op == CH_GEMM) return i;
         return -1;
     };
-    int wcur = 0;                                         // buffer holding the upcoming GEMM stage's weights
+    int wcur = 0;
     {
         const int first = next_gemm(0);
         if (first >= 0) issue_weights(first, 0);
@@ -67,50 +71,51 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(const ChainArgs ar
         const ChainStage& st = args.st[si];
         if (st.op == CH_LOAD) {
             float* d = slot_ptr(st.dst);
-            const int ld = slot_ld(st.dst), w4 = st.width / 4;
-            for (int f = t; f < C::R * w4; f += kChainThreads) {
-                const int r = f / w4, cc = (f % w4) * 4;
+            const int w4 = st.width / 4;
+            const bool live = row0 + er < n_rows;
+            for (int c4 = ec; c4 < w4; c4 += NT / R) {
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row0 + r < n_rows) {
-                    v = ld4(st.g0 + (size_t)(row0 + r) * st.ld_g + cc);
-                    if (st.g1) v = v + ld4(st.g1 + (size_t)(row0 + r) * st.ld_g + cc);
-                    if (st.out_a) st4(st.out_a + (size_t)(row0 + r) * st.ld_out + cc, v);
+                if (live) {
+                    v = ld4(st.g0 + (size_t)(row0 + er) * st.ld_g + c4 * 4);
+                    if (st.g1) v = v + ld4(st.g1 + (size_t)(row0 + er) * st.ld_g + c4 * 4);
+                    if (st.out_a) st4(st.out_a + (size_t)(row0 + er) * st.ld_out + c4 * 4, v);
                 }
-                st4(d + r * ld + cc, v);
+                float* q = d + (c4 * 4) * R + er;
+                q[0] = v.x; q[R] = v.y; q[2 * R] = v.z; q[3 * R] = v.w;
             }
             __syncthreads();
         } else if (st.op == CH_HEADS_BWD) {
             // grad of o3 from the two heads: g_att * W + g_out * W_out.weight
             float* d = slot_ptr(st.dst);
-            for (int f = t; f < C::R * (D / 4); f += kChainThreads) {
-                const int r = f / (D / 4), cc = (f % (D / 4)) * 4;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row0 + r < n_rows) {
-                    const float ga = st.g0[row0 + r], go = st.g1[row0 + r];
-                    const float4 w = ld4(st.W + cc), wo = ld4(st.bias + cc);
-                    v = make_float4(ga * w.x + go * wo.x, ga * w.y + go * wo.y, ga * w.z + go * wo.z,
-                                    ga * w.w + go * wo.w);
-                }
-                st4(d + r * C::LD + cc, v);
+            const bool live = row0 + er < n_rows;
+            const float ga = live ? st.g0[row0 + er] : 0.f, go = live ? st.g1[row0 + er] : 0.f;
+            for (int c4 = ec; c4 < D / 4; c4 += NT / R) {
+                const float4 w = ld4(st.W + c4 * 4), wo = ld4(st.bias + c4 * 4);
+                float* q = d + (c4 * 4) * R + er;
+                q[0] = ga * w.x + go * wo.x; q[R] = ga * w.y + go * wo.y;
+                q[2 * R] = ga * w.z + go * wo.z; q[3 * R] = ga * w.w + go * wo.w;
             }
             __syncthreads();
         } else if (st.op == CH_DOT2) {
-            // att = o . W (global_message_passing.py:47), out = o . W_out.weight + b (:48); one warp per row
+            // att = o . W (global_message_passing.py:47), out = o . W_out.weight + b (:48)
             const float* s = slot_ptr(st.src);
+            float a = 0.f, o = 0.f;
+            for (int cc = ec; cc < D; cc += NT / R) {
+                const float x = s[cc * R + er];
+                a = fmaf(x, st.W[cc], a);
+                o = fmaf(x, st.bias[cc], o);
+            }
+            // lanes with equal (lane & 7) hold the same row: fold lane bits 3 and 4, then the warps via smem
+            a += __shfl_xor_sync(0xffffffffu, a, 8);  o += __shfl_xor_sync(0xffffffffu, o, 8);
+            a += __shfl_xor_sync(0xffffffffu, a, 16); o += __shfl_xor_sync(0xffffffffu, o, 16);
             const int lane = t & 31, warp = t >> 5;
-            for (int r = warp; r < C::R; r += kChainThreads / 32) {
-                float a = 0.f, o = 0.f;
-                for (int cc = lane; cc < D; cc += 32) {
-                    const float x = s[r * C::LD + cc];
-                    a = fmaf(x, st.W[cc], a);
-                    o = fmaf(x, st.bias[cc], o);
-                }
-                a = warp_sum(a);
-                o = warp_sum(o);
-                if (lane == 0 && row0 + r < n_rows) {
-                    st.out_z[row0 + r] = a;
-                    st.out_a[row0 + r] = o + st.g0[0];
-                }
+            if (lane < R) { red[(warp * R + lane) * 2] = a; red[(warp * R + lane) * 2 + 1] = o; }
+            __syncthreads();
+            if (t < R && row0 + t < n_rows) {
+                float sa = 0.f, so = 0.f;
+                for (int w = 0; w < NT / 32; ++w) { sa += red[(w * R + t) * 2]; so += red[(w * R + t) * 2 + 1]; }
+                st.out_z[row0 + t] = sa;
+                st.out_a[row0 + t] = so + st.g0[0];
             }
             __syncthreads();
         } else {  // CH_GEMM
@@ -119,58 +124,59 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(const ChainArgs ar
             const int nxt = next_gemm(si + 1);
             if (nxt >= 0) issue_weights(nxt, wcur ^ 1);
 
-            const float* in = slot_ptr(st.src) + st.src_off;
-            int in_ld = slot_ld(st.src);
+            const float* in = slot_ptr(st.src) + st.src_off * R;
             if (st.psrc >= 0) {
                 float* p = slot_ptr(st.psrc);
-                for (int f = t; f < C::R * (D / 4); f += kChainThreads) {
-                    const int r = f / (D / 4), cc = (f % (D / 4)) * 4;
+                const bool live = row0 + er < n_rows;
+                for (int c4 = ec; c4 < D / 4; c4 += NT / R) {
+                    const float* g = in + (c4 * 4) * R + er;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (row0 + r < n_rows) {
-                        const float4 g = ld4(in + r * in_ld + cc);
-                        v = g * dsilu4(ld4(st.zmul + (size_t)(row0 + r) * D + cc));
-                        if (st.save_src) st4(st.save_src + (size_t)(row0 + r) * D + cc, v);
+                    if (live) {
+                        const float4 dz = dsilu4(ld4(st.zmul + (size_t)(row0 + er) * D + c4 * 4));
+                        v = make_float4(g[0] * dz.x, g[R] * dz.y, g[2 * R] * dz.z, g[3 * R] * dz.w);
+                        if (st.save_src) st4(st.save_src + (size_t)(row0 + er) * D + c4 * 4, v);
                     }
-                    st4(p + r * C::LD + cc, v);
+                    float* q = p + (c4 * 4) * R + er;
+                    q[0] = v.x; q[R] = v.y; q[2 * R] = v.z; q[3 * R] = v.w;
                 }
                 in = p;
-                in_ld = C::LD;
             }
             if (nxt >= 0) cp_async_wait<1>(); else cp_async_wait<0>();
             __syncthreads();                              // weights landed for everyone; prologue visible
 
-            float acc[RT];
+            float acc[R];
 #pragma unroll
-            for (int i = 0; i < RT; ++i) acc[i] = 0.f;
-            const float* wk = wbuf + wcur * D * D + c;
-            const float* a0 = in + r0 * in_ld;
-#pragma unroll 4
-            for (int k = 0; k < D; k += 4) {
-                float4 a[RT];
-#pragma unroll
-                for (int i = 0; i < RT; ++i) a[i] = ld4(a0 + i * in_ld + k);
-                const float w0 = wk[(k + 0) * D], w1 = wk[(k + 1) * D], w2 = wk[(k + 2) * D], w3 = wk[(k + 3) * D];
-#pragma unroll
-                for (int i = 0; i < RT; ++i) {
-                    acc[i] = fmaf(a[i].x, w0, acc[i]);
-                    acc[i] = fmaf(a[i].y, w1, acc[i]);
-                    acc[i] = fmaf(a[i].z, w2, acc[i]);
-                    acc[i] = fmaf(a[i].w, w3, acc[i]);
-                }
+            for (int i = 0; i < R; ++i) acc[i] = 0.f;
+            const float* wp = wbuf + wcur * D * D + (ks * KL) * D + c;
+            const float* ap = in + (ks * KL) * R;
+#pragma unroll 8
+            for (int kk = 0; kk < KL; ++kk) {
+                const float w = wp[kk * D];
+                const float4 a0 = ld4(ap + kk * R), a1 = ld4(ap + kk * R + 4);
+                acc[0] = fmaf(a0.x, w, acc[0]); acc[1] = fmaf(a0.y, w, acc[1]);
+                acc[2] = fmaf(a0.z, w, acc[2]); acc[3] = fmaf(a0.w, w, acc[3]);
+                acc[4] = fmaf(a1.x, w, acc[4]); acc[5] = fmaf(a1.y, w, acc[5]);
+                acc[6] = fmaf(a1.z, w, acc[6]); acc[7] = fmaf(a1.w, w, acc[7]);
             }
-            // epilogue: lanes own consecutive columns -> coalesced row segments
+#pragma unroll
+            for (int i = 0; i < R; ++i) red[(ks * R + i) * D + c] = acc[i];
+            __syncthreads();
+
+            // thread (c, ks) finishes rows 2ks and 2ks+1: slices summed in fixed order -> deterministic
             const float b = st.bias ? st.bias[c] : 0.f;
 #pragma unroll
-            for (int i = 0; i < RT; ++i) {
-                const int r = r0 + i;
+            for (int i = 0; i < R / kChainKS; ++i) {
+                const int r = ks * (R / kChainKS) + i;
+                float v = b;
+#pragma unroll
+                for (int s2 = 0; s2 < kChainKS; ++s2) v += red[(s2 * R + r) * D + c];
                 const bool live = row0 + r < n_rows;
-                float v = acc[i] + b;
                 if (live && st.out_z) st.out_z[(size_t)(row0 + r) * st.ld_out + c] = v;
                 if (st.act) v = silu(v);
-                if (st.add_slot >= 0) v += slot_ptr(st.add_slot)[r * C::LD + c];
+                if (st.add_slot >= 0) v += slot_ptr(st.add_slot)[c * R + r];
                 if (live && st.add_g) v += st.add_g[(size_t)(row0 + r) * st.ld_add + c];
                 if (!live) v = 0.f;
-                if (st.dst >= 0) slot_ptr(st.dst)[r * C::LD + c] = v;
+                if (st.dst >= 0) slot_ptr(st.dst)[c * R + r] = v;
                 if (live && st.out_a) st.out_a[(size_t)(row0 + r) * st.ld_out + c] = v;
             }
             wcur ^= 1;
@@ -179,13 +185,13 @@ __global__ void __launch_bounds__(kChainThreads) chain_kernel(const ChainArgs ar
     }
 }
 
-template <int D, int RT>
+template <int D>
 static int chain_launch_t(const ChainArgs& args, cudaStream_t st) {
-    using C = ChainCfg<D, RT>;
+    using C = ChainCfg<D>;
     const size_t smem = C::smem_floats * sizeof(float);
-    static bool configured = false;   // per (D, RT) instantiation; attribute is per-function and idempotent
+    static bool configured = false;   // per-D instantiation; the attribute is per-function and idempotent
     if (!configured) {
-        PAMNET_CUDA(cudaFuncSetAttribute(chain_kernel<D, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PAMNET_CUDA(cudaFuncSetAttribute(chain_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     double bytes = 0.0;
@@ -199,7 +205,7 @@ static int chain_launch_t(const ChainArgs& args, cudaStream_t st) {
         if (s.op == CH_DOT2 || s.op == CH_HEADS_BWD) bytes += 8.0 * args.n_rows + 8.0 * D;
     }
     prof_begin(KC_CHAIN, bytes, st);
-    chain_kernel<D, RT><<<ceil_div(args.n_rows, C::R), kChainThreads, smem, st>>>(args);
+    chain_kernel<D><<<ceil_div(args.n_rows, C::R), C::T, smem, st>>>(args);
     prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;
@@ -214,13 +220,11 @@ int chain_launch(int dim, const ChainArgs& args, cudaStream_t st) {
             PAMNET_CHECK_ARG(s.dst != s.src && (s.psrc < 0 || s.dst != s.psrc) && s.dst != kChainWide,
                              "chain stage %d: output slot aliases its input", i);
     }
-    // rows per CTA = (256 / D) * RT: small CTAs until the row count fills the 148 SMs twice over
-    const int n = args.n_rows;
     switch (dim) {
-        case 128: return (n >= 148 * 32) ? chain_launch_t<128, 8>(args, st) : chain_launch_t<128, 4>(args, st);
-        case 64:  return (n >= 148 * 64) ? chain_launch_t<64, 8>(args, st) : chain_launch_t<64, 4>(args, st);
-        case 32:  return (n >= 148 * 128) ? chain_launch_t<32, 8>(args, st) : chain_launch_t<32, 4>(args, st);
-        case 16:  return (n >= 148 * 256) ? chain_launch_t<16, 8>(args, st) : chain_launch_t<16, 4>(args, st);
+        case 128: return chain_launch_t<128>(args, st);
+        case 64:  return chain_launch_t<64>(args, st);
+        case 32:  return chain_launch_t<32>(args, st);
+        case 16:  return chain_launch_t<16>(args, st);
         default:
             set_error("chain: unsupported dim %d (16, 32, 64, 128)", dim);
             return -1;

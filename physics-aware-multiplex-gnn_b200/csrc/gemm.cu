@@ -24,8 +24,8 @@ __device__ __forceinline__ float4 load4_guard(const float* __restrict__ p, int v
 
 // Micro-tile rows: TM/4 groups of 4 consecutive rows, group g at offset g * (BM / (TM/4)) + ty*4 (same for
 // columns): keeps every shared-memory read a conflict-free / broadcast 128-bit access.
-template <int BM, int BN, int TM, int TN>
-__global__ void __launch_bounds__(GT) gemm_kernel(const GemmArgs args) {
+template <int BM, int BN, int TM, int TN, int EPI>
+__global__ void __launch_bounds__(GT, (TM >= 8 ? 2 : 3)) gemm_kernel(const GemmArgs args) {
     static_assert((BM / TM) * (BN / TN) == GT, "256 threads");
     constexpr int GM = TM / 4, GN = TN / 4;          // 4-wide groups per thread
     constexpr int SM_ = BM / GM, SN_ = BN / GN;      // group stride
@@ -130,7 +130,9 @@ __global__ void __launch_bounds__(GT) gemm_kernel(const GemmArgs args) {
     for (int k0 = k_begin; k0 < k_end; k0 += BK) {
         const bool more = (k0 + BK < k_end);
         if (more) fetch(k0 + BK);
-#pragma unroll
+        // the 8x8 body is 68 instructions per k: unrolling all 16 would be ~17 KB of code and thrash the
+        // instruction cache (ncu: "no_instructions" was the top stall), so the big tile unrolls 4
+#pragma unroll(TM >= 8 ? 4 : 16)
         for (int kk = 0; kk < BK; ++kk) {
             float av[TM], bv[TN];
 #pragma unroll
@@ -159,7 +161,9 @@ __global__ void __launch_bounds__(GT) gemm_kernel(const GemmArgs args) {
         }
     }
 
-    // epilogue
+    // epilogue: each thread owns groups of 4 consecutive columns -> 128-bit stores when the row is aligned
+    const bool c_vec = aligned16(sl.C) && (sl.ldc % 4 == 0) && (sl.C2 == nullptr || mode == GEMM_TN || aligned16(sl.C2)) &&
+                       (EPI != EPI_MUL_DSILU || (aligned16(sl.Z) && sl.ldz % 4 == 0));
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
         const int m = m0 + (i / 4) * SM_ + ty * 4 + (i & 3);
@@ -168,32 +172,41 @@ __global__ void __launch_bounds__(GT) gemm_kernel(const GemmArgs args) {
             if (args.ksplit > 1) atomicAdd(&sl.C2[m], bsum[i]); else sl.C2[m] = bsum[i];
         }
 #pragma unroll
-        for (int j = 0; j < TN; ++j) {
-            const int n = n0 + (j / 4) * SN_ + tx * 4 + (j & 3);
+        for (int gj = 0; gj < GN; ++gj) {
+            const int n = n0 + gj * SN_ + tx * 4;
             if (n >= N) continue;
-            float v = acc[i][j];
+            float v[4] = {acc[i][gj * 4 + 0], acc[i][gj * 4 + 1], acc[i][gj * 4 + 2], acc[i][gj * 4 + 3]};
             const size_t ci = (size_t)m * sl.ldc + n;
-            if (args.ksplit > 1) {
-                atomicAdd(&sl.C[ci], v);
+            const int nv = min(4, N - n);
+            if (EPI == EPI_NONE && args.ksplit > 1) {
+                for (int j = 0; j < nv; ++j) atomicAdd(&sl.C[ci + j], v[j]);
                 continue;
             }
-            switch (args.epi) {
-                case EPI_BIAS:
-                    if (sl.bias) v += sl.bias[n];
-                    break;
-                case EPI_BIAS_SILU: {
-                    if (sl.bias) v += sl.bias[n];
-                    if (sl.C2) sl.C2[ci] = v;   // pre-activation (NT mode only)
-                    v = silu(v);
-                    break;
+            const bool vec = c_vec && nv == 4;
+            if (EPI == EPI_BIAS || EPI == EPI_BIAS_SILU) {
+                if (sl.bias)
+                    for (int j = 0; j < nv; ++j) v[j] += sl.bias[n + j];
+                if (EPI == EPI_BIAS_SILU) {
+                    if (sl.C2) {   // pre-activation (NT mode only)
+                        if (vec) st4(sl.C2 + ci, make_float4(v[0], v[1], v[2], v[3]));
+                        else for (int j = 0; j < nv; ++j) sl.C2[ci + j] = v[j];
+                    }
+                    for (int j = 0; j < nv; ++j) v[j] = silu(v[j]);
                 }
-                case EPI_MUL_DSILU:
-                    v *= dsilu(sl.Z[(size_t)m * sl.ldz + n]);
-                    break;
-                default:
-                    break;
+            } else if (EPI == EPI_MUL_DSILU) {
+                const size_t zi = (size_t)m * sl.ldz + n;
+                if (vec) {
+                    const float4 z = ld4(sl.Z + zi);
+                    v[0] *= dsilu(z.x); v[1] *= dsilu(z.y); v[2] *= dsilu(z.z); v[3] *= dsilu(z.w);
+                } else {
+                    for (int j = 0; j < nv; ++j) v[j] *= dsilu(sl.Z[zi + j]);
+                }
             }
-            if (sl.C) sl.C[ci] = args.accumulate ? sl.C[ci] + v : v;
+            if (!sl.C) continue;
+            if (args.accumulate)
+                for (int j = 0; j < nv; ++j) v[j] += sl.C[ci + j];
+            if (vec) st4(sl.C + ci, make_float4(v[0], v[1], v[2], v[3]));
+            else for (int j = 0; j < nv; ++j) sl.C[ci + j] = v[j];
         }
     }
 }
@@ -213,13 +226,23 @@ int gemm_launch(const GemmArgs& a, cudaStream_t st) {
     const long big_ctas = (long)ceil_div(a.M, 128) * ceil_div(a.N, 128) * ks * a.nslots;
     const bool big = a.M >= 128 && a.N >= 128 && big_ctas >= 2 * kNumSM;
     prof_begin(KC_GEMM, bytes, st);
-    if (big) {
-        dim3 grid(ceil_div(a.M, 128) * ceil_div(a.N, 128), ks, a.nslots);
-        gemm_kernel<128, 128, 8, 8><<<grid, GT, 0, st>>>(a);
-    } else {
-        dim3 grid(ceil_div(a.M, 64) * ceil_div(a.N, 64), ks, a.nslots);
-        gemm_kernel<64, 64, 4, 4><<<grid, GT, 0, st>>>(a);
+#define GEMM_LAUNCH(EPI_)                                                              \
+    do {                                                                               \
+        if (big) {                                                                     \
+            dim3 grid(ceil_div(a.M, 128) * ceil_div(a.N, 128), ks, a.nslots);          \
+            gemm_kernel<128, 128, 8, 8, EPI_><<<grid, GT, 0, st>>>(a);                 \
+        } else {                                                                       \
+            dim3 grid(ceil_div(a.M, 64) * ceil_div(a.N, 64), ks, a.nslots);            \
+            gemm_kernel<64, 64, 4, 4, EPI_><<<grid, GT, 0, st>>>(a);                   \
+        }                                                                              \
+    } while (0)
+    switch (a.epi) {
+        case EPI_NONE: GEMM_LAUNCH(EPI_NONE); break;
+        case EPI_BIAS: GEMM_LAUNCH(EPI_BIAS); break;
+        case EPI_BIAS_SILU: GEMM_LAUNCH(EPI_BIAS_SILU); break;
+        default: GEMM_LAUNCH(EPI_MUL_DSILU); break;
     }
+#undef GEMM_LAUNCH
     prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;

@@ -520,7 +520,7 @@ void plan_layout(const pamnet_sizes_t& sz, void* base, void* trip, Plan* out, si
     const int64_t Emax = Eg > El ? Eg : El;
     Plan p;
     p.n2g = take_i(N); p.gptr = take_i(G + 1);
-    p.g_ptr = take_i(N + 1); p.g_src = take_i(Eg); p.g_eid = take_i(Eg); p.g_optr = take_i(N + 1); p.g_opos = take_i(Eg);
+    p.g_ptr = take_i(N + 1); p.g_src = take_i(Eg); p.g_dst = take_i(Eg); p.g_eid = take_i(Eg); p.g_optr = take_i(N + 1); p.g_opos = take_i(Eg);
     p.l_ptr = take_i(N + 1); p.l_src = take_i(El); p.l_dst = take_i(El); p.l_eid = take_i(El);
     p.l_optr = take_i(N + 1); p.l_opos = take_i(El);
     p.t_split = take_i(El); p.t_cnt = take_i(El); p.t_ptr = take_i(El + 1); p.tt_ptr = take_i(El + 1);
@@ -636,7 +636,7 @@ int plan_count(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const int64
     // global graph: x_i = x[edge_index[dst_row]] is also the aggregation target (PyG propagate)
     const int g_dst_row = (cfg.flow == PAMNET_TARGET_TO_SOURCE) ? 0 : 1;
     PAMNET_TRY(build_in_csr(edge_index_g, Eg, N, g_dst_row, p.tmp_a, p.tmp_b, p.cnt, p.tmp_c, p.g_ptr, p.g_eid,
-                            p.g_src, nullptr, st));
+                            p.g_src, p.g_dst, st));
     PAMNET_TRY(build_buckets(p.g_src, Eg, N, nullptr, p.cnt, p.g_optr, p.g_opos, p.tmp_c, st));
     // local graph: i = edge_index[1] always (local_message_passing.py:37)
     PAMNET_TRY(build_in_csr(edge_index_l, El, N, 1, p.tmp_a, p.tmp_b, p.cnt, p.tmp_c, p.l_ptr, p.l_eid, p.l_src,

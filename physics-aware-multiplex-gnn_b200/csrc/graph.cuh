@@ -8,7 +8,7 @@ namespace pamnet {
 // incoming CSR of a graph; all per-edge tensors of the layer kernels are stored in slot order.
 struct Plan {
     int32_t *n2g, *gptr;                                  // graph id per node; node range per graph
-    int32_t *g_ptr, *g_src, *g_eid, *g_optr, *g_opos;     // global: in-CSR (ptr, source, API edge id), out-CSR (slots)
+    int32_t *g_ptr, *g_src, *g_dst, *g_eid, *g_optr, *g_opos;   // global: in-CSR (ptr, source, dest, API edge id), out-CSR
     int32_t *l_ptr, *l_src, *l_dst, *l_eid, *l_optr, *l_opos;   // local, same
     int32_t *t_split, *t_cnt, *t_ptr;                     // per local slot: #two-hop, #total, segment start
     int32_t *t_gather, *t_owner;                          // per triplet: gathered slot, owning slot

@@ -13,74 +13,74 @@ constexpr int kUnroll = 4;       // independent row loads kept in flight per war
 // ---------------------------------------------------------------------------------------------
 // global layer
 // ---------------------------------------------------------------------------------------------
+// One CTA (4 warps) per destination node: warp w takes incoming edges e0+w, e0+w+4, ... (kUnroll of them in
+// flight), partial sums meet in shared memory and are added in warp order -> deterministic, and 4x the
+// memory-level parallelism of a warp-per-node walk (620 nodes alone cannot hide L2 latency on 148 SMs).
 template <int D>
 __global__ void __launch_bounds__(kMsgThreads) global_msg_fwd_kernel(const GlobalMsgArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int n = blockIdx.x * (kMsgThreads / 32) + (threadIdx.x >> 5);
-    if (n >= a.n_nodes) return;
+    __shared__ __align__(16) float part[kMsgThreads / 32][D];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int n = blockIdx.x;
     RowVec<D> pi, acc;
     pi.load(a.P + (size_t)n * 2 * D, lane);
     acc.zero();
     const int e0 = a.ptr[n], e1 = a.ptr[n + 1];
-    for (int k = e0; k < e1; k += kUnroll) {          // kUnroll edges in flight; summed in edge order
+    constexpr int W = kMsgThreads / 32;
+    for (int k = e0 + w; k < e1; k += W * kUnroll) {
         RowVec<D> pj[kUnroll], q[kUnroll], tt[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
-            if (k + u < e1) {
-                const int s = a.src[k + u];
+            const int kk = k + u * W;
+            if (kk < e1) {
+                const int s = a.src[kk];
                 pj[u].load(a.P + (size_t)s * 2 * D + D, lane);
-                q[u].load(a.QT + (size_t)(k + u) * a.ldq, lane);
-                tt[u].load(a.QT + (size_t)(k + u) * a.ldq + D, lane);
+                q[u].load(a.QT + (size_t)kk * a.ldq, lane);
+                tt[u].load(a.QT + (size_t)kk * a.ldq + D, lane);
             }
         }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
-            if (k + u < e1) {
+            if (k + u * W < e1) {
                 ROW_FOR(i) acc.v[i] += silu(pi.v[i] + pj[u].v[i] + q[u].v[i]) * tt[u].v[i];
             }
         }
     }
-    RowVec<D> x;
-    x.load(a.x1 + (size_t)n * D, lane);
-    ROW_FOR(i) x.v[i] += acc.v[i];
-    x.store(a.h + (size_t)n * D, lane);
+    acc.store(&part[w][0], lane);
+    __syncthreads();
+    if (w == 0) {
+        RowVec<D> x;
+        x.load(a.x1 + (size_t)n * D, lane);
+#pragma unroll
+        for (int ww = 0; ww < W; ++ww) {
+            RowVec<D> p;
+            p.load(&part[ww][0], lane);
+            ROW_FOR(i) x.v[i] += p.v[i];
+        }
+        x.store(a.h + (size_t)n * D, lane);
+    }
 }
 
+// one warp per edge slot: every output row is per-edge, so the backward is embarrassingly edge-parallel
 template <int D>
 __global__ void __launch_bounds__(kMsgThreads) global_msg_bwd_kernel(const GlobalMsgArgs a) {
     const int lane = threadIdx.x & 31;
-    const int n = blockIdx.x * (kMsgThreads / 32) + (threadIdx.x >> 5);
-    if (n >= a.n_nodes) return;
-    RowVec<D> pi, g;
+    const int k = blockIdx.x * (kMsgThreads / 32) + (threadIdx.x >> 5);
+    if (k >= a.n_edges) return;
+    const int n = a.dst[k], s = a.src[k];
+    RowVec<D> pi, g, pj, q, tt, gz, gt;
     pi.load(a.P + (size_t)n * 2 * D, lane);
     g.load(a.g_h + (size_t)n * D, lane);
-    const int e0 = a.ptr[n], e1 = a.ptr[n + 1];
-    for (int k = e0; k < e1; k += kUnroll) {
-        RowVec<D> pj[kUnroll], q[kUnroll], tt[kUnroll];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            if (k + u < e1) {
-                const int s = a.src[k + u];
-                pj[u].load(a.P + (size_t)s * 2 * D + D, lane);
-                q[u].load(a.QT + (size_t)(k + u) * a.ldq, lane);
-                tt[u].load(a.QT + (size_t)(k + u) * a.ldq + D, lane);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            if (k + u < e1) {
-                RowVec<D> gz, gt;
-                ROW_FOR(i) {
-                    const float z = pi.v[i] + pj[u].v[i] + q[u].v[i];
-                    const float sg = sigmoidf_(z);
-                    gt.v[i] = g.v[i] * (z * sg);                                        // grad Tt = g * SiLU(z)
-                    gz.v[i] = g.v[i] * tt[u].v[i] * (sg * (1.0f + z * (1.0f - sg)));   // grad z  = g * Tt * SiLU'(z)
-                }
-                gz.store(a.gQT + (size_t)(k + u) * a.ldq, lane);
-                gt.store(a.gQT + (size_t)(k + u) * a.ldq + D, lane);
-            }
-        }
+    pj.load(a.P + (size_t)s * 2 * D + D, lane);
+    q.load(a.QT + (size_t)k * a.ldq, lane);
+    tt.load(a.QT + (size_t)k * a.ldq + D, lane);
+    ROW_FOR(i) {
+        const float z = pi.v[i] + pj.v[i] + q.v[i];
+        const float sg = sigmoidf_(z);
+        gt.v[i] = g.v[i] * (z * sg);                                     // grad Tt = g * SiLU(z)
+        gz.v[i] = g.v[i] * tt.v[i] * (sg * (1.0f + z * (1.0f - sg)));   // grad z  = g * Tt * SiLU'(z)
     }
+    gz.store(a.gQT + (size_t)k * a.ldq, lane);
+    gt.store(a.gQT + (size_t)k * a.ldq + D, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -101,91 +101,103 @@ __global__ void __launch_bounds__(kMsgThreads) local_edge_fwd_kernel(const Local
     r.store(a.m_nb + (size_t)k * D, lane);
 }
 
+// one warp per edge slot: msum[k] = m_ji + sum_t m_nb[g_t] * SiLU(zq_t)   (local_message_passing.py:47-51)
+template <int D>
+__global__ void __launch_bounds__(kMsgThreads) local_trip_fwd_kernel(const LocalMsgArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int k = blockIdx.x * (kMsgThreads / 32) + (threadIdx.x >> 5);
+    if (k >= a.n_edges) return;
+    const int n = a.dst[k], j = a.src[k];
+    RowVec<D> pi, pj, q, ms;
+    pi.load(a.P + (size_t)n * 4 * D, lane);
+    pj.load(a.P + (size_t)j * 4 * D + D, lane);
+    q.load(a.QR + (size_t)k * a.ldq, lane);
+    ROW_FOR(c) ms.v[c] = silu(pi.v[c] + pj.v[c] + q.v[c]);              // m_ji
+    const int t0 = a.t_ptr[k], t1 = a.t_ptr[k + 1];
+    for (int t = t0; t < t1; t += kUnroll) {                               // + m_other, in the reference's order
+        RowVec<D> mn[kUnroll], zq[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (t + u < t1) {
+                mn[u].load(a.m_nb + (size_t)a.t_gather[t + u] * D, lane);
+                zq[u].load(a.zq + (size_t)(t + u) * a.ldt, lane);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (t + u < t1) {
+                ROW_FOR(c) ms.v[c] += mn[u].v[c] * silu(zq[u].v[c]);
+            }
+        }
+    }
+    ms.store(a.msum + (size_t)k * D, lane);
+}
+
+// one warp per destination node: h = x1 + sum_k msum[k] * Rout[k]   (local_message_passing.py:53-54)
 template <int D>
 __global__ void __launch_bounds__(kMsgThreads) local_msg_fwd_kernel(const LocalMsgArgs a) {
     const int lane = threadIdx.x & 31;
     const int n = blockIdx.x * (kMsgThreads / 32) + (threadIdx.x >> 5);
     if (n >= a.n_nodes) return;
-    RowVec<D> pi, acc;
-    pi.load(a.P + (size_t)n * 4 * D, lane);
-    acc.zero();
+    RowVec<D> acc;
+    acc.load(a.x1 + (size_t)n * D, lane);
     const int e0 = a.ptr[n], e1 = a.ptr[n + 1];
-    for (int k = e0; k < e1; ++k) {
-        const int j = a.src[k];
-        RowVec<D> pj, q, ms;
-        pj.load(a.P + (size_t)j * 4 * D + D, lane);
-        q.load(a.QR + (size_t)k * a.ldq, lane);
-        ROW_FOR(c) ms.v[c] = silu(pi.v[c] + pj.v[c] + q.v[c]);          // m_ji
-        const int t0 = a.t_ptr[k], t1 = a.t_ptr[k + 1];
-        for (int t = t0; t < t1; t += kUnroll) {                           // + m_other, in the reference's order
-            RowVec<D> mn[kUnroll], zq[kUnroll];
+    for (int k = e0; k < e1; k += kUnroll) {
+        RowVec<D> ms[kUnroll], ro[kUnroll];
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                if (t + u < t1) {
-                    mn[u].load(a.m_nb + (size_t)a.t_gather[t + u] * D, lane);
-                    zq[u].load(a.zq + (size_t)(t + u) * a.ldt, lane);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                if (t + u < t1) {
-                    ROW_FOR(c) ms.v[c] += mn[u].v[c] * silu(zq[u].v[c]);
-                }
+        for (int u = 0; u < kUnroll; ++u) {
+            if (k + u < e1) {
+                ms[u].load(a.msum + (size_t)(k + u) * D, lane);
+                ro[u].load(a.QR + (size_t)(k + u) * a.ldq + 3 * D, lane);
             }
         }
-        ms.store(a.msum + (size_t)k * D, lane);
-        RowVec<D> ro;
-        ro.load(a.QR + (size_t)k * a.ldq + 3 * D, lane);
-        ROW_FOR(c) acc.v[c] += ms.v[c] * ro.v[c];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (k + u < e1) {
+                ROW_FOR(c) acc.v[c] += ms[u].v[c] * ro[u].v[c];
+            }
+        }
     }
-    RowVec<D> x;
-    x.load(a.x1 + (size_t)n * D, lane);
-    ROW_FOR(c) x.v[c] += acc.v[c];
-    x.store(a.h + (size_t)n * D, lane);
+    acc.store(a.h + (size_t)n * D, lane);
 }
 
-// per destination node: grad Rout, grad (m_ji + m_other) = g_s, grad z_ji, and grad of the triplet gate q
+// one warp per edge slot: grad Rout, grad (m_ji + m_other) = g_s, grad z_ji, and grad of the triplet gate zq
 template <int D>
 __global__ void __launch_bounds__(kMsgThreads) local_msg_bwd_kernel(const LocalMsgArgs a) {
     const int lane = threadIdx.x & 31;
-    const int n = blockIdx.x * (kMsgThreads / 32) + (threadIdx.x >> 5);
-    if (n >= a.n_nodes) return;
-    RowVec<D> pi, g;
+    const int k = blockIdx.x * (kMsgThreads / 32) + (threadIdx.x >> 5);
+    if (k >= a.n_edges) return;
+    const int n = a.dst[k], j = a.src[k];
+    RowVec<D> pi, g, ro, ms, gs, gro, pj, q, gz;
     pi.load(a.P + (size_t)n * 4 * D, lane);
     g.load(a.g_h + (size_t)n * D, lane);
-    const int e0 = a.ptr[n], e1 = a.ptr[n + 1];
-    for (int k = e0; k < e1; ++k) {
-        const int j = a.src[k];
-        RowVec<D> ro, ms, gs, gro;
-        ro.load(a.QR + (size_t)k * a.ldq + 3 * D, lane);
-        ms.load(a.msum + (size_t)k * D, lane);
-        ROW_FOR(c) {
-            gro.v[c] = g.v[c] * ms.v[c];
-            gs.v[c] = g.v[c] * ro.v[c];
-        }
-        gro.store(a.gQR + (size_t)k * a.ldq + 3 * D, lane);
-        gs.store(a.g_s + (size_t)k * D, lane);
-        RowVec<D> pj, q, gz;
-        pj.load(a.P + (size_t)j * 4 * D + D, lane);
-        q.load(a.QR + (size_t)k * a.ldq, lane);
-        ROW_FOR(c) gz.v[c] = gs.v[c] * dsilu(pi.v[c] + pj.v[c] + q.v[c]);
-        gz.store(a.gQR + (size_t)k * a.ldq, lane);
-        const int t0 = a.t_ptr[k], t1 = a.t_ptr[k + 1];
-        for (int t = t0; t < t1; t += kUnroll) {
-            RowVec<D> mn[kUnroll], zq[kUnroll];
+    ro.load(a.QR + (size_t)k * a.ldq + 3 * D, lane);
+    ms.load(a.msum + (size_t)k * D, lane);
+    pj.load(a.P + (size_t)j * 4 * D + D, lane);
+    q.load(a.QR + (size_t)k * a.ldq, lane);
+    ROW_FOR(c) {
+        gro.v[c] = g.v[c] * ms.v[c];
+        gs.v[c] = g.v[c] * ro.v[c];
+        gz.v[c] = gs.v[c] * dsilu(pi.v[c] + pj.v[c] + q.v[c]);
+    }
+    gro.store(a.gQR + (size_t)k * a.ldq + 3 * D, lane);
+    gs.store(a.g_s + (size_t)k * D, lane);
+    gz.store(a.gQR + (size_t)k * a.ldq, lane);
+    const int t0 = a.t_ptr[k], t1 = a.t_ptr[k + 1];
+    for (int t = t0; t < t1; t += kUnroll) {
+        RowVec<D> mn[kUnroll], zq[kUnroll];
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                if (t + u < t1) {
-                    mn[u].load(a.m_nb + (size_t)a.t_gather[t + u] * D, lane);
-                    zq[u].load(a.zq + (size_t)(t + u) * a.ldt, lane);
-                }
+        for (int u = 0; u < kUnroll; ++u) {
+            if (t + u < t1) {
+                mn[u].load(a.m_nb + (size_t)a.t_gather[t + u] * D, lane);
+                zq[u].load(a.zq + (size_t)(t + u) * a.ldt, lane);
             }
+        }
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                if (t + u < t1) {
-                    ROW_FOR(c) zq[u].v[c] = gs.v[c] * mn[u].v[c] * dsilu(zq[u].v[c]);   // grad zq = g_s m_nb SiLU'(zq)
-                    zq[u].store(a.gzq + (size_t)(t + u) * a.ldt, lane);
-                }
+        for (int u = 0; u < kUnroll; ++u) {
+            if (t + u < t1) {
+                ROW_FOR(c) zq[u].v[c] = gs.v[c] * mn[u].v[c] * dsilu(zq[u].v[c]);   // grad zq = g_s m_nb SiLU'(zq)
+                zq[u].store(a.gzq + (size_t)(t + u) * a.ldt, lane);
             }
         }
     }
@@ -234,37 +246,31 @@ __global__ void __launch_bounds__(kMsgThreads) local_trip_bwd_kernel(const Local
     gr.store(a.gQR + (size_t)k * a.ldq + 2 * D, lane);
 }
 
+// one warp per (node, task): task 2b = sum of gz_b over incoming slots, 2b+1 = over outgoing slots
 template <int D>
 __global__ void __launch_bounds__(kMsgThreads) node_grad_gather_kernel(const NodeGatherArgs a) {
     const int lane = threadIdx.x & 31;
-    const int n = blockIdx.x * (kMsgThreads / 32) + (threadIdx.x >> 5);
-    if (n >= a.n_nodes) return;
-    const int w = 2 * a.n_blocks * D;
-    for (int b = 0; b < a.n_blocks; ++b) {
-        RowVec<D> s;
-        s.zero();
-        for (int k = a.ptr[n], k1 = a.ptr[n + 1]; k < k1; k += kUnroll) {
-            RowVec<D> v[kUnroll];
+    const int item = blockIdx.x * (kMsgThreads / 32) + (threadIdx.x >> 5);
+    const int ntask = 2 * a.n_blocks;
+    if (item >= a.n_nodes * ntask) return;
+    const int n = item / ntask, task = item % ntask, b = task >> 1;
+    const bool outgoing = task & 1;
+    const int32_t* ptr = outgoing ? a.optr : a.ptr;
+    RowVec<D> s;
+    s.zero();
+    for (int k = ptr[n], k1 = ptr[n + 1]; k < k1; k += kUnroll) {
+        RowVec<D> v[kUnroll];
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u)
-                if (k + u < k1) v[u].load(a.gz + (size_t)(k + u) * a.ldq + b * D, lane);
+        for (int u = 0; u < kUnroll; ++u)
+            if (k + u < k1) {
+                const int slot = outgoing ? a.opos[k + u] : k + u;
+                v[u].load(a.gz + (size_t)slot * a.ldq + b * D, lane);
+            }
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u)
-                if (k + u < k1) { ROW_FOR(c) s.v[c] += v[u].v[c]; }
-        }
-        s.store(a.g_P + (size_t)n * w + (2 * b) * D, lane);
-        s.zero();
-        for (int k = a.optr[n], k1 = a.optr[n + 1]; k < k1; k += kUnroll) {
-            RowVec<D> v[kUnroll];
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u)
-                if (k + u < k1) v[u].load(a.gz + (size_t)a.opos[k + u] * a.ldq + b * D, lane);
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u)
-                if (k + u < k1) { ROW_FOR(c) s.v[c] += v[u].v[c]; }
-        }
-        s.store(a.g_P + (size_t)n * w + (2 * b + 1) * D, lane);
+        for (int u = 0; u < kUnroll; ++u)
+            if (k + u < k1) { ROW_FOR(c) s.v[c] += v[u].v[c]; }
     }
+    s.store(a.g_P + (size_t)n * ntask * D + task * D, lane);
 }
 
 #define DISPATCH_DIM(dim, KERNEL, rows, args, CLS, BYTES)                                             \
@@ -290,23 +296,29 @@ static double nbytes(int dim, double node_rows, double edge_rows, double trip_ro
 }
 
 int global_msg_fwd(int dim, const GlobalMsgArgs& a, int n_edges, cudaStream_t st) {
-    DISPATCH_DIM(dim, global_msg_fwd_kernel, a.n_nodes, a, KC_GLOBAL_MSG_FWD,
+    // one CTA per node: rows = n_nodes * warps-per-CTA so the dispatch macro's grid = n_nodes
+    DISPATCH_DIM(dim, global_msg_fwd_kernel, a.n_nodes * (kMsgThreads / 32), a, KC_GLOBAL_MSG_FWD,
                  nbytes(dim, 3.0 * a.n_nodes, 3.0 * n_edges, 0, a.n_nodes + n_edges));
 }
 int global_msg_bwd(int dim, const GlobalMsgArgs& a, int n_edges, cudaStream_t st) {
-    DISPATCH_DIM(dim, global_msg_bwd_kernel, a.n_nodes, a, KC_GLOBAL_MSG_BWD,
+    DISPATCH_DIM(dim, global_msg_bwd_kernel, a.n_edges, a, KC_GLOBAL_MSG_BWD,
                  nbytes(dim, 2.0 * a.n_nodes, 5.0 * n_edges, 0, a.n_nodes + n_edges));
 }
 int local_edge_fwd(int dim, const LocalMsgArgs& a, cudaStream_t st) {
     DISPATCH_DIM(dim, local_edge_fwd_kernel, a.n_edges, a, KC_LOCAL_EDGE_FWD,
                  nbytes(dim, 0, 5.0 * a.n_edges, 0, 2.0 * a.n_edges));
 }
+int local_trip_fwd(int dim, const LocalMsgArgs& a, int n_trip, cudaStream_t st) {
+    DISPATCH_DIM(dim, local_trip_fwd_kernel, a.n_edges, a, KC_LOCAL_MSG_FWD,
+                 nbytes(dim, 0, 4.0 * a.n_edges, 2.0 * n_trip, 3.0 * a.n_edges + n_trip));
+}
 int local_msg_fwd(int dim, const LocalMsgArgs& a, int n_trip, cudaStream_t st) {
+    (void)n_trip;
     DISPATCH_DIM(dim, local_msg_fwd_kernel, a.n_nodes, a, KC_LOCAL_MSG_FWD,
-                 nbytes(dim, 3.0 * a.n_nodes, 4.0 * a.n_edges, 2.0 * n_trip, a.n_nodes + 2.0 * a.n_edges + n_trip));
+                 nbytes(dim, 2.0 * a.n_nodes, 2.0 * a.n_edges, 0, a.n_nodes + a.n_edges));
 }
 int local_msg_bwd(int dim, const LocalMsgArgs& a, int n_trip, cudaStream_t st) {
-    DISPATCH_DIM(dim, local_msg_bwd_kernel, a.n_nodes, a, KC_LOCAL_MSG_BWD,
+    DISPATCH_DIM(dim, local_msg_bwd_kernel, a.n_edges, a, KC_LOCAL_MSG_BWD,
                  nbytes(dim, 2.0 * a.n_nodes, 7.0 * a.n_edges, 3.0 * n_trip, a.n_nodes + 2.0 * a.n_edges + n_trip));
 }
 int local_trip_bwd(int dim, const LocalMsgArgs& a, int n_trip, cudaStream_t st) {
@@ -314,7 +326,7 @@ int local_trip_bwd(int dim, const LocalMsgArgs& a, int n_trip, cudaStream_t st) 
                  nbytes(dim, 0, 6.0 * a.n_edges, 2.0 * n_trip, 3.0 * a.n_edges + 2.0 * n_trip));
 }
 int node_grad_gather(int dim, const NodeGatherArgs& a, int n_edges, cudaStream_t st) {
-    DISPATCH_DIM(dim, node_grad_gather_kernel, a.n_nodes, a, KC_NODE_GATHER,
+    DISPATCH_DIM(dim, node_grad_gather_kernel, a.n_nodes * 2 * a.n_blocks, a, KC_NODE_GATHER,
                  nbytes(dim, 2.0 * a.n_blocks * a.n_nodes, 2.0 * a.n_blocks * n_edges, 0, 2.0 * a.n_nodes + n_edges));
 }
 

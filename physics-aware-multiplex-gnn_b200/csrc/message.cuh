@@ -14,8 +14,8 @@
 namespace pamnet {
 
 struct GlobalMsgArgs {
-    int n_nodes;
-    const int32_t *ptr, *src;        // incoming CSR
+    int n_nodes, n_edges;
+    const int32_t *ptr, *src, *dst;  // incoming CSR (+ destination per slot)
     const float* P;                  // [N, 2D]  Pi | Pj
     const float* QT;                 // [E, ldq] at this layer's column block: Q | Tt
     int ldq;
@@ -49,6 +49,7 @@ struct LocalMsgArgs {
     float* gzq;                      // [T, ldt] at this layer's block: grad of zq
 };
 int local_edge_fwd(int dim, const LocalMsgArgs& a, cudaStream_t st);
+int local_trip_fwd(int dim, const LocalMsgArgs& a, int n_trip, cudaStream_t st);
 int local_msg_fwd(int dim, const LocalMsgArgs& a, int n_trip, cudaStream_t st);
 int local_msg_bwd(int dim, const LocalMsgArgs& a, int n_trip, cudaStream_t st);
 int local_trip_bwd(int dim, const LocalMsgArgs& a, int n_trip, cudaStream_t st);

@@ -496,7 +496,7 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
         if (!is_local(hh)) {
             GlobalMsgArgs a;
             memset(&a, 0, sizeof(a));
-            a.n_nodes = (int)N; a.ptr = pl.g_ptr; a.src = pl.g_src; a.P = hw.P;
+            a.n_nodes = (int)N; a.n_edges = (int)Eg; a.ptr = pl.g_ptr; a.src = pl.g_src; a.dst = pl.g_dst; a.P = hw.P;
             a.QT = w.QT + l * 2 * D; a.ldq = L * 2 * D; a.x1 = hw.x1; a.h = hw.h;
             PAMNET_TRY(global_msg_fwd(D, a, (int)Eg, st));
         } else {
@@ -507,6 +507,7 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
             a.QR = w.QR + l * 4 * D; a.ldq = L * 4 * D; a.zq = w.zq2 + l * D; a.ldt = L * D;
             a.x1 = hw.x1; a.m_nb = hw.m_nb; a.msum = hw.msum; a.h = hw.h;
             PAMNET_TRY(local_edge_fwd(D, a, st));
+            PAMNET_TRY(local_trip_fwd(D, a, (int)T, st));
             PAMNET_TRY(local_msg_fwd(D, a, (int)T, st));
         }
         Prog p((int)N);
@@ -571,7 +572,7 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
         if (!is_local(hh)) {
             GlobalMsgArgs a;
             memset(&a, 0, sizeof(a));
-            a.n_nodes = (int)N; a.ptr = pl.g_ptr; a.src = pl.g_src; a.P = hw.P;
+            a.n_nodes = (int)N; a.n_edges = (int)Eg; a.ptr = pl.g_ptr; a.src = pl.g_src; a.dst = pl.g_dst; a.P = hw.P;
             a.QT = w.QT + l * 2 * D; a.ldq = L * 2 * D; a.g_h = w.g_h; a.gQT = w.gQT + l * 2 * D;
             PAMNET_TRY(global_msg_bwd(D, a, (int)Eg, st));
             ng.n_blocks = 1; ng.ptr = pl.g_ptr; ng.optr = pl.g_optr; ng.opos = pl.g_opos;

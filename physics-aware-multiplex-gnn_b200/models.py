@@ -43,16 +43,21 @@ class GraphPlan:
 
 
 class _PAMNetFunction(torch.autograd.Function):
+    """One autograd node for the whole model.  Its only differentiable input is the flat parameter buffer; the
+    backward writes the hand-written CUDA gradients straight into the module's flat gradient buffer and
+    (re)attaches ``p.grad`` views with the usual accumulate semantics (see _PAMNetBase._deliver_grads) --
+    routing 390 tensors through autograd costs more host time than the whole GPU step."""
+
     @staticmethod
-    def forward(ctx, mod, plan, node_in, sign, pos, *params):
+    def forward(ctx, mod, plan, node_in, sign, pos, flat):
         lib = _lib.load()
         dev = pos.device
         cfg, sz = mod._ccfg, plan.sizes
         ws_bytes = lib.pamnet_workspace_bytes(cfg, sz)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         out = torch.empty(sz.n_graphs, dtype=torch.float32, device=dev)
-        need_grad = any(ctx.needs_input_grad[5:])
-        _lib.check(lib.pamnet_model_forward(cfg, sz, sbf_consts_struct(), mod._flat.data_ptr(), node_in.data_ptr(),
+        need_grad = ctx.needs_input_grad[5]
+        _lib.check(lib.pamnet_model_forward(cfg, sz, sbf_consts_struct(), flat.data_ptr(), node_in.data_ptr(),
                                             _lib.ptr(sign), pos.data_ptr(), plan.base.data_ptr(),
                                             plan.trip.data_ptr(), ws.data_ptr(), ws_bytes, int(need_grad),
                                             out.data_ptr(), torch.cuda.current_stream().cuda_stream),
@@ -60,27 +65,22 @@ class _PAMNetFunction(torch.autograd.Function):
         if need_grad:
             ctx.mod, ctx.plan, ctx.ws, ctx.ws_bytes = mod, plan, ws, ws_bytes
             ctx.node_in, ctx.sign, ctx.pos = node_in, sign, pos
-            ctx.flat_version = mod._flat._version
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         lib = _lib.load()
         mod, plan = ctx.mod, ctx.plan
-        if mod._flat._version != ctx.flat_version:
-            raise RuntimeError("PAMNet parameters were modified in place between forward and backward")
         grad_out = grad_out.contiguous().float()
-        gflat = torch.empty(mod._flat.numel(), dtype=torch.float32, device=grad_out.device)
+        target, direct = mod._grad_target()
         _lib.check(lib.pamnet_model_backward(mod._ccfg, plan.sizes, sbf_consts_struct(), mod._flat.data_ptr(),
                                              ctx.node_in.data_ptr(), _lib.ptr(ctx.sign), ctx.pos.data_ptr(),
                                              plan.base.data_ptr(), plan.trip.data_ptr(), ctx.ws.data_ptr(),
-                                             ctx.ws_bytes, grad_out.data_ptr(), gflat.data_ptr(),
+                                             ctx.ws_bytes, grad_out.data_ptr(), target.data_ptr(),
                                              torch.cuda.current_stream().cuda_stream), "model_backward")
         ctx.ws = None
-        grads = []
-        for (name, p), off, used in zip(mod._param_list, mod._offsets, mod._param_used):
-            grads.append(gflat[off:off + p.numel()].view(p.shape) if used else None)
-        return (None, None, None, None, None, *grads)
+        mod._deliver_grads(target, direct)
+        return (None, None, None, None, None, None)
 
 
 class _PAMNetBase(nn.Module):
@@ -109,7 +109,47 @@ class _PAMNetBase(nn.Module):
         self._param_used = [not ((name == "init_linear.weight" and kind != 1) or (name == "embeddings" and kind == 1))
                             for name, _ in self._param_list]
         self._flat = None
+        self._gflat = None
+        self._gviews = None
+        self._alias_tick = 0
         self._flatten()
+
+    # ---- gradients ------------------------------------------------------------------------------------
+    def _grad_views(self):
+        if self._gflat is None or self._gflat.device != self._flat.device:
+            self._gflat = torch.zeros(self._total, dtype=torch.float32, device=self._flat.device)
+            self._gviews = [self._gflat[off:off + p.numel()].view(p.shape)
+                            for (_, p), off in zip(self._param_list, self._offsets)]
+        return self._gviews
+
+    def _grad_target(self):
+        """Where backward should write: straight into the flat gradient buffer when no parameter holds a
+        gradient yet (after zero_grad(set_to_none=True)), otherwise into a scratch buffer that is then added."""
+        self._grad_views()
+        if all(p.grad is None for _, p in self._param_list):
+            return self._gflat, True
+        return torch.empty_like(self._gflat), False
+
+    def _deliver_grads(self, target, direct):
+        views = self._grad_views()
+        if direct:
+            for (_, p), v, used in zip(self._param_list, views, self._param_used):
+                if used and p.requires_grad:
+                    p.grad = v
+            return
+        attached = all((p.grad is v) or not (used and p.requires_grad)
+                       for (_, p), v, used in zip(self._param_list, views, self._param_used))
+        if attached:
+            self._gflat.add_(target)           # one launch: every p.grad is a view of the flat buffer
+            return
+        for (_, p), off, used in zip(self._param_list, self._offsets, self._param_used):
+            if not (used and p.requires_grad):
+                continue
+            g = target[off:off + p.numel()].view(p.shape)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.add_(g)
 
     def _flatten(self):
         """(Re)pack all parameters into one flat buffer; parameters become views of it."""
@@ -122,11 +162,22 @@ class _PAMNetBase(nn.Module):
             for p, off in zip(ps, self._offsets):
                 flat[off:off + p.numel()].copy_(p.detach().reshape(-1))
                 p.data = flat[off:off + p.numel()].view(p.shape)
-        self._flat = flat
+        self._flat = flat.requires_grad_(True)     # the single differentiable input of _PAMNetFunction
+        self._gflat = None
 
-    def _aliased(self):
+    def _aliased(self, full=True):
+        """Do the parameters still alias the flat buffer?  (utils/ema.py:27,32 swap param.data wholesale.)
+        full=False checks the first, the last and a rotating window of 16 parameters; every 64th call is full."""
         base = self._flat.data_ptr()
-        return all(p.data_ptr() == base + 4 * off for (_, p), off in zip(self._param_list, self._offsets))
+        pl, offs = self._param_list, self._offsets
+        if not full:
+            self._alias_tick += 1
+            if self._alias_tick % 64:
+                n = len(pl)
+                lo = (self._alias_tick * 16) % n
+                idx = [0, n - 1] + [(lo + i) % n for i in range(16)]
+                return all(pl[i][1].data_ptr() == base + 4 * offs[i] for i in idx)
+        return all(p.data_ptr() == base + 4 * off for (_, p), off in zip(pl, offs))
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
@@ -181,7 +232,7 @@ class _PAMNetBase(nn.Module):
                                    "(there is no CPU fallback)")
         if self._flat.device != x_raw.device:
             raise RuntimeError("model and data are on different devices")
-        if not self._aliased():      # e.g. EMA.assign swapped param.data (utils/ema.py:27)
+        if not self._aliased(full=False):      # e.g. EMA.assign swapped param.data (utils/ema.py:27)
             self._flatten()
         kind = self._ccfg.dataset
         batch = batch.to(torch.int64).contiguous()
@@ -204,7 +255,7 @@ class _PAMNetBase(nn.Module):
                 node_in = xr[:, -1].contiguous()
         plan = self._build_plan(pos, batch, int(n_graphs), el_in, max_nb)
         self.last_plan = plan
-        return _PAMNetFunction.apply(self, plan, node_in, sign, pos, *[p for _, p in self._param_list])
+        return _PAMNetFunction.apply(self, plan, node_in, sign, pos, self._flat)
 
     def _init_embeddings(self):
         stdv = math.sqrt(3)

@@ -9,19 +9,15 @@ import torch.distributed as dist
 
 
 def flat_grad(model):
-    """The flat gradient buffer if every p.grad is a view into one (the layout our backward produces), else None."""
-    ps = [p for (_, p), used in zip(model._param_list, model._param_used) if used]
-    if any(p.grad is None for p in ps):
+    """The module's flat gradient buffer if every live p.grad is a view into it (what our backward delivers
+    after zero_grad), else None."""
+    gflat, views = getattr(model, "_gflat", None), getattr(model, "_gviews", None)
+    if gflat is None or views is None:
         return None
-    first = ps[0].grad
-    base = first._base if first._base is not None else first
-    if base.dim() != 1 or base.numel() != model._total:
-        return None
-    start = base.data_ptr()
-    offs = [off for off, used in zip(model._offsets, model._param_used) if used]
-    if all(p.grad.data_ptr() == start + 4 * off for p, off in zip(ps, offs)):
-        return base
-    return None
+    for (_, p), v, used in zip(model._param_list, views, model._param_used):
+        if used and p.requires_grad and p.grad is not v:
+            return None
+    return gflat
 
 
 def allreduce_gradients(model, group=None, average=True):
