@@ -6,7 +6,7 @@
 namespace pamnet {
 
 constexpr int kChainRows = 8;     // rows per CTA
-constexpr int kChainKS = 4;       // k-slices: a CTA has kChainKS * D threads
+constexpr int kChainKS = 8;       // k-slices: a CTA has kChainKS * D / 2 threads (each owns two columns)
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -16,22 +16,23 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// Thread (c, ks): output column c = tid % D, k-slice ks = tid / D.  It accumulates all 8 rows of its column over
-// its quarter of K: per k one conflict-free 128 B weight request per warp plus two broadcast 128-bit loads of
-// the 8 row values (activations are kept TRANSPOSED in shared memory, [k][8]).  The four partial sums meet in
-// shared memory and thread (c, ks) finishes rows 2ks, 2ks+1.  4*D threads per CTA = 16 warps at D = 128, which
-// is what hides the shared-memory latency that a 2-warp-per-scheduler version could not (ncu: short_scoreboard).
+// Thread (c, ks): output columns c and c + D/2 (c = tid % (D/2)), k-slice ks = tid / (D/2) of 8.  It accumulates
+// all 8 rows of its two columns over its eighth of K: per k two conflict-free 128 B weight requests per warp plus
+// two broadcast 128-bit loads of the 8 row values (activations are kept TRANSPOSED in shared memory, [k][8]) feed
+// 16 FMAs.  The eight partial sums meet in shared memory and thread (c, ks) finishes row ks of its two columns.
+// 4*D threads per CTA = 16 warps at D = 128: enough warps to hide the shared-memory latency that a 2-warp-per-
+// scheduler version could not (ncu: short_scoreboard), at 4 shared-memory wavefronts per 16 FMAs.
 template <int D>
 struct ChainCfg {
     static constexpr int R = kChainRows;
-    static constexpr int T = kChainKS * D;               // threads
+    static constexpr int T = kChainKS * D / 2;           // threads
     static constexpr int KL = D / kChainKS;              // k per slice
     static constexpr size_t smem_floats = 2 * (size_t)D * D + (size_t)kChainSlots * D * R + 4 * (size_t)D * R +
                                           (size_t)kChainKS * R * D;
 };
 
 template <int D>
-__global__ void __launch_bounds__(kChainKS * D) chain_kernel(const ChainArgs args) {
+__global__ void __launch_bounds__(kChainKS * D / 2) chain_kernel(const ChainArgs args) {
     using C = ChainCfg<D>;
     constexpr int R = C::R, NT = C::T, KL = C::KL;
     extern __shared__ __align__(16) float smem[];
@@ -41,7 +42,8 @@ __global__ void __launch_bounds__(kChainKS * D) chain_kernel(const ChainArgs arg
     auto slot_ptr = [&](int s) -> float* { return slots + s * D * R; };   // wide slot = index 3 (4x larger)
 
     const int t = threadIdx.x;
-    const int c = t % D, ks = t / D;
+    constexpr int H = D / 2;
+    const int c = t % H, ks = t / H;
     const int row0 = blockIdx.x * R;
     const int n_rows = args.n_rows;
     // element-wise stages walk (r, c4) with r fastest so that a warp touches 8 rows x 64 contiguous bytes
@@ -144,40 +146,48 @@ __global__ void __launch_bounds__(kChainKS * D) chain_kernel(const ChainArgs arg
             if (nxt >= 0) cp_async_wait<1>(); else cp_async_wait<0>();
             __syncthreads();                              // weights landed for everyone; prologue visible
 
-            float acc[R];
+            float acc0[R], acc1[R];
 #pragma unroll
-            for (int i = 0; i < R; ++i) acc[i] = 0.f;
+            for (int i = 0; i < R; ++i) acc0[i] = acc1[i] = 0.f;
             const float* wp = wbuf + wcur * D * D + (ks * KL) * D + c;
             const float* ap = in + (ks * KL) * R;
 #pragma unroll 8
             for (int kk = 0; kk < KL; ++kk) {
-                const float w = wp[kk * D];
+                const float w0 = wp[kk * D], w1 = wp[kk * D + H];
                 const float4 a0 = ld4(ap + kk * R), a1 = ld4(ap + kk * R + 4);
-                acc[0] = fmaf(a0.x, w, acc[0]); acc[1] = fmaf(a0.y, w, acc[1]);
-                acc[2] = fmaf(a0.z, w, acc[2]); acc[3] = fmaf(a0.w, w, acc[3]);
-                acc[4] = fmaf(a1.x, w, acc[4]); acc[5] = fmaf(a1.y, w, acc[5]);
-                acc[6] = fmaf(a1.z, w, acc[6]); acc[7] = fmaf(a1.w, w, acc[7]);
+                acc0[0] = fmaf(a0.x, w0, acc0[0]); acc0[1] = fmaf(a0.y, w0, acc0[1]);
+                acc0[2] = fmaf(a0.z, w0, acc0[2]); acc0[3] = fmaf(a0.w, w0, acc0[3]);
+                acc0[4] = fmaf(a1.x, w0, acc0[4]); acc0[5] = fmaf(a1.y, w0, acc0[5]);
+                acc0[6] = fmaf(a1.z, w0, acc0[6]); acc0[7] = fmaf(a1.w, w0, acc0[7]);
+                acc1[0] = fmaf(a0.x, w1, acc1[0]); acc1[1] = fmaf(a0.y, w1, acc1[1]);
+                acc1[2] = fmaf(a0.z, w1, acc1[2]); acc1[3] = fmaf(a0.w, w1, acc1[3]);
+                acc1[4] = fmaf(a1.x, w1, acc1[4]); acc1[5] = fmaf(a1.y, w1, acc1[5]);
+                acc1[6] = fmaf(a1.z, w1, acc1[6]); acc1[7] = fmaf(a1.w, w1, acc1[7]);
             }
 #pragma unroll
-            for (int i = 0; i < R; ++i) red[(ks * R + i) * D + c] = acc[i];
+            for (int i = 0; i < R; ++i) {
+                red[(ks * R + i) * D + c] = acc0[i];
+                red[(ks * R + i) * D + c + H] = acc1[i];
+            }
             __syncthreads();
 
-            // thread (c, ks) finishes rows 2ks and 2ks+1: slices summed in fixed order -> deterministic
-            const float b = st.bias ? st.bias[c] : 0.f;
+            // thread (c, ks) finishes row ks of its two columns: slices summed in fixed order -> deterministic
+            static_assert(kChainKS == kChainRows, "one row per k-slice thread group");
+            const int r = ks;
+            const bool live = row0 + r < n_rows;
 #pragma unroll
-            for (int i = 0; i < R / kChainKS; ++i) {
-                const int r = ks * (R / kChainKS) + i;
-                float v = b;
+            for (int h = 0; h < 2; ++h) {
+                const int col = c + h * H;
+                float v = st.bias ? st.bias[col] : 0.f;
 #pragma unroll
-                for (int s2 = 0; s2 < kChainKS; ++s2) v += red[(s2 * R + r) * D + c];
-                const bool live = row0 + r < n_rows;
-                if (live && st.out_z) st.out_z[(size_t)(row0 + r) * st.ld_out + c] = v;
+                for (int s2 = 0; s2 < kChainKS; ++s2) v += red[(s2 * R + r) * D + col];
+                if (live && st.out_z) st.out_z[(size_t)(row0 + r) * st.ld_out + col] = v;
                 if (st.act) v = silu(v);
-                if (st.add_slot >= 0) v += slot_ptr(st.add_slot)[c * R + r];
-                if (live && st.add_g) v += st.add_g[(size_t)(row0 + r) * st.ld_add + c];
+                if (st.add_slot >= 0) v += slot_ptr(st.add_slot)[col * R + r];
+                if (live && st.add_g) v += st.add_g[(size_t)(row0 + r) * st.ld_add + col];
                 if (!live) v = 0.f;
-                if (st.dst >= 0) slot_ptr(st.dst)[c * R + r] = v;
-                if (live && st.out_a) st.out_a[(size_t)(row0 + r) * st.ld_out + c] = v;
+                if (st.dst >= 0) slot_ptr(st.dst)[col * R + r] = v;
+                if (live && st.out_a) st.out_a[(size_t)(row0 + r) * st.ld_out + col] = v;
             }
             wcur ^= 1;
             __syncthreads();

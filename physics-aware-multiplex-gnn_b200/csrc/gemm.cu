@@ -4,6 +4,8 @@
 // reference's nn.Linear layers (layers/basic.py:19-22).
 #include "gemm.cuh"
 
+#include <stdlib.h>
+
 namespace pamnet {
 
 constexpr int BK = 16, GT = 256;
@@ -211,6 +213,36 @@ __global__ void __launch_bounds__(GT, (TM >= 8 ? 2 : 3)) gemm_kernel(const GemmA
     }
 }
 
+// bias gradients of a batch of weight-gradient slots: C2[m] (+)= sum_k A[k*lda + m]   (tensor-core path)
+__global__ void __launch_bounds__(128) colsum_slots_kernel(const GemmArgs args, int rows_per_block) {
+    const GemmSlot& sl = args.slot[blockIdx.z];
+    if (!sl.C2) return;
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= args.M) return;
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(args.K, r0 + rows_per_block);
+    float s = 0.f;
+    for (int r = r0; r < r1; ++r) s += sl.A[(size_t)r * sl.lda + m];
+    atomicAdd(&sl.C2[m], s);
+}
+
+// C[m, n] *= silu'(Z[m, n]) for a batch of slots (second half of a split-K data-gradient GEMM)
+__global__ void __launch_bounds__(256) mul_dsilu_slots_kernel(const GemmArgs args) {
+    const GemmSlot& sl = args.slot[blockIdx.y];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)args.M * args.N) return;
+    const int m = (int)(i / args.N), n = (int)(i % args.N);
+    sl.C[(size_t)m * sl.ldc + n] *= dsilu(sl.Z[(size_t)m * sl.ldz + n]);
+}
+
+static int gemm_backend() {      // 0 = FFMA only, 1 = tensor cores where eligible
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("PAMNET_GEMM");
+        mode = (e && strcmp(e, "ffma") == 0) ? 0 : 1;
+    }
+    return mode;
+}
+
 int gemm_launch(const GemmArgs& a, cudaStream_t st) {
     PAMNET_CHECK_ARG(a.nslots >= 1 && a.nslots <= kGemmMaxSlots, "gemm: nslots=%d", a.nslots);
     PAMNET_CHECK_ARG(a.nseg <= kGemmMaxSeg, "gemm: nseg=%d", a.nseg);
@@ -222,6 +254,35 @@ int gemm_launch(const GemmArgs& a, cudaStream_t st) {
     double bytes = 4.0 * a.nslots * ((double)a.M * a.K + (double)a.K * a.N + (double)a.M * a.N);
     if (a.epi == EPI_MUL_DSILU || (a.epi == EPI_BIAS_SILU && a.slot[0].C2)) bytes += 4.0 * a.nslots * (double)a.M * a.N;
     const int ks = a.ksplit > 1 ? a.ksplit : 1;
+    if (gemm_backend() == 1 && gemm_tc_eligible(a)) {
+        // The tensor core adds each MMA into the fp32 accumulator with truncation, so the error of one
+        // accumulation chain grows linearly with its length (measured: 1e-5 relative at K = 1536).  Long
+        // reductions are therefore split into <= 128-deep chains per CTA and combined with fp32 atomics
+        // (round-to-nearest); a SiLU' epilogue then runs as a separate pass over the summed result.
+        GemmArgs b = a;
+        const bool long_nn = a.mode == GEMM_NN && a.K > 256 && a.ksplit <= 1 &&
+                             (a.epi == EPI_NONE || a.epi == EPI_MUL_DSILU);
+        if (long_nn) {
+            for (int i = 0; i < a.nslots; ++i) {
+                PAMNET_CHECK_ARG(a.slot[i].ldc == a.N, "gemm: split data-gradient needs a contiguous output");
+                PAMNET_CUDA(cudaMemsetAsync(a.slot[i].C, 0, sizeof(float) * (size_t)a.M * a.N, st));
+            }
+            b.ksplit = ceil_div(a.K, 128);
+            b.epi = EPI_NONE;
+        }
+        prof_begin(KC_GEMM, bytes, st);
+        PAMNET_TRY(gemm_tc_launch(b, st));
+        prof_end(st);
+        PAMNET_LAUNCH_CHECK();
+        if (long_nn && a.epi == EPI_MUL_DSILU) {
+            dim3 grid(ceil_div((int64_t)a.M * a.N, 256), a.nslots);
+            prof_begin(KC_GEMM, 0.0, st);
+            mul_dsilu_slots_kernel<<<grid, 256, 0, st>>>(a);
+            prof_end(st);
+            PAMNET_LAUNCH_CHECK();
+        }
+        return 0;
+    }
     // big tiles only when they still give >= 2 waves of CTAs on 148 SMs
     const long big_ctas = (long)ceil_div(a.M, 128) * ceil_div(a.N, 128) * ks * a.nslots;
     const bool big = a.M >= 128 && a.N >= 128 && big_ctas >= 2 * kNumSM;

@@ -47,6 +47,10 @@ struct GemmArgs {
 
 int gemm_launch(const GemmArgs& args, cudaStream_t st);
 
+// tensor-core (tcgen05, 3xTF32) path, gemm_tc.cu; chosen by gemm_launch unless PAMNET_GEMM=ffma
+bool gemm_tc_eligible(const GemmArgs& a);
+int gemm_tc_launch(const GemmArgs& a, cudaStream_t st);
+
 // out[c] += sum_r X[r*ld + c]  (bias gradients); out must be zero-initialised by the caller
 int colsum_launch(const float* X, int64_t rows, int cols, int ld, float* out, cudaStream_t st);
 

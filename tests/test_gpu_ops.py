@@ -147,17 +147,20 @@ def test_linear(ops, n_in, n_out, rows):
     g = torch.Generator().manual_seed(2)
     x, w, b = torch.randn(rows, n_in, generator=g), torch.randn(n_out, n_in, generator=g) / n_in ** 0.5, torch.randn(n_out, generator=g)
     ref = x.double() @ w.double().T + b.double()
-    assert rel_err(ops.linear(x.cuda(), w.cuda(), b.cuda()), ref) < 2e-6
-    assert rel_err(ops.linear(x.cuda(), w.cuda(), b.cuda(), silu=True), ref * torch.sigmoid(ref)) < 2e-6
-    assert rel_err(ops.linear(x.cuda(), w.cuda()), x.double() @ w.double().T) < 2e-6
+    assert rel_err(ops.linear(x.cuda(), w.cuda(), b.cuda()), ref) < 4e-6
+    assert rel_err(ops.linear(x.cuda(), w.cuda(), b.cuda(), silu=True), ref * torch.sigmoid(ref)) < 4e-6
+    assert rel_err(ops.linear(x.cuda(), w.cuda()), x.double() @ w.double().T) < 4e-6
 
 
-@pytest.mark.parametrize("m,n,k,ksplit", [(128, 128, 599, 1), (128, 16, 5000, 4), (1, 128, 300, 1), (70, 88, 1000, 3)])
+@pytest.mark.parametrize("m,n,k,ksplit", [(128, 128, 599, 1), (128, 16, 5000, 4), (1, 128, 300, 1), (70, 88, 1000, 3),
+                                            (300, 128, 128, 1), (1000, 256, 64, 1), (128, 384, 2000, 8), (130, 100, 16, 1),
+                                            (257, 129, 40, 2)])
 def test_gemm_modes(ops, m, n, k, ksplit):
     g = torch.Generator().manual_seed(3)
     a, b = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g)
     # fp32 running sums of k unit-variance terms: rounding error grows ~ eps * k / sqrt(2) in absolute terms
-    tol = 2e-7 * k
+    # (tensor-core path: 3xTF32 keeps ~2^-21 relative error per product -> ~5e-7 * sqrt(k) more)
+    tol = 2e-7 * k + 1e-5 * k ** 0.5
 
     def err(x, ref):
         return float((x.double().cpu() - ref).abs().max())
