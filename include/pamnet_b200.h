@@ -126,16 +126,19 @@ int pamnet_plan_fill(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, const
  *           PDBbind  : 18 features per node [n_nodes,18] (models.py:119).
  * sign    : PDBbind only, +-1 per node (models.py:122-125), else NULL.
  * out     : [n_graphs].  workspace keeps what backward needs; it must stay untouched between the calls.
- * backward: grad_out [n_graphs] -> grad_params (flat, same layout as params; fully overwritten). */
+ * backward: grad_out [n_graphs] -> grad_params (flat, same layout as params; fully overwritten).
+ * aux_stream: optional second stream (NULL = none): the x-independent GEMMs run on it, overlapped with the
+ *             sequential layer loop on `stream`; both calls return with all their work ordered before later
+ *             work on `stream`. */
 size_t pamnet_workspace_bytes(const pamnet_config_t* cfg, const pamnet_sizes_t* sz);
 int pamnet_model_forward(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, const pamnet_sbf_consts_t* sbf,
                          const float* params, const float* node_in, const float* sign, const float* pos,
                          void* plan_base, void* plan_trip, void* workspace, size_t workspace_bytes,
-                         int32_t save_for_backward, float* out, void* stream);
+                         int32_t save_for_backward, float* out, void* stream, void* aux_stream);
 int pamnet_model_backward(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, const pamnet_sbf_consts_t* sbf,
                           const float* params, const float* node_in, const float* sign, const float* pos,
                           void* plan_base, void* plan_trip, void* workspace, size_t workspace_bytes,
-                          const float* grad_out, float* grad_params, void* stream);
+                          const float* grad_out, float* grad_params, void* stream, void* aux_stream);
 
 /* L1 / MSE loss + its gradient w.r.t. the prediction in one launch (main_qm9.py:108 F.l1_loss,
  * main_pdbbind.py MSE): loss_dev[0] = mean(|out-y|) or mean((out-y)^2); grad_out[g] = d loss / d out[g]. */

@@ -158,21 +158,21 @@ size_t pamnet_workspace_bytes(const pamnet_config_t* cfg, const pamnet_sizes_t* 
 int pamnet_model_forward(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, const pamnet_sbf_consts_t* sbf,
                          const float* params, const float* node_in, const float* sign, const float* pos,
                          void* plan_base, void* plan_trip, void* workspace, size_t workspace_bytes,
-                         int32_t save_for_backward, float* out, void* stream) {
+                         int32_t save_for_backward, float* out, void* stream, void* aux_stream) {
     REQUIRE(cfg); REQUIRE(sz); REQUIRE(sbf); REQUIRE(params); REQUIRE(node_in); REQUIRE(pos); REQUIRE(plan_base);
     REQUIRE(plan_trip); REQUIRE(workspace); REQUIRE(out);
     (void)save_for_backward;
     return model_forward(*cfg, *sz, *sbf, params, node_in, sign, pos, plan_base, plan_trip, workspace,
-                         workspace_bytes, out, ST(stream));
+                         workspace_bytes, out, ST(stream), ST(aux_stream));
 }
 int pamnet_model_backward(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, const pamnet_sbf_consts_t* sbf,
                           const float* params, const float* node_in, const float* sign, const float* pos,
                           void* plan_base, void* plan_trip, void* workspace, size_t workspace_bytes,
-                          const float* grad_out, float* grad_params, void* stream) {
+                          const float* grad_out, float* grad_params, void* stream, void* aux_stream) {
     REQUIRE(cfg); REQUIRE(sz); REQUIRE(sbf); REQUIRE(params); REQUIRE(node_in); REQUIRE(pos); REQUIRE(plan_base);
     REQUIRE(plan_trip); REQUIRE(workspace); REQUIRE(grad_out); REQUIRE(grad_params);
     return model_backward(*cfg, *sz, *sbf, params, node_in, sign, pos, plan_base, plan_trip, workspace,
-                          workspace_bytes, grad_out, grad_params, ST(stream));
+                          workspace_bytes, grad_out, grad_params, ST(stream), ST(aux_stream));
 }
 
 int64_t pamnet_debug_ws_offset(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, const char* name, int32_t half) {

@@ -63,6 +63,8 @@ __global__ void __launch_bounds__(kChainKS * D / 2) chain_kernel(const ChainArgs
             if (args.st[i].op == CH_GEMM) return i;
         return -1;
     };
+    float4 zpre = make_float4(0.f, 0.f, 0.f, 0.f);   // prefetched SiLU' operand of stage zpre_stage (thread's first c4)
+    int zpre_stage = -1;
     int wcur = 0;
     {
         const int first = next_gemm(0);
@@ -127,6 +129,15 @@ __global__ void __launch_bounds__(kChainKS * D / 2) chain_kernel(const ChainArgs
             if (nxt >= 0) issue_weights(nxt, wcur ^ 1);
 
             const float* in = slot_ptr(st.src) + st.src_off * R;
+            // operands of this stage's epilogue: requested now, consumed after the k-loop (an exposed L2 round
+            // trip per stage was the largest remaining cost of the chain)
+            const bool live_r = row0 + ks < n_rows;
+            float bias_v[2] = {0.f, 0.f}, addg_v[2] = {0.f, 0.f};
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (st.bias) bias_v[h] = st.bias[c + h * H];
+                if (st.add_g && live_r) addg_v[h] = st.add_g[(size_t)(row0 + ks) * st.ld_add + c + h * H];
+            }
             if (st.psrc >= 0) {
                 float* p = slot_ptr(st.psrc);
                 const bool live = row0 + er < n_rows;
@@ -134,7 +145,9 @@ __global__ void __launch_bounds__(kChainKS * D / 2) chain_kernel(const ChainArgs
                     const float* g = in + (c4 * 4) * R + er;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (live) {
-                        const float4 dz = dsilu4(ld4(st.zmul + (size_t)(row0 + er) * D + c4 * 4));
+                        // zmul of this stage was prefetched during the previous GEMM stage when possible
+                        const float4 zz = (zpre_stage == si && c4 == ec) ? zpre : ld4(st.zmul + (size_t)(row0 + er) * D + c4 * 4);
+                        const float4 dz = dsilu4(zz);
                         v = make_float4(g[0] * dz.x, g[R] * dz.y, g[2 * R] * dz.z, g[3 * R] * dz.w);
                         if (st.save_src) st4(st.save_src + (size_t)(row0 + er) * D + c4 * 4, v);
                     }
@@ -142,6 +155,11 @@ __global__ void __launch_bounds__(kChainKS * D / 2) chain_kernel(const ChainArgs
                     q[0] = v.x; q[R] = v.y; q[2 * R] = v.z; q[3 * R] = v.w;
                 }
                 in = p;
+            }
+            // prefetch the NEXT GEMM stage's SiLU' operand (its prologue runs right after this stage's barrier)
+            if (nxt >= 0 && args.st[nxt].psrc >= 0 && ec < D / 4 && row0 + er < n_rows) {
+                zpre = ld4(args.st[nxt].zmul + (size_t)(row0 + er) * D + ec * 4);
+                zpre_stage = nxt;
             }
             if (nxt >= 0) cp_async_wait<1>(); else cp_async_wait<0>();
             __syncthreads();                              // weights landed for everyone; prologue visible
@@ -178,13 +196,13 @@ __global__ void __launch_bounds__(kChainKS * D / 2) chain_kernel(const ChainArgs
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int col = c + h * H;
-                float v = st.bias ? st.bias[col] : 0.f;
+                float v = bias_v[h];
 #pragma unroll
                 for (int s2 = 0; s2 < kChainKS; ++s2) v += red[(s2 * R + r) * D + col];
                 if (live && st.out_z) st.out_z[(size_t)(row0 + r) * st.ld_out + col] = v;
                 if (st.act) v = silu(v);
                 if (st.add_slot >= 0) v += slot_ptr(st.add_slot)[col * R + r];
-                if (live && st.add_g) v += st.add_g[(size_t)(row0 + r) * st.ld_add + col];
+                if (live && st.add_g) v += addg_v[h];
                 if (!live) v = 0.f;
                 if (st.dst >= 0) slot_ptr(st.dst)[col * R + r] = v;
                 if (live && st.out_a) st.out_a[(size_t)(row0 + r) * st.ld_out + col] = v;

@@ -234,6 +234,22 @@ __global__ void __launch_bounds__(256) mul_dsilu_slots_kernel(const GemmArgs arg
     sl.C[(size_t)m * sl.ldc + n] *= dsilu(sl.Z[(size_t)m * sl.ldz + n]);
 }
 
+__global__ void mul_dsilu_kernel(float* __restrict__ c, const float* __restrict__ z, int64_t n4) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = ld4(c + 4 * i) * dsilu4(ld4(z + 4 * i));
+    st4(c + 4 * i, v);
+}
+// c[i] *= silu'(z[i]), n a multiple of 4 (rows of D floats)
+int mul_dsilu_launch(float* c, const float* z, int64_t n, cudaStream_t st) {
+    if (n <= 0) return 0;
+    prof_begin(KC_GEMM, 12.0 * n, st);
+    mul_dsilu_kernel<<<ceil_div(n / 4, 256), 256, 0, st>>>(c, z, n / 4);
+    prof_end(st);
+    PAMNET_LAUNCH_CHECK();
+    return 0;
+}
+
 static int gemm_backend() {      // 0 = FFMA only, 1 = tensor cores where eligible
     static int mode = -1;
     if (mode < 0) {

@@ -51,6 +51,8 @@ int gemm_launch(const GemmArgs& args, cudaStream_t st);
 bool gemm_tc_eligible(const GemmArgs& a);
 int gemm_tc_launch(const GemmArgs& a, cudaStream_t st);
 
+int mul_dsilu_launch(float* c, const float* z, int64_t n, cudaStream_t st);
+
 // out[c] += sum_r X[r*ld + c]  (bias gradients); out must be zero-initialised by the caller
 int colsum_launch(const float* X, int64_t rows, int cols, int ld, float* out, cudaStream_t st);
 

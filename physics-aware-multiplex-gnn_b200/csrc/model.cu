@@ -115,6 +115,7 @@ struct HalfWs {
     float *m_nb, *msum;                     // local only, [El, D]
     // backward
     float *gz_x1, *gz_x2, *gz_A[3], *gz_B[3], *gz_o[3];
+    float *g_P;                             // [N, nP*D] grad of P (kept per half: consumed on the auxiliary stream)
 };
 
 struct Ws {
@@ -172,6 +173,7 @@ size_t ws_layout(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, void* bas
         h.gz_x1 = take(N * D); h.gz_x2 = take(N * D);
         for (int r = 0; r < 3; ++r) { h.gz_A[r] = take(N * D); h.gz_B[r] = take(N * D); }
         for (int s = 0; s < 3; ++s) h.gz_o[s] = take(N * D);
+        h.g_P = take(N * nP_of(hh) * D);
     }
     w.g_att = take(H * N); w.g_out = take(H * N);
     w.g_h = take(N * D); w.g_resx = take(N * D); w.g_P = take(N * 4 * D); w.g_s = take(El * D); w.g_x0 = take(N * D);
@@ -257,7 +259,7 @@ void add_post_fwd(Prog& p, const float* params, const HalfP& hp, const HalfWs& h
 void add_pre_bwd(Prog& p, const float* params, const HalfP& hp, const HalfWs& hw, int hh, int D, const Ws& w,
                  float* g_x_out) {
     const int nP = nP_of(hh);
-    p.add(st_load(kChainWide, w.g_P, nP * D, nP * D));
+    p.add(st_load(kChainWide, hw.g_P, nP * D, nP * D));
     p.add(st_load(0, w.g_h, D, D));
     int cur = 0;
     for (int c = 0; c < nP; ++c) {
@@ -371,7 +373,7 @@ int64_t debug_ws_offset(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, co
         {"zq2", w.zq2}, {"att", w.att}, {"out", w.out}, {"node_val", w.node_val},
         {"P", h.P}, {"x1", h.x1}, {"h", h.h}, {"a_x2", h.a_x2}, {"r0", h.r[0]}, {"r1", h.r[1]}, {"r2", h.r[2]},
         {"a_o2", h.a_o[2]}, {"m_nb", h.m_nb}, {"msum", h.msum}, {"x1T", h.x1T},
-        {"g_att", w.g_att}, {"g_out", w.g_out}, {"g_h", w.g_h}, {"g_P", w.g_P}, {"g_x0", w.g_x0},
+        {"g_att", w.g_att}, {"g_out", w.g_out}, {"g_h", w.g_h}, {"g_P", h.g_P}, {"g_x0", w.g_x0},
         {"gQT", w.gQT}, {"gQR", w.gQR}, {"gzq2", w.gzq2}, {"gz_s", w.gz_s}, {"gz_eg", w.gz_eg}, {"gz_el", w.gz_el},
         {"gz_x1", h.gz_x1}, {"gz_x2", h.gz_x2}, {"gz_o2", h.gz_o[2]},
     };
@@ -381,11 +383,75 @@ int64_t debug_ws_offset(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, co
 }
 
 // ---------------------------------------------------------------------------------------------
+// two-stream schedule
+// ---------------------------------------------------------------------------------------------
+// The x-independent dense work (phase A / A') only meets the sequential layer loop (phase B) at one point per
+// layer, so it runs on an auxiliary stream supplied by the caller and overlaps the latency-bound node chains,
+// which occupy about half of the SMs.  Events come from a small per-thread pool (created once, re-recorded).
+namespace {
+struct Sched {
+    cudaStream_t st, s2;
+    bool dual;
+    std::vector<cudaEvent_t>* pool;
+    int next = 0;
+    cudaEvent_t fresh() {
+        if ((size_t)next == pool->size()) {
+            cudaEvent_t e;
+            cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+            pool->push_back(e);
+        }
+        return (*pool)[next++];
+    }
+    // everything issued so far on `from` happens before anything issued later on `to`
+    int order(cudaStream_t from, cudaStream_t to) {
+        if (!dual) return 0;
+        cudaEvent_t e = fresh();
+        PAMNET_CUDA(cudaEventRecord(e, from));
+        PAMNET_CUDA(cudaStreamWaitEvent(to, e, 0));
+        return 0;
+    }
+    int record(cudaStream_t from, cudaEvent_t* e) {
+        if (!dual) return 0;
+        *e = fresh();
+        PAMNET_CUDA(cudaEventRecord(*e, from));
+        return 0;
+    }
+    int wait(cudaStream_t to, cudaEvent_t e) {
+        if (!dual) return 0;
+        PAMNET_CUDA(cudaStreamWaitEvent(to, e, 0));
+        return 0;
+    }
+};
+thread_local std::vector<cudaEvent_t> g_event_pool;
+
+// group boundaries over the layers: a short first group (its results are needed first in forward, last in backward),
+// then growing ones
+std::vector<int> layer_groups(int L) {
+    std::vector<int> g{0};
+    int step = 1;
+    while (g.back() < L) {
+        g.push_back(g.back() + step > L ? L : g.back() + step);
+        step = step < 3 ? step + 1 : 3;
+    }
+    return g;
+}
+
+Sched make_sched(cudaStream_t st, cudaStream_t aux) {
+    Sched s;
+    s.st = st;
+    s.dual = aux != nullptr && aux != st;
+    s.s2 = s.dual ? aux : st;
+    s.pool = &g_event_pool;
+    return s;
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
 int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pamnet_sbf_consts_t& sbf,
                   const float* params, const float* node_in, const float* sign, const float* pos, void* plan_base,
-                  void* plan_trip, void* workspace, size_t ws_bytes, float* out, cudaStream_t st) {
+                  void* plan_trip, void* workspace, size_t ws_bytes, float* out, cudaStream_t st, cudaStream_t aux) {
     Ctx c;
     PAMNET_TRY(make_ctx(cfg, sz, sbf, plan_base, plan_trip, workspace, ws_bytes, &c));
     const int D = c.D, L = c.L, H = c.H;
@@ -393,8 +459,74 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
     const ModelP& mp = c.mp;
     Ws& w = c.w;
     const Plan& pl = c.plan;
+    Sched sc = make_sched(st, aux);
+    cudaStream_t s2 = sc.s2;
 
-    // ---- transposed (k-major) copies of the chain weights -------------------------------------------
+    PAMNET_TRY(sc.order(st, s2));     // the plan and the inputs were produced on the main stream
+
+    // ================= auxiliary stream: phase A (models.py:180-188 and the x-independent halves of the layers)
+    PAMNET_TRY(rbf_forward(pl.dist_g, Eg, params + mp.freq_g, cfg.cutoff_g, w.rbf_g, s2));
+    {
+        GemmArgs a = gemm_zero(GEMM_NT, EPI_BIAS_SILU, (int)Eg, D, kNumRbf);
+        a.nslots = 1;
+        a.slot[0] = slot(w.rbf_g, kNumRbf, params + mp.rbf_g.w, kNumRbf, w.e_g, D, params + mp.rbf_g.b, w.z_eg);
+        PAMNET_TRY(gemm_launch(a, s2));
+    }
+    PAMNET_TRY(rbf_forward(pl.dist_l, El, params + mp.freq_l, cfg.cutoff_l, w.rbf_l, s2));
+    PAMNET_TRY(sbf_radial(c.tab, pl.dist_l, El, cfg.cutoff_l, w.radial, s2));
+    PAMNET_TRY(sbf_ext_forward(c.tab, pl, El, T, pos, w.radial, w.sbf_ext, s2));
+    PAMNET_TRY(sbf_weight_pack(D, cfg.simple ? nullptr : params + mp.sbf2.w, cfg.simple ? nullptr : params + mp.sbf2.b,
+                               params + mp.sbf1.w, params + mp.sbf1.b, w.w_ext, s2));
+    {
+        GemmArgs a = gemm_zero(GEMM_NT, EPI_BIAS_SILU, (int)El, D, kNumRbf);
+        a.nslots = 1;
+        a.slot[0] = slot(w.rbf_l, kNumRbf, params + mp.rbf_l.w, kNumRbf, w.e_l, D, params + mp.rbf_l.b, w.z_el);
+        PAMNET_TRY(gemm_launch(a, s2));
+        a.M = (int)T; a.K = kSbfExt;
+        a.slot[0] = slot(w.sbf_ext, kSbfExt, w.w_ext, kSbfExt, w.s, D, nullptr, w.z_s);
+        PAMNET_TRY(gemm_launch(a, s2));
+    }
+    // layers are grouped ([0,1), [1,3), [3,L) for L = 6): one batched GEMM launch per group and operand keeps the
+    // tiles-per-launch high (a tensor-core tile has a ~15 us latency floor) while later groups overlap phase B
+    std::vector<int> grp = layer_groups(L);
+    const int ngrp = (int)grp.size() - 1;
+    std::vector<cudaEvent_t> ev_g(ngrp), ev_l(ngrp);
+    std::vector<int> group_of(L);
+    for (int gi = 0; gi < ngrp; ++gi) {
+        const int l0 = grp[gi], l1 = grp[gi + 1];
+        for (int l = l0; l < l1; ++l) group_of[l] = gi;
+        {   // global: Q | Tt = e_g [W_m,e ; W_e]^T (+ b_m)      (global_message_passing.py:52-56)
+            const int ldq = L * 2 * D;
+            std::vector<GemmSlot> sl;
+            for (int l = l0; l < l1; ++l) {
+                const HalfP& hp = mp.g[l];
+                sl.push_back(slot(w.e_g, D, params + hp.m.w + 2 * D, 3 * D, w.QT + l * 2 * D, ldq, params + hp.m.b));
+                sl.push_back(slot(w.e_g, D, params + hp.We.w, D, w.QT + l * 2 * D + D, ldq));
+            }
+            PAMNET_TRY(gemm_multi(gemm_zero(GEMM_NT, EPI_BIAS, (int)Eg, D, D), sl, s2));
+            PAMNET_TRY(sc.record(s2, &ev_g[gi]));
+        }
+        {   // local: Qji | Qkj | R | Rout and the triplet gate MLP   (local_message_passing.py:46-53)
+            const int ldq = L * 4 * D, ldt = L * D;
+            std::vector<GemmSlot> sl, s1, s2v;
+            for (int l = l0; l < l1; ++l) {
+                const HalfP& hp = mp.l[l];
+                float* base = w.QR + l * 4 * D;
+                sl.push_back(slot(w.e_l, D, params + hp.m_ji.w + 2 * D, 3 * D, base, ldq, params + hp.m_ji.b));
+                sl.push_back(slot(w.e_l, D, params + hp.m_kj.w + 2 * D, 3 * D, base + D, ldq, params + hp.m_kj.b));
+                sl.push_back(slot(w.e_l, D, params + hp.lin_rbf.w, D, base + 2 * D, ldq));
+                sl.push_back(slot(w.e_l, D, params + hp.lin_rbf_out.w, D, base + 3 * D, ldq));
+                s1.push_back(slot(w.s, D, params + hp.sbf[0].w, D, w.aq1 + l * D, ldt, params + hp.sbf[0].b, w.zq1 + l * D));
+                s2v.push_back(slot(w.aq1 + l * D, ldt, params + hp.sbf[1].w, D, w.zq2 + l * D, ldt, params + hp.sbf[1].b));
+            }
+            PAMNET_TRY(gemm_multi(gemm_zero(GEMM_NT, EPI_BIAS, (int)El, D, D), sl, s2));
+            PAMNET_TRY(gemm_multi(gemm_zero(GEMM_NT, EPI_BIAS_SILU, (int)T, D, D), s1, s2));
+            PAMNET_TRY(gemm_multi(gemm_zero(GEMM_NT, EPI_BIAS, (int)T, D, D), s2v, s2));
+            PAMNET_TRY(sc.record(s2, &ev_l[gi]));
+        }
+    }
+
+    // ================= main stream: node input, transposed chain weights, phase B
     {
         std::vector<TransposeJob> jobs;
         const float* ws_base = reinterpret_cast<const float*>(workspace);
@@ -417,89 +549,32 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
         }
         PAMNET_TRY(transpose_batch(params, reinterpret_cast<float*>(workspace), jobs.data(), (int)jobs.size(), st));
     }
-
-    // ---- node input (models.py:107,119,140) ----------------------------------------------------------
-    if (cfg.dataset == PAMNET_PDBBIND) {
+    if (cfg.dataset == PAMNET_PDBBIND) {          // models.py:119
         GemmArgs a = gemm_zero(GEMM_NT, EPI_NONE, (int)N, D, kFeatPdb);
         a.nslots = 1;
         a.slot[0] = slot(node_in, kFeatPdb, params + mp.init_linear, kFeatPdb, w.x0, D);
         PAMNET_TRY(gemm_launch(a, st));
-    } else {
+    } else {                                      // models.py:107,140
         PAMNET_TRY(embed_forward(node_in, N, params + mp.emb, mp.n_embed, D, w.x0, st));
     }
-
-    // ---- phase A: bases and embeddings (models.py:180-188) ------------------------------------------
-    PAMNET_TRY(rbf_forward(pl.dist_g, Eg, params + mp.freq_g, cfg.cutoff_g, w.rbf_g, st));
-    PAMNET_TRY(rbf_forward(pl.dist_l, El, params + mp.freq_l, cfg.cutoff_l, w.rbf_l, st));
-    PAMNET_TRY(sbf_radial(c.tab, pl.dist_l, El, cfg.cutoff_l, w.radial, st));
-    PAMNET_TRY(sbf_ext_forward(c.tab, pl, El, T, pos, w.radial, w.sbf_ext, st));
-    PAMNET_TRY(sbf_weight_pack(D, cfg.simple ? nullptr : params + mp.sbf2.w, cfg.simple ? nullptr : params + mp.sbf2.b,
-                               params + mp.sbf1.w, params + mp.sbf1.b, w.w_ext, st));
-    {
-        GemmArgs a = gemm_zero(GEMM_NT, EPI_BIAS_SILU, (int)Eg, D, kNumRbf);
-        a.nslots = 1;
-        a.slot[0] = slot(w.rbf_g, kNumRbf, params + mp.rbf_g.w, kNumRbf, w.e_g, D, params + mp.rbf_g.b, w.z_eg);
-        PAMNET_TRY(gemm_launch(a, st));
-        a.M = (int)El;
-        a.slot[0] = slot(w.rbf_l, kNumRbf, params + mp.rbf_l.w, kNumRbf, w.e_l, D, params + mp.rbf_l.b, w.z_el);
-        PAMNET_TRY(gemm_launch(a, st));
-        a.M = (int)T; a.K = kSbfExt;
-        a.slot[0] = slot(w.sbf_ext, kSbfExt, w.w_ext, kSbfExt, w.s, D, nullptr, w.z_s);
-        PAMNET_TRY(gemm_launch(a, st));
-    }
-    // ---- phase A: per-layer edge / triplet projections for all layers --------------------------------
-    {
-        std::vector<GemmSlot> sl;
-        const int ldq = L * 2 * D;
-        for (int l = 0; l < L; ++l) {
-            const HalfP& hp = mp.g[l];
-            sl.push_back(slot(w.e_g, D, params + hp.m.w + 2 * D, 3 * D, w.QT + l * 2 * D, ldq, params + hp.m.b));
-            sl.push_back(slot(w.e_g, D, params + hp.We.w, D, w.QT + l * 2 * D + D, ldq));
-        }
-        PAMNET_TRY(gemm_multi(gemm_zero(GEMM_NT, EPI_BIAS, (int)Eg, D, D), sl, st));
-    }
-    {
-        std::vector<GemmSlot> sl;
-        const int ldq = L * 4 * D;
-        for (int l = 0; l < L; ++l) {
-            const HalfP& hp = mp.l[l];
-            float* base = w.QR + l * 4 * D;
-            sl.push_back(slot(w.e_l, D, params + hp.m_ji.w + 2 * D, 3 * D, base, ldq, params + hp.m_ji.b));
-            sl.push_back(slot(w.e_l, D, params + hp.m_kj.w + 2 * D, 3 * D, base + D, ldq, params + hp.m_kj.b));
-            sl.push_back(slot(w.e_l, D, params + hp.lin_rbf.w, D, base + 2 * D, ldq));
-            sl.push_back(slot(w.e_l, D, params + hp.lin_rbf_out.w, D, base + 3 * D, ldq));
-        }
-        PAMNET_TRY(gemm_multi(gemm_zero(GEMM_NT, EPI_BIAS, (int)El, D, D), sl, st));
-    }
-    {
-        const int ldt = L * D;
-        std::vector<GemmSlot> s1, s2;
-        for (int l = 0; l < L; ++l) {
-            const HalfP& hp = mp.l[l];
-            s1.push_back(slot(w.s, D, params + hp.sbf[0].w, D, w.aq1 + l * D, ldt, params + hp.sbf[0].b, w.zq1 + l * D));
-            s2.push_back(slot(w.aq1 + l * D, ldt, params + hp.sbf[1].w, D, w.zq2 + l * D, ldt, params + hp.sbf[1].b));
-        }
-        PAMNET_TRY(gemm_multi(gemm_zero(GEMM_NT, EPI_BIAS_SILU, (int)T, D, D), s1, st));
-        PAMNET_TRY(gemm_multi(gemm_zero(GEMM_NT, EPI_BIAS, (int)T, D, D), s2, st));
-    }
-
-    // ---- phase B: the layer loop (models.py:196-204) -------------------------------------------------
     {
         Prog p((int)N);
         p.add(st_load(2, w.x0, D, D));
         add_pre_fwd(p, params, half_params(mp, 0), w.half[0], 0, D, 2);
         PAMNET_TRY(chain_launch(D, p.a, st));
     }
-    for (int hh = 0; hh < H; ++hh) {
+    for (int hh = 0; hh < H; ++hh) {              // models.py:196-204
         const HalfWs& hw = w.half[hh];
         const int l = hh >> 1;
         if (!is_local(hh)) {
+            if (l == grp[group_of[l]]) PAMNET_TRY(sc.wait(st, ev_g[group_of[l]]));
             GlobalMsgArgs a;
             memset(&a, 0, sizeof(a));
             a.n_nodes = (int)N; a.n_edges = (int)Eg; a.ptr = pl.g_ptr; a.src = pl.g_src; a.dst = pl.g_dst; a.P = hw.P;
             a.QT = w.QT + l * 2 * D; a.ldq = L * 2 * D; a.x1 = hw.x1; a.h = hw.h;
             PAMNET_TRY(global_msg_fwd(D, a, (int)Eg, st));
         } else {
+            if (l == grp[group_of[l]]) PAMNET_TRY(sc.wait(st, ev_l[group_of[l]]));
             LocalMsgArgs a;
             memset(&a, 0, sizeof(a));
             a.n_nodes = (int)N; a.n_edges = (int)El; a.ptr = pl.l_ptr; a.src = pl.l_src; a.dst = pl.l_dst;
@@ -524,6 +599,7 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
     r.sign = cfg.dataset == PAMNET_PDBBIND ? sign : nullptr;
     r.gptr = pl.gptr; r.n2g = pl.n2g; r.att = w.att; r.out = w.out; r.node_val = w.node_val; r.pooled = out;
     PAMNET_TRY(readout_forward(r, st));
+    PAMNET_TRY(sc.order(s2, st));      // nothing of this call is still running on the auxiliary stream afterwards
     return 0;
 }
 
@@ -533,7 +609,7 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
 int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pamnet_sbf_consts_t& sbf,
                    const float* params, const float* node_in, const float* sign, const float* pos, void* plan_base,
                    void* plan_trip, void* workspace, size_t ws_bytes, const float* grad_out, float* gp,
-                   cudaStream_t st) {
+                   cudaStream_t st, cudaStream_t aux) {
     (void)pos;
     Ctx c;
     PAMNET_TRY(make_ctx(cfg, sz, sbf, plan_base, plan_trip, workspace, ws_bytes, &c));
@@ -542,8 +618,15 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
     const ModelP& mp = c.mp;
     Ws& w = c.w;
     const Plan& pl = c.plan;
+    Sched sc = make_sched(st, aux);
+    cudaStream_t s2 = sc.s2;
 
     PAMNET_CUDA(cudaMemsetAsync(gp, 0, sizeof(float) * mp.total, st));
+    PAMNET_TRY(sc.order(st, s2));      // gradients zeroed (split-K GEMMs accumulate into them) before s2 starts
+    // accumulators of the per-edge / per-triplet embedding gradients, summed over layers with fp32 atomics
+    PAMNET_CUDA(cudaMemsetAsync(w.gz_eg, 0, sizeof(float) * Eg * D, s2));
+    PAMNET_CUDA(cudaMemsetAsync(w.gz_el, 0, sizeof(float) * El * D, s2));
+    PAMNET_CUDA(cudaMemsetAsync(w.gz_s, 0, sizeof(float) * T * D, s2));
 
     ReadoutArgs r;
     memset(&r, 0, sizeof(r));
@@ -553,7 +636,131 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
     PAMNET_TRY(readout_backward(r, st));
 
     const int ks_n = pick_ksplit(N);
-    // ---- phase B reversed -----------------------------------------------------------------------------
+    // weight gradients of the node-chain linears whose grad_z a finished chain kernel has written:
+    // the post-chain of half `hh` (hh >= 0) and mlp_x1 of half `x1_half` (x1_half >= 0)
+    auto chain_wgrads = [&](int hh, int x1_half, cudaStream_t s) -> int {
+        std::vector<GemmSlot> sl, heads;
+        auto lin = [&](const float* gz, const float* a_in, const Lin& p) {
+            sl.push_back(slot(gz, D, a_in, D, gp + p.w, D, nullptr, gp + p.b));
+        };
+        if (x1_half >= 0) {
+            const float* x_in = x1_half == 0 ? w.x0 : w.half[x1_half - 1].r[2];
+            lin(w.half[x1_half].gz_x1, x_in, half_params(mp, x1_half).x1);
+        }
+        if (hh >= 0) {
+            const HalfWs& hw = w.half[hh];
+            const HalfP& hp = half_params(mp, hh);
+            lin(hw.gz_x2, hw.h, hp.x2);
+            for (int rr = 0; rr < 3; ++rr) {
+                lin(hw.gz_A[rr], rr == 0 ? hw.a_x2 : hw.r[rr - 1], hp.res[rr][0]);
+                lin(hw.gz_B[rr], hw.a_A[rr], hp.res[rr][1]);
+            }
+            lin(hw.gz_o[0], hw.r[2], hp.out[0]);
+            lin(hw.gz_o[1], hw.a_o[0], hp.out[1]);
+            lin(hw.gz_o[2], hw.a_o[1], hp.out[2]);
+            // heads: dW = o3^T g_att, dW_out = o3^T g_out (+ bias)
+            heads.push_back(slot(w.g_att + (size_t)hh * N, 1, hw.a_o[2], D, gp + hp.W, D));
+            heads.push_back(slot(w.g_out + (size_t)hh * N, 1, hw.a_o[2], D, gp + hp.W_out.w, D, nullptr, gp + hp.W_out.b));
+        }
+        GemmArgs a = gemm_zero(GEMM_TN, EPI_NONE, D, D, (int)N);
+        a.ksplit = ks_n;
+        PAMNET_TRY(gemm_multi(a, sl, s));
+        if (!heads.empty()) {
+            a.M = 1;
+            PAMNET_TRY(gemm_multi(a, heads, s));
+        }
+        return 0;
+    };
+    // per-node halves of the edge MLPs of half hh: dW[:, cD:(c+1)D] = g_P_c^T x1
+    auto proj_wgrads = [&](int hh, cudaStream_t s) -> int {
+        const HalfWs& hw = w.half[hh];
+        const HalfP& hp = half_params(mp, hh);
+        const int nP = nP_of(hh);
+        std::vector<GemmSlot> sl;
+        for (int cblk = 0; cblk < nP; ++cblk) {
+            int64_t woff;
+            if (!is_local(hh)) woff = hp.m.w + cblk * D;
+            else woff = (cblk < 2 ? hp.m_ji.w : hp.m_kj.w) + (cblk & 1) * D;
+            sl.push_back(slot(hw.g_P + cblk * D, nP * D, hw.x1, D, gp + woff, 3 * D));
+        }
+        GemmArgs a = gemm_zero(GEMM_TN, EPI_NONE, D, D, (int)N);
+        a.ksplit = ks_n;
+        return gemm_multi(a, sl, s);
+    };
+    // phase A' of layers [l0, l1): per-edge / per-triplet gradients -> weight gradients (batched over the layers of
+    // the group), and their contribution to the gradient of the layer-invariant embeddings, accumulated over
+    // groups in gz_eg / gz_el / gz_s with fp32 atomics (split-K)
+    auto edge_wgrads = [&](int l0, int l1, cudaStream_t s) -> int {
+        const int nl = l1 - l0;
+        {   // global edges
+            const int ldq = L * 2 * D;
+            std::vector<GemmSlot> sl;
+            GemmArgs b = gemm_zero(GEMM_NN, EPI_NONE, (int)Eg, D, nl * 2 * D);
+            b.nslots = 1; b.nseg = 2 * nl; b.seg_len = D; b.ksplit = 2 * nl;
+            for (int l = l0; l < l1; ++l) {
+                const HalfP& hp = mp.g[l];
+                const float* g = w.gQT + l * 2 * D;
+                sl.push_back(slot(g, ldq, w.e_g, D, gp + hp.m.w + 2 * D, 3 * D, nullptr, gp + hp.m.b));
+                sl.push_back(slot(g + D, ldq, w.e_g, D, gp + hp.We.w, D));
+                b.seg_B[2 * (l - l0)] = params + hp.m.w + 2 * D; b.seg_ldb[2 * (l - l0)] = 3 * D;
+                b.seg_B[2 * (l - l0) + 1] = params + hp.We.w; b.seg_ldb[2 * (l - l0) + 1] = D;
+            }
+            GemmArgs a = gemm_zero(GEMM_TN, EPI_NONE, D, D, (int)Eg);
+            a.ksplit = pick_ksplit(Eg);
+            PAMNET_TRY(gemm_multi(a, sl, s));
+            b.slot[0] = slot(w.gQT + l0 * 2 * D, ldq, nullptr, 0, w.gz_eg, D);   // gz_eg += [gQ | gTt] [W_m,e ; W_e]
+            PAMNET_TRY(gemm_launch(b, s));
+        }
+        {   // local edges
+            const int ldq = L * 4 * D;
+            std::vector<GemmSlot> sl;
+            GemmArgs b = gemm_zero(GEMM_NN, EPI_NONE, (int)El, D, nl * 4 * D);
+            b.nslots = 1; b.nseg = 4 * nl; b.seg_len = D; b.ksplit = 4 * nl;
+            for (int l = l0; l < l1; ++l) {
+                const HalfP& hp = mp.l[l];
+                const float* g = w.gQR + l * 4 * D;
+                sl.push_back(slot(g, ldq, w.e_l, D, gp + hp.m_ji.w + 2 * D, 3 * D, nullptr, gp + hp.m_ji.b));
+                sl.push_back(slot(g + D, ldq, w.e_l, D, gp + hp.m_kj.w + 2 * D, 3 * D, nullptr, gp + hp.m_kj.b));
+                sl.push_back(slot(g + 2 * D, ldq, w.e_l, D, gp + hp.lin_rbf.w, D));
+                sl.push_back(slot(g + 3 * D, ldq, w.e_l, D, gp + hp.lin_rbf_out.w, D));
+                const int o = 4 * (l - l0);
+                b.seg_B[o] = params + hp.m_ji.w + 2 * D; b.seg_ldb[o] = 3 * D;
+                b.seg_B[o + 1] = params + hp.m_kj.w + 2 * D; b.seg_ldb[o + 1] = 3 * D;
+                b.seg_B[o + 2] = params + hp.lin_rbf.w; b.seg_ldb[o + 2] = D;
+                b.seg_B[o + 3] = params + hp.lin_rbf_out.w; b.seg_ldb[o + 3] = D;
+            }
+            GemmArgs a = gemm_zero(GEMM_TN, EPI_NONE, D, D, (int)El);
+            a.ksplit = pick_ksplit(El);
+            PAMNET_TRY(gemm_multi(a, sl, s));
+            b.slot[0] = slot(w.gQR + l0 * 4 * D, ldq, nullptr, 0, w.gz_el, D);
+            PAMNET_TRY(gemm_launch(b, s));
+        }
+        {   // triplet gate MLP (local_message_passing.py:17,49)
+            const int ldt = L * D;
+            std::vector<GemmSlot> w2, dg, w1;
+            GemmArgs bs = gemm_zero(GEMM_NN, EPI_NONE, (int)T, D, nl * D);       // gz_s += gzq1 W_sbf0
+            bs.nslots = 1; bs.nseg = nl; bs.seg_len = D; bs.ksplit = nl > 1 ? nl : 2;
+            for (int l = l0; l < l1; ++l) {
+                const HalfP& hp = mp.l[l];
+                w2.push_back(slot(w.gzq2 + l * D, ldt, w.aq1 + l * D, ldt, gp + hp.sbf[1].w, D, nullptr, gp + hp.sbf[1].b));
+                dg.push_back(slot(w.gzq2 + l * D, ldt, params + hp.sbf[1].w, D, w.gzq1 + l * D, ldt, nullptr, nullptr,
+                                  w.zq1 + l * D, ldt));
+                w1.push_back(slot(w.gzq1 + l * D, ldt, w.s, D, gp + hp.sbf[0].w, D, nullptr, gp + hp.sbf[0].b));
+                bs.seg_B[l - l0] = params + hp.sbf[0].w; bs.seg_ldb[l - l0] = D;
+            }
+            GemmArgs t = gemm_zero(GEMM_TN, EPI_NONE, D, D, (int)T);
+            t.ksplit = pick_ksplit(T);
+            PAMNET_TRY(gemm_multi(t, w2, s));
+            PAMNET_TRY(gemm_multi(gemm_zero(GEMM_NN, EPI_MUL_DSILU, (int)T, D, D), dg, s));
+            PAMNET_TRY(gemm_multi(t, w1, s));
+            bs.slot[0] = slot(w.gzq1 + l0 * D, ldt, nullptr, 0, w.gz_s, D);
+            PAMNET_TRY(gemm_launch(bs, s));
+        }
+        return 0;
+    };
+    std::vector<int> grp = layer_groups(L);
+
+    // ---- main stream: phase B reversed; auxiliary stream: weight gradients as soon as their inputs exist --------
     for (int hh = H - 1; hh >= 0; --hh) {
         const HalfWs& hw = w.half[hh];
         const HalfP& hp = half_params(mp, hh);
@@ -564,11 +771,12 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
             if (has_gx) add_pre_bwd(p, params, half_params(mp, hh + 1), w.half[hh + 1], hh + 1, D, w, nullptr);
             add_post_bwd(p, params, hp, hw, D, w, w.g_att + (size_t)hh * N, w.g_out + (size_t)hh * N, has_gx);
             PAMNET_TRY(chain_launch(D, p.a, st));
+            PAMNET_TRY(sc.order(st, s2));
+            PAMNET_TRY(chain_wgrads(hh, has_gx ? hh + 1 : -1, s2));
         }
-        const int nP = nP_of(hh);
         NodeGatherArgs ng;
         memset(&ng, 0, sizeof(ng));
-        ng.n_nodes = (int)N; ng.g_P = w.g_P;
+        ng.n_nodes = (int)N; ng.g_P = hw.g_P;
         if (!is_local(hh)) {
             GlobalMsgArgs a;
             memset(&a, 0, sizeof(a));
@@ -591,24 +799,15 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
             ng.gz = w.gQR + l * 4 * D; ng.ldq = L * 4 * D;
         }
         PAMNET_TRY(node_grad_gather(D, ng, is_local(hh) ? (int)El : (int)Eg, st));
-        // weight gradients of the per-node halves of the edge MLPs: dW[:, cD:(c+1)D] = g_P_c^T x1
-        {
-            std::vector<GemmSlot> sl;
-            for (int cblk = 0; cblk < nP; ++cblk) {
-                int64_t woff;
-                if (!is_local(hh)) woff = hp.m.w + cblk * D;
-                else woff = (cblk < 2 ? hp.m_ji.w : hp.m_kj.w) + (cblk & 1) * D;
-                sl.push_back(slot(w.g_P + cblk * D, nP * D, hw.x1, D, gp + woff, 3 * D));
-            }
-            GemmArgs a = gemm_zero(GEMM_TN, EPI_NONE, D, D, (int)N);
-            a.ksplit = ks_n;
-            PAMNET_TRY(gemm_multi(a, sl, st));
-        }
+        PAMNET_TRY(sc.order(st, s2));
+        PAMNET_TRY(proj_wgrads(hh, s2));
+        if (!is_local(hh))                      // a layer is complete once its global half is done
+            for (size_t gi = 0; gi + 1 < grp.size(); ++gi)
+                if (grp[gi] == l) PAMNET_TRY(edge_wgrads(grp[gi], grp[gi + 1], s2));
     }
     {   // into the node input
         Prog p((int)N);
         add_pre_bwd(p, params, half_params(mp, 0), w.half[0], 0, D, w, w.g_x0);
-        // half 0 has no res_x contribution from a previous layer: g_resx currently holds half 0's own skip grad
         PAMNET_TRY(chain_launch(D, p.a, st));
     }
     if (cfg.dataset == PAMNET_PDBBIND) {
@@ -619,131 +818,45 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
     } else {
         PAMNET_TRY(embed_backward(node_in, N, w.g_x0, mp.n_embed, D, gp + mp.emb, st));
     }
+    PAMNET_TRY(sc.order(st, s2));
+    PAMNET_TRY(chain_wgrads(-1, 0, s2));
 
-    // ---- weight gradients of the node chains (all halves batched) ------------------------------------
+    // ---- auxiliary stream: through the SiLU of the embeddings into their weights and the RBF frequencies -------
+    PAMNET_TRY(mul_dsilu_launch(w.gz_eg, w.z_eg, Eg * D, s2));
+    PAMNET_TRY(mul_dsilu_launch(w.gz_el, w.z_el, El * D, s2));
+    PAMNET_TRY(mul_dsilu_launch(w.gz_s, w.z_s, T * D, s2));
     {
-        std::vector<GemmSlot> sl, heads;
-        for (int hh = 0; hh < H; ++hh) {
-            const HalfWs& hw = w.half[hh];
-            const HalfP& hp = half_params(mp, hh);
-            const float* x_in = hh == 0 ? w.x0 : w.half[hh - 1].r[2];
-            auto lin = [&](const float* gz, const float* a_in, const Lin& p) {
-                sl.push_back(slot(gz, D, a_in, D, gp + p.w, D, nullptr, gp + p.b));
-            };
-            lin(hw.gz_x1, x_in, hp.x1);
-            lin(hw.gz_x2, hw.h, hp.x2);
-            for (int rr = 0; rr < 3; ++rr) {
-                lin(hw.gz_A[rr], rr == 0 ? hw.a_x2 : hw.r[rr - 1], hp.res[rr][0]);
-                lin(hw.gz_B[rr], hw.a_A[rr], hp.res[rr][1]);
-            }
-            lin(hw.gz_o[0], hw.r[2], hp.out[0]);
-            lin(hw.gz_o[1], hw.a_o[0], hp.out[1]);
-            lin(hw.gz_o[2], hw.a_o[1], hp.out[2]);
-            // heads: dW = o3^T g_att, dW_out = o3^T g_out (+ bias)
-            heads.push_back(slot(w.g_att + (size_t)hh * N, 1, hw.a_o[2], D, gp + hp.W, D));
-            heads.push_back(slot(w.g_out + (size_t)hh * N, 1, hw.a_o[2], D, gp + hp.W_out.w, D, nullptr, gp + hp.W_out.b));
-        }
-        GemmArgs a = gemm_zero(GEMM_TN, EPI_NONE, D, D, (int)N);
-        a.ksplit = ks_n;
-        PAMNET_TRY(gemm_multi(a, sl, st));
-        a.M = 1;
-        PAMNET_TRY(gemm_multi(a, heads, st));
-    }
-
-    // ---- phase A': per-edge / per-triplet gradients -> weights -----------------------------------------
-    {   // global edges
-        const int ldq = L * 2 * D;
-        std::vector<GemmSlot> sl;
-        for (int l = 0; l < L; ++l) {
-            const HalfP& hp = mp.g[l];
-            sl.push_back(slot(w.gQT + l * 2 * D, ldq, w.e_g, D, gp + hp.m.w + 2 * D, 3 * D, nullptr, gp + hp.m.b));
-            sl.push_back(slot(w.gQT + l * 2 * D + D, ldq, w.e_g, D, gp + hp.We.w, D));
-        }
-        GemmArgs a = gemm_zero(GEMM_TN, EPI_NONE, D, D, (int)Eg);
-        a.ksplit = pick_ksplit(Eg);
-        PAMNET_TRY(gemm_multi(a, sl, st));
-        // grad e_g = sum_l [gQ_l | gTt_l] . [W_m,e ; W_e]_l, then through SiLU of the embedding
-        GemmArgs b = gemm_zero(GEMM_NN, EPI_MUL_DSILU, (int)Eg, D, L * 2 * D);
-        b.nslots = 1; b.nseg = 2 * L; b.seg_len = D;
-        for (int l = 0; l < L; ++l) {
-            b.seg_B[2 * l] = params + mp.g[l].m.w + 2 * D; b.seg_ldb[2 * l] = 3 * D;
-            b.seg_B[2 * l + 1] = params + mp.g[l].We.w; b.seg_ldb[2 * l + 1] = D;
-        }
-        b.slot[0] = slot(w.gQT, ldq, nullptr, 0, w.gz_eg, D, nullptr, nullptr, w.z_eg, D);
-        PAMNET_TRY(gemm_launch(b, st));
         GemmArgs cw = gemm_zero(GEMM_TN, EPI_NONE, D, kNumRbf, (int)Eg);
         cw.nslots = 1; cw.ksplit = pick_ksplit(Eg);
         cw.slot[0] = slot(w.gz_eg, D, w.rbf_g, kNumRbf, gp + mp.rbf_g.w, kNumRbf, nullptr, gp + mp.rbf_g.b);
-        PAMNET_TRY(gemm_launch(cw, st));
+        PAMNET_TRY(gemm_launch(cw, s2));
         GemmArgs d = gemm_zero(GEMM_NN, EPI_NONE, (int)Eg, kNumRbf, D);
         d.nslots = 1;
         d.slot[0] = slot(w.gz_eg, D, params + mp.rbf_g.w, kNumRbf, w.g_rbf_g, kNumRbf);
-        PAMNET_TRY(gemm_launch(d, st));
-        PAMNET_TRY(rbf_freq_backward(pl.dist_g, Eg, params + mp.freq_g, cfg.cutoff_g, w.g_rbf_g, gp + mp.freq_g, st));
+        PAMNET_TRY(gemm_launch(d, s2));
+        PAMNET_TRY(rbf_freq_backward(pl.dist_g, Eg, params + mp.freq_g, cfg.cutoff_g, w.g_rbf_g, gp + mp.freq_g, s2));
     }
-    {   // local edges
-        const int ldq = L * 4 * D;
-        std::vector<GemmSlot> sl;
-        for (int l = 0; l < L; ++l) {
-            const HalfP& hp = mp.l[l];
-            const float* base = w.gQR + l * 4 * D;
-            sl.push_back(slot(base, ldq, w.e_l, D, gp + hp.m_ji.w + 2 * D, 3 * D, nullptr, gp + hp.m_ji.b));
-            sl.push_back(slot(base + D, ldq, w.e_l, D, gp + hp.m_kj.w + 2 * D, 3 * D, nullptr, gp + hp.m_kj.b));
-            sl.push_back(slot(base + 2 * D, ldq, w.e_l, D, gp + hp.lin_rbf.w, D));
-            sl.push_back(slot(base + 3 * D, ldq, w.e_l, D, gp + hp.lin_rbf_out.w, D));
-        }
-        GemmArgs a = gemm_zero(GEMM_TN, EPI_NONE, D, D, (int)El);
-        a.ksplit = pick_ksplit(El);
-        PAMNET_TRY(gemm_multi(a, sl, st));
-        GemmArgs b = gemm_zero(GEMM_NN, EPI_MUL_DSILU, (int)El, D, L * 4 * D);
-        b.nslots = 1; b.nseg = 4 * L; b.seg_len = D;
-        for (int l = 0; l < L; ++l) {
-            const HalfP& hp = mp.l[l];
-            b.seg_B[4 * l] = params + hp.m_ji.w + 2 * D; b.seg_ldb[4 * l] = 3 * D;
-            b.seg_B[4 * l + 1] = params + hp.m_kj.w + 2 * D; b.seg_ldb[4 * l + 1] = 3 * D;
-            b.seg_B[4 * l + 2] = params + hp.lin_rbf.w; b.seg_ldb[4 * l + 2] = D;
-            b.seg_B[4 * l + 3] = params + hp.lin_rbf_out.w; b.seg_ldb[4 * l + 3] = D;
-        }
-        b.slot[0] = slot(w.gQR, ldq, nullptr, 0, w.gz_el, D, nullptr, nullptr, w.z_el, D);
-        PAMNET_TRY(gemm_launch(b, st));
+    {
         GemmArgs cw = gemm_zero(GEMM_TN, EPI_NONE, D, kNumRbf, (int)El);
         cw.nslots = 1; cw.ksplit = pick_ksplit(El);
         cw.slot[0] = slot(w.gz_el, D, w.rbf_l, kNumRbf, gp + mp.rbf_l.w, kNumRbf, nullptr, gp + mp.rbf_l.b);
-        PAMNET_TRY(gemm_launch(cw, st));
+        PAMNET_TRY(gemm_launch(cw, s2));
         GemmArgs d = gemm_zero(GEMM_NN, EPI_NONE, (int)El, kNumRbf, D);
         d.nslots = 1;
         d.slot[0] = slot(w.gz_el, D, params + mp.rbf_l.w, kNumRbf, w.g_rbf_l, kNumRbf);
-        PAMNET_TRY(gemm_launch(d, st));
-        PAMNET_TRY(rbf_freq_backward(pl.dist_l, El, params + mp.freq_l, cfg.cutoff_l, w.g_rbf_l, gp + mp.freq_l, st));
+        PAMNET_TRY(gemm_launch(d, s2));
+        PAMNET_TRY(rbf_freq_backward(pl.dist_l, El, params + mp.freq_l, cfg.cutoff_l, w.g_rbf_l, gp + mp.freq_l, s2));
     }
-    {   // triplet gate MLP (local_message_passing.py:17,49) and the SBF embeddings (models.py:187-188)
-        const int ldt = L * D;
-        std::vector<GemmSlot> w2, dg, w1;
-        for (int l = 0; l < L; ++l) {
-            const HalfP& hp = mp.l[l];
-            w2.push_back(slot(w.gzq2 + l * D, ldt, w.aq1 + l * D, ldt, gp + hp.sbf[1].w, D, nullptr, gp + hp.sbf[1].b));
-            dg.push_back(slot(w.gzq2 + l * D, ldt, params + hp.sbf[1].w, D, w.gzq1 + l * D, ldt, nullptr, nullptr,
-                              w.zq1 + l * D, ldt));
-            w1.push_back(slot(w.gzq1 + l * D, ldt, w.s, D, gp + hp.sbf[0].w, D, nullptr, gp + hp.sbf[0].b));
-        }
-        GemmArgs a = gemm_zero(GEMM_TN, EPI_NONE, D, D, (int)T);
-        a.ksplit = pick_ksplit(T);
-        PAMNET_TRY(gemm_multi(a, w2, st));
-        PAMNET_TRY(gemm_multi(gemm_zero(GEMM_NN, EPI_MUL_DSILU, (int)T, D, D), dg, st));
-        PAMNET_TRY(gemm_multi(a, w1, st));
-        GemmArgs b = gemm_zero(GEMM_NN, EPI_MUL_DSILU, (int)T, D, L * D);
-        b.nslots = 1; b.nseg = L; b.seg_len = D;
-        for (int l = 0; l < L; ++l) { b.seg_B[l] = params + mp.l[l].sbf[0].w; b.seg_ldb[l] = D; }
-        b.slot[0] = slot(w.gzq1, ldt, nullptr, 0, w.gz_s, D, nullptr, nullptr, w.z_s, D);
-        PAMNET_TRY(gemm_launch(b, st));
-        PAMNET_CUDA(cudaMemsetAsync(w.gw_ext, 0, sizeof(float) * D * kSbfExt, st));
+    {   // SBF embeddings (models.py:187-188)
+        PAMNET_CUDA(cudaMemsetAsync(w.gw_ext, 0, sizeof(float) * D * kSbfExt, s2));
         GemmArgs cw = gemm_zero(GEMM_TN, EPI_NONE, D, kSbfExt, (int)T);
         cw.nslots = 1; cw.ksplit = pick_ksplit(T);
         cw.slot[0] = slot(w.gz_s, D, w.sbf_ext, kSbfExt, w.gw_ext, kSbfExt);
-        PAMNET_TRY(gemm_launch(cw, st));
+        PAMNET_TRY(gemm_launch(cw, s2));
         PAMNET_TRY(sbf_weight_unpack_grad(D, w.gw_ext, cfg.simple ? nullptr : gp + mp.sbf2.w,
-                                          cfg.simple ? nullptr : gp + mp.sbf2.b, gp + mp.sbf1.w, gp + mp.sbf1.b, st));
+                                          cfg.simple ? nullptr : gp + mp.sbf2.b, gp + mp.sbf1.w, gp + mp.sbf1.b, s2));
     }
+    PAMNET_TRY(sc.order(s2, st));
     return 0;
 }
 

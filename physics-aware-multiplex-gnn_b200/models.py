@@ -60,8 +60,8 @@ class _PAMNetFunction(torch.autograd.Function):
         _lib.check(lib.pamnet_model_forward(cfg, sz, sbf_consts_struct(), flat.data_ptr(), node_in.data_ptr(),
                                             _lib.ptr(sign), pos.data_ptr(), plan.base.data_ptr(),
                                             plan.trip.data_ptr(), ws.data_ptr(), ws_bytes, int(need_grad),
-                                            out.data_ptr(), torch.cuda.current_stream().cuda_stream),
-                   "model_forward")
+                                            out.data_ptr(), torch.cuda.current_stream().cuda_stream,
+                                            mod._aux_stream_ptr(dev)), "model_forward")
         if need_grad:
             ctx.mod, ctx.plan, ctx.ws, ctx.ws_bytes = mod, plan, ws, ws_bytes
             ctx.node_in, ctx.sign, ctx.pos = node_in, sign, pos
@@ -77,7 +77,8 @@ class _PAMNetFunction(torch.autograd.Function):
                                              ctx.node_in.data_ptr(), _lib.ptr(ctx.sign), ctx.pos.data_ptr(),
                                              plan.base.data_ptr(), plan.trip.data_ptr(), ctx.ws.data_ptr(),
                                              ctx.ws_bytes, grad_out.data_ptr(), target.data_ptr(),
-                                             torch.cuda.current_stream().cuda_stream), "model_backward")
+                                             torch.cuda.current_stream().cuda_stream,
+                                             mod._aux_stream_ptr(grad_out.device)), "model_backward")
         ctx.ws = None
         mod._deliver_grads(target, direct)
         return (None, None, None, None, None, None)
@@ -113,6 +114,16 @@ class _PAMNetBase(nn.Module):
         self._gviews = None
         self._alias_tick = 0
         self._flatten()
+
+    def _aux_stream_ptr(self, dev):
+        """Second CUDA stream for the x-independent GEMMs (PAMNET_STREAMS=1 disables the overlap)."""
+        import os
+        if os.environ.get("PAMNET_STREAMS", "2") == "1":
+            return None
+        aux = getattr(self, "_aux_stream", None)
+        if aux is None or aux.device != dev:
+            aux = self._aux_stream = torch.cuda.Stream(device=dev)
+        return aux.cuda_stream
 
     # ---- gradients ------------------------------------------------------------------------------------
     def _grad_views(self):
