@@ -180,6 +180,8 @@ int64_t pamnet_debug_launch_count(void);
  * csrc/common.cuh); returns the class count.  Not thread-safe; off by default. */
 void pamnet_debug_profile_begin(void);
 int pamnet_debug_profile_end(double* ms, int64_t* launches, double* bytes);
+/* Same records as a timeline (call instead of profile_end): class, stream tag, start/end ms; returns the count. */
+int pamnet_debug_profile_timeline(int32_t* cls, int32_t* stream_tag, float* t0_ms, float* t1_ms, int32_t cap);
 
 #ifdef __cplusplus
 }

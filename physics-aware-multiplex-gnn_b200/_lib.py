@@ -63,6 +63,7 @@ SIGNATURES = {
     "pamnet_debug_launch_count": (c_i64, []),
     "pamnet_debug_profile_begin": (None, []),
     "pamnet_debug_profile_end": (c_i32, [c_vp, c_vp, c_vp]),
+    "pamnet_debug_profile_timeline": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32]),
 }
 
 _lib = None
@@ -110,6 +111,14 @@ def profile_end():
     got = load().pamnet_debug_profile_end(ms, cnt, byt)
     assert got == n, "kernel class table out of sync with csrc/common.cuh"
     return {k: (ms[i], int(cnt[i]), byt[i]) for i, k in enumerate(KERNEL_CLASSES)}
+
+
+def profile_timeline(cap=4096):
+    """-> list of (class name, stream tag, t0 ms, t1 ms) since profile_begin()."""
+    cls, tag = (c_i32 * cap)(), (c_i32 * cap)()
+    t0, t1 = (c_f32 * cap)(), (c_f32 * cap)()
+    n = load().pamnet_debug_profile_timeline(cls, tag, t0, t1, cap)
+    return [(KERNEL_CLASSES[cls[i]], int(tag[i]), float(t0[i]), float(t1[i])) for i in range(max(n, 0))]
 
 
 def check(rc, what=""):

@@ -25,7 +25,7 @@ const char* get_error() { return g_err; }
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-struct ProfRec { int cls; double bytes; cudaEvent_t e0, e1; };
+struct ProfRec { int cls; double bytes; cudaEvent_t e0, e1; cudaStream_t st; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof_recs;
 static std::vector<cudaEvent_t> g_prof_pool;
@@ -40,7 +40,7 @@ static cudaEvent_t prof_event() {
 }
 void prof_begin(int cls, double bytes, cudaStream_t st) {
     if (!g_prof_on) return;
-    ProfRec r{cls, bytes, prof_event(), prof_event()};
+    ProfRec r{cls, bytes, prof_event(), prof_event(), st};
     cudaEventRecord(r.e0, st);
     g_prof_recs.push_back(r);
 }
@@ -214,6 +214,30 @@ int pamnet_debug_profile_end(double* ms, int64_t* launches, double* bytes) {
     g_prof_recs.clear();
     g_prof_used = 0;
     return KC_COUNT;
+}
+
+// Timeline of the records since profile_begin (call INSTEAD of profile_end): per launch the kernel class, a stream
+// tag (0 = first stream seen, 1 = second, ...) and start / end in ms relative to the first record.  Returns the
+// number of records written (<= cap).
+int pamnet_debug_profile_timeline(int32_t* cls, int32_t* stream_tag, float* t0_ms, float* t1_ms, int32_t cap) {
+    g_prof_on = false;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    std::vector<cudaStream_t> streams;
+    int n = 0;
+    for (auto& r : g_prof_recs) {
+        if (n >= cap) break;
+        float a = 0.f, b = 0.f;
+        if (cudaEventElapsedTime(&a, g_prof_recs[0].e0, r.e0) != cudaSuccess) continue;
+        if (cudaEventElapsedTime(&b, g_prof_recs[0].e0, r.e1) != cudaSuccess) continue;
+        int tag = -1;
+        for (size_t i = 0; i < streams.size(); ++i) if (streams[i] == r.st) tag = (int)i;
+        if (tag < 0) { streams.push_back(r.st); tag = (int)streams.size() - 1; }
+        cls[n] = r.cls; stream_tag[n] = tag; t0_ms[n] = a; t1_ms[n] = b;
+        ++n;
+    }
+    g_prof_recs.clear();
+    g_prof_used = 0;
+    return n;
 }
 
 int pamnet_loss(const float* out, const float* y, int64_t n, int32_t kind, float* loss_dev, float* grad_out,

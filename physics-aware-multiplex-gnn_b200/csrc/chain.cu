@@ -169,10 +169,14 @@ __global__ void __launch_bounds__(kChainKS * D / 2) chain_kernel(const ChainArgs
             for (int i = 0; i < R; ++i) acc0[i] = acc1[i] = 0.f;
             const float* wp = wbuf + wcur * D * D + (ks * KL) * D + c;
             const float* ap = in + (ks * KL) * R;
-#pragma unroll 8
+            // explicit software pipeline: operands of step kk+1 are requested before the 16 FMAs of step kk issue
+            float w0 = wp[0], w1 = wp[H];
+            float4 a0 = ld4(ap), a1 = ld4(ap + 4);
+#pragma unroll
             for (int kk = 0; kk < KL; ++kk) {
-                const float w0 = wp[kk * D], w1 = wp[kk * D + H];
-                const float4 a0 = ld4(ap + kk * R), a1 = ld4(ap + kk * R + 4);
+                const int kn = (kk + 1 < KL) ? kk + 1 : kk;
+                const float w0n = wp[kn * D], w1n = wp[kn * D + H];
+                const float4 a0n = ld4(ap + kn * R), a1n = ld4(ap + kn * R + 4);
                 acc0[0] = fmaf(a0.x, w0, acc0[0]); acc0[1] = fmaf(a0.y, w0, acc0[1]);
                 acc0[2] = fmaf(a0.z, w0, acc0[2]); acc0[3] = fmaf(a0.w, w0, acc0[3]);
                 acc0[4] = fmaf(a1.x, w0, acc0[4]); acc0[5] = fmaf(a1.y, w0, acc0[5]);
@@ -181,6 +185,7 @@ __global__ void __launch_bounds__(kChainKS * D / 2) chain_kernel(const ChainArgs
                 acc1[2] = fmaf(a0.z, w1, acc1[2]); acc1[3] = fmaf(a0.w, w1, acc1[3]);
                 acc1[4] = fmaf(a1.x, w1, acc1[4]); acc1[5] = fmaf(a1.y, w1, acc1[5]);
                 acc1[6] = fmaf(a1.z, w1, acc1[6]); acc1[7] = fmaf(a1.w, w1, acc1[7]);
+                w0 = w0n; w1 = w1n; a0 = a0n; a1 = a1n;
             }
 #pragma unroll
             for (int i = 0; i < R; ++i) {

@@ -526,6 +526,8 @@ void plan_layout(const pamnet_sizes_t& sz, void* base, void* trip, Plan* out, si
     p.t_split = take_i(El); p.t_cnt = take_i(El); p.t_ptr = take_i(El + 1); p.tt_ptr = take_i(El + 1);
     p.dist_g = take_f(Eg); p.dist_l = take_f(El);
     p.tmp_a = take_i(Emax); p.tmp_b = take_i(Emax); p.tmp_c = take_i(Emax);
+    p.tmp_d = take_i(Emax); p.tmp_e = take_i(Emax); p.tmp_f = take_i(Emax);
+    p.cnt4 = take_i(4 * (N + 1)); p.tmp4 = take_i(2 * Eg + 2 * El);
     p.cnt = take_i((N > El ? N : El) + 2);
     if (base_bytes) *base_bytes = off;
     off = 0;
@@ -613,11 +615,158 @@ __global__ void plan_tfill_kernel(const int32_t* __restrict__ l_ptr, const int32
     }
 }
 
-__global__ void csr_dist_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ src, int64_t n_nodes,
-                                const float* __restrict__ pos, float* __restrict__ dist) {
+__global__ void csr_dist_kernel(const int32_t* __restrict__ ptr_g, const int32_t* __restrict__ src_g,
+                                const int32_t* __restrict__ ptr_l, const int32_t* __restrict__ src_l, int64_t n_nodes,
+                                const float* __restrict__ pos, float* __restrict__ dist_g, float* __restrict__ dist_l) {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= n_nodes) return;
+    const int32_t* ptr = blockIdx.y ? ptr_l : ptr_g;
+    const int32_t* src = blockIdx.y ? src_l : src_g;
+    float* dist = blockIdx.y ? dist_l : dist_g;
     for (int p = ptr[n]; p < ptr[n + 1]; ++p) dist[p] = edge_len(pos, n, src[p]);
+}
+
+// ---- four CSRs (global in / out, local in / out) built by the SAME six launches -------------------------------
+// job j: bucket key per API edge, bucket order key (key2, item): in-CSR = (source id, edge id) which is
+// SparseTensor's order (models.py:72); out-CSR = edge id.
+struct CsrJobs {
+    const int32_t* keys[4];
+    const int32_t* key2[4];
+    int64_t n[4];
+    int32_t *cnt[4], *ptr[4], *tmp[4], *items[4];
+    int64_t n_buckets;
+};
+
+__global__ void split_edges2_kernel(const int64_t* __restrict__ eg, int64_t n_g, int g_dst_row,
+                                    const int64_t* __restrict__ el, int64_t n_l, int32_t* __restrict__ g_dst,
+                                    int32_t* __restrict__ g_src, int32_t* __restrict__ l_dst, int32_t* __restrict__ l_src,
+                                    const int64_t* __restrict__ batch, int64_t n_nodes, int64_t n_graphs,
+                                    int32_t* __restrict__ n2g, int32_t* __restrict__ gptr) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_g) {
+        g_dst[i] = (int32_t)eg[(int64_t)g_dst_row * n_g + i];
+        g_src[i] = (int32_t)eg[(int64_t)(1 - g_dst_row) * n_g + i];
+    }
+    if (i < n_l) {            // local graph: i = edge_index[1] always (local_message_passing.py:37)
+        l_dst[i] = (int32_t)el[n_l + i];
+        l_src[i] = (int32_t)el[i];
+    }
+    if (i < n_nodes) n2g[i] = (int32_t)batch[i];
+    if (i <= n_graphs) gptr[i] = (int32_t)lower_bound_i64(batch, n_nodes, i);
+}
+
+__global__ void hist4_kernel(const CsrJobs j) {
+    const int q = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < j.n[q]) atomicAdd(&j.cnt[q][j.keys[q][i]], 1);
+}
+
+// block q scans job q (same algorithm as scan_exclusive_kernel)
+__global__ void __launch_bounds__(kScanThreads) scan4_kernel(const CsrJobs j) {
+    __shared__ int32_t warp_tot[32];
+    __shared__ int32_t carry_s;
+    const int q = blockIdx.x;
+    const int32_t* in = j.cnt[q];
+    int32_t* out = j.ptr[q];
+    const int64_t n = j.n_buckets;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n; base += (int64_t)kScanThreads * kScanItems) {
+        int32_t v[kScanItems];
+        int32_t local = 0;
+        const int64_t i0 = base + (int64_t)tid * kScanItems;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            v[k] = (i0 + k < n) ? in[i0 + k] : 0;
+            local += v[k];
+        }
+        int32_t incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_tot[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            int32_t w = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int32_t t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += t;
+            }
+            warp_tot[lane] = w;
+        }
+        __syncthreads();
+        const int32_t carry = carry_s;
+        int32_t excl = carry + incl - local + (wid > 0 ? warp_tot[wid - 1] : 0);
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            if (i0 + k < n) out[i0 + k] = excl;
+            excl += v[k];
+        }
+        __syncthreads();
+        if (tid == kScanThreads - 1) carry_s = carry + warp_tot[31];
+        __syncthreads();
+    }
+    if (tid == 0) out[n] = carry_s;
+}
+
+__global__ void fill4_kernel(const CsrJobs j) {
+    const int q = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= j.n[q]) return;
+    const int k = j.keys[q][i];
+    j.tmp[q][j.ptr[q][k] + atomicAdd(&j.cnt[q][k], 1)] = (int32_t)i;
+}
+
+__global__ void __launch_bounds__(128) sort4_kernel(const CsrJobs j) {
+    const int q = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= j.n_buckets) return;
+    const int32_t* ptr = j.ptr[q];
+    const int32_t* in = j.tmp[q];
+    const int32_t* key2 = j.key2[q];
+    const int s = ptr[b], e = ptr[b + 1];
+    for (int i = s + lane; i < e; i += 32) {
+        const int it = in[i];
+        const int k2 = key2 ? key2[it] : 0;
+        int rank = 0;
+        for (int u = s; u < e; ++u) {
+            const int jt = in[u];
+            const int j2 = key2 ? key2[jt] : 0;
+            rank += (j2 < k2) || (j2 == k2 && jt < it);
+        }
+        j.items[q][s + rank] = it;
+    }
+}
+
+// in-CSR: per-slot source / destination and the inverse permutation edge id -> slot
+__global__ void csr_finish1_kernel(const int32_t* __restrict__ g_eid, const int32_t* __restrict__ g_src_api,
+                                   const int32_t* __restrict__ g_dst_api, int64_t n_g, int32_t* __restrict__ g_src,
+                                   int32_t* __restrict__ g_dst, int32_t* __restrict__ g_pos_of,
+                                   const int32_t* __restrict__ l_eid, const int32_t* __restrict__ l_src_api,
+                                   const int32_t* __restrict__ l_dst_api, int64_t n_l, int32_t* __restrict__ l_src,
+                                   int32_t* __restrict__ l_dst, int32_t* __restrict__ l_pos_of) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n_g) {
+        const int e = g_eid[k];
+        g_src[k] = g_src_api[e]; g_dst[k] = g_dst_api[e]; g_pos_of[e] = (int32_t)k;
+    }
+    if (k < n_l) {
+        const int e = l_eid[k];
+        l_src[k] = l_src_api[e]; l_dst[k] = l_dst_api[e]; l_pos_of[e] = (int32_t)k;
+    }
+}
+
+// out-CSR entries (edge ids, ascending per source) -> slots; triplet counts per local slot
+__global__ void csr_finish2_kernel(int32_t* __restrict__ g_opos, const int32_t* __restrict__ g_pos_of, int64_t n_g,
+                                   int32_t* __restrict__ l_opos, const int32_t* __restrict__ l_pos_of, int64_t n_l) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < n_g) g_opos[u] = g_pos_of[g_opos[u]];
+    if (u < n_l) l_opos[u] = l_pos_of[l_opos[u]];
 }
 
 int plan_count(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const int64_t* edge_index_g,
@@ -626,22 +775,63 @@ int plan_count(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const int64
     Plan p;
     plan_layout(sz, plan_base, nullptr, &p, nullptr, nullptr);
     const int64_t N = sz.n_nodes, Eg = sz.n_edges_g, El = sz.n_edges_l;
+    const int64_t Emax = Eg > El ? Eg : El;
+    // global graph: x_i = x[edge_index[dst_row]] is also the aggregation target (PyG propagate)
+    const int g_dst_row = (cfg.flow == PAMNET_TARGET_TO_SOURCE) ? 0 : 1;
     {
-        const int64_t n = (N > sz.n_graphs + 1 ? N : sz.n_graphs + 1);
+        int64_t n = Emax > N ? Emax : N;
+        n = n > sz.n_graphs + 1 ? n : sz.n_graphs + 1;
         prof_begin(KC_GRAPH, 0.0, st);
-        n2g_kernel<<<ceil_div(n, 256), 256, 0, st>>>(batch, N, sz.n_graphs, p.n2g, p.gptr);
+        split_edges2_kernel<<<ceil_div(n, 256), 256, 0, st>>>(edge_index_g, Eg, g_dst_row, edge_index_l, El, p.tmp_a,
+                                                              p.tmp_b, p.tmp_d, p.tmp_e, batch, N, sz.n_graphs, p.n2g,
+                                                              p.gptr);
         prof_end(st);
         PAMNET_LAUNCH_CHECK();
     }
-    // global graph: x_i = x[edge_index[dst_row]] is also the aggregation target (PyG propagate)
-    const int g_dst_row = (cfg.flow == PAMNET_TARGET_TO_SOURCE) ? 0 : 1;
-    PAMNET_TRY(build_in_csr(edge_index_g, Eg, N, g_dst_row, p.tmp_a, p.tmp_b, p.cnt, p.tmp_c, p.g_ptr, p.g_eid,
-                            p.g_src, p.g_dst, st));
-    PAMNET_TRY(build_buckets(p.g_src, Eg, N, nullptr, p.cnt, p.g_optr, p.g_opos, p.tmp_c, st));
-    // local graph: i = edge_index[1] always (local_message_passing.py:37)
-    PAMNET_TRY(build_in_csr(edge_index_l, El, N, 1, p.tmp_a, p.tmp_b, p.cnt, p.tmp_c, p.l_ptr, p.l_eid, p.l_src,
-                            p.l_dst, st));
-    PAMNET_TRY(build_buckets(p.l_src, El, N, nullptr, p.cnt, p.l_optr, p.l_opos, p.tmp_c, st));
+    CsrJobs j;
+    memset(&j, 0, sizeof(j));
+    j.n_buckets = N;
+    const int32_t* keys[4] = {p.tmp_a, p.tmp_b, p.tmp_d, p.tmp_e};          // g dst, g src, l dst, l src
+    const int32_t* key2[4] = {p.tmp_b, nullptr, p.tmp_e, nullptr};
+    int32_t* ptrs[4] = {p.g_ptr, p.g_optr, p.l_ptr, p.l_optr};
+    int32_t* items[4] = {p.g_eid, p.g_opos, p.l_eid, p.l_opos};
+    for (int q = 0; q < 4; ++q) {
+        j.keys[q] = keys[q]; j.key2[q] = key2[q]; j.n[q] = q < 2 ? Eg : El;
+        j.cnt[q] = p.cnt4 + q * (N + 1); j.ptr[q] = ptrs[q]; j.items[q] = items[q];
+        j.tmp[q] = p.tmp4 + (q < 2 ? q * Eg : 2 * Eg + (q - 2) * El);
+    }
+    PAMNET_CUDA(cudaMemsetAsync(p.cnt4, 0, sizeof(int32_t) * 4 * (N + 1), st));
+    if (Emax > 0) {
+        prof_begin(KC_GRAPH, 0.0, st);
+        hist4_kernel<<<dim3(ceil_div(Emax, 256), 4), 256, 0, st>>>(j);
+        prof_end(st);
+        PAMNET_LAUNCH_CHECK();
+    }
+    prof_begin(KC_GRAPH, 0.0, st);
+    scan4_kernel<<<4, kScanThreads, 0, st>>>(j);
+    prof_end(st);
+    PAMNET_LAUNCH_CHECK();
+    PAMNET_CUDA(cudaMemsetAsync(p.cnt4, 0, sizeof(int32_t) * 4 * (N + 1), st));
+    if (Emax > 0) {
+        prof_begin(KC_GRAPH, 0.0, st);
+        fill4_kernel<<<dim3(ceil_div(Emax, 256), 4), 256, 0, st>>>(j);
+        prof_end(st);
+        PAMNET_LAUNCH_CHECK();
+        prof_begin(KC_GRAPH, 0.0, st);
+        sort4_kernel<<<dim3(ceil_div(N, 4), 4), 128, 0, st>>>(j);
+        prof_end(st);
+        PAMNET_LAUNCH_CHECK();
+        prof_begin(KC_GRAPH, 0.0, st);
+        csr_finish1_kernel<<<ceil_div(Emax, 256), 256, 0, st>>>(p.g_eid, p.tmp_b, p.tmp_a, Eg, p.g_src, p.g_dst,
+                                                                p.tmp_c, p.l_eid, p.tmp_e, p.tmp_d, El, p.l_src,
+                                                                p.l_dst, p.tmp_f);
+        prof_end(st);
+        PAMNET_LAUNCH_CHECK();
+        prof_begin(KC_GRAPH, 0.0, st);
+        csr_finish2_kernel<<<ceil_div(Emax, 256), 256, 0, st>>>(p.g_opos, p.tmp_c, Eg, p.l_opos, p.tmp_f, El);
+        prof_end(st);
+        PAMNET_LAUNCH_CHECK();
+    }
     PAMNET_CUDA(cudaMemsetAsync(counts_dev, 0, 2 * sizeof(int64_t), st));
     if (El > 0) {
         prof_begin(KC_GRAPH, 0.0, st);
@@ -670,11 +860,8 @@ int plan_fill(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const float*
     PAMNET_TRY(build_buckets(p.t_gather, T, El, nullptr, p.cnt, p.tt_ptr, p.tt_t, p.t_tmp, st));
     if (N > 0) {
         prof_begin(KC_GRAPH, 0.0, st);
-        csr_dist_kernel<<<ceil_div(N, 128), 128, 0, st>>>(p.g_ptr, p.g_src, N, pos, p.dist_g);
-        prof_end(st);
-        PAMNET_LAUNCH_CHECK();
-        prof_begin(KC_GRAPH, 0.0, st);
-        csr_dist_kernel<<<ceil_div(N, 128), 128, 0, st>>>(p.l_ptr, p.l_src, N, pos, p.dist_l);
+        csr_dist_kernel<<<dim3(ceil_div(N, 128), 2), 128, 0, st>>>(p.g_ptr, p.g_src, p.l_ptr, p.l_src, N, pos, p.dist_g,
+                                                                   p.dist_l);
         prof_end(st);
         PAMNET_LAUNCH_CHECK();
     }

@@ -14,7 +14,7 @@ struct Plan {
     int32_t *t_gather, *t_owner;                          // per triplet: gathered slot, owning slot
     int32_t *tt_ptr, *tt_t;                               // triplets grouped by gathered slot (ascending id)
     float *t_angle, *dist_g, *dist_l;
-    int32_t *tmp_a, *tmp_b, *tmp_c, *t_tmp, *cnt;         // build scratch
+    int32_t *tmp_a, *tmp_b, *tmp_c, *tmp_d, *tmp_e, *tmp_f, *cnt4, *tmp4, *t_tmp, *cnt;   // build scratch
 };
 
 void plan_layout(const pamnet_sizes_t& sz, void* base, void* trip, Plan* out, size_t* base_bytes, size_t* trip_bytes);

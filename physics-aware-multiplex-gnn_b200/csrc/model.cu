@@ -492,9 +492,10 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
     const int ngrp = (int)grp.size() - 1;
     std::vector<cudaEvent_t> ev_g(ngrp), ev_l(ngrp);
     std::vector<int> group_of(L);
-    for (int gi = 0; gi < ngrp; ++gi) {
+    for (int gi = 0; gi < ngrp; ++gi)
+        for (int l = grp[gi]; l < grp[gi + 1]; ++l) group_of[l] = gi;
+    auto issue_group = [&](int gi) -> int {
         const int l0 = grp[gi], l1 = grp[gi + 1];
-        for (int l = l0; l < l1; ++l) group_of[l] = gi;
         {   // global: Q | Tt = e_g [W_m,e ; W_e]^T (+ b_m)      (global_message_passing.py:52-56)
             const int ldq = L * 2 * D;
             std::vector<GemmSlot> sl;
@@ -524,7 +525,11 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
             PAMNET_TRY(gemm_multi(gemm_zero(GEMM_NT, EPI_BIAS, (int)T, D, D), s2v, s2));
             PAMNET_TRY(sc.record(s2, &ev_l[gi]));
         }
-    }
+        return 0;
+    };
+    // host issue order matters right after the plan sync: group 0 first, then the main stream's first kernels,
+    // then group gi+1 is issued just before the main stream works through the layers of group gi
+    PAMNET_TRY(issue_group(0));
 
     // ================= main stream: node input, transposed chain weights, phase B
     {
@@ -566,6 +571,7 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
     for (int hh = 0; hh < H; ++hh) {              // models.py:196-204
         const HalfWs& hw = w.half[hh];
         const int l = hh >> 1;
+        if (!is_local(hh) && l == grp[group_of[l]] && group_of[l] + 1 < ngrp) PAMNET_TRY(issue_group(group_of[l] + 1));
         if (!is_local(hh)) {
             if (l == grp[group_of[l]]) PAMNET_TRY(sc.wait(st, ev_g[group_of[l]]));
             GlobalMsgArgs a;
