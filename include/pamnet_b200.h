@@ -182,6 +182,9 @@ void pamnet_debug_profile_begin(void);
 int pamnet_debug_profile_end(double* ms, int64_t* launches, double* bytes);
 /* Same records as a timeline (call instead of profile_end): class, stream tag, start/end ms; returns the count. */
 int pamnet_debug_profile_timeline(int32_t* cls, int32_t* stream_tag, float* t0_ms, float* t1_ms, int32_t cap);
+/* clock64 timeline of CTA 0 of the last tensor-core GEMM launch (HOST buffer of n <= 256 slots).  Only libraries
+ * built with -DPAMNET_TC_TRACE record it; otherwise returns -1. */
+int pamnet_debug_tc_trace(long long* out, int32_t n);
 
 #ifdef __cplusplus
 }

@@ -292,4 +292,7 @@ int pamnet_gemm(int32_t mode, const float* A, int32_t lda, const float* B, int32
     return gemm_launch(a, ST(stream));
 }
 
+// debugging aid: clock64 timeline of the tensor-core GEMM's CTA 0 (library built with -DPAMNET_TC_TRACE only)
+int pamnet_debug_tc_trace(long long* out, int32_t n) { return tc_trace_read(out, n); }
+
 }  // extern "C"

@@ -276,15 +276,18 @@ int gemm_launch(const GemmArgs& a, cudaStream_t st) {
         // reductions are therefore split into <= 128-deep chains per CTA and combined with fp32 atomics
         // (round-to-nearest); a SiLU' epilogue then runs as a separate pass over the summed result.
         GemmArgs b = a;
-        const bool long_nn = a.mode == GEMM_NN && a.K > 256 && a.ksplit <= 1 &&
-                             (a.epi == EPI_NONE || a.epi == EPI_MUL_DSILU);
+        const bool splittable = a.mode != GEMM_NT && (a.epi == EPI_NONE || a.epi == EPI_MUL_DSILU);
+        const int want = ceil_div(a.K, 128);
+        const bool long_nn = splittable && a.ksplit <= 1 && a.K > 256;     // plain-store semantics: zero C first
         if (long_nn) {
             for (int i = 0; i < a.nslots; ++i) {
-                PAMNET_CHECK_ARG(a.slot[i].ldc == a.N, "gemm: split data-gradient needs a contiguous output");
+                PAMNET_CHECK_ARG(a.slot[i].ldc == a.N, "gemm: split reduction needs a contiguous output");
                 PAMNET_CUDA(cudaMemsetAsync(a.slot[i].C, 0, sizeof(float) * (size_t)a.M * a.N, st));
             }
-            b.ksplit = ceil_div(a.K, 128);
+            b.ksplit = want;
             b.epi = EPI_NONE;
+        } else if (a.ksplit > 1 && want > a.ksplit) {
+            b.ksplit = want;                                                // already accumulating with atomics
         }
         prof_begin(KC_GEMM, bytes, st);
         PAMNET_TRY(gemm_tc_launch(b, st));

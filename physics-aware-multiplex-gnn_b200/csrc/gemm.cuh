@@ -50,6 +50,7 @@ int gemm_launch(const GemmArgs& args, cudaStream_t st);
 // tensor-core (tcgen05, 3xTF32) path, gemm_tc.cu; chosen by gemm_launch unless PAMNET_GEMM=ffma
 bool gemm_tc_eligible(const GemmArgs& a);
 int gemm_tc_launch(const GemmArgs& a, cudaStream_t st);
+int tc_trace_read(long long* out, int n);
 
 int mul_dsilu_launch(float* c, const float* z, int64_t n, cudaStream_t st);
 
