@@ -82,6 +82,10 @@ __global__ void __launch_bounds__(kChainKS * D / 2) chain_kernel(const ChainArgs
                 if (live) {
                     v = ld4(st.g0 + (size_t)(row0 + er) * st.ld_g + c4 * 4);
                     if (st.g1) v = v + ld4(st.g1 + (size_t)(row0 + er) * st.ld_g + c4 * 4);
+                    if (st.add_slot >= 0) {     // + a slot already in shared memory (same thread wrote / reads it)
+                        const float* a = slot_ptr(st.add_slot) + (c4 * 4) * R + er;
+                        v = v + make_float4(a[0], a[R], a[2 * R], a[3 * R]);
+                    }
                     if (st.out_a) st4(st.out_a + (size_t)(row0 + er) * st.ld_out + c4 * 4, v);
                 }
                 float* q = d + (c4 * 4) * R + er;

@@ -36,10 +36,11 @@ __global__ void __launch_bounds__(GT, (TM >= 8 ? 2 : 3)) gemm_kernel(const GemmA
     __shared__ __align__(16) float Bs[2][BK][BN + PAD];
 
     const GemmSlot& sl = args.slot[blockIdx.z];
-    const int M = args.M, N = args.N, K = args.K, mode = args.mode;
+    const int M = sl.m > 0 ? sl.m : args.M, N = args.N, K = args.K, mode = args.mode;
     const int tiles_n = (N + BN - 1) / BN;
     const int m0 = (blockIdx.x / tiles_n) * BM, n0 = (blockIdx.x % tiles_n) * BN;
     const int t = threadIdx.x;
+    if (m0 >= M) return;
 
     int k_begin = 0, k_end = K;
     if (args.ksplit > 1) {
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(128) colsum_slots_kernel(const GemmArgs args, 
     const GemmSlot& sl = args.slot[blockIdx.z];
     if (!sl.C2) return;
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= args.M) return;
+    if (m >= (sl.m > 0 ? sl.m : args.M)) return;
     const int r0 = blockIdx.y * rows_per_block, r1 = min(args.K, r0 + rows_per_block);
     float s = 0.f;
     for (int r = r0; r < r1; ++r) s += sl.A[(size_t)r * sl.lda + m];

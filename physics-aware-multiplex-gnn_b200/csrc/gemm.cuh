@@ -30,6 +30,8 @@ struct GemmSlot {
     float* C;
     float* C2;
     int lda, ldb, ldc, ldz;
+    int m;                // > 0: this slot has only m (< GemmArgs::M) rows; 0: GemmArgs::M
+    int pad_;
 };
 
 struct GemmArgs {

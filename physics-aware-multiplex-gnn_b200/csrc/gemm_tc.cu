@@ -163,10 +163,11 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const GemmArgs args
     constexpr uint32_t IDESC = make_idesc(0, 0);   // both operands are staged K-major
 
     const GemmSlot& sl = args.slot[blockIdx.z];
-    const int M = args.M, N = args.N, K = args.K;
+    const int M = sl.m > 0 ? sl.m : args.M, N = args.N, K = args.K;
     const int tiles_n = (N + TN - 1) / TN;
     const int m0 = (blockIdx.x / tiles_n) * TM, n0 = (blockIdx.x % tiles_n) * TN;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    if (m0 >= M) return;                        // uniform per CTA (slots with fewer rows than the launch)
 #ifdef PAMNET_TC_TRACE
     const bool trace_on = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (t == 0 || t == kConv);
 #endif

@@ -116,6 +116,7 @@ struct HalfWs {
     // backward
     float *gz_x1, *gz_x2, *gz_A[3], *gz_B[3], *gz_o[3];
     float *g_P;                             // [N, nP*D] grad of P (kept per half: consumed on the auxiliary stream)
+    float *g_heads;                         // [N, D] grad of the half's x output through its two readout heads
 };
 
 struct Ws {
@@ -174,6 +175,7 @@ size_t ws_layout(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, void* bas
         for (int r = 0; r < 3; ++r) { h.gz_A[r] = take(N * D); h.gz_B[r] = take(N * D); }
         for (int s = 0; s < 3; ++s) h.gz_o[s] = take(N * D);
         h.g_P = take(N * nP_of(hh) * D);
+        h.g_heads = take(N * D);
     }
     w.g_att = take(H * N); w.g_out = take(H * N);
     w.g_h = take(N * D); w.g_resx = take(N * D); w.g_P = take(N * 4 * D); w.g_s = take(El * D); w.g_x0 = take(N * D);
@@ -223,9 +225,8 @@ void add_pre_fwd(Prog& p, const float* params, const HalfP& hp, const HalfWs& hw
     }
 }
 
-// forward update block + heads (global_message_passing.py:39-48); leaves x_out in slot 1
-void add_post_fwd(Prog& p, const float* params, const HalfP& hp, const HalfWs& hw, int D, const float* res_x,
-                  float* att, float* out) {
+// forward update block (global_message_passing.py:39-44); leaves x_out in slot 1 (and in hw.r[2])
+void add_post_fwd(Prog& p, const float* params, const HalfP& hp, const HalfWs& hw, int D, const float* res_x) {
     p.add(st_load(0, hw.h, D, D));
     { ChainStage& s = p.add(st_gemm(0, 1, hw.x2T, D, params + hp.x2.b, 1)); s.out_z = hw.z_x2; s.out_a = hw.a_x2; s.ld_out = D; }
     int cur = 1;                                    // slot holding the Res input
@@ -238,12 +239,16 @@ void add_post_fwd(Prog& p, const float* params, const HalfP& hp, const HalfWs& h
           if (r == 0) { s.add_g = res_x; s.ld_add = D; } }
         cur = nxt;
     }
-    // cur == 1 after three rotations (1 -> 2 -> 0 -> 1); heads read mlp_out(x)
-    const int xs = cur;
-    int a = xs;
+    // cur == 1 after three rotations (1 -> 2 -> 0 -> 1)
+}
+
+// the two readout heads of a half (global_message_passing.py:46-48): o = mlp_out(x_out), att = o . W, out = W_out o + b.
+// Nothing in the layer loop depends on them, so they run as their own small chain off the critical path.
+void add_heads_fwd(Prog& p, const float* params, const HalfP& hp, const HalfWs& hw, int D, float* att, float* out) {
+    p.add(st_load(0, hw.r[2], D, D));
+    int a = 0;
     for (int s3 = 0; s3 < 3; ++s3) {
-        int d = (a + 1) % 3;
-        if (d == xs) d = (d + 1) % 3;
+        const int d = a ^ 1;
         ChainStage& s = p.add(st_gemm(a, d, hw.outT[s3], D, params + hp.out[s3].b, 1));
         s.out_z = hw.z_o[s3]; s.out_a = hw.a_o[s3]; s.ld_out = D;
         a = d;
@@ -276,20 +281,31 @@ void add_pre_bwd(Prog& p, const float* params, const HalfP& hp, const HalfWs& hw
     s.out_a = g_x_out; s.ld_out = D;
 }
 
-// backward of add_post_fwd; expects grad wrt x_out in slot 2 when has_gx; writes g_h and g_resx
-void add_post_bwd(Prog& p, const float* params, const HalfP& hp, const HalfWs& hw, int D, const Ws& w,
-                  const float* g_att, const float* g_out, bool has_gx) {
+// backward of add_heads_fwd: grad of the half's x output through the heads -> hw.g_heads (and the grad_z of mlp_out).
+// Depends only on the readout gradient, so all halves run up front, off the critical path.
+void add_heads_bwd(Prog& p, const float* params, const HalfP& hp, const HalfWs& hw, int D, const float* g_att,
+                   const float* g_out) {
     ChainStage hb = stage_zero();
     hb.op = CH_HEADS_BWD; hb.dst = 0; hb.g0 = g_att; hb.g1 = g_out; hb.W = params + hp.W; hb.bias = params + hp.W_out.w;
     p.add(hb);
+    auto bwd = [&](int src, int dst, const float* z, float* save, const float* W) -> ChainStage& {
+        ChainStage& s = p.add(st_gemm(src, dst, W, D, nullptr, 0));
+        s.psrc = src; s.zmul = z; s.save_src = save;
+        return s;
+    };
+    bwd(0, 1, hw.z_o[2], hw.gz_o[2], params + hp.out[2].w);
+    bwd(1, 0, hw.z_o[1], hw.gz_o[1], params + hp.out[1].w);
+    { ChainStage& s = bwd(0, 1, hw.z_o[0], hw.gz_o[0], params + hp.out[0].w); s.out_a = hw.g_heads; s.ld_out = D; }
+}
+
+// backward of add_post_fwd; expects grad wrt x_out (from the next half) in slot 2 when has_gx; writes g_h and g_resx
+void add_post_bwd(Prog& p, const float* params, const HalfP& hp, const HalfWs& hw, int D, const Ws& w, bool has_gx) {
     auto bwd = [&](int src, int psrc, int dst, const float* z, float* save, const float* W, int add_slot) -> ChainStage& {
         ChainStage& s = p.add(st_gemm(src, dst, W, D, nullptr, 0));
         s.psrc = psrc; s.zmul = z; s.save_src = save; s.add_slot = add_slot;
         return s;
     };
-    bwd(0, 0, 1, hw.z_o[2], hw.gz_o[2], params + hp.out[2].w, -1);
-    bwd(1, 1, 0, hw.z_o[1], hw.gz_o[1], params + hp.out[1].w, -1);
-    bwd(0, 0, 1, hw.z_o[0], hw.gz_o[0], params + hp.out[0].w, has_gx ? 2 : -1);      // slot1 = g_r3
+    { ChainStage& s = p.add(st_load(1, hw.g_heads, D, D)); s.add_slot = has_gx ? 2 : -1; }   // slot1 = g_r3
     bwd(1, 0, 2, hw.z_B[2], hw.gz_B[2], params + hp.res[2][1].w, -1);
     bwd(2, 2, 0, hw.z_A[2], hw.gz_A[2], params + hp.res[2][0].w, 1);                 // slot0 = g_r2
     bwd(0, 1, 2, hw.z_B[1], hw.gz_B[1], params + hp.res[1][1].w, -1);
@@ -311,6 +327,7 @@ GemmSlot slot(const float* A, int lda, const float* B, int ldb, float* C, int ld
               float* C2 = nullptr, const float* Z = nullptr, int ldz = 0) {
     GemmSlot s;
     s.A = A; s.B = B; s.bias = bias; s.Z = Z; s.C = C; s.C2 = C2; s.lda = lda; s.ldb = ldb; s.ldc = ldc; s.ldz = ldz;
+    s.m = 0; s.pad_ = 0;
     return s;
 }
 // split-K factor of the weight-gradient GEMMs: ~128 reduction rows per CTA keeps the dependent k-loop short
@@ -390,7 +407,7 @@ int64_t debug_ws_offset(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, co
 // which occupy about half of the SMs.  Events come from a small per-thread pool (created once, re-recorded).
 namespace {
 struct Sched {
-    cudaStream_t st, s2;
+    cudaStream_t st, s2, s3;     // main, auxiliary (large x-independent GEMMs), internal (small weight-gradient GEMMs)
     bool dual;
     std::vector<cudaEvent_t>* pool;
     int next = 0;
@@ -423,6 +440,10 @@ struct Sched {
     }
 };
 thread_local std::vector<cudaEvent_t> g_event_pool;
+// The node-level weight gradients are 128 x 128 outputs over ~600 rows: a dozen CTAs per launch.  They run on a third,
+// library-owned stream so that they fill SMs the other two streams leave idle instead of queueing behind the large
+// per-edge GEMMs.  Created once per host thread, joined back into the caller's stream before every return.
+thread_local cudaStream_t g_small_stream = nullptr;
 
 // group boundaries over the layers: a short first group (its results are needed first in forward, last in backward),
 // then growing ones
@@ -441,6 +462,12 @@ Sched make_sched(cudaStream_t st, cudaStream_t aux) {
     s.st = st;
     s.dual = aux != nullptr && aux != st;
     s.s2 = s.dual ? aux : st;
+    s.s3 = st;
+    if (s.dual) {
+        if (!g_small_stream && cudaStreamCreateWithFlags(&g_small_stream, cudaStreamNonBlocking) != cudaSuccess)
+            g_small_stream = nullptr;
+        s.s3 = g_small_stream ? g_small_stream : s.s2;
+    }
     s.pool = &g_event_pool;
     return s;
 }
@@ -593,10 +620,17 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
         }
         Prog p((int)N);
         const float* res_x = hh == 0 ? w.x0 : w.half[hh - 1].r[2];
-        add_post_fwd(p, params, half_params(mp, hh), hw, D, res_x, w.att + (size_t)hh * N, w.out + (size_t)hh * N);
+        add_post_fwd(p, params, half_params(mp, hh), hw, D, res_x);
         if (hh + 1 < H) add_pre_fwd(p, params, half_params(mp, hh + 1), w.half[hh + 1], hh + 1, D, 1);
         PAMNET_TRY(chain_launch(D, p.a, st));
+        {   // readout heads of this half, concurrently with the next half
+            PAMNET_TRY(sc.order(st, sc.s3));
+            Prog ph((int)N);
+            add_heads_fwd(ph, params, half_params(mp, hh), hw, D, w.att + (size_t)hh * N, w.out + (size_t)hh * N);
+            PAMNET_TRY(chain_launch(D, ph.a, sc.s3));
+        }
     }
+    if (sc.s3 != st) PAMNET_TRY(sc.order(sc.s3, st));
 
     // ---- readout (models.py:206-224) ------------------------------------------------------------------
     ReadoutArgs r;
@@ -625,10 +659,11 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
     Ws& w = c.w;
     const Plan& pl = c.plan;
     Sched sc = make_sched(st, aux);
-    cudaStream_t s2 = sc.s2;
+    cudaStream_t s2 = sc.s2, s3 = sc.s3;
 
     PAMNET_CUDA(cudaMemsetAsync(gp, 0, sizeof(float) * mp.total, st));
-    PAMNET_TRY(sc.order(st, s2));      // gradients zeroed (split-K GEMMs accumulate into them) before s2 starts
+    PAMNET_TRY(sc.order(st, s2));      // gradients zeroed (split-K GEMMs accumulate into them) before s2 / s3 start
+    if (s3 != s2) PAMNET_TRY(sc.order(st, s3));
     // accumulators of the per-edge / per-triplet embedding gradients, summed over layers with fp32 atomics
     PAMNET_CUDA(cudaMemsetAsync(w.gz_eg, 0, sizeof(float) * Eg * D, s2));
     PAMNET_CUDA(cudaMemsetAsync(w.gz_el, 0, sizeof(float) * El * D, s2));
@@ -641,11 +676,24 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
     r.gptr = pl.gptr; r.n2g = pl.n2g; r.att = w.att; r.out = w.out; r.g_pooled = grad_out; r.g_att = w.g_att; r.g_out = w.g_out;
     PAMNET_TRY(readout_backward(r, st));
 
+    // ---- readout heads of every half, in the order the main stream will need them --------------------------------
+    std::vector<cudaEvent_t> ev_heads(H);
+    PAMNET_TRY(sc.order(st, s3));
+    for (int hh = H - 1; hh >= 0; --hh) {
+        Prog ph((int)N);
+        add_heads_bwd(ph, params, half_params(mp, hh), w.half[hh], D, w.g_att + (size_t)hh * N, w.g_out + (size_t)hh * N);
+        PAMNET_TRY(chain_launch(D, ph.a, s3));
+        PAMNET_TRY(sc.record(s3, &ev_heads[hh]));
+    }
+
     const int ks_n = pick_ksplit(N);
-    // weight gradients of the node-chain linears whose grad_z a finished chain kernel has written:
-    // the post-chain of half `hh` (hh >= 0) and mlp_x1 of half `x1_half` (x1_half >= 0)
-    auto chain_wgrads = [&](int hh, int x1_half, cudaStream_t s) -> int {
-        std::vector<GemmSlot> sl, heads;
+    // ONE launch per half for every weight gradient that is a [D, D] (or [1, D]) reduction over the nodes:
+    //  * the post-chain of half `hh` (hh >= 0) and mlp_x1 of half `x1_half` (x1_half >= 0), whose grad_z a finished
+    //    chain kernel has written;
+    //  * the two heads of half hh: dW = o3^T g_att, dW_out = o3^T g_out (+ bias) -- one-row slots (GemmSlot::m);
+    //  * the per-node halves of the edge MLPs of half `proj_half`: dW[:, cD:(c+1)D] = g_P_c^T x1.
+    auto node_wgrads = [&](int hh, int x1_half, int proj_half, cudaStream_t s) -> int {
+        std::vector<GemmSlot> sl;
         auto lin = [&](const float* gz, const float* a_in, const Lin& p) {
             sl.push_back(slot(gz, D, a_in, D, gp + p.w, D, nullptr, gp + p.b));
         };
@@ -664,30 +712,22 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
             lin(hw.gz_o[0], hw.r[2], hp.out[0]);
             lin(hw.gz_o[1], hw.a_o[0], hp.out[1]);
             lin(hw.gz_o[2], hw.a_o[1], hp.out[2]);
-            // heads: dW = o3^T g_att, dW_out = o3^T g_out (+ bias)
-            heads.push_back(slot(w.g_att + (size_t)hh * N, 1, hw.a_o[2], D, gp + hp.W, D));
-            heads.push_back(slot(w.g_out + (size_t)hh * N, 1, hw.a_o[2], D, gp + hp.W_out.w, D, nullptr, gp + hp.W_out.b));
+            GemmSlot h1 = slot(w.g_att + (size_t)hh * N, 1, hw.a_o[2], D, gp + hp.W, D);
+            GemmSlot h2 = slot(w.g_out + (size_t)hh * N, 1, hw.a_o[2], D, gp + hp.W_out.w, D, nullptr, gp + hp.W_out.b);
+            h1.m = h2.m = 1;
+            sl.push_back(h1);
+            sl.push_back(h2);
         }
-        GemmArgs a = gemm_zero(GEMM_TN, EPI_NONE, D, D, (int)N);
-        a.ksplit = ks_n;
-        PAMNET_TRY(gemm_multi(a, sl, s));
-        if (!heads.empty()) {
-            a.M = 1;
-            PAMNET_TRY(gemm_multi(a, heads, s));
-        }
-        return 0;
-    };
-    // per-node halves of the edge MLPs of half hh: dW[:, cD:(c+1)D] = g_P_c^T x1
-    auto proj_wgrads = [&](int hh, cudaStream_t s) -> int {
-        const HalfWs& hw = w.half[hh];
-        const HalfP& hp = half_params(mp, hh);
-        const int nP = nP_of(hh);
-        std::vector<GemmSlot> sl;
-        for (int cblk = 0; cblk < nP; ++cblk) {
-            int64_t woff;
-            if (!is_local(hh)) woff = hp.m.w + cblk * D;
-            else woff = (cblk < 2 ? hp.m_ji.w : hp.m_kj.w) + (cblk & 1) * D;
-            sl.push_back(slot(hw.g_P + cblk * D, nP * D, hw.x1, D, gp + woff, 3 * D));
+        if (proj_half >= 0) {
+            const HalfWs& hw = w.half[proj_half];
+            const HalfP& hp = half_params(mp, proj_half);
+            const int nP = nP_of(proj_half);
+            for (int cblk = 0; cblk < nP; ++cblk) {
+                int64_t woff;
+                if (!is_local(proj_half)) woff = hp.m.w + cblk * D;
+                else woff = (cblk < 2 ? hp.m_ji.w : hp.m_kj.w) + (cblk & 1) * D;
+                sl.push_back(slot(hw.g_P + cblk * D, nP * D, hw.x1, D, gp + woff, 3 * D));
+            }
         }
         GemmArgs a = gemm_zero(GEMM_TN, EPI_NONE, D, D, (int)N);
         a.ksplit = ks_n;
@@ -764,7 +804,10 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
         }
         return 0;
     };
-    std::vector<int> grp = layer_groups(L);
+    // backward hands every finished layer to the auxiliary stream at once (forward groups layers because its
+    // first result is needed immediately; here the stream would otherwise idle until half of the layers are done)
+    std::vector<int> grp(L + 1);
+    for (int l = 0; l <= L; ++l) grp[l] = l;
 
     // ---- main stream: phase B reversed; auxiliary stream: weight gradients as soon as their inputs exist --------
     for (int hh = H - 1; hh >= 0; --hh) {
@@ -775,10 +818,9 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
             Prog p((int)N);
             const bool has_gx = hh + 1 < H;   // the last layer's x output is unused (models.py:201-204)
             if (has_gx) add_pre_bwd(p, params, half_params(mp, hh + 1), w.half[hh + 1], hh + 1, D, w, nullptr);
-            add_post_bwd(p, params, hp, hw, D, w, w.g_att + (size_t)hh * N, w.g_out + (size_t)hh * N, has_gx);
+            add_post_bwd(p, params, hp, hw, D, w, has_gx);
+            PAMNET_TRY(sc.wait(st, ev_heads[hh]));
             PAMNET_TRY(chain_launch(D, p.a, st));
-            PAMNET_TRY(sc.order(st, s2));
-            PAMNET_TRY(chain_wgrads(hh, has_gx ? hh + 1 : -1, s2));
         }
         NodeGatherArgs ng;
         memset(&ng, 0, sizeof(ng));
@@ -805,11 +847,14 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
             ng.gz = w.gQR + l * 4 * D; ng.ldq = L * 4 * D;
         }
         PAMNET_TRY(node_grad_gather(D, ng, is_local(hh) ? (int)El : (int)Eg, st));
-        PAMNET_TRY(sc.order(st, s2));
-        PAMNET_TRY(proj_wgrads(hh, s2));
+        PAMNET_TRY(sc.order(st, s3));
+        PAMNET_TRY(node_wgrads(hh, hh + 1 < H ? hh + 1 : -1, hh, s3));
         if (!is_local(hh))                      // a layer is complete once its global half is done
             for (size_t gi = 0; gi + 1 < grp.size(); ++gi)
-                if (grp[gi] == l) PAMNET_TRY(edge_wgrads(grp[gi], grp[gi + 1], s2));
+                if (grp[gi] == l) {
+                    if (s3 != s2) PAMNET_TRY(sc.order(st, s2));
+                    PAMNET_TRY(edge_wgrads(grp[gi], grp[gi + 1], s2));
+                }
     }
     {   // into the node input
         Prog p((int)N);
@@ -824,8 +869,9 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
     } else {
         PAMNET_TRY(embed_backward(node_in, N, w.g_x0, mp.n_embed, D, gp + mp.emb, st));
     }
-    PAMNET_TRY(sc.order(st, s2));
-    PAMNET_TRY(chain_wgrads(-1, 0, s2));
+    PAMNET_TRY(sc.order(st, s3));
+    PAMNET_TRY(node_wgrads(-1, 0, -1, s3));
+    if (s3 != s2) PAMNET_TRY(sc.order(st, s2));
 
     // ---- auxiliary stream: through the SiLU of the embeddings into their weights and the RBF frequencies -------
     PAMNET_TRY(mul_dsilu_launch(w.gz_eg, w.z_eg, Eg * D, s2));
@@ -863,6 +909,7 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
                                           cfg.simple ? nullptr : gp + mp.sbf2.b, gp + mp.sbf1.w, gp + mp.sbf1.b, s2));
     }
     PAMNET_TRY(sc.order(s2, st));
+    if (s3 != s2) PAMNET_TRY(sc.order(s3, st));
     return 0;
 }
 
