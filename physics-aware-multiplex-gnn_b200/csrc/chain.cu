@@ -1,6 +1,6 @@
 // Stage interpreter for row-local node chains (see chain.cuh).  One CTA = 8 rows; activations live (transposed)
-// in shared memory across all stages; whole D x D weight matrices are streamed k-major through a cp.async
-// double buffer, the next stage's matrix in flight while the current one multiplies.
+// in shared memory across all stages; whole D x D weight matrices are streamed k-major through a double buffer
+// filled by the bulk-copy engine, the next stage's matrix in flight while the current one multiplies.
 #include "chain.cuh"
 
 namespace pamnet {
@@ -8,13 +8,31 @@ namespace pamnet {
 constexpr int kChainRows = 8;     // rows per CTA
 constexpr int kChainKS = 8;       // k-slices: a CTA has kChainKS * D / 2 threads (each owns two columns)
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+// ---- weight streaming with the bulk-copy (TMA) engine --------------------------------------------------------------
+// A D x D weight matrix per stage is 64 KB at D = 128.  Copying it with per-thread cp.async cost 8 LDGSTS.128 per
+// thread and stage -- more load/store-unit time than the multiply loop's own shared-memory reads.  One warp now asks
+// the bulk-copy engine for the rows (a single request when the matrix is contiguous) and every thread waits on the
+// mbarrier whose transaction count the copies complete.
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    unsigned ok = 0;
+    for (unsigned spin = 0; !ok; ++spin) {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+        if (spin > (1u << 24)) asm volatile("trap;");      // a protocol bug must not hang the GPU
+    }
+}
 
 // Thread (c, ks): output columns c and c + D/2 (c = tid % (D/2)), k-slice ks = tid / (D/2) of 8.  It accumulates
 // all 8 rows of its two columns over its eighth of K: per k two conflict-free 128 B weight requests per warp plus
@@ -49,14 +67,29 @@ __global__ void __launch_bounds__(kChainKS * D / 2) chain_kernel(const ChainArgs
     // element-wise stages walk (r, c4) with r fastest so that a warp touches 8 rows x 64 contiguous bytes
     const int er = t & (R - 1), ec = t / R;
 
+    __shared__ __align__(8) uint64_t wbar[2];
+    if (t == 0) {
+        mbar_init(&wbar[0], 1);
+        mbar_init(&wbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned wphase[2] = {0u, 0u};
+    // warp 0 requests stage si's weights into buffer buf (all earlier reads of that buffer are behind a barrier)
     auto issue_weights = [&](int si, int buf) {
+        if (t >= 32) return;
         const ChainStage& st = args.st[si];
         float* dstw = wbuf + buf * D * D;
-        for (int f = t; f < D * (D / 4); f += NT) {
-            const int r = f / (D / 4), cc = (f % (D / 4)) * 4;
-            cp_async16(dstw + r * D + cc, st.W + (size_t)r * st.ldw + cc);
+        if (t == 0) mbar_expect_tx(&wbar[buf], (unsigned)(D * D * sizeof(float)));
+        __syncwarp();
+        if (st.ldw == D) {
+            constexpr int kParts = D >= 32 ? 4 : 1;
+            if (t < kParts) bulk_g2s(dstw + t * (D * D / kParts), st.W + t * (D * D / kParts),
+                                     (unsigned)(D * D / kParts * sizeof(float)), &wbar[buf]);
+        } else {
+            for (int r = t; r < D; r += 32)
+                bulk_g2s(dstw + r * D, st.W + (size_t)r * st.ldw, (unsigned)(D * sizeof(float)), &wbar[buf]);
         }
-        cp_async_commit();
     };
     auto next_gemm = [&](int from) {
         for (int i = from; i < args.n_stages; ++i)
@@ -165,8 +198,9 @@ __global__ void __launch_bounds__(kChainKS * D / 2) chain_kernel(const ChainArgs
                 zpre = ld4(args.st[nxt].zmul + (size_t)(row0 + er) * D + ec * 4);
                 zpre_stage = nxt;
             }
-            if (nxt >= 0) cp_async_wait<1>(); else cp_async_wait<0>();
-            __syncthreads();                              // weights landed for everyone; prologue visible
+            mbar_wait(&wbar[wcur], wphase[wcur]);         // this stage's weights have landed
+            wphase[wcur] ^= 1u;
+            __syncthreads();                              // prologue visible
 
             float acc0[R], acc1[R];
 #pragma unroll

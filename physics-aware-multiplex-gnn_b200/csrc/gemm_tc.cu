@@ -108,15 +108,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// tf32 split with round-to-nearest: x = hi + lo + O(2^-22 |x|)
+// tf32 split with round-to-nearest: x = hi + lo + O(2^-22 |x|).  The rounding is done with integer ALU ops (add half
+// an ulp of the 10-bit mantissa, clear the 13 low bits = cvt.rna.tf32.f32 for finite normal inputs): the cvt
+// instruction runs on the 16-lane conversion pipe and alone cost ~500 cycles per chunk (in-kernel trace).
+__device__ __forceinline__ float rna_tf32(float x) {
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    uint32_t h;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-    hi = __uint_as_float(h);
-    const float rest = x - hi;
-    uint32_t l;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(rest));
-    lo = __uint_as_float(l);
+    hi = rna_tf32(x);
+    lo = rna_tf32(x - hi);
 }
 __device__ __forceinline__ void split4(const float4& x, float4& hi, float4& lo) {
     split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y);
