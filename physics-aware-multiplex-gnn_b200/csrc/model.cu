@@ -408,6 +408,7 @@ int64_t debug_ws_offset(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, co
 namespace {
 struct Sched {
     cudaStream_t st, s2, s3;     // main, auxiliary (large x-independent GEMMs), internal (small weight-gradient GEMMs)
+    cudaStream_t s4, s5;         // internal: independent per-edge / per-triplet GEMM chains of backward run side by side
     bool dual;
     std::vector<cudaEvent_t>* pool;
     int next = 0;
@@ -444,6 +445,11 @@ thread_local std::vector<cudaEvent_t> g_event_pool;
 // library-owned stream so that they fill SMs the other two streams leave idle instead of queueing behind the large
 // per-edge GEMMs.  Created once per host thread, joined back into the caller's stream before every return.
 thread_local cudaStream_t g_small_stream = nullptr;
+thread_local cudaStream_t g_extra_stream[2] = {nullptr, nullptr};
+// The sequential layer loop is the critical path; its kernels need whole SMs (the node chain keeps ~190 KB of shared
+// memory per CTA) and otherwise queue behind the GEMM CTAs of the other streams whenever SMs free up.  It therefore
+// runs on a library-owned stream of the highest priority, forked from / joined into the caller's stream.
+thread_local cudaStream_t g_main_stream = nullptr;
 
 // group boundaries over the layers: a short first group (its results are needed first in forward, last in backward),
 // then growing ones
@@ -462,11 +468,22 @@ Sched make_sched(cudaStream_t st, cudaStream_t aux) {
     s.st = st;
     s.dual = aux != nullptr && aux != st;
     s.s2 = s.dual ? aux : st;
-    s.s3 = st;
+    s.s3 = s.s4 = s.s5 = st;
     if (s.dual) {
+        if (!g_main_stream) {
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);     // hi = numerically lowest = greatest priority
+            if (cudaStreamCreateWithPriority(&g_main_stream, cudaStreamNonBlocking, hi) != cudaSuccess) g_main_stream = nullptr;
+        }
+        if (g_main_stream) s.st = g_main_stream;
         if (!g_small_stream && cudaStreamCreateWithFlags(&g_small_stream, cudaStreamNonBlocking) != cudaSuccess)
             g_small_stream = nullptr;
         s.s3 = g_small_stream ? g_small_stream : s.s2;
+        for (int i = 0; i < 2; ++i)
+            if (!g_extra_stream[i] && cudaStreamCreateWithFlags(&g_extra_stream[i], cudaStreamNonBlocking) != cudaSuccess)
+                g_extra_stream[i] = nullptr;
+        s.s4 = g_extra_stream[0] ? g_extra_stream[0] : s.s2;
+        s.s5 = g_extra_stream[1] ? g_extra_stream[1] : s.s2;
     }
     s.pool = &g_event_pool;
     return s;
@@ -478,7 +495,7 @@ Sched make_sched(cudaStream_t st, cudaStream_t aux) {
 // ---------------------------------------------------------------------------------------------
 int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pamnet_sbf_consts_t& sbf,
                   const float* params, const float* node_in, const float* sign, const float* pos, void* plan_base,
-                  void* plan_trip, void* workspace, size_t ws_bytes, float* out, cudaStream_t st, cudaStream_t aux) {
+                  void* plan_trip, void* workspace, size_t ws_bytes, float* out, cudaStream_t st_user, cudaStream_t aux) {
     Ctx c;
     PAMNET_TRY(make_ctx(cfg, sz, sbf, plan_base, plan_trip, workspace, ws_bytes, &c));
     const int D = c.D, L = c.L, H = c.H;
@@ -486,10 +503,11 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
     const ModelP& mp = c.mp;
     Ws& w = c.w;
     const Plan& pl = c.plan;
-    Sched sc = make_sched(st, aux);
-    cudaStream_t s2 = sc.s2;
+    Sched sc = make_sched(st_user, aux);
+    cudaStream_t st = sc.st, s2 = sc.s2;
 
-    PAMNET_TRY(sc.order(st, s2));     // the plan and the inputs were produced on the main stream
+    if (st != st_user) PAMNET_TRY(sc.order(st_user, st));     // the plan and the inputs were produced on the caller's stream
+    PAMNET_TRY(sc.order(st, s2));
 
     // ================= auxiliary stream: phase A (models.py:180-188 and the x-independent halves of the layers)
     PAMNET_TRY(rbf_forward(pl.dist_g, Eg, params + mp.freq_g, cfg.cutoff_g, w.rbf_g, s2));
@@ -640,6 +658,7 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
     r.gptr = pl.gptr; r.n2g = pl.n2g; r.att = w.att; r.out = w.out; r.node_val = w.node_val; r.pooled = out;
     PAMNET_TRY(readout_forward(r, st));
     PAMNET_TRY(sc.order(s2, st));      // nothing of this call is still running on the auxiliary stream afterwards
+    if (st != st_user) PAMNET_TRY(sc.order(st, st_user));
     return 0;
 }
 
@@ -649,7 +668,7 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
 int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pamnet_sbf_consts_t& sbf,
                    const float* params, const float* node_in, const float* sign, const float* pos, void* plan_base,
                    void* plan_trip, void* workspace, size_t ws_bytes, const float* grad_out, float* gp,
-                   cudaStream_t st, cudaStream_t aux) {
+                   cudaStream_t st_user, cudaStream_t aux) {
     (void)pos;
     Ctx c;
     PAMNET_TRY(make_ctx(cfg, sz, sbf, plan_base, plan_trip, workspace, ws_bytes, &c));
@@ -658,16 +677,19 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
     const ModelP& mp = c.mp;
     Ws& w = c.w;
     const Plan& pl = c.plan;
-    Sched sc = make_sched(st, aux);
-    cudaStream_t s2 = sc.s2, s3 = sc.s3;
+    Sched sc = make_sched(st_user, aux);
+    cudaStream_t st = sc.st, s2 = sc.s2, s3 = sc.s3;
 
+    if (st != st_user) PAMNET_TRY(sc.order(st_user, st));
     PAMNET_CUDA(cudaMemsetAsync(gp, 0, sizeof(float) * mp.total, st));
     PAMNET_TRY(sc.order(st, s2));      // gradients zeroed (split-K GEMMs accumulate into them) before s2 / s3 start
     if (s3 != s2) PAMNET_TRY(sc.order(st, s3));
     // accumulators of the per-edge / per-triplet embedding gradients, summed over layers with fp32 atomics
+    if (sc.s4 != s2) PAMNET_TRY(sc.order(st, sc.s4));
+    if (sc.s5 != s2 && sc.s5 != sc.s4) PAMNET_TRY(sc.order(st, sc.s5));
     PAMNET_CUDA(cudaMemsetAsync(w.gz_eg, 0, sizeof(float) * Eg * D, s2));
-    PAMNET_CUDA(cudaMemsetAsync(w.gz_el, 0, sizeof(float) * El * D, s2));
-    PAMNET_CUDA(cudaMemsetAsync(w.gz_s, 0, sizeof(float) * T * D, s2));
+    PAMNET_CUDA(cudaMemsetAsync(w.gz_el, 0, sizeof(float) * El * D, sc.s4));
+    PAMNET_CUDA(cudaMemsetAsync(w.gz_s, 0, sizeof(float) * T * D, sc.s5));
 
     ReadoutArgs r;
     memset(&r, 0, sizeof(r));
@@ -736,7 +758,9 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
     // phase A' of layers [l0, l1): per-edge / per-triplet gradients -> weight gradients (batched over the layers of
     // the group), and their contribution to the gradient of the layer-invariant embeddings, accumulated over
     // groups in gz_eg / gz_el / gz_s with fp32 atomics (split-K)
-    auto edge_wgrads = [&](int l0, int l1, cudaStream_t s) -> int {
+    // The three families are independent of each other (they only meet in the atomically accumulated gz_* buffers),
+    // and each launch is at most one wave of ~10 us tiles: on separate streams they pack the SMs side by side.
+    auto global_wgrads = [&](int l0, int l1, cudaStream_t s) -> int {
         const int nl = l1 - l0;
         {   // global edges
             const int ldq = L * 2 * D;
@@ -757,6 +781,10 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
             b.slot[0] = slot(w.gQT + l0 * 2 * D, ldq, nullptr, 0, w.gz_eg, D);   // gz_eg += [gQ | gTt] [W_m,e ; W_e]
             PAMNET_TRY(gemm_launch(b, s));
         }
+        return 0;
+    };
+    auto local_wgrads = [&](int l0, int l1, cudaStream_t s, cudaStream_t sdg) -> int {
+        const int nl = l1 - l0;
         {   // local edges
             const int ldq = L * 4 * D;
             std::vector<GemmSlot> sl;
@@ -797,17 +825,50 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
             GemmArgs t = gemm_zero(GEMM_TN, EPI_NONE, D, D, (int)T);
             t.ksplit = pick_ksplit(T);
             PAMNET_TRY(gemm_multi(t, w2, s));
-            PAMNET_TRY(gemm_multi(gemm_zero(GEMM_NN, EPI_MUL_DSILU, (int)T, D, D), dg, s));
-            PAMNET_TRY(gemm_multi(t, w1, s));
+            PAMNET_TRY(gemm_multi(gemm_zero(GEMM_NN, EPI_MUL_DSILU, (int)T, D, D), dg, sdg));
+            PAMNET_TRY(gemm_multi(t, w1, sdg));
             bs.slot[0] = slot(w.gzq1 + l0 * D, ldt, nullptr, 0, w.gz_s, D);
-            PAMNET_TRY(gemm_launch(bs, s));
+            PAMNET_TRY(gemm_launch(bs, sdg));
         }
         return 0;
     };
-    // backward hands every finished layer to the auxiliary stream at once (forward groups layers because its
-    // first result is needed immediately; here the stream would otherwise idle until half of the layers are done)
-    std::vector<int> grp(L + 1);
-    for (int l = 0; l <= L; ++l) grp[l] = l;
+    // ---- through the SiLU of the layer-invariant embeddings into their weights and the RBF frequencies.  Each family
+    // finishes on the stream that accumulated its gz_* buffer, as soon as its last layer is in (only the global one
+    // is left for after the main loop).
+    auto embed_tail_global = [&](cudaStream_t s) -> int {
+        PAMNET_TRY(mul_dsilu_launch(w.gz_eg, w.z_eg, Eg * D, s));
+        GemmArgs cw = gemm_zero(GEMM_TN, EPI_NONE, D, kNumRbf, (int)Eg);
+        cw.nslots = 1; cw.ksplit = pick_ksplit(Eg);
+        cw.slot[0] = slot(w.gz_eg, D, w.rbf_g, kNumRbf, gp + mp.rbf_g.w, kNumRbf, nullptr, gp + mp.rbf_g.b);
+        PAMNET_TRY(gemm_launch(cw, s));
+        GemmArgs d = gemm_zero(GEMM_NN, EPI_NONE, (int)Eg, kNumRbf, D);
+        d.nslots = 1;
+        d.slot[0] = slot(w.gz_eg, D, params + mp.rbf_g.w, kNumRbf, w.g_rbf_g, kNumRbf);
+        PAMNET_TRY(gemm_launch(d, s));
+        return rbf_freq_backward(pl.dist_g, Eg, params + mp.freq_g, cfg.cutoff_g, w.g_rbf_g, gp + mp.freq_g, s);
+    };
+    auto embed_tail_local = [&](cudaStream_t s) -> int {
+        PAMNET_TRY(mul_dsilu_launch(w.gz_el, w.z_el, El * D, s));
+        GemmArgs cw = gemm_zero(GEMM_TN, EPI_NONE, D, kNumRbf, (int)El);
+        cw.nslots = 1; cw.ksplit = pick_ksplit(El);
+        cw.slot[0] = slot(w.gz_el, D, w.rbf_l, kNumRbf, gp + mp.rbf_l.w, kNumRbf, nullptr, gp + mp.rbf_l.b);
+        PAMNET_TRY(gemm_launch(cw, s));
+        GemmArgs d = gemm_zero(GEMM_NN, EPI_NONE, (int)El, kNumRbf, D);
+        d.nslots = 1;
+        d.slot[0] = slot(w.gz_el, D, params + mp.rbf_l.w, kNumRbf, w.g_rbf_l, kNumRbf);
+        PAMNET_TRY(gemm_launch(d, s));
+        return rbf_freq_backward(pl.dist_l, El, params + mp.freq_l, cfg.cutoff_l, w.g_rbf_l, gp + mp.freq_l, s);
+    };
+    auto embed_tail_sbf = [&](cudaStream_t s) -> int {      // SBF embeddings (models.py:187-188)
+        PAMNET_TRY(mul_dsilu_launch(w.gz_s, w.z_s, T * D, s));
+        PAMNET_CUDA(cudaMemsetAsync(w.gw_ext, 0, sizeof(float) * D * kSbfExt, s));
+        GemmArgs cw = gemm_zero(GEMM_TN, EPI_NONE, D, kSbfExt, (int)T);
+        cw.nslots = 1; cw.ksplit = pick_ksplit(T);
+        cw.slot[0] = slot(w.gz_s, D, w.sbf_ext, kSbfExt, w.gw_ext, kSbfExt);
+        PAMNET_TRY(gemm_launch(cw, s));
+        return sbf_weight_unpack_grad(D, w.gw_ext, cfg.simple ? nullptr : gp + mp.sbf2.w,
+                                      cfg.simple ? nullptr : gp + mp.sbf2.b, gp + mp.sbf1.w, gp + mp.sbf1.b, s);
+    };
 
     // ---- main stream: phase B reversed; auxiliary stream: weight gradients as soon as their inputs exist --------
     for (int hh = H - 1; hh >= 0; --hh) {
@@ -849,12 +910,19 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
         PAMNET_TRY(node_grad_gather(D, ng, is_local(hh) ? (int)El : (int)Eg, st));
         PAMNET_TRY(sc.order(st, s3));
         PAMNET_TRY(node_wgrads(hh, hh + 1 < H ? hh + 1 : -1, hh, s3));
-        if (!is_local(hh))                      // a layer is complete once its global half is done
-            for (size_t gi = 0; gi + 1 < grp.size(); ++gi)
-                if (grp[gi] == l) {
-                    if (s3 != s2) PAMNET_TRY(sc.order(st, s2));
-                    PAMNET_TRY(edge_wgrads(grp[gi], grp[gi + 1], s2));
-                }
+        // per-edge / per-triplet weight gradients of this half: everything they read is complete now
+        if (is_local(hh)) {
+            if (sc.s4 != s3) PAMNET_TRY(sc.order(st, sc.s4));
+            if (sc.s5 != sc.s4) PAMNET_TRY(sc.order(st, sc.s5));
+            PAMNET_TRY(local_wgrads(l, l + 1, sc.s4, sc.s5));
+            if (l == 0) {                        // last local half: both local families are complete
+                PAMNET_TRY(embed_tail_local(sc.s4));
+                PAMNET_TRY(embed_tail_sbf(sc.s5));
+            }
+        } else {
+            if (s3 != s2) PAMNET_TRY(sc.order(st, s2));
+            PAMNET_TRY(global_wgrads(l, l + 1, s2));
+        }
     }
     {   // into the node input
         Prog p((int)N);
@@ -874,42 +942,12 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
     if (s3 != s2) PAMNET_TRY(sc.order(st, s2));
 
     // ---- auxiliary stream: through the SiLU of the embeddings into their weights and the RBF frequencies -------
-    PAMNET_TRY(mul_dsilu_launch(w.gz_eg, w.z_eg, Eg * D, s2));
-    PAMNET_TRY(mul_dsilu_launch(w.gz_el, w.z_el, El * D, s2));
-    PAMNET_TRY(mul_dsilu_launch(w.gz_s, w.z_s, T * D, s2));
-    {
-        GemmArgs cw = gemm_zero(GEMM_TN, EPI_NONE, D, kNumRbf, (int)Eg);
-        cw.nslots = 1; cw.ksplit = pick_ksplit(Eg);
-        cw.slot[0] = slot(w.gz_eg, D, w.rbf_g, kNumRbf, gp + mp.rbf_g.w, kNumRbf, nullptr, gp + mp.rbf_g.b);
-        PAMNET_TRY(gemm_launch(cw, s2));
-        GemmArgs d = gemm_zero(GEMM_NN, EPI_NONE, (int)Eg, kNumRbf, D);
-        d.nslots = 1;
-        d.slot[0] = slot(w.gz_eg, D, params + mp.rbf_g.w, kNumRbf, w.g_rbf_g, kNumRbf);
-        PAMNET_TRY(gemm_launch(d, s2));
-        PAMNET_TRY(rbf_freq_backward(pl.dist_g, Eg, params + mp.freq_g, cfg.cutoff_g, w.g_rbf_g, gp + mp.freq_g, s2));
-    }
-    {
-        GemmArgs cw = gemm_zero(GEMM_TN, EPI_NONE, D, kNumRbf, (int)El);
-        cw.nslots = 1; cw.ksplit = pick_ksplit(El);
-        cw.slot[0] = slot(w.gz_el, D, w.rbf_l, kNumRbf, gp + mp.rbf_l.w, kNumRbf, nullptr, gp + mp.rbf_l.b);
-        PAMNET_TRY(gemm_launch(cw, s2));
-        GemmArgs d = gemm_zero(GEMM_NN, EPI_NONE, (int)El, kNumRbf, D);
-        d.nslots = 1;
-        d.slot[0] = slot(w.gz_el, D, params + mp.rbf_l.w, kNumRbf, w.g_rbf_l, kNumRbf);
-        PAMNET_TRY(gemm_launch(d, s2));
-        PAMNET_TRY(rbf_freq_backward(pl.dist_l, El, params + mp.freq_l, cfg.cutoff_l, w.g_rbf_l, gp + mp.freq_l, s2));
-    }
-    {   // SBF embeddings (models.py:187-188)
-        PAMNET_CUDA(cudaMemsetAsync(w.gw_ext, 0, sizeof(float) * D * kSbfExt, s2));
-        GemmArgs cw = gemm_zero(GEMM_TN, EPI_NONE, D, kSbfExt, (int)T);
-        cw.nslots = 1; cw.ksplit = pick_ksplit(T);
-        cw.slot[0] = slot(w.gz_s, D, w.sbf_ext, kSbfExt, w.gw_ext, kSbfExt);
-        PAMNET_TRY(gemm_launch(cw, s2));
-        PAMNET_TRY(sbf_weight_unpack_grad(D, w.gw_ext, cfg.simple ? nullptr : gp + mp.sbf2.w,
-                                          cfg.simple ? nullptr : gp + mp.sbf2.b, gp + mp.sbf1.w, gp + mp.sbf1.b, s2));
-    }
+    PAMNET_TRY(embed_tail_global(s2));
     PAMNET_TRY(sc.order(s2, st));
     if (s3 != s2) PAMNET_TRY(sc.order(s3, st));
+    if (sc.s4 != s2) PAMNET_TRY(sc.order(sc.s4, st));
+    if (sc.s5 != s2 && sc.s5 != sc.s4) PAMNET_TRY(sc.order(sc.s5, st));
+    if (st != st_user) PAMNET_TRY(sc.order(st, st_user));
     return 0;
 }
 
