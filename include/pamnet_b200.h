@@ -185,6 +185,9 @@ int pamnet_debug_profile_timeline(int32_t* cls, int32_t* stream_tag, float* t0_m
 /* clock64 timeline of CTA 0 of the last tensor-core GEMM launch (HOST buffer of n <= 256 slots).  Only libraries
  * built with -DPAMNET_TC_TRACE record it; otherwise returns -1. */
 int pamnet_debug_tc_trace(long long* out, int32_t n);
+/* Same for the node chain kernel: 8 stamps per stage of CTA 0 of the last launch (stage start, prologue done, weights
+ * landed, barrier, multiply loop done, partials exchanged, epilogue done, stage end). */
+int pamnet_debug_chain_trace(long long* out, int32_t n);
 
 #ifdef __cplusplus
 }

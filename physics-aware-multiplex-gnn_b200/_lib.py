@@ -65,6 +65,7 @@ SIGNATURES = {
     "pamnet_debug_profile_end": (c_i32, [c_vp, c_vp, c_vp]),
     "pamnet_debug_profile_timeline": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32]),
     "pamnet_debug_tc_trace": (c_i32, [c_vp, c_i32]),
+    "pamnet_debug_chain_trace": (c_i32, [c_vp, c_i32]),
 }
 
 _lib = None

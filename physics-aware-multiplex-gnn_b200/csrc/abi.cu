@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "basis.cuh"
+#include "chain.cuh"
 #include "gemm.cuh"
 #include "graph.cuh"
 #include "message.cuh"
@@ -294,5 +295,6 @@ int pamnet_gemm(int32_t mode, const float* A, int32_t lda, const float* B, int32
 
 // debugging aid: clock64 timeline of the tensor-core GEMM's CTA 0 (library built with -DPAMNET_TC_TRACE only)
 int pamnet_debug_tc_trace(long long* out, int32_t n) { return tc_trace_read(out, n); }
+int pamnet_debug_chain_trace(long long* out, int32_t n) { return chain_trace_read(out, n); }
 
 }  // extern "C"

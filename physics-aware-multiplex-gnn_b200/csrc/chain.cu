@@ -5,8 +5,26 @@
 
 namespace pamnet {
 
+// optional clock64 timeline of CTA 0 / thread 0 (-DPAMNET_TC_TRACE builds; tools/chain_trace.py): 8 stamps per stage
+#ifdef PAMNET_TC_TRACE
+__device__ long long g_chain_trace[16 * 16];
+#define CH_STAMP(si, i) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (si) < 16) g_chain_trace[(si) * 16 + (i)] = clock64(); } while (0)
+#else
+#define CH_STAMP(si, i) do { } while (0)
+#endif
+int chain_trace_read(long long* out, int n) {
+#ifdef PAMNET_TC_TRACE
+    PAMNET_CUDA(cudaMemcpyFromSymbol(out, g_chain_trace, sizeof(long long) * (n < 256 ? n : 256)));
+    return 0;
+#else
+    (void)out; (void)n;
+    set_error("built without PAMNET_TC_TRACE");
+    return -1;
+#endif
+}
+
 constexpr int kChainRows = 8;     // rows per CTA
-constexpr int kChainKS = 8;       // k-slices: a CTA has kChainKS * D / 2 threads (each owns two columns)
+constexpr int kChainKS = 8;       // k-slices: a CTA has kChainKS * 2 * D / 4 threads (4 x 4 tiles, two row groups)
 
 // ---- weight streaming with the bulk-copy (TMA) engine --------------------------------------------------------------
 // A D x D weight matrix per stage is 64 KB at D = 128.  Copying it with per-thread cp.async cost 8 LDGSTS.128 per
@@ -34,12 +52,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
     }
 }
 
-// Thread (c, ks): output columns c and c + D/2 (c = tid % (D/2)), k-slice ks = tid / (D/2) of 8.  It accumulates
-// all 8 rows of its two columns over its eighth of K: per k two conflict-free 128 B weight requests per warp plus
-// two broadcast 128-bit loads of the 8 row values (activations are kept TRANSPOSED in shared memory, [k][8]) feed
-// 16 FMAs.  The eight partial sums meet in shared memory and thread (c, ks) finishes row ks of its two columns.
-// 4*D threads per CTA = 16 warps at D = 128: enough warps to hide the shared-memory latency that a 2-warp-per-
-// scheduler version could not (ncu: short_scoreboard), at 4 shared-memory wavefronts per 16 FMAs.
+// Multiply loop: thread (cg, rg, ks) owns a 4 x 4 tile -- output columns 4 cg .. 4 cg + 3 (cg = tid % (D/4)), rows
+// 4 rg .. 4 rg + 3 (rg = 0, 1) -- over k-slice ks of 8.  Per k one conflict-free 128-bit weight load (a warp reads a
+// whole 512 B weight row at D = 128) and one broadcast 128-bit load of four row values (activations are kept
+// TRANSPOSED in shared memory, [k][8]) feed 16 independent FMAs.
+// Reduction: the eight partial sums meet in shared memory as [ks][column][row half] 16-byte chunks (XOR-swizzled so
+// that both the writers' and the readers' accesses are conflict-free); thread t then finishes two rows of one column
+// with eight 64-bit loads and stores its result as one 64-bit word of the transposed activation slot.
+// 4*D threads per CTA (16 warps at D = 128): everything outside the multiply loop is a chain of dependent latencies
+// (ncu: 78 % of the stall samples), which four warps per scheduler hide better than two at the same FMA issue load.
 template <int D>
 struct ChainCfg {
     static constexpr int R = kChainRows;
@@ -60,13 +81,28 @@ __global__ void __launch_bounds__(kChainKS * D / 2) chain_kernel(const ChainArgs
     auto slot_ptr = [&](int s) -> float* { return slots + s * D * R; };   // wide slot = index 3 (4x larger)
 
     const int t = threadIdx.x;
-    constexpr int H = D / 2;
-    const int c = t % H, ks = t / H;
+    static_assert(R == 8 && kChainKS == 8, "float4 pairs over 8 rows; 3-bit chunk swizzle over 8 k-slices");
+    constexpr int CG = D / 4;
+    const int cg = t % CG, rg = (t / CG) & 1, ks = t / (2 * CG);      // multiply role
+    // finishing role: 8-byte piece t of the slice = rows frow, frow + 1 of column fc
+    const int fc = t >> 2, frow = ((t >> 1) & 1) * 4 + (t & 1) * 2;
     const int row0 = blockIdx.x * R;
     const int n_rows = args.n_rows;
     // element-wise stages walk (r, c4) with r fastest so that a warp touches 8 rows x 64 contiguous bytes
     const int er = t & (R - 1), ec = t / R;
 
+    // The stage table is a 3 KB kernel parameter; indexing it dynamically turns every field access into a dependent
+    // constant-bank load, and cold constant-cache lines cost ~150 cycles each (clock64 trace: ~1000 cycles of stage
+    // prologue and ~1500 of epilogue were nothing but these).  Stage descriptors are therefore staged in shared
+    // memory once and each stage copies its descriptor into registers with independent loads.
+    __shared__ __align__(16) ChainStage s_stage[kChainMaxStages];
+    {
+        static_assert(sizeof(ChainStage) % 4 == 0, "word copy");
+        const int nwords = args.n_stages * (int)(sizeof(ChainStage) / 4);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(args.st);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(s_stage);
+        for (int i = t; i < nwords; i += NT) dst[i] = src[i];
+    }
     __shared__ __align__(8) uint64_t wbar[2];
     if (t == 0) {
         mbar_init(&wbar[0], 1);
@@ -78,22 +114,20 @@ __global__ void __launch_bounds__(kChainKS * D / 2) chain_kernel(const ChainArgs
     // warp 0 requests stage si's weights into buffer buf (all earlier reads of that buffer are behind a barrier)
     auto issue_weights = [&](int si, int buf) {
         if (t >= 32) return;
-        const ChainStage& st = args.st[si];
+        const ChainStage& st = s_stage[si];
         float* dstw = wbuf + buf * D * D;
         if (t == 0) mbar_expect_tx(&wbar[buf], (unsigned)(D * D * sizeof(float)));
-        __syncwarp();
-        if (st.ldw == D) {
-            constexpr int kParts = D >= 32 ? 4 : 1;
-            if (t < kParts) bulk_g2s(dstw + t * (D * D / kParts), st.W + t * (D * D / kParts),
-                                     (unsigned)(D * D / kParts * sizeof(float)), &wbar[buf]);
+        if (st.ldw == D) {                                // contiguous matrix: one request
+            if (t == 0) bulk_g2s(dstw, st.W, (unsigned)(D * D * sizeof(float)), &wbar[buf]);
         } else {
+            __syncwarp();
             for (int r = t; r < D; r += 32)
                 bulk_g2s(dstw + r * D, st.W + (size_t)r * st.ldw, (unsigned)(D * sizeof(float)), &wbar[buf]);
         }
     };
     auto next_gemm = [&](int from) {
         for (int i = from; i < args.n_stages; ++i)
-            if (args.st[i].op == CH_GEMM) return i;
+            if (s_stage[i].op == CH_GEMM) return i;
         return -1;
     };
     float4 zpre = make_float4(0.f, 0.f, 0.f, 0.f);   // prefetched SiLU' operand of stage zpre_stage (thread's first c4)
@@ -104,8 +138,10 @@ __global__ void __launch_bounds__(kChainKS * D / 2) chain_kernel(const ChainArgs
         if (first >= 0) issue_weights(first, 0);
     }
 
-    for (int si = 0; si < args.n_stages; ++si) {
-        const ChainStage& st = args.st[si];
+    const int n_stages = args.n_stages;
+    for (int si = 0; si < n_stages; ++si) {
+        const ChainStage st = s_stage[si];                // register copy (independent shared-memory loads)
+        CH_STAMP(si, 0);
         if (st.op == CH_LOAD) {
             float* d = slot_ptr(st.dst);
             const int w4 = st.width / 4;
@@ -162,19 +198,22 @@ __global__ void __launch_bounds__(kChainKS * D / 2) chain_kernel(const ChainArgs
         } else {  // CH_GEMM
             // prefetch the NEXT GEMM stage's weights into the other buffer (free since the previous stage's
             // trailing barrier), then wait only for this stage's group
-            const int nxt = next_gemm(si + 1);
+            const int nxt = st.next_gemm;
+            CH_STAMP(si, 8);
             if (nxt >= 0) issue_weights(nxt, wcur ^ 1);
+            CH_STAMP(si, 9);
 
             const float* in = slot_ptr(st.src) + st.src_off * R;
             // operands of this stage's epilogue: requested now, consumed after the k-loop (an exposed L2 round
             // trip per stage was the largest remaining cost of the chain)
-            const bool live_r = row0 + ks < n_rows;
-            float bias_v[2] = {0.f, 0.f}, addg_v[2] = {0.f, 0.f};
+            float bias_v = st.bias ? st.bias[fc] : 0.f;
+            float addg_v[2] = {0.f, 0.f};
+            if (st.add_g) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                if (st.bias) bias_v[h] = st.bias[c + h * H];
-                if (st.add_g && live_r) addg_v[h] = st.add_g[(size_t)(row0 + ks) * st.ld_add + c + h * H];
+                for (int i = 0; i < 2; ++i)
+                    if (row0 + frow + i < n_rows) addg_v[i] = st.add_g[(size_t)(row0 + frow + i) * st.ld_add + fc];
             }
+            CH_STAMP(si, 10);
             if (st.psrc >= 0) {
                 float* p = slot_ptr(st.psrc);
                 const bool live = row0 + er < n_rows;
@@ -194,64 +233,90 @@ __global__ void __launch_bounds__(kChainKS * D / 2) chain_kernel(const ChainArgs
                 in = p;
             }
             // prefetch the NEXT GEMM stage's SiLU' operand (its prologue runs right after this stage's barrier)
-            if (nxt >= 0 && args.st[nxt].psrc >= 0 && ec < D / 4 && row0 + er < n_rows) {
-                zpre = ld4(args.st[nxt].zmul + (size_t)(row0 + er) * D + ec * 4);
+            if (nxt >= 0 && s_stage[nxt].psrc >= 0 && ec < D / 4 && row0 + er < n_rows) {
+                zpre = ld4(s_stage[nxt].zmul + (size_t)(row0 + er) * D + ec * 4);
                 zpre_stage = nxt;
             }
+            CH_STAMP(si, 1);
             mbar_wait(&wbar[wcur], wphase[wcur]);         // this stage's weights have landed
             wphase[wcur] ^= 1u;
+            CH_STAMP(si, 2);
             __syncthreads();                              // prologue visible
+            CH_STAMP(si, 3);
 
-            float acc0[R], acc1[R];
+            float acc[4][4];
 #pragma unroll
-            for (int i = 0; i < R; ++i) acc0[i] = acc1[i] = 0.f;
-            const float* wp = wbuf + wcur * D * D + (ks * KL) * D + c;
-            const float* ap = in + (ks * KL) * R;
-            // explicit software pipeline: operands of step kk+1 are requested before the 16 FMAs of step kk issue
-            float w0 = wp[0], w1 = wp[H];
-            float4 a0 = ld4(ap), a1 = ld4(ap + 4);
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+            const float* wp = wbuf + wcur * D * D + (ks * KL) * D + 4 * cg;
+            const float* ap = in + (ks * KL) * R + 4 * rg;
+            // explicit software pipeline: operands of step kk+1 are requested before the 16 FMAs of step kk issue.
+            // (Packed FFMA2 was tried: same FMA throughput, plus operand packing -- 25 % slower in the clock64 trace.)
+            float4 wv = ld4(wp), a0 = ld4(ap);
 #pragma unroll
             for (int kk = 0; kk < KL; ++kk) {
                 const int kn = (kk + 1 < KL) ? kk + 1 : kk;
-                const float w0n = wp[kn * D], w1n = wp[kn * D + H];
-                const float4 a0n = ld4(ap + kn * R), a1n = ld4(ap + kn * R + 4);
-                acc0[0] = fmaf(a0.x, w0, acc0[0]); acc0[1] = fmaf(a0.y, w0, acc0[1]);
-                acc0[2] = fmaf(a0.z, w0, acc0[2]); acc0[3] = fmaf(a0.w, w0, acc0[3]);
-                acc0[4] = fmaf(a1.x, w0, acc0[4]); acc0[5] = fmaf(a1.y, w0, acc0[5]);
-                acc0[6] = fmaf(a1.z, w0, acc0[6]); acc0[7] = fmaf(a1.w, w0, acc0[7]);
-                acc1[0] = fmaf(a0.x, w1, acc1[0]); acc1[1] = fmaf(a0.y, w1, acc1[1]);
-                acc1[2] = fmaf(a0.z, w1, acc1[2]); acc1[3] = fmaf(a0.w, w1, acc1[3]);
-                acc1[4] = fmaf(a1.x, w1, acc1[4]); acc1[5] = fmaf(a1.y, w1, acc1[5]);
-                acc1[6] = fmaf(a1.z, w1, acc1[6]); acc1[7] = fmaf(a1.w, w1, acc1[7]);
-                w0 = w0n; w1 = w1n; a0 = a0n; a1 = a1n;
-            }
+                const float4 wn = ld4(wp + kn * D);
+                const float4 a0n = ld4(ap + kn * R);
+                const float av[4] = {a0.x, a0.y, a0.z, a0.w};
 #pragma unroll
-            for (int i = 0; i < R; ++i) {
-                red[(ks * R + i) * D + c] = acc0[i];
-                red[(ks * R + i) * D + c + H] = acc1[i];
+                for (int i = 0; i < 4; ++i) {
+                    acc[i][0] = fmaf(av[i], wv.x, acc[i][0]);
+                    acc[i][1] = fmaf(av[i], wv.y, acc[i][1]);
+                    acc[i][2] = fmaf(av[i], wv.z, acc[i][2]);
+                    acc[i][3] = fmaf(av[i], wv.w, acc[i][3]);
+                }
+                wv = wn; a0 = a0n;
+            }
+            CH_STAMP(si, 4);
+            {   // partial sums -> red[ks][chunk], chunk (column, row half) = 2 * column + half, low 3 bits swizzled
+                float* rk = red + ks * (D * R);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int chunk = 8 * cg + ((2 * j + rg) ^ (cg & 7));
+                    st4(rk + chunk * 4, make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]));
+                }
             }
             __syncthreads();
+            CH_STAMP(si, 5);
 
-            // thread (c, ks) finishes row ks of its two columns: slices summed in fixed order -> deterministic
-            static_assert(kChainKS == kChainRows, "one row per k-slice thread group");
-            const int r = ks;
-            const bool live = row0 + r < n_rows;
+            // thread t finishes rows frow, frow + 1 of column fc: slices summed in fixed order -> deterministic
+            {
+                const int lc = t >> 1, chunk = lc ^ ((lc >> 3) & 7);
+                const float* rp = red + chunk * 4 + (t & 1) * 2;
+                float2 v = make_float2(bias_v, bias_v);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int col = c + h * H;
-                float v = bias_v[h];
+                for (int s2 = 0; s2 < kChainKS; ++s2) {
+                    const float2 p = *reinterpret_cast<const float2*>(rp + s2 * (D * R));
+                    v.x += p.x; v.y += p.y;
+                }
+                float x[2] = {v.x, v.y};
+                if (x[0] == 12345.678f) CH_STAMP(si, 15);   // (forces the loads to complete before the next stamp)
+                CH_STAMP(si, 11);
+                float addv[2] = {0.f, 0.f};
+                if (st.add_slot >= 0) {
+                    const float2 a = *reinterpret_cast<const float2*>(slot_ptr(st.add_slot) + fc * R + frow);
+                    addv[0] = a.x; addv[1] = a.y;
+                }
 #pragma unroll
-                for (int s2 = 0; s2 < kChainKS; ++s2) v += red[(s2 * R + r) * D + col];
-                if (live && st.out_z) st.out_z[(size_t)(row0 + r) * st.ld_out + col] = v;
-                if (st.act) v = silu(v);
-                if (st.add_slot >= 0) v += slot_ptr(st.add_slot)[col * R + r];
-                if (live && st.add_g) v += addg_v[h];
-                if (!live) v = 0.f;
-                if (st.dst >= 0) slot_ptr(st.dst)[col * R + r] = v;
-                if (live && st.out_a) st.out_a[(size_t)(row0 + r) * st.ld_out + col] = v;
+                for (int i = 0; i < 2; ++i) {
+                    const int r = frow + i;
+                    const bool live = row0 + r < n_rows;
+                    if (live && st.out_z) st.out_z[(size_t)(row0 + r) * st.ld_out + fc] = x[i];
+                    if (st.act) x[i] = silu(x[i]);
+                    x[i] += addv[i];
+                    if (live && st.add_g) x[i] += addg_v[i];
+                    if (!live) x[i] = 0.f;
+                    if (live && st.out_a) st.out_a[(size_t)(row0 + r) * st.ld_out + fc] = x[i];
+                }
+                CH_STAMP(si, 12);
+                if (st.dst >= 0) *reinterpret_cast<float2*>(slot_ptr(st.dst) + fc * R + frow) = make_float2(x[0], x[1]);
             }
+            CH_STAMP(si, 6);
             wcur ^= 1;
             __syncthreads();
+            CH_STAMP(si, 7);
         }
     }
 }
@@ -275,8 +340,13 @@ static int chain_launch_t(const ChainArgs& args, cudaStream_t st) {
                                           (s.out_a ? 1 : 0) + (s.add_g ? 1 : 0));
         if (s.op == CH_DOT2 || s.op == CH_HEADS_BWD) bytes += 8.0 * args.n_rows + 8.0 * D;
     }
+    ChainArgs a = args;
+    for (int i = a.n_stages - 1, nxt = -1; i >= 0; --i) {
+        a.st[i].next_gemm = nxt;
+        if (a.st[i].op == CH_GEMM) nxt = i;
+    }
     prof_begin(KC_CHAIN, bytes, st);
-    chain_kernel<D><<<ceil_div(args.n_rows, C::R), C::T, smem, st>>>(args);
+    chain_kernel<D><<<ceil_div(args.n_rows, C::R), C::T, smem, st>>>(a);
     prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;

@@ -26,6 +26,7 @@ struct ChainStage {
     int act;            // 1 = SiLU
     int width;          // LOAD: columns
     int ldw, ld_out, ld_add, ld_g;
+    int next_gemm;      // index of the next CH_GEMM stage (-1: none); filled in by chain_launch
     const float* W;     // GEMM: [D(k)][D(n)] k-major (transposed weight in forward, weight itself in backward)
     const float* bias;
     const float* zmul;
@@ -44,5 +45,6 @@ struct ChainArgs {
 };
 
 int chain_launch(int dim, const ChainArgs& args, cudaStream_t st);
+int chain_trace_read(long long* out, int n);
 
 }  // namespace pamnet
