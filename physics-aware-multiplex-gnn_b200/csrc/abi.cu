@@ -1,5 +1,6 @@
 // extern "C" surface of libpamnet_sm100.so (declared in include/pamnet_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <vector>
@@ -21,6 +22,15 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 const char* get_error() { return g_err; }
+
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("PAMNET_PDL");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on != 0;
+}
 
 // ---- launch counter + event profiler (single-threaded use: bench / tests) --------------------------
 static std::atomic<long long> g_launches{0};

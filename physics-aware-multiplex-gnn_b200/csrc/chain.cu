@@ -137,10 +137,14 @@ __global__ void __launch_bounds__(kChainKS * D / 2) chain_kernel(const ChainArgs
         const int first = next_gemm(0);
         if (first >= 0) issue_weights(first, 0);
     }
+    // Everything above touched only kernel parameters and weights (written by kernels that finished before the
+    // predecessor of this launch started); from here on the predecessor's outputs are read.
+    pdl_wait();
 
     const int n_stages = args.n_stages;
     for (int si = 0; si < n_stages; ++si) {
         const ChainStage st = s_stage[si];                // register copy (independent shared-memory loads)
+        if (si == n_stages - 1) pdl_trigger();            // the next kernel's CTAs may start arriving
         CH_STAMP(si, 0);
         if (st.op == CH_LOAD) {
             float* d = slot_ptr(st.dst);
@@ -346,7 +350,7 @@ static int chain_launch_t(const ChainArgs& args, cudaStream_t st) {
         if (a.st[i].op == CH_GEMM) nxt = i;
     }
     prof_begin(KC_CHAIN, bytes, st);
-    chain_kernel<D><<<ceil_div(args.n_rows, C::R), C::T, smem, st>>>(a);
+    launch_pdl(chain_kernel<D>, dim3(ceil_div(args.n_rows, C::R)), dim3(C::T), smem, st, a);
     prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;

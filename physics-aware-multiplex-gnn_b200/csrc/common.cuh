@@ -59,6 +59,30 @@ void count_launch();
     } while (0)
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------------------------
+// The layer loop is ~90 short dependent kernels on one stream; between two of them the GPU idles for the launch
+// latency (~3 us, 13 % of the step in the CUDA-event timeline).  Kernels of that loop are launched with the
+// programmatic-stream-serialization attribute: the next kernel's CTAs may become resident while the previous one
+// drains, run their prologue (shared-memory carve-up, barrier init, weight prefetch) and then block in
+// griddepcontrol.wait until the predecessor has completed and its writes are visible.  PAMNET_PDL=0 disables it.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+#ifdef __CUDACC__
+// block until the preceding kernel of the stream has completed (no-op for ordinary launches)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// allow the next kernel of the stream to start launching (it still waits for this grid in its own pdl_wait)
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 // ---------------------------------------------------------------------------------------------

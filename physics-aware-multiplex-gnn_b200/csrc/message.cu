@@ -18,6 +18,8 @@ constexpr int kUnroll = 4;       // independent row loads kept in flight per war
 // memory-level parallelism of a warp-per-node walk (620 nodes alone cannot hide L2 latency on 148 SMs).
 template <int D>
 __global__ void __launch_bounds__(kMsgThreads) global_msg_fwd_kernel(const GlobalMsgArgs a) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ __align__(16) float part[kMsgThreads / 32][D];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int n = blockIdx.x;
@@ -63,6 +65,8 @@ __global__ void __launch_bounds__(kMsgThreads) global_msg_fwd_kernel(const Globa
 // one warp per edge slot: every output row is per-edge, so the backward is embarrassingly edge-parallel
 template <int D>
 __global__ void __launch_bounds__(kMsgThreads) global_msg_bwd_kernel(const GlobalMsgArgs a) {
+    pdl_wait();
+    pdl_trigger();
     const int lane = threadIdx.x & 31;
     const int k = blockIdx.x * (kMsgThreads / 32) + (threadIdx.x >> 5);
     if (k >= a.n_edges) return;
@@ -88,6 +92,8 @@ __global__ void __launch_bounds__(kMsgThreads) global_msg_bwd_kernel(const Globa
 // ---------------------------------------------------------------------------------------------
 template <int D>
 __global__ void __launch_bounds__(kMsgThreads) local_edge_fwd_kernel(const LocalMsgArgs a) {
+    pdl_wait();
+    pdl_trigger();
     const int lane = threadIdx.x & 31;
     const int k = blockIdx.x * (kMsgThreads / 32) + (threadIdx.x >> 5);
     if (k >= a.n_edges) return;
@@ -104,6 +110,8 @@ __global__ void __launch_bounds__(kMsgThreads) local_edge_fwd_kernel(const Local
 // one warp per edge slot: msum[k] = m_ji + sum_t m_nb[g_t] * SiLU(zq_t)   (local_message_passing.py:47-51)
 template <int D>
 __global__ void __launch_bounds__(kMsgThreads) local_trip_fwd_kernel(const LocalMsgArgs a) {
+    pdl_wait();
+    pdl_trigger();
     const int lane = threadIdx.x & 31;
     const int k = blockIdx.x * (kMsgThreads / 32) + (threadIdx.x >> 5);
     if (k >= a.n_edges) return;
@@ -136,6 +144,8 @@ __global__ void __launch_bounds__(kMsgThreads) local_trip_fwd_kernel(const Local
 // one warp per destination node: h = x1 + sum_k msum[k] * Rout[k]   (local_message_passing.py:53-54)
 template <int D>
 __global__ void __launch_bounds__(kMsgThreads) local_msg_fwd_kernel(const LocalMsgArgs a) {
+    pdl_wait();
+    pdl_trigger();
     const int lane = threadIdx.x & 31;
     const int n = blockIdx.x * (kMsgThreads / 32) + (threadIdx.x >> 5);
     if (n >= a.n_nodes) return;
@@ -164,6 +174,8 @@ __global__ void __launch_bounds__(kMsgThreads) local_msg_fwd_kernel(const LocalM
 // one warp per edge slot: grad Rout, grad (m_ji + m_other) = g_s, grad z_ji, and grad of the triplet gate zq
 template <int D>
 __global__ void __launch_bounds__(kMsgThreads) local_msg_bwd_kernel(const LocalMsgArgs a) {
+    pdl_wait();
+    pdl_trigger();
     const int lane = threadIdx.x & 31;
     const int k = blockIdx.x * (kMsgThreads / 32) + (threadIdx.x >> 5);
     if (k >= a.n_edges) return;
@@ -207,6 +219,8 @@ __global__ void __launch_bounds__(kMsgThreads) local_msg_bwd_kernel(const LocalM
 // back through m_nb = SiLU(z_kj) * R
 template <int D>
 __global__ void __launch_bounds__(kMsgThreads) local_trip_bwd_kernel(const LocalMsgArgs a) {
+    pdl_wait();
+    pdl_trigger();
     const int lane = threadIdx.x & 31;
     const int k = blockIdx.x * (kMsgThreads / 32) + (threadIdx.x >> 5);
     if (k >= a.n_edges) return;
@@ -249,6 +263,8 @@ __global__ void __launch_bounds__(kMsgThreads) local_trip_bwd_kernel(const Local
 // one warp per (node, task): task 2b = sum of gz_b over incoming slots, 2b+1 = over outgoing slots
 template <int D>
 __global__ void __launch_bounds__(kMsgThreads) node_grad_gather_kernel(const NodeGatherArgs a) {
+    pdl_wait();
+    pdl_trigger();
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * (kMsgThreads / 32) + (threadIdx.x >> 5);
     const int ntask = 2 * a.n_blocks;
@@ -279,10 +295,10 @@ __global__ void __launch_bounds__(kMsgThreads) node_grad_gather_kernel(const Nod
         const int grid = ceil_div((rows), kMsgThreads / 32);                                          \
         prof_begin(CLS, BYTES, st);                                                                   \
         switch (dim) {                                                                                \
-            case 128: KERNEL<128><<<grid, kMsgThreads, 0, st>>>(args); break;                         \
-            case 64:  KERNEL<64><<<grid, kMsgThreads, 0, st>>>(args); break;                          \
-            case 32:  KERNEL<32><<<grid, kMsgThreads, 0, st>>>(args); break;                          \
-            case 16:  KERNEL<16><<<grid, kMsgThreads, 0, st>>>(args); break;                          \
+            case 128: launch_pdl(KERNEL<128>, dim3(grid), dim3(kMsgThreads), 0, st, args); break;     \
+            case 64:  launch_pdl(KERNEL<64>, dim3(grid), dim3(kMsgThreads), 0, st, args); break;      \
+            case 32:  launch_pdl(KERNEL<32>, dim3(grid), dim3(kMsgThreads), 0, st, args); break;      \
+            case 16:  launch_pdl(KERNEL<16>, dim3(grid), dim3(kMsgThreads), 0, st, args); break;      \
             default: set_error("unsupported dim %d (16, 32, 64, 128)", dim); return -1;               \
         }                                                                                             \
         prof_end(st);                                                                                 \
