@@ -188,11 +188,13 @@ def run_ours(args):
 
     params = list(model.parameters())
 
+    import torch.nn.functional as F
+
     def step(batch):
         for p in params:             # == optimizer.zero_grad(set_to_none=True)
             p.grad = None
         out = model(batch)
-        loss = (out - batch.y).abs().mean()
+        loss = F.l1_loss(out, batch.y)      # main_qm9.py:108
         loss.backward()
         if world > 1:
             allreduce_gradients(model)
@@ -292,8 +294,13 @@ def run_ours(args):
         dom = max(kernels, key=lambda k: kernels[k]["share"])
         d = prof[dom]
         achieved = (d[2] / 1e9) / (d[0] * 1e-3)
+        traffic = None
+        try:        # dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full capture
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(dom, {}).get("dram_bytes_per_launch")
+        except (OSError, ValueError):
+            pass
         line["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                            "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                            "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                             "share_of_step": kernels[dom]["share"],
                             "note": "algorithmic bytes of the kernel's operands / CUDA-event duration per launch, "
                                     "averaged over its launches in a step; fp32 FFMA GEMMs are compute-bound, see DESIGN.md"}

@@ -277,6 +277,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const GemmArgs args
         cp_commit();     // always: keeps the group count per iteration uniform
     };
 
+    pdl_wait();          // operands (and the zeroed split-K output) come from earlier kernels of the stream
     if (warp < kConv / 32) {
 #pragma unroll
         for (int p = 0; p < kAhead; ++p) issue(p);
@@ -361,6 +362,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const GemmArgs args
             mbar_wait(&mma_done[last % kRing], (last / kRing) & 1);
         }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        pdl_trigger();   // the next kernel of the stream may set itself up while this tile is written back
         if (t == 0) TC_STAMP(2);
 
         // ---- epilogue ---------------------------------------------------------------------------------------------
@@ -443,7 +445,7 @@ int launch_tc(const GemmArgs& a, dim3 grid, cudaStream_t st) {
         PAMNET_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
         configured = true;
     }
-    gemm_tc_kernel<MODE, EPI><<<grid, TC_THREADS, kTcSmem, st>>>(a);
+    PAMNET_CUDA(launch_pdl(gemm_tc_kernel<MODE, EPI>, grid, dim3(TC_THREADS), kTcSmem, st, a));
     return 0;
 }
 
