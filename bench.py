@@ -58,7 +58,7 @@ def cpu_step_fn(cfg, batch, seed=0):
         out = O.forward(leaves, cfg, batch, consts=consts)
         loss = (out - batch.y).abs().mean()
         loss.backward()
-        return float(loss)
+        return float(loss.detach())
     return step
 
 

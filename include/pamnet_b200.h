@@ -145,6 +145,22 @@ int pamnet_model_backward(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, 
 int pamnet_loss(const float* out, const float* y, int64_t n, int32_t kind /*0 = L1, 1 = MSE*/, float* loss_dev,
                 float* grad_out, void* stream);
 
+/* Fused optimizer step on the flat buffers (replaces, per step, the reference's
+ * clip_grad_norm_(model.parameters(), max_norm) -> optim.Adam.step() -> EMA.__call__(model)
+ * (main_qm9.py:111-112,117, utils/ema.py:13-20) with two launches and no host synchronisation.
+ *   params / grads / exp_avg / exp_avg_sq / ema_shadow: device fp32 buffers of n elements in the layout of
+ *   pamnet_param_offsets (n = pamnet_param_total, a multiple of 4); ema_shadow may be NULL (no EMA).
+ *   skip_ranges: n_skip (<= 4) pairs [begin, end) of element offsets of tensors that carry no gradient on this
+ *   dataset (torch.optim skips parameters whose .grad is None); they are left untouched.
+ *   step: 1-based Adam step count (bias corrections are evaluated in double on the host side of this call).
+ *   max_norm <= 0 disables clipping; otherwise sumsq_dev (device double) receives the squared total gradient norm
+ *   of this step, as clip_grad_norm_ would return it, and gradients are scaled by min(1, max_norm / (norm + 1e-6)).
+ *   write_clipped_grad != 0 also stores the scaled gradients back, as clip_grad_norm_ does in place. */
+int pamnet_optimizer_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, float* ema_shadow,
+                          int64_t n, const int64_t* skip_ranges, int32_t n_skip, int64_t step, float lr, float beta1,
+                          float beta2, float eps, float weight_decay, float max_norm, float ema_decay,
+                          int32_t write_clipped_grad, double* sumsq_dev, void* stream);
+
 /* ---- operator surface, also the unit-test hooks ----------------------------------
  * torch_scatter.scatter(src, index, dim=0, dim_size, 'add') (local_message_passing.py:50,54) for a
  * non-decreasing or arbitrary index: out[dim_size, width] zero-initialised then summed in index order per row

@@ -1,4 +1,5 @@
 // extern "C" surface of libpamnet_sm100.so (declared in include/pamnet_b200.h).
+#include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
 
@@ -11,6 +12,7 @@
 #include "graph.cuh"
 #include "message.cuh"
 #include "model.cuh"
+#include "optim.cuh"
 #include "readout.cuh"
 
 namespace pamnet {
@@ -23,14 +25,15 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
-bool pdl_enabled() {
-    static int on = -1;
-    if (on < 0) {
+int pdl_level() {
+    static int lvl = -1;
+    if (lvl < 0) {
         const char* e = getenv("PAMNET_PDL");
-        on = (e && e[0] == '0') ? 0 : 1;
+        lvl = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
     }
-    return on != 0;
+    return lvl;
 }
+bool pdl_enabled() { return pdl_level() != 0; }
 
 // ---- launch counter + event profiler (single-threaded use: bench / tests) --------------------------
 static std::atomic<long long> g_launches{0};
@@ -249,6 +252,30 @@ int pamnet_debug_profile_timeline(int32_t* cls, int32_t* stream_tag, float* t0_m
     g_prof_recs.clear();
     g_prof_used = 0;
     return n;
+}
+
+int pamnet_optimizer_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, float* ema_shadow,
+                          int64_t n, const int64_t* skip_ranges, int32_t n_skip, int64_t step, float lr, float beta1,
+                          float beta2, float eps, float weight_decay, float max_norm, float ema_decay,
+                          int32_t write_clipped_grad, double* sumsq_dev, void* stream) {
+    REQUIRE(params); REQUIRE(grads); REQUIRE(exp_avg); REQUIRE(exp_avg_sq);
+    if (n % 4 != 0 || n < 0 || step < 1 || n_skip < 0 || n_skip > kOptMaxSkip || (n_skip > 0 && !skip_ranges)) {
+        set_error("optimizer_step: n=%lld must be a non-negative multiple of 4, step >= 1, n_skip in [0, %d]",
+                  (long long)n, kOptMaxSkip);
+        return -1;
+    }
+    OptimArgs a;
+    memset(&a, 0, sizeof(a));
+    a.p = params; a.g = grads; a.m = exp_avg; a.v = exp_avg_sq; a.shadow = ema_shadow; a.sumsq = sumsq_dev;
+    a.n4 = n / 4; a.n_skip = n_skip; a.write_clipped_grad = write_clipped_grad;
+    for (int i = 0; i < n_skip; ++i) { a.skip_begin[i] = skip_ranges[2 * i]; a.skip_end[i] = skip_ranges[2 * i + 1]; }
+    // bias corrections as torch.optim.Adam computes them (python floats = double), rounded once to fp32
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    a.step_size = (float)((double)lr / bc1);
+    a.bc2_sqrt = (float)sqrt(bc2);
+    a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.max_norm = max_norm;
+    a.ema_decay = ema_decay;
+    return optimizer_step(a, ST(stream));
 }
 
 int pamnet_loss(const float* out, const float* y, int64_t n, int32_t kind, float* loss_dev, float* grad_out,

@@ -65,8 +65,10 @@ static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b)
 // latency (~3 us, 13 % of the step in the CUDA-event timeline).  Kernels of that loop are launched with the
 // programmatic-stream-serialization attribute: the next kernel's CTAs may become resident while the previous one
 // drains, run their prologue (shared-memory carve-up, barrier init, weight prefetch) and then block in
-// griddepcontrol.wait until the predecessor has completed and its writes are visible.  PAMNET_PDL=0 disables it.
+// griddepcontrol.wait until the predecessor has completed and its writes are visible.  PAMNET_PDL=0 disables it,
+// PAMNET_PDL=2 keeps it for the layer loop only (not for the GEMMs of the auxiliary streams).
 bool pdl_enabled();
+int pdl_level();
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg = {};

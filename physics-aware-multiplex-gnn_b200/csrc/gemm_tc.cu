@@ -445,7 +445,8 @@ int launch_tc(const GemmArgs& a, dim3 grid, cudaStream_t st) {
         PAMNET_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
         configured = true;
     }
-    PAMNET_CUDA(launch_pdl(gemm_tc_kernel<MODE, EPI>, grid, dim3(TC_THREADS), kTcSmem, st, a));
+    if (pdl_level() == 1) PAMNET_CUDA(launch_pdl(gemm_tc_kernel<MODE, EPI>, grid, dim3(TC_THREADS), kTcSmem, st, a));
+    else gemm_tc_kernel<MODE, EPI><<<grid, TC_THREADS, kTcSmem, st>>>(a);
     return 0;
 }
 

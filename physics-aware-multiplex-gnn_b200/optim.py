@@ -1,0 +1,103 @@
+"""Fused optimizer step for the PAMNet modules of this package.
+
+The reference's training step ends with three Python loops over 390 tensors (main_qm9.py:111-112,117):
+
+    clip_grad_norm_(model.parameters(), max_norm=1000, norm_type=2)
+    optimizer.step()                     # optim.Adam(lr, weight_decay, amsgrad=False), main_qm9.py:91
+    ema(model)                           # utils/ema.py:13-20
+
+``FusedAdamEMA.step()`` does the same arithmetic in two CUDA launches on the module's flat parameter / gradient
+buffers (csrc/optim.cu) with no host synchronisation.  It is a ``torch.optim.Optimizer`` with one parameter group,
+so the reference's LR schedulers (ExponentialLR + GradualWarmupScheduler, main_qm9.py:92-93) drive it unchanged.
+There is no CPU fallback.
+"""
+import torch
+
+from . import _lib
+
+
+class FusedAdamEMA(torch.optim.Optimizer):
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_norm=None, ema_decay=None):
+        if not hasattr(model, "_flat"):
+            raise TypeError("FusedAdamEMA needs a pamnet_b200 PAMNet / PAMNet_s module (flat parameter storage)")
+        super().__init__(list(model.parameters()), dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.model = model
+        self.max_norm = None if max_norm is None else float(max_norm)
+        self.ema_decay = None if ema_decay is None else float(ema_decay)
+        self.num_steps = 0
+        flat = model._flat
+        if not flat.is_cuda:
+            raise _lib.PamnetError("FusedAdamEMA runs on CUDA parameters only: move the model to a GPU first")
+        self.exp_avg = torch.zeros_like(flat, requires_grad=False)
+        self.exp_avg_sq = torch.zeros_like(flat, requires_grad=False)
+        # utils/ema.py:9-11: the shadow starts as a copy of the parameters at construction time
+        self.shadow = flat.detach().clone() if self.ema_decay is not None else None
+        self._original = None
+        self._sumsq = torch.zeros(1, dtype=torch.float64, device=flat.device)
+        skip = []
+        for (_, p), off, used in zip(model._param_list, model._offsets, model._param_used):
+            if not (used and p.requires_grad):          # torch.optim skips parameters whose .grad is None
+                skip += [off, off + p.numel()]
+        if len(skip) > 8:
+            raise ValueError("more than 4 gradient-free tensors: not a reference PAMNet configuration")
+        self._skip = (_lib.c_i64 * max(len(skip), 1))(*skip)
+        self._n_skip = len(skip) // 2
+
+    def _flat_grad(self):
+        """The flat gradient buffer, valid when every p.grad is the view backward attached (the normal case after
+        zero_grad(set_to_none=True) + backward); gradients assigned by other means are packed into it first."""
+        m = self.model
+        views = m._grad_views()
+        for (_, p), v, used in zip(m._param_list, views, m._param_used):
+            if not (used and p.requires_grad):
+                continue
+            if p.grad is None:
+                v.zero_()
+            elif p.grad is not v:
+                v.copy_(p.grad)
+        return m._gflat
+
+    @torch.no_grad()
+    def step(self, closure=None, num_updates=99999):
+        if closure is not None:
+            raise NotImplementedError("closures are not used by the reference trainers")
+        m = self.model
+        if not m._aliased(full=False):          # e.g. someone replaced param.data wholesale
+            m._flatten()
+        flat = m._flat
+        if self.exp_avg.device != flat.device:
+            raise RuntimeError("the model moved to another device after the optimizer was built")
+        g = self._flat_grad()
+        group = self.param_groups[0]
+        beta1, beta2 = group["betas"]
+        self.num_steps += 1
+        decay = 0.0
+        if self.shadow is not None:             # utils/ema.py:14
+            decay = min(self.ema_decay, (1.0 + num_updates) / (10.0 + num_updates))
+        lib = _lib.load()
+        _lib.check(lib.pamnet_optimizer_step(
+            flat.data_ptr(), g.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+            _lib.ptr(self.shadow), flat.numel(), self._skip, self._n_skip, self.num_steps, float(group["lr"]),
+            float(beta1), float(beta2), float(group["eps"]), float(group["weight_decay"]),
+            float(self.max_norm) if self.max_norm is not None else 0.0, float(decay), 1,
+            self._sumsq.data_ptr(), torch.cuda.current_stream().cuda_stream), "optimizer_step")
+
+    def total_norm(self):
+        """Gradient norm of the last step as clip_grad_norm_ returns it (device scalar, no synchronisation)."""
+        return self._sumsq.sqrt().float()[0]
+
+    # ---- utils/ema.py:22-33 on the flat buffers (one copy each instead of a loop over the tensors) ----------------
+    @torch.no_grad()
+    def ema_assign(self):
+        if self.shadow is None:
+            raise RuntimeError("built without ema_decay")
+        flat = self.model._flat
+        self._original = flat.detach().clone()
+        flat.data.copy_(self.shadow)
+
+    @torch.no_grad()
+    def ema_resume(self):
+        if self._original is None:
+            raise RuntimeError("ema_resume() without ema_assign()")
+        self.model._flat.data.copy_(self._original)
+        self._original = None
