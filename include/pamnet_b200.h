@@ -121,6 +121,25 @@ int pamnet_plan_count(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, cons
 int pamnet_plan_fill(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, const float* pos, void* plan_base,
                      void* plan_trip, void* stream);
 
+/* The whole front end of PAMNet.forward (models.py:104-177: radius / kNN graph, self-loop and cutoff filters, the
+ * destination-sorted plan, triplet lists, distances, angles) in ONE call.  The host must learn E_g, E_l and the triplet
+ * counts to size the caller-owned buffers, so the call synchronises the stream two or three times internally (pinned
+ * 64-byte read-backs) instead of returning to the host language in between.
+ *   edge_index_in [2, n_edges_in]: data.edge_index (QM9 only, else NULL / 0).
+ *   eg_buf / el_buf: int64 buffers of 2 * cap_eg / 2 * cap_el elements; on success they hold edge_index_g [2, E_g] and
+ *   edge_index_l [2, E_l] packed with row stride E (the local list is NOT copied when nothing was filtered: then the
+ *   plan refers to edge_index_in (QM9) or to eg_buf (PDBbind) and el_buf is untouched).
+ *   plan_base / plan_trip: blobs of cap_base / cap_trip bytes (layout: pamnet_plan_bytes of the final sizes).
+ *   scratch: pamnet_plan_build_scratch_bytes(cfg, n_nodes, n_edges_in, cap_eg) bytes.
+ * Returns 0 and fills *sizes_out; returns 1 when a capacity was too small -- need[0..3] = {E_g, E_l, base bytes, trip
+ * bytes} as far as they are known (0 = not reached): grow and call again; < 0 / > 1 are errors as everywhere. */
+size_t pamnet_plan_build_scratch_bytes(const pamnet_config_t* cfg, int64_t n_nodes, int64_t n_edges_in, int64_t cap_eg);
+int pamnet_plan_build(const pamnet_config_t* cfg, const float* pos, const int64_t* batch, int64_t n_nodes,
+                      int64_t n_graphs, const int64_t* edge_index_in, int64_t n_edges_in, int32_t max_nb,
+                      int64_t* eg_buf, int64_t cap_eg, int64_t* el_buf, int64_t cap_el, void* plan_base,
+                      size_t cap_base, void* plan_trip, size_t cap_trip, void* scratch, size_t scratch_bytes,
+                      pamnet_sizes_t* sizes_out, int64_t* need, void* stream);
+
 /* ---- the hot path: PAMNet.forward / autograd backward (models.py:100-224, main_qm9.py:107-110) -----
  * node_in : QM9 / RNA: atom-type id per node as fp32 [n_nodes] (models.py:107,140);
  *           PDBbind  : 18 features per node [n_nodes,18] (models.py:119).

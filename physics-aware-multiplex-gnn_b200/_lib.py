@@ -58,6 +58,9 @@ SIGNATURES = {
     "pamnet_spherical_basis": (c_i32, [_PB, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "pamnet_linear": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp]),
     "pamnet_gemm": (c_i32, [c_i32, c_vp, c_i32, c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "pamnet_plan_build_scratch_bytes": (c_sz, [_PC, c_i64, c_i64, c_i64]),
+    "pamnet_plan_build": (c_i32, [_PC, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i32, c_vp, c_i64, c_vp, c_i64, c_vp, c_sz,
+                                  c_vp, c_sz, c_vp, c_sz, _PS, c_vp, c_vp]),
     "pamnet_optimizer_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i32, c_i64, c_f32, c_f32, c_f32, c_f32,
                                       c_f32, c_f32, c_f32, c_i32, c_vp, c_vp]),
     "pamnet_debug_ws_offset": (c_i64, [_PC, _PS, C.c_char_p, c_i32]),

@@ -165,6 +165,123 @@ int pamnet_plan_fill(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, const
     return plan_fill(*cfg, *sz, pos, plan_base, plan_trip, ST(stream));
 }
 
+// ---- whole front end in one call ---------------------------------------------------------------------------------
+namespace {
+struct BuildScratch {
+    int64_t* counts;
+    int32_t *deg_a, *ptr_a, *deg_b, *ptr_b, *keep, *pk, *nbr;
+    float* d2;
+};
+constexpr int kKnnK = 50;            // models.py:143
+size_t build_scratch_layout(int kind, int64_t n, int64_t n_edges_in, int64_t cap_eg, void* base, BuildScratch* out) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        void* p = base ? static_cast<char*>(base) + off : nullptr;
+        off += align_up(bytes ? bytes : 1);
+        return p;
+    };
+    BuildScratch b;
+    const int64_t ne = kind == PAMNET_PDBBIND ? cap_eg : n_edges_in;
+    b.counts = static_cast<int64_t*>(take(8 * sizeof(int64_t)));
+    b.deg_a = static_cast<int32_t*>(take(sizeof(int32_t) * n));
+    b.ptr_a = static_cast<int32_t*>(take(sizeof(int32_t) * (n + 1)));
+    b.deg_b = static_cast<int32_t*>(take(sizeof(int32_t) * n));
+    b.ptr_b = static_cast<int32_t*>(take(sizeof(int32_t) * (n + 1)));
+    b.keep = static_cast<int32_t*>(take(sizeof(int32_t) * ne));
+    b.pk = static_cast<int32_t*>(take(sizeof(int32_t) * (ne + 1)));
+    b.nbr = static_cast<int32_t*>(take(kind == PAMNET_RNA ? sizeof(int32_t) * n * kKnnK : 0));
+    b.d2 = static_cast<float*>(take(kind == PAMNET_RNA ? sizeof(float) * n * kKnnK : 0));
+    if (out) *out = b;
+    return off;
+}
+thread_local int64_t* g_host_counts = nullptr;      // pinned: the counters are read back between the build phases
+int read_counts(const int64_t* dev, cudaStream_t st) {
+    if (!g_host_counts) PAMNET_CUDA(cudaMallocHost(reinterpret_cast<void**>(&g_host_counts), 8 * sizeof(int64_t)));
+    PAMNET_CUDA(cudaMemcpyAsync(g_host_counts, dev, 8 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    PAMNET_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+}  // namespace
+
+size_t pamnet_plan_build_scratch_bytes(const pamnet_config_t* cfg, int64_t n_nodes, int64_t n_edges_in, int64_t cap_eg) {
+    if (!cfg) return 0;
+    return build_scratch_layout(cfg->dataset, n_nodes, n_edges_in, cap_eg, nullptr, nullptr);
+}
+
+int pamnet_plan_build(const pamnet_config_t* cfg, const float* pos, const int64_t* batch, int64_t n_nodes,
+                      int64_t n_graphs, const int64_t* edge_index_in, int64_t n_edges_in, int32_t max_nb,
+                      int64_t* eg_buf, int64_t cap_eg, int64_t* el_buf, int64_t cap_el, void* plan_base,
+                      size_t cap_base, void* plan_trip, size_t cap_trip, void* scratch, size_t scratch_bytes,
+                      pamnet_sizes_t* sizes_out, int64_t* need, void* stream) {
+    REQUIRE(cfg); REQUIRE(pos); REQUIRE(batch); REQUIRE(eg_buf); REQUIRE(el_buf); REQUIRE(plan_base); REQUIRE(plan_trip);
+    REQUIRE(scratch); REQUIRE(sizes_out); REQUIRE(need);
+    const int kind = cfg->dataset;
+    PAMNET_CHECK_ARG(kind >= PAMNET_QM9 && kind <= PAMNET_RNA, "bad dataset id %d", kind);
+    PAMNET_CHECK_ARG(n_nodes > 0 && n_graphs > 0 && max_nb > 0, "plan_build: n_nodes=%lld n_graphs=%lld",
+                     (long long)n_nodes, (long long)n_graphs);
+    PAMNET_CHECK_ARG(kind != PAMNET_QM9 || n_edges_in == 0 || edge_index_in, "plan_build: QM9 needs data.edge_index");
+    BuildScratch b;
+    const size_t want = build_scratch_layout(kind, n_nodes, n_edges_in, cap_eg, scratch, &b);
+    PAMNET_CHECK_ARG(scratch_bytes >= want, "plan_build: scratch too small: %zu < %zu", scratch_bytes, want);
+    cudaStream_t st = ST(stream);
+    for (int i = 0; i < 4; ++i) need[i] = 0;
+    PAMNET_CUDA(cudaMemsetAsync(b.counts, 0, 8 * sizeof(int64_t), st));
+
+    // ---- phase 1: edge counts (models.py:110,115 / 128,131-136 / 143-157) ----------------------------------------
+    if (kind == PAMNET_RNA) {
+        PAMNET_TRY(knn(pos, batch, n_nodes, kKnnK, b.nbr, b.d2, st));
+        PAMNET_TRY(knn_edges_count(b.nbr, pos, n_nodes, kKnnK, cfg->cutoff_g, b.deg_a, b.ptr_a, b.counts + 0, st));
+        PAMNET_TRY(knn_edges_count(b.nbr, pos, n_nodes, kKnnK, cfg->cutoff_l, b.deg_b, b.ptr_b, b.counts + 1, st));
+    } else {
+        PAMNET_TRY(radius_count(pos, batch, n_nodes, cfg->cutoff_g, max_nb, 1, b.deg_a, b.ptr_a, b.counts + 0, st));
+        if (kind == PAMNET_QM9)
+            PAMNET_TRY(edge_filter_count(edge_index_in, n_edges_in, nullptr, 0.f, b.keep, b.pk, b.counts + 1, st));
+    }
+    PAMNET_TRY(read_counts(b.counts, st));
+    int64_t Eg = g_host_counts[0], El = kind == PAMNET_PDBBIND ? 0 : g_host_counts[1];
+    need[0] = Eg; need[1] = El;
+    if (Eg > cap_eg || El > cap_el) return 1;
+
+    // ---- phase 2: edge lists, CSRs, triplet counts ------------------------------------------------------------------
+    const int64_t* el = el_buf;
+    if (kind == PAMNET_RNA) {
+        PAMNET_TRY(knn_edges_fill(b.nbr, pos, n_nodes, kKnnK, cfg->cutoff_g, b.ptr_a, Eg, eg_buf, st));
+        PAMNET_TRY(knn_edges_fill(b.nbr, pos, n_nodes, kKnnK, cfg->cutoff_l, b.ptr_b, El, el_buf, st));
+    } else {
+        PAMNET_TRY(radius_fill(pos, batch, n_nodes, cfg->cutoff_g, max_nb, 1, b.ptr_a, Eg, eg_buf, st));
+        if (kind == PAMNET_QM9) {
+            if (El == n_edges_in) el = edge_index_in;            // nothing dropped: use the caller's list in place
+            else PAMNET_TRY(edge_filter_fill(edge_index_in, n_edges_in, b.keep, b.pk, El, el_buf, st));
+        } else {
+            PAMNET_TRY(edge_filter_count(eg_buf, Eg, pos, cfg->cutoff_l, b.keep, b.pk, b.counts + 1, st));
+            PAMNET_TRY(read_counts(b.counts, st));
+            El = g_host_counts[1];
+            need[1] = El;
+            if (El > cap_el) return 1;
+            if (El == Eg) el = eg_buf;
+            else PAMNET_TRY(edge_filter_fill(eg_buf, Eg, b.keep, b.pk, El, el_buf, st));
+        }
+    }
+    pamnet_sizes_t sz;
+    memset(&sz, 0, sizeof(sz));
+    sz.n_nodes = n_nodes; sz.n_graphs = n_graphs; sz.n_edges_g = Eg; sz.n_edges_l = El;
+    size_t bb = 0, tb = 0;
+    plan_layout(sz, nullptr, nullptr, nullptr, &bb, &tb);
+    need[2] = (int64_t)bb;
+    if (bb > cap_base) return 1;
+    PAMNET_TRY(plan_count(*cfg, sz, eg_buf, el, batch, plan_base, b.counts + 2, st));
+    PAMNET_TRY(read_counts(b.counts, st));
+    sz.n_t2 = g_host_counts[2]; sz.n_t1 = g_host_counts[3];
+    plan_layout(sz, nullptr, nullptr, nullptr, &bb, &tb);
+    need[3] = (int64_t)tb;
+    if (tb > cap_trip) return 1;
+
+    // ---- phase 3: triplet lists, angles, distances -------------------------------------------------------------------
+    PAMNET_TRY(plan_fill(*cfg, sz, pos, plan_base, plan_trip, st));
+    *sizes_out = sz;
+    return 0;
+}
+
 size_t pamnet_workspace_bytes(const pamnet_config_t* cfg, const pamnet_sizes_t* sz) {
     if (!cfg || !sz) return 0;
     return workspace_bytes(*cfg, *sz);

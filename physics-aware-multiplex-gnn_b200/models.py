@@ -198,6 +198,63 @@ class _PAMNetBase(nn.Module):
 
     # ---- graph construction ---------------------------------------------------------------------------
     def _build_plan(self, pos, batch, n_graphs, edge_index_l_in, max_nb):
+        """The front end in ONE C call (pamnet_plan_build): the two or three count read-backs it needs happen inside
+        the library instead of through Python.  Buffers are allocated here at remembered capacities (the caller owns
+        all memory); a too-small capacity makes the call return 1 with the needed sizes, and it is repeated once."""
+        import os
+        if os.environ.get("PAMNET_PLAN", "") == "stepwise":
+            return self._build_plan_stepwise(pos, batch, n_graphs, edge_index_l_in, max_nb)
+        lib = _lib.load()
+        cfg, dev = self._ccfg, pos.device
+        n, kind = pos.shape[0], cfg.dataset
+        el_in = edge_index_l_in.to(torch.int64).contiguous() if kind == 0 else None
+        e_in = int(el_in.shape[1]) if el_in is not None else 0
+        caps = getattr(self, "_plan_caps", None)
+        if caps is None:
+            caps = {"eg": 50 * n if kind == 2 else 24 * n, "el": e_in if kind == 0 else (50 * n if kind == 2 else 8 * n),
+                    "base": 0, "trip": 0}
+        if kind == 0:
+            caps["el"] = max(caps["el"], e_in)
+        base_b, trip_b = _lib.c_sz(), _lib.c_sz()
+        need = (_lib.c_i64 * 4)()
+        sz = _lib.Sizes(n, n_graphs, 0, 0, 0, 0)
+        stream = torch.cuda.current_stream().cuda_stream
+        for attempt in range(4):
+            guess = _lib.Sizes(n, n_graphs, caps["eg"], caps["el"], 4 * caps["el"], 4 * caps["el"])
+            _lib.check(lib.pamnet_plan_bytes(cfg, guess, base_b, trip_b), "plan_bytes")
+            caps["base"], caps["trip"] = max(caps["base"], base_b.value), max(caps["trip"], trip_b.value)
+            eg_buf = torch.empty(2 * max(caps["eg"], 1), dtype=torch.int64, device=dev)
+            el_buf = torch.empty(2 * max(caps["el"], 1), dtype=torch.int64, device=dev)
+            base = torch.empty(caps["base"], dtype=torch.uint8, device=dev)
+            trip = torch.empty(caps["trip"], dtype=torch.uint8, device=dev)
+            sb = lib.pamnet_plan_build_scratch_bytes(cfg, n, e_in, caps["eg"])
+            scratch = torch.empty(sb, dtype=torch.uint8, device=dev)
+            rc = lib.pamnet_plan_build(cfg, pos.data_ptr(), batch.data_ptr(), n, n_graphs, _lib.ptr(el_in), e_in,
+                                       int(max_nb), eg_buf.data_ptr(), caps["eg"], el_buf.data_ptr(), caps["el"],
+                                       base.data_ptr(), caps["base"], trip.data_ptr(), caps["trip"],
+                                       scratch.data_ptr(), sb, sz, need, stream)
+            if rc == 0:
+                break
+            if rc != 1:
+                _lib.check(rc, "plan_build")
+            grow = lambda have, want: max(have, int(want * 1.25) + 64)
+            caps["eg"], caps["el"] = grow(caps["eg"], need[0]), grow(caps["el"], need[1])
+            caps["base"], caps["trip"] = grow(caps["base"], need[2]), grow(caps["trip"], need[3])
+        else:
+            raise _lib.PamnetError("plan_build: capacities did not converge")
+        self._plan_caps = caps
+        e_g, e_l = int(sz.n_edges_g), int(sz.n_edges_l)
+        eg = eg_buf[:2 * e_g].view(2, e_g)
+        if kind == 0 and e_l == e_in:
+            el = el_in
+        elif kind == 1 and e_l == e_g:
+            el = eg
+        else:
+            el = el_buf[:2 * e_l].view(2, e_l)
+        return GraphPlan(sz, base, trip, eg, el)
+
+    def _build_plan_stepwise(self, pos, batch, n_graphs, edge_index_l_in, max_nb):
+        """Same plan through the granular operator calls (PAMNET_PLAN=stepwise; the path the operator tests cover)."""
         lib = _lib.load()
         cfg, dev = self._ccfg, pos.device
         n = pos.shape[0]
