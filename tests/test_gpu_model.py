@@ -149,3 +149,86 @@ def test_cpu_input_fails_loudly():
     model = _model(gold)
     with pytest.raises((PamnetError, RuntimeError)):
         model(batch_of(gold))
+
+
+# ---- BASELINE.json configs[2] / configs[3] at full size: size-independent properties ---------------------------------
+def _split_batch(b, lo, hi):
+    """Graphs lo..hi-1 of a collated batch as their own batch (node / edge indices re-based)."""
+    from pamnet_b200.data import Batch
+    nodes = (b.batch >= lo) & (b.batch < hi)
+    first = int(nodes.nonzero()[0])
+    f = dict(x=b.x[nodes], batch=b.batch[nodes] - lo, y=b.y[lo:hi])
+    if getattr(b, "pos", None) is not None:
+        f["pos"] = b.pos[nodes]
+    if getattr(b, "edge_index", None) is not None:
+        e = nodes[b.edge_index[0]]
+        f["edge_index"] = b.edge_index[:, e] - first
+    return Batch(**f)
+
+
+def test_c3_batch256_equals_its_32_molecule_shards():
+    """configs[2] size (QM9 dim=128 L=6 bs=256; fp32 -- the bf16 node-MLP variant is not built): molecules are
+    independent, so the batch-256 outputs are the outputs of its eight 32-molecule shards and the
+    gradient of the summed loss is the sum of the shard gradients."""
+    from pamnet_b200 import Config, PAMNet
+    from pamnet_b200.data import synthetic_qm9_batch
+    torch.manual_seed(0)
+    model = PAMNet(Config("QM9", 128, 6, 5.0, 5.0)).cuda()
+    big = synthetic_qm9_batch(256, seed=0)
+    model.zero_grad()
+    out = model(big.to("cuda"))
+    (out - big.y.cuda()).abs().sum().backward()
+    g_big = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+    model.zero_grad()
+    outs = []
+    for s in range(8):
+        sb = _split_batch(big, 32 * s, 32 * (s + 1)).to("cuda")
+        o = model(sb)
+        (o - sb.y).abs().sum().backward()            # accumulates over the shards
+        outs.append(o.detach())
+    assert rel_err(out.detach(), torch.cat(outs)) < 2e-6
+    for k, p in model.named_parameters():
+        if p.grad is not None:
+            assert rel_err(g_big[k], p.grad) < 2e-5, k
+
+
+def test_c4_rna_batch8_large_graphs():
+    """configs[3] size (rna dim=16 L=1, 8 graphs of ~2k atoms, target_to_source, kNN-50): batched == per graph, every
+    node has exactly 49 incoming global messages, and a 3-graph slice matches the fp64 oracle forward + backward."""
+    import types
+    from pamnet_b200 import Config, PAMNet
+    from pamnet_b200.data import synthetic_rna_batch
+    from oracle import pamnet_oracle as O
+    cfg = types.SimpleNamespace(dataset="rna_native", dim=16, n_layer=1, cutoff_l=2.6, cutoff_g=20.0, flow="target_to_source")
+    sd = O.init_state_dict(cfg, seed=0)
+    model = PAMNet(Config(**vars(cfg)))
+    model.load_state_dict(sd)
+    model = model.cuda()
+    # ~2k-atom graphs without the generator's quadratic rejection loop: five translated copies of a 300-500 atom chain
+    from pamnet_b200.data import Batch
+    base = synthetic_rna_batch(8, seed=0, min_atoms=300, max_atoms=500)
+    xs, bs = [], []
+    for g in range(8):
+        xg = base.x[base.batch == g]
+        for c in range(5):
+            xs.append(xg + torch.tensor([37.0 * c, 11.0 * c, 0.0, 0.0]))
+            bs.append(torch.full((xg.shape[0],), g, dtype=torch.long))
+    big = Batch(x=torch.cat(xs), batch=torch.cat(bs), y=base.y)
+    with torch.no_grad():
+        out = model(big.to("cuda"))
+        plan = model.last_plan
+        n = big.x.shape[0]
+        assert plan.sizes.n_edges_g == 49 * n                       # SURVEY.md 8: E_g = 49 N exactly
+        assert torch.equal(torch.bincount(plan.edge_index_g[0].cpu(), minlength=n), torch.full((n,), 49))
+        per = torch.cat([model(_split_batch(big, g, g + 1).to("cuda")) for g in range(8)])
+    assert rel_err(out, per) < 2e-6
+    small = synthetic_rna_batch(3, seed=1, min_atoms=300, max_atoms=500)
+    o, l, grads = _step(model, small)
+    o64, _, g64 = oracle_step(sd, cfg, small, dtype=torch.float64)
+    o32, _, g32 = oracle_step(sd, cfg, small, dtype=torch.float32)
+    ok, e_new, e_ref = ladder_ok(o, o32, o64)
+    assert ok, (e_new, e_ref)
+    for k, ref64 in g64.items():
+        if ref64 is not None:
+            ok, e_new, e_ref = ladder_ok(grads[k], g32[k], ref64)
+            assert ok, (k, e_new, e_ref)
