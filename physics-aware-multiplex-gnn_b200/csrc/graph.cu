@@ -19,6 +19,8 @@ constexpr int kScanItems = 4;
 __global__ void __launch_bounds__(kScanThreads) scan_exclusive_kernel(const int32_t* __restrict__ in,
                                                                       int32_t* __restrict__ out, int64_t n,
                                                                       int64_t* __restrict__ total64) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ int32_t warp_tot[32];
     __shared__ int32_t carry_s;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -70,7 +72,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_exclusive_kernel(const int3
 
 int scan_exclusive(const int32_t* in, int32_t* out, int64_t n, int64_t* total64, cudaStream_t st) {
     prof_begin(KC_GRAPH, 0.0, st);
-    scan_exclusive_kernel<<<1, kScanThreads, 0, st>>>(in, out, n, total64);
+    launch_pdl(scan_exclusive_kernel, dim3(1), dim3(kScanThreads), 0, st, in, out, n, total64);
     prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;
@@ -99,6 +101,8 @@ template <bool FILL>
 __global__ void radius_kernel(const float* __restrict__ pos, const int64_t* __restrict__ batch, int64_t n_nodes,
                               float r2, int max_nb, int drop_self, int32_t* __restrict__ deg,
                               const int32_t* __restrict__ ptr, int64_t total, int64_t* __restrict__ edge_index) {
+    pdl_wait();
+    pdl_trigger();
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n_nodes) return;
     const int64_t g = batch[q];
@@ -127,7 +131,7 @@ int radius_count(const float* pos, const int64_t* batch, int64_t n_nodes, float 
                  int32_t* deg, int32_t* ptr, int64_t* total_dev, cudaStream_t st) {
     if (n_nodes > 0) {
         prof_begin(KC_GRAPH, 0.0, st);
-        radius_kernel<false><<<ceil_div(n_nodes, 128), 128, 0, st>>>(pos, batch, n_nodes, r * r, max_nb, drop_self,
+        launch_pdl(radius_kernel<false>, dim3(ceil_div(n_nodes, 128)), dim3(128), 0, st, pos, batch, n_nodes, r * r, max_nb, drop_self,
                                                                      deg, nullptr, 0, nullptr);
         prof_end(st);
         PAMNET_LAUNCH_CHECK();
@@ -139,7 +143,7 @@ int radius_fill(const float* pos, const int64_t* batch, int64_t n_nodes, float r
                 const int32_t* ptr, int64_t total, int64_t* edge_index, cudaStream_t st) {
     if (n_nodes == 0 || total == 0) return 0;
     prof_begin(KC_GRAPH, 0.0, st);
-    radius_kernel<true><<<ceil_div(n_nodes, 128), 128, 0, st>>>(pos, batch, n_nodes, r * r, max_nb, drop_self,
+    launch_pdl(radius_kernel<true>, dim3(ceil_div(n_nodes, 128)), dim3(128), 0, st, pos, batch, n_nodes, r * r, max_nb, drop_self,
                                                                 nullptr, ptr, total, edge_index);
     prof_end(st);
     PAMNET_LAUNCH_CHECK();
@@ -154,6 +158,8 @@ constexpr int kKnnThreads = 64;
 __global__ void __launch_bounds__(kKnnThreads) knn_kernel(const float* __restrict__ pos,
                                                           const int64_t* __restrict__ batch, int64_t n_nodes, int k,
                                                           int32_t* __restrict__ nbr, float* __restrict__ d2out) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ unsigned char smem_raw[];
     float* sd = reinterpret_cast<float*>(smem_raw);                 // [k][kKnnThreads]
     int32_t* si = reinterpret_cast<int32_t*>(sd + (size_t)k * kKnnThreads);
@@ -189,7 +195,7 @@ int knn(const float* pos, const int64_t* batch, int64_t n_nodes, int k, int32_t*
     PAMNET_CHECK_ARG(smem <= 200 * 1024, "knn: k=%d too large", k);
     PAMNET_CUDA(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     prof_begin(KC_GRAPH, 0.0, st);
-    knn_kernel<<<ceil_div(n_nodes, kKnnThreads), kKnnThreads, smem, st>>>(pos, batch, n_nodes, k, nbr, d2);
+    launch_pdl(knn_kernel, dim3(ceil_div(n_nodes, kKnnThreads)), dim3(kKnnThreads), smem, st, pos, batch, n_nodes, k, nbr, d2);
     prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;
@@ -205,6 +211,8 @@ template <bool FILL>
 __global__ void knn_edges_kernel(const int32_t* __restrict__ nbr, const float* __restrict__ pos, int64_t n_nodes,
                                  int k, float cutoff, int32_t* __restrict__ deg, const int32_t* __restrict__ ptr,
                                  int64_t total, int64_t* __restrict__ edge_index) {
+    pdl_wait();
+    pdl_trigger();
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n_nodes) return;
     int kept = 0;
@@ -228,7 +236,7 @@ int knn_edges_count(const int32_t* nbr, const float* pos, int64_t n_nodes, int k
                     int32_t* ptr, int64_t* total_dev, cudaStream_t st) {
     if (n_nodes > 0) {
         prof_begin(KC_GRAPH, 0.0, st);
-        knn_edges_kernel<false><<<ceil_div(n_nodes, 128), 128, 0, st>>>(nbr, pos, n_nodes, k, cutoff, deg, nullptr, 0,
+        launch_pdl(knn_edges_kernel<false>, dim3(ceil_div(n_nodes, 128)), dim3(128), 0, st, nbr, pos, n_nodes, k, cutoff, deg, nullptr, 0,
                                                                         nullptr);
         prof_end(st);
         PAMNET_LAUNCH_CHECK();
@@ -240,7 +248,7 @@ int knn_edges_fill(const int32_t* nbr, const float* pos, int64_t n_nodes, int k,
                    int64_t total, int64_t* edge_index, cudaStream_t st) {
     if (n_nodes == 0 || total == 0) return 0;
     prof_begin(KC_GRAPH, 0.0, st);
-    knn_edges_kernel<true><<<ceil_div(n_nodes, 128), 128, 0, st>>>(nbr, pos, n_nodes, k, cutoff, nullptr, ptr, total,
+    launch_pdl(knn_edges_kernel<true>, dim3(ceil_div(n_nodes, 128)), dim3(128), 0, st, nbr, pos, n_nodes, k, cutoff, nullptr, ptr, total,
                                                                    edge_index);
     prof_end(st);
     PAMNET_LAUNCH_CHECK();
@@ -252,6 +260,8 @@ int knn_edges_fill(const int32_t* nbr, const float* pos, int64_t n_nodes, int k,
 // ---------------------------------------------------------------------------------------------
 __global__ void edge_keep_kernel(const int64_t* __restrict__ ei, int64_t n_edges, const float* __restrict__ pos,
                                  float cutoff, int32_t* __restrict__ keep) {
+    pdl_wait();
+    pdl_trigger();
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_edges) return;
     const int64_t a = ei[e], b = ei[n_edges + e];
@@ -262,6 +272,8 @@ __global__ void edge_keep_kernel(const int64_t* __restrict__ ei, int64_t n_edges
 
 __global__ void edge_compact_kernel(const int64_t* __restrict__ ei, int64_t n_edges, const int32_t* __restrict__ keep,
                                     const int32_t* __restrict__ ptr, int64_t total, int64_t* __restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_edges || !keep[e]) return;
     out[ptr[e]] = ei[e];
@@ -272,7 +284,7 @@ int edge_filter_count(const int64_t* ei, int64_t n_edges, const float* pos, floa
                       int64_t* total_dev, cudaStream_t st) {
     if (n_edges > 0) {
         prof_begin(KC_GRAPH, 0.0, st);
-        edge_keep_kernel<<<ceil_div(n_edges, 256), 256, 0, st>>>(ei, n_edges, pos, cutoff, keep);
+        launch_pdl(edge_keep_kernel, dim3(ceil_div(n_edges, 256)), dim3(256), 0, st, ei, n_edges, pos, cutoff, keep);
         prof_end(st);
         PAMNET_LAUNCH_CHECK();
     }
@@ -283,7 +295,7 @@ int edge_filter_fill(const int64_t* ei, int64_t n_edges, const int32_t* keep, co
                      int64_t* out, cudaStream_t st) {
     if (n_edges == 0 || total == 0) return 0;
     prof_begin(KC_GRAPH, 0.0, st);
-    edge_compact_kernel<<<ceil_div(n_edges, 256), 256, 0, st>>>(ei, n_edges, keep, ptr, total, out);
+    launch_pdl(edge_compact_kernel, dim3(ceil_div(n_edges, 256)), dim3(256), 0, st, ei, n_edges, keep, ptr, total, out);
     prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;
@@ -294,6 +306,8 @@ int edge_filter_fill(const int64_t* ei, int64_t n_edges, const int32_t* keep, co
 // ---------------------------------------------------------------------------------------------
 __global__ void split_edges_kernel(const int64_t* __restrict__ ei, int64_t n_edges, int dst_row,
                                    int32_t* __restrict__ dst, int32_t* __restrict__ src) {
+    pdl_wait();
+    pdl_trigger();
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_edges) return;
     dst[e] = (int32_t)ei[(int64_t)dst_row * n_edges + e];
@@ -301,12 +315,16 @@ __global__ void split_edges_kernel(const int64_t* __restrict__ ei, int64_t n_edg
 }
 
 __global__ void hist_kernel(const int32_t* __restrict__ keys, int64_t n, int32_t* __restrict__ cnt) {
+    pdl_wait();
+    pdl_trigger();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) atomicAdd(&cnt[keys[i]], 1);
 }
 
 __global__ void bucket_fill_kernel(const int32_t* __restrict__ keys, int64_t n, const int32_t* __restrict__ ptr,
                                    int32_t* __restrict__ cursor, int32_t* __restrict__ items) {
+    pdl_wait();
+    pdl_trigger();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int k = keys[i];
@@ -319,6 +337,8 @@ __global__ void __launch_bounds__(128) bucket_sort_kernel(const int32_t* __restr
                                                           const int32_t* __restrict__ items_in,
                                                           int32_t* __restrict__ items_out,
                                                           const int32_t* __restrict__ key2) {
+    pdl_wait();
+    pdl_trigger();
     const int lane = threadIdx.x & 31;
     const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (b >= n_buckets) return;
@@ -342,7 +362,7 @@ int build_buckets(const int32_t* keys, int64_t n, int64_t n_buckets, const int32
     PAMNET_CUDA(cudaMemsetAsync(cnt_scratch, 0, sizeof(int32_t) * (n_buckets + 1), st));
     if (n > 0) {
         prof_begin(KC_GRAPH, 0.0, st);
-        hist_kernel<<<ceil_div(n, 256), 256, 0, st>>>(keys, n, cnt_scratch);
+        launch_pdl(hist_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, st, keys, n, cnt_scratch);
         prof_end(st);
         PAMNET_LAUNCH_CHECK();
     }
@@ -350,11 +370,11 @@ int build_buckets(const int32_t* keys, int64_t n, int64_t n_buckets, const int32
     if (n > 0) {
         PAMNET_CUDA(cudaMemsetAsync(cnt_scratch, 0, sizeof(int32_t) * (n_buckets + 1), st));
         prof_begin(KC_GRAPH, 0.0, st);
-        bucket_fill_kernel<<<ceil_div(n, 256), 256, 0, st>>>(keys, n, ptr, cnt_scratch, items_tmp);
+        launch_pdl(bucket_fill_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, st, keys, n, ptr, cnt_scratch, items_tmp);
         prof_end(st);
         PAMNET_LAUNCH_CHECK();
         prof_begin(KC_GRAPH, 0.0, st);
-        bucket_sort_kernel<<<ceil_div(n_buckets, 4), 128, 0, st>>>(ptr, n_buckets, items_tmp, items, key2);
+        launch_pdl(bucket_sort_kernel, dim3(ceil_div(n_buckets, 4)), dim3(128), 0, st, ptr, n_buckets, items_tmp, items, key2);
         prof_end(st);
         PAMNET_LAUNCH_CHECK();
     }
@@ -363,11 +383,15 @@ int build_buckets(const int32_t* keys, int64_t n, int64_t n_buckets, const int32
 
 __global__ void gather_i32_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ idx, int64_t n,
                                   int32_t* __restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = src[idx[i]];
 }
 
 __global__ void invert_perm_kernel(const int32_t* __restrict__ perm, int64_t n, int32_t* __restrict__ inv) {
+    pdl_wait();
+    pdl_trigger();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) inv[perm[i]] = (int32_t)i;
 }
@@ -379,19 +403,19 @@ int build_in_csr(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, in
                  int32_t* dst_csr, cudaStream_t st) {
     if (n_edges > 0) {
         prof_begin(KC_GRAPH, 0.0, st);
-        split_edges_kernel<<<ceil_div(n_edges, 256), 256, 0, st>>>(edge_index, n_edges, dst_row, dst_api, src_api);
+        launch_pdl(split_edges_kernel, dim3(ceil_div(n_edges, 256)), dim3(256), 0, st, edge_index, n_edges, dst_row, dst_api, src_api);
         prof_end(st);
         PAMNET_LAUNCH_CHECK();
     }
     PAMNET_TRY(build_buckets(dst_api, n_edges, n_nodes, src_api, cnt_scratch, ptr, eid, tmp, st));
     if (n_edges > 0) {
         prof_begin(KC_GRAPH, 0.0, st);
-        gather_i32_kernel<<<ceil_div(n_edges, 256), 256, 0, st>>>(src_api, eid, n_edges, src_csr);
+        launch_pdl(gather_i32_kernel, dim3(ceil_div(n_edges, 256)), dim3(256), 0, st, src_api, eid, n_edges, src_csr);
         prof_end(st);
         PAMNET_LAUNCH_CHECK();
         if (dst_csr) {
             prof_begin(KC_GRAPH, 0.0, st);
-            gather_i32_kernel<<<ceil_div(n_edges, 256), 256, 0, st>>>(dst_api, eid, n_edges, dst_csr);
+            launch_pdl(gather_i32_kernel, dim3(ceil_div(n_edges, 256)), dim3(256), 0, st, dst_api, eid, n_edges, dst_csr);
             prof_end(st);
             PAMNET_LAUNCH_CHECK();
         }
@@ -407,6 +431,8 @@ __global__ void triplet_count_kernel(const int32_t* __restrict__ dst_api, const 
                                      int64_t n_edges, const int32_t* __restrict__ ptr,
                                      const int32_t* __restrict__ src_csr, int32_t* __restrict__ c2,
                                      int32_t* __restrict__ c1) {
+    pdl_wait();
+    pdl_trigger();
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_edges) return;
     const int j = src_api[e], i = dst_api[e];
@@ -426,6 +452,8 @@ __global__ void triplet_fill_kernel(const int32_t* __restrict__ dst_api, const i
                                     int64_t* __restrict__ idx_ji, int64_t* __restrict__ idx_i_pair,
                                     int64_t* __restrict__ idx_j1_pair, int64_t* __restrict__ idx_j2_pair,
                                     int64_t* __restrict__ idx_jj_pair, int64_t* __restrict__ idx_ji_pair) {
+    pdl_wait();
+    pdl_trigger();
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_edges) return;
     const int j = src_api[e], i = dst_api[e];
@@ -476,7 +504,7 @@ int triplet_count(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, v
                             s.src_csr, nullptr, st));
     if (n_edges > 0) {
         prof_begin(KC_GRAPH, 0.0, st);
-        triplet_count_kernel<<<ceil_div(n_edges, 128), 128, 0, st>>>(s.dst_api, s.src_api, n_edges, s.ptr, s.src_csr,
+        launch_pdl(triplet_count_kernel, dim3(ceil_div(n_edges, 128)), dim3(128), 0, st, s.dst_api, s.src_api, n_edges, s.ptr, s.src_csr,
                                                                      s.c2, s.c1);
         prof_end(st);
         PAMNET_LAUNCH_CHECK();
@@ -493,7 +521,7 @@ int triplet_fill(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes, co
     triplet_scratch_layout(n_nodes, n_edges, const_cast<void*>(scratch), &s);
     if (n_edges == 0) return 0;
     prof_begin(KC_GRAPH, 0.0, st);
-    triplet_fill_kernel<<<ceil_div(n_edges, 128), 128, 0, st>>>(s.dst_api, s.src_api, n_edges, s.ptr, s.src_csr, s.eid,
+    launch_pdl(triplet_fill_kernel, dim3(ceil_div(n_edges, 128)), dim3(128), 0, st, s.dst_api, s.src_api, n_edges, s.ptr, s.src_csr, s.eid,
                                                                 s.off2, s.off1, out[0], out[1], out[2], out[3], out[4],
                                                                 out[5], out[6], out[7], out[8], out[9]);
     prof_end(st);
@@ -539,6 +567,8 @@ void plan_layout(const pamnet_sizes_t& sz, void* base, void* trip, Plan* out, si
 
 __global__ void n2g_kernel(const int64_t* __restrict__ batch, int64_t n, int64_t n_graphs, int32_t* __restrict__ n2g,
                            int32_t* __restrict__ gptr) {
+    pdl_wait();
+    pdl_trigger();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) n2g[i] = (int32_t)batch[i];
     if (i <= n_graphs) gptr[i] = (int32_t)lower_bound_i64(batch, n, i);
@@ -549,6 +579,8 @@ __global__ void plan_tcount_kernel(const int32_t* __restrict__ l_ptr, const int3
                                    const int32_t* __restrict__ l_dst, int64_t n_edges, int two_hop,
                                    int32_t* __restrict__ t_split, int32_t* __restrict__ t_cnt,
                                    unsigned long long* __restrict__ totals) {
+    pdl_wait();
+    pdl_trigger();
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int n2 = 0, n1 = 0;
     if (k < n_edges) {
@@ -593,6 +625,8 @@ __global__ void plan_tfill_kernel(const int32_t* __restrict__ l_ptr, const int32
                                   const int32_t* __restrict__ t_ptr, const float* __restrict__ pos,
                                   int32_t* __restrict__ t_gather, int32_t* __restrict__ t_owner,
                                   float* __restrict__ t_angle) {
+    pdl_wait();
+    pdl_trigger();
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_edges) return;
     const int j = l_src[k], i = l_dst[k];
@@ -618,6 +652,8 @@ __global__ void plan_tfill_kernel(const int32_t* __restrict__ l_ptr, const int32
 __global__ void csr_dist_kernel(const int32_t* __restrict__ ptr_g, const int32_t* __restrict__ src_g,
                                 const int32_t* __restrict__ ptr_l, const int32_t* __restrict__ src_l, int64_t n_nodes,
                                 const float* __restrict__ pos, float* __restrict__ dist_g, float* __restrict__ dist_l) {
+    pdl_wait();
+    pdl_trigger();
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= n_nodes) return;
     const int32_t* ptr = blockIdx.y ? ptr_l : ptr_g;
@@ -642,6 +678,8 @@ __global__ void split_edges2_kernel(const int64_t* __restrict__ eg, int64_t n_g,
                                     int32_t* __restrict__ g_src, int32_t* __restrict__ l_dst, int32_t* __restrict__ l_src,
                                     const int64_t* __restrict__ batch, int64_t n_nodes, int64_t n_graphs,
                                     int32_t* __restrict__ n2g, int32_t* __restrict__ gptr) {
+    pdl_wait();
+    pdl_trigger();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_g) {
         g_dst[i] = (int32_t)eg[(int64_t)g_dst_row * n_g + i];
@@ -656,6 +694,8 @@ __global__ void split_edges2_kernel(const int64_t* __restrict__ eg, int64_t n_g,
 }
 
 __global__ void hist4_kernel(const CsrJobs j) {
+    pdl_wait();
+    pdl_trigger();
     const int q = blockIdx.y;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < j.n[q]) atomicAdd(&j.cnt[q][j.keys[q][i]], 1);
@@ -663,6 +703,8 @@ __global__ void hist4_kernel(const CsrJobs j) {
 
 // block q scans job q (same algorithm as scan_exclusive_kernel)
 __global__ void __launch_bounds__(kScanThreads) scan4_kernel(const CsrJobs j) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ int32_t warp_tot[32];
     __shared__ int32_t carry_s;
     const int q = blockIdx.x;
@@ -714,6 +756,8 @@ __global__ void __launch_bounds__(kScanThreads) scan4_kernel(const CsrJobs j) {
 }
 
 __global__ void fill4_kernel(const CsrJobs j) {
+    pdl_wait();
+    pdl_trigger();
     const int q = blockIdx.y;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= j.n[q]) return;
@@ -722,6 +766,8 @@ __global__ void fill4_kernel(const CsrJobs j) {
 }
 
 __global__ void __launch_bounds__(128) sort4_kernel(const CsrJobs j) {
+    pdl_wait();
+    pdl_trigger();
     const int q = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -750,6 +796,8 @@ __global__ void csr_finish1_kernel(const int32_t* __restrict__ g_eid, const int3
                                    const int32_t* __restrict__ l_eid, const int32_t* __restrict__ l_src_api,
                                    const int32_t* __restrict__ l_dst_api, int64_t n_l, int32_t* __restrict__ l_src,
                                    int32_t* __restrict__ l_dst, int32_t* __restrict__ l_pos_of) {
+    pdl_wait();
+    pdl_trigger();
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k < n_g) {
         const int e = g_eid[k];
@@ -764,6 +812,8 @@ __global__ void csr_finish1_kernel(const int32_t* __restrict__ g_eid, const int3
 // out-CSR entries (edge ids, ascending per source) -> slots; triplet counts per local slot
 __global__ void csr_finish2_kernel(int32_t* __restrict__ g_opos, const int32_t* __restrict__ g_pos_of, int64_t n_g,
                                    int32_t* __restrict__ l_opos, const int32_t* __restrict__ l_pos_of, int64_t n_l) {
+    pdl_wait();
+    pdl_trigger();
     const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (u < n_g) g_opos[u] = g_pos_of[g_opos[u]];
     if (u < n_l) l_opos[u] = l_pos_of[l_opos[u]];
@@ -782,7 +832,7 @@ int plan_count(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const int64
         int64_t n = Emax > N ? Emax : N;
         n = n > sz.n_graphs + 1 ? n : sz.n_graphs + 1;
         prof_begin(KC_GRAPH, 0.0, st);
-        split_edges2_kernel<<<ceil_div(n, 256), 256, 0, st>>>(edge_index_g, Eg, g_dst_row, edge_index_l, El, p.tmp_a,
+        launch_pdl(split_edges2_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, st, edge_index_g, Eg, g_dst_row, edge_index_l, El, p.tmp_a,
                                                               p.tmp_b, p.tmp_d, p.tmp_e, batch, N, sz.n_graphs, p.n2g,
                                                               p.gptr);
         prof_end(st);
@@ -803,39 +853,39 @@ int plan_count(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const int64
     PAMNET_CUDA(cudaMemsetAsync(p.cnt4, 0, sizeof(int32_t) * 4 * (N + 1), st));
     if (Emax > 0) {
         prof_begin(KC_GRAPH, 0.0, st);
-        hist4_kernel<<<dim3(ceil_div(Emax, 256), 4), 256, 0, st>>>(j);
+        launch_pdl(hist4_kernel, dim3(dim3(ceil_div(Emax, 256), 4)), dim3(256), 0, st, j);
         prof_end(st);
         PAMNET_LAUNCH_CHECK();
     }
     prof_begin(KC_GRAPH, 0.0, st);
-    scan4_kernel<<<4, kScanThreads, 0, st>>>(j);
+    launch_pdl(scan4_kernel, dim3(4), dim3(kScanThreads), 0, st, j);
     prof_end(st);
     PAMNET_LAUNCH_CHECK();
     PAMNET_CUDA(cudaMemsetAsync(p.cnt4, 0, sizeof(int32_t) * 4 * (N + 1), st));
     if (Emax > 0) {
         prof_begin(KC_GRAPH, 0.0, st);
-        fill4_kernel<<<dim3(ceil_div(Emax, 256), 4), 256, 0, st>>>(j);
+        launch_pdl(fill4_kernel, dim3(dim3(ceil_div(Emax, 256), 4)), dim3(256), 0, st, j);
         prof_end(st);
         PAMNET_LAUNCH_CHECK();
         prof_begin(KC_GRAPH, 0.0, st);
-        sort4_kernel<<<dim3(ceil_div(N, 4), 4), 128, 0, st>>>(j);
+        launch_pdl(sort4_kernel, dim3(dim3(ceil_div(N, 4), 4)), dim3(128), 0, st, j);
         prof_end(st);
         PAMNET_LAUNCH_CHECK();
         prof_begin(KC_GRAPH, 0.0, st);
-        csr_finish1_kernel<<<ceil_div(Emax, 256), 256, 0, st>>>(p.g_eid, p.tmp_b, p.tmp_a, Eg, p.g_src, p.g_dst,
+        launch_pdl(csr_finish1_kernel, dim3(ceil_div(Emax, 256)), dim3(256), 0, st, p.g_eid, p.tmp_b, p.tmp_a, Eg, p.g_src, p.g_dst,
                                                                 p.tmp_c, p.l_eid, p.tmp_e, p.tmp_d, El, p.l_src,
                                                                 p.l_dst, p.tmp_f);
         prof_end(st);
         PAMNET_LAUNCH_CHECK();
         prof_begin(KC_GRAPH, 0.0, st);
-        csr_finish2_kernel<<<ceil_div(Emax, 256), 256, 0, st>>>(p.g_opos, p.tmp_c, Eg, p.l_opos, p.tmp_f, El);
+        launch_pdl(csr_finish2_kernel, dim3(ceil_div(Emax, 256)), dim3(256), 0, st, p.g_opos, p.tmp_c, Eg, p.l_opos, p.tmp_f, El);
         prof_end(st);
         PAMNET_LAUNCH_CHECK();
     }
     PAMNET_CUDA(cudaMemsetAsync(counts_dev, 0, 2 * sizeof(int64_t), st));
     if (El > 0) {
         prof_begin(KC_GRAPH, 0.0, st);
-        plan_tcount_kernel<<<ceil_div(El, 128), 128, 0, st>>>(p.l_ptr, p.l_src, p.l_dst, El, cfg.simple ? 0 : 1,
+        launch_pdl(plan_tcount_kernel, dim3(ceil_div(El, 128)), dim3(128), 0, st, p.l_ptr, p.l_src, p.l_dst, El, cfg.simple ? 0 : 1,
                                                               p.t_split, p.t_cnt,
                                                               reinterpret_cast<unsigned long long*>(counts_dev));
         prof_end(st);
@@ -852,7 +902,7 @@ int plan_fill(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const float*
     const int64_t N = sz.n_nodes, El = sz.n_edges_l, T = sz.n_t2 + sz.n_t1;
     if (El > 0 && T > 0) {
         prof_begin(KC_GRAPH, 0.0, st);
-        plan_tfill_kernel<<<ceil_div(El, 128), 128, 0, st>>>(p.l_ptr, p.l_src, p.l_dst, El, cfg.simple ? 0 : 1, p.t_ptr,
+        launch_pdl(plan_tfill_kernel, dim3(ceil_div(El, 128)), dim3(128), 0, st, p.l_ptr, p.l_src, p.l_dst, El, cfg.simple ? 0 : 1, p.t_ptr,
                                                              pos, p.t_gather, p.t_owner, p.t_angle);
         prof_end(st);
         PAMNET_LAUNCH_CHECK();
@@ -860,7 +910,7 @@ int plan_fill(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const float*
     PAMNET_TRY(build_buckets(p.t_gather, T, El, nullptr, p.cnt, p.tt_ptr, p.tt_t, p.t_tmp, st));
     if (N > 0) {
         prof_begin(KC_GRAPH, 0.0, st);
-        csr_dist_kernel<<<dim3(ceil_div(N, 128), 2), 128, 0, st>>>(p.g_ptr, p.g_src, p.l_ptr, p.l_src, N, pos, p.dist_g,
+        launch_pdl(csr_dist_kernel, dim3(dim3(ceil_div(N, 128), 2)), dim3(128), 0, st, p.g_ptr, p.g_src, p.l_ptr, p.l_src, N, pos, p.dist_g,
                                                                    p.dist_l);
         prof_end(st);
         PAMNET_LAUNCH_CHECK();
