@@ -299,11 +299,29 @@ def run_ours(args):
             traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(dom, {}).get("dram_bytes_per_launch")
         except (OSError, ValueError):
             pass
-        line["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                            "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                            "share_of_step": kernels[dom]["share"],
-                            "note": "algorithmic bytes of the kernel's operands / CUDA-event duration per launch, "
-                                    "averaged over its launches in a step; fp32 FFMA GEMMs are compute-bound, see DESIGN.md"}
+        hbm_view = {"achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "peak_source": peak_src}
+        if d[3] > 0:
+            # the dominant class is the 3xTF32 tcgen05 GEMM: each fp32-accurate multiply-add is three tf32 tensor-core
+            # multiply-adds, so the executed tensor work is 3 x the fp32-equivalent flops; tf32 runs at half the bf16
+            # rate, hence peak = measured dense bf16 / 2
+            bf16 = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1650.0)))
+            tf32_peak = bf16 / 2.0
+            tens = 3.0 * d[3] / 1e12 / (d[0] * 1e-3)
+            line["roofline"] = {"kernel": dom, "bound": "tensor", "achieved": tens, "peak": tf32_peak, "unit": "TFLOP/s",
+                                "frac": tens / tf32_peak, "traffic": traffic,
+                                "peak_source": "MEASURED_PEAKS.json dense bf16 (sustained) / 2 = tf32 rate" if peaks else
+                                               "fallback 1650 TFLOP/s bf16 / 2",
+                                "share_of_step": kernels[dom]["share"], "fp32_equivalent_tflops": tens / 3.0,
+                                "hbm_view": hbm_view,
+                                "note": "3xTF32 GEMM class: achieved = 3 x fp32-equivalent flops of its launches / their "
+                                        "CUDA-event time (concurrent streams share the SMs); hbm_view = algorithmic operand "
+                                        "bytes / the same time"}
+        else:
+            line["roofline"] = {"kernel": dom, "bound": "hbm", **hbm_view, "traffic": traffic,
+                                "share_of_step": kernels[dom]["share"],
+                                "note": "algorithmic bytes of the kernel's operands / CUDA-event duration per launch, "
+                                        "averaged over its launches in a step"}
         b_step = algorithmic_bytes_step(sizes, args.dim, args.n_layer)
         line["step_roofline"] = {"algorithmic_bytes": b_step, "achieved": b_step / 1e9 / (dev_ms * 1e-3), "peak": hbm_peak,
                                  "unit": "GB/s", "frac": b_step / 1e9 / (dev_ms * 1e-3) / hbm_peak,

@@ -214,7 +214,7 @@ int64_t pamnet_debug_launch_count(void);
  * end synchronises and fills ms / launches / algorithmic bytes per class (13 classes, order of KernelClass in
  * csrc/common.cuh); returns the class count.  Not thread-safe; off by default. */
 void pamnet_debug_profile_begin(void);
-int pamnet_debug_profile_end(double* ms, int64_t* launches, double* bytes);
+int pamnet_debug_profile_end(double* ms, int64_t* launches, double* bytes, double* flops /* fp32-equivalent, GEMM classes; may be NULL */);
 /* Same records as a timeline (call instead of profile_end): class, stream tag, start/end ms; returns the count. */
 int pamnet_debug_profile_timeline(int32_t* cls, int32_t* stream_tag, float* t0_ms, float* t1_ms, int32_t cap);
 /* clock64 timeline of CTA 0 of the last tensor-core GEMM launch (HOST buffer of n <= 256 slots).  Only libraries

@@ -67,7 +67,7 @@ SIGNATURES = {
     "pamnet_debug_plan_offset": (c_i64, [_PS, c_i32, C.POINTER(c_i32)]),
     "pamnet_debug_launch_count": (c_i64, []),
     "pamnet_debug_profile_begin": (None, []),
-    "pamnet_debug_profile_end": (c_i32, [c_vp, c_vp, c_vp]),
+    "pamnet_debug_profile_end": (c_i32, [c_vp, c_vp, c_vp, c_vp]),
     "pamnet_debug_profile_timeline": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32]),
     "pamnet_debug_tc_trace": (c_i32, [c_vp, c_i32]),
     "pamnet_debug_chain_trace": (c_i32, [c_vp, c_i32]),
@@ -112,12 +112,12 @@ def profile_begin():
 
 
 def profile_end():
-    """-> {class: (ms, launches, algorithmic_bytes)} accumulated since profile_begin()."""
+    """-> {class: (ms, launches, algorithmic_bytes, fp32-equivalent flops)} accumulated since profile_begin()."""
     n = len(KERNEL_CLASSES)
-    ms, cnt, byt = (C.c_double * n)(), (c_i64 * n)(), (C.c_double * n)()
-    got = load().pamnet_debug_profile_end(ms, cnt, byt)
+    ms, cnt, byt, flo = (C.c_double * n)(), (c_i64 * n)(), (C.c_double * n)(), (C.c_double * n)()
+    got = load().pamnet_debug_profile_end(ms, cnt, byt, flo)
     assert got == n, "kernel class table out of sync with csrc/common.cuh"
-    return {k: (ms[i], int(cnt[i]), byt[i]) for i, k in enumerate(KERNEL_CLASSES)}
+    return {k: (ms[i], int(cnt[i]), byt[i], flo[i]) for i, k in enumerate(KERNEL_CLASSES)}
 
 
 def profile_timeline(cap=4096):

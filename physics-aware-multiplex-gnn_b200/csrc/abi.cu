@@ -39,7 +39,7 @@ bool pdl_enabled() { return pdl_level() != 0; }
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-struct ProfRec { int cls; double bytes; cudaEvent_t e0, e1; cudaStream_t st; };
+struct ProfRec { int cls; double bytes; cudaEvent_t e0, e1; cudaStream_t st; double flops; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof_recs;
 static std::vector<cudaEvent_t> g_prof_pool;
@@ -54,9 +54,12 @@ static cudaEvent_t prof_event() {
 }
 void prof_begin(int cls, double bytes, cudaStream_t st) {
     if (!g_prof_on) return;
-    ProfRec r{cls, bytes, prof_event(), prof_event(), st};
+    ProfRec r{cls, bytes, prof_event(), prof_event(), st, 0.0};
     cudaEventRecord(r.e0, st);
     g_prof_recs.push_back(r);
+}
+void prof_flops(double flops) {     // attach fp32-equivalent flops to the record opened by the last prof_begin
+    if (g_prof_on && !g_prof_recs.empty()) g_prof_recs.back().flops = flops;
 }
 void prof_end(cudaStream_t st) {
     if (!g_prof_on || g_prof_recs.empty()) return;
@@ -333,14 +336,15 @@ void pamnet_debug_profile_begin(void) {
     g_prof_on = true;
 }
 // ms[KC_COUNT], launches[KC_COUNT], bytes[KC_COUNT]; synchronises the device
-int pamnet_debug_profile_end(double* ms, int64_t* launches, double* bytes) {
+int pamnet_debug_profile_end(double* ms, int64_t* launches, double* bytes, double* flops) {
     g_prof_on = false;
     PAMNET_CUDA(cudaDeviceSynchronize());
-    for (int i = 0; i < KC_COUNT; ++i) { ms[i] = 0; launches[i] = 0; bytes[i] = 0; }
+    for (int i = 0; i < KC_COUNT; ++i) { ms[i] = 0; launches[i] = 0; bytes[i] = 0; if (flops) flops[i] = 0; }
     for (auto& r : g_prof_recs) {
         float t = 0.f;
         if (cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess) continue;
         ms[r.cls] += t; launches[r.cls] += 1; bytes[r.cls] += r.bytes;
+        if (flops) flops[r.cls] += r.flops;
     }
     g_prof_recs.clear();
     g_prof_used = 0;

@@ -44,6 +44,7 @@ enum KernelClass : int {
 };
 void prof_begin(int cls, double alg_bytes, cudaStream_t st);   // call right before a kernel launch
 void prof_end(cudaStream_t st);                                // call right after it
+void prof_flops(double flops);                                 // optional, right after prof_begin: fp32-equivalent flops
 void count_launch();
 
 #define PAMNET_LAUNCH_CHECK()                 \

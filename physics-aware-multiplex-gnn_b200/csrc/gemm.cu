@@ -271,6 +271,8 @@ int gemm_launch(const GemmArgs& a, cudaStream_t st) {
     double bytes = 4.0 * a.nslots * ((double)a.M * a.K + (double)a.K * a.N + (double)a.M * a.N);
     if (a.epi == EPI_MUL_DSILU || (a.epi == EPI_BIAS_SILU && a.slot[0].C2)) bytes += 4.0 * a.nslots * (double)a.M * a.N;
     const int ks = a.ksplit > 1 ? a.ksplit : 1;
+    double flops = 0.0;
+    for (int i = 0; i < a.nslots; ++i) flops += 2.0 * (a.slot[i].m > 0 ? a.slot[i].m : a.M) * (double)a.N * a.K;
     if (gemm_backend() == 1 && gemm_tc_eligible(a)) {
         // The tensor core adds each MMA into the fp32 accumulator with truncation, so the error of one
         // accumulation chain grows linearly with its length (measured: 1e-5 relative at K = 1536).  Long
@@ -291,6 +293,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t st) {
             b.ksplit = want;                                                // already accumulating with atomics
         }
         prof_begin(KC_GEMM, bytes, st);
+        prof_flops(flops);
         PAMNET_TRY(gemm_tc_launch(b, st));
         prof_end(st);
         PAMNET_LAUNCH_CHECK();
@@ -307,6 +310,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t st) {
     const long big_ctas = (long)ceil_div(a.M, 128) * ceil_div(a.N, 128) * ks * a.nslots;
     const bool big = a.M >= 128 && a.N >= 128 && big_ctas >= 2 * kNumSM;
     prof_begin(KC_GEMM, bytes, st);
+    prof_flops(flops);
 #define GEMM_LAUNCH(EPI_)                                                              \
     do {                                                                               \
         if (big) {                                                                     \

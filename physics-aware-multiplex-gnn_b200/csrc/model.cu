@@ -440,16 +440,38 @@ struct Sched {
         return 0;
     }
 };
-thread_local std::vector<cudaEvent_t> g_event_pool;
-// The node-level weight gradients are 128 x 128 outputs over ~600 rows: a dozen CTAs per launch.  They run on a third,
-// library-owned stream so that they fill SMs the other two streams leave idle instead of queueing behind the large
-// per-edge GEMMs.  Created once per host thread, joined back into the caller's stream before every return.
-thread_local cudaStream_t g_small_stream = nullptr;
-thread_local cudaStream_t g_extra_stream[2] = {nullptr, nullptr};
-// The sequential layer loop is the critical path; its kernels need whole SMs (the node chain keeps ~190 KB of shared
-// memory per CTA) and otherwise queue behind the GEMM CTAs of the other streams whenever SMs free up.  It therefore
-// runs on a library-owned stream of the highest priority, forked from / joined into the caller's stream.
-thread_local cudaStream_t g_main_stream = nullptr;
+// Library-owned streams and events, per host thread AND per device (streams / events belong to the device that was
+// current when they were created; forward and backward run on different host threads under autograd).
+//  * small: the node-level weight gradients are 128 x 128 outputs over ~600 rows, a dozen CTAs per launch; on their own
+//    stream they fill SMs the other streams leave idle instead of queueing behind the large per-edge GEMMs;
+//  * extra[2]: independent per-edge / per-triplet GEMM families of backward side by side;
+//  * main: the sequential layer loop is the critical path; its kernels need whole SMs (the node chain keeps ~190 KB of
+//    shared memory per CTA) and otherwise queue behind GEMM CTAs whenever SMs free up -> highest priority.
+// All of them are forked from / joined into the caller's stream with events before every return.
+constexpr int kMaxDevices = 16;
+struct DeviceStreams {
+    cudaStream_t main = nullptr, small = nullptr, extra[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> events;
+    bool tried = false;
+};
+thread_local DeviceStreams g_dev_streams[kMaxDevices];
+
+DeviceStreams* device_streams() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+    DeviceStreams& d = g_dev_streams[dev];
+    if (!d.tried) {
+        d.tried = true;
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);     // hi = numerically lowest = greatest priority
+        if (cudaStreamCreateWithPriority(&d.main, cudaStreamNonBlocking, hi) != cudaSuccess) d.main = nullptr;
+        if (cudaStreamCreateWithFlags(&d.small, cudaStreamNonBlocking) != cudaSuccess) d.small = nullptr;
+        for (int i = 0; i < 2; ++i)
+            if (cudaStreamCreateWithFlags(&d.extra[i], cudaStreamNonBlocking) != cudaSuccess) d.extra[i] = nullptr;
+    }
+    return &d;
+}
+thread_local std::vector<cudaEvent_t> g_fallback_events;
 
 // group boundaries over the layers: a short first group (its results are needed first in forward, last in backward),
 // then growing ones
@@ -469,23 +491,16 @@ Sched make_sched(cudaStream_t st, cudaStream_t aux) {
     s.dual = aux != nullptr && aux != st;
     s.s2 = s.dual ? aux : st;
     s.s3 = s.s4 = s.s5 = st;
-    if (s.dual) {
-        if (!g_main_stream) {
-            int lo = 0, hi = 0;
-            cudaDeviceGetStreamPriorityRange(&lo, &hi);     // hi = numerically lowest = greatest priority
-            if (cudaStreamCreateWithPriority(&g_main_stream, cudaStreamNonBlocking, hi) != cudaSuccess) g_main_stream = nullptr;
-        }
-        if (g_main_stream) s.st = g_main_stream;
-        if (!g_small_stream && cudaStreamCreateWithFlags(&g_small_stream, cudaStreamNonBlocking) != cudaSuccess)
-            g_small_stream = nullptr;
-        s.s3 = g_small_stream ? g_small_stream : s.s2;
-        for (int i = 0; i < 2; ++i)
-            if (!g_extra_stream[i] && cudaStreamCreateWithFlags(&g_extra_stream[i], cudaStreamNonBlocking) != cudaSuccess)
-                g_extra_stream[i] = nullptr;
-        s.s4 = g_extra_stream[0] ? g_extra_stream[0] : s.s2;
-        s.s5 = g_extra_stream[1] ? g_extra_stream[1] : s.s2;
+    DeviceStreams* d = device_streams();
+    if (s.dual && d) {
+        if (d->main) s.st = d->main;
+        s.s3 = d->small ? d->small : s.s2;
+        s.s4 = d->extra[0] ? d->extra[0] : s.s2;
+        s.s5 = d->extra[1] ? d->extra[1] : s.s2;
+    } else if (s.dual) {
+        s.s3 = s.s4 = s.s5 = s.s2;
     }
-    s.pool = &g_event_pool;
+    s.pool = d ? &d->events : &g_fallback_events;
     return s;
 }
 }  // namespace
@@ -835,12 +850,15 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
     // ---- through the SiLU of the layer-invariant embeddings into their weights and the RBF frequencies.  Each family
     // finishes on the stream that accumulated its gz_* buffer, as soon as its last layer is in (only the global one
     // is left for after the main loop).
+    // (this one is the tail of the whole step: its weight-gradient GEMM runs beside the data-gradient -> frequency
+    // chain on the small-GEMM stream instead of in front of it)
     auto embed_tail_global = [&](cudaStream_t s) -> int {
         PAMNET_TRY(mul_dsilu_launch(w.gz_eg, w.z_eg, Eg * D, s));
         GemmArgs cw = gemm_zero(GEMM_TN, EPI_NONE, D, kNumRbf, (int)Eg);
         cw.nslots = 1; cw.ksplit = pick_ksplit(Eg);
         cw.slot[0] = slot(w.gz_eg, D, w.rbf_g, kNumRbf, gp + mp.rbf_g.w, kNumRbf, nullptr, gp + mp.rbf_g.b);
-        PAMNET_TRY(gemm_launch(cw, s));
+        if (s3 != s) PAMNET_TRY(sc.order(s, s3));
+        PAMNET_TRY(gemm_launch(cw, s3 != s ? s3 : s));
         GemmArgs d = gemm_zero(GEMM_NN, EPI_NONE, (int)Eg, kNumRbf, D);
         d.nslots = 1;
         d.slot[0] = slot(w.gz_eg, D, params + mp.rbf_g.w, kNumRbf, w.g_rbf_g, kNumRbf);
