@@ -319,6 +319,7 @@ struct TransposeArgs {
     int src_off[kTransJobs], dst_off[kTransJobs];
     short rows[kTransJobs], cols[kTransJobs];
     int ld[kTransJobs];
+    char copy[kTransJobs];
 };
 
 // 32x32 tiles through shared memory; grid.y = job
@@ -336,8 +337,13 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
         for (int r = ty; r < 32; r += 8)
             if (r0 + r < rows && c0 + tx < cols) tile[r][tx] = src[(size_t)(r0 + r) * ld + c0 + tx];
         __syncthreads();
-        for (int c = ty; c < 32; c += 8)
-            if (c0 + c < cols && r0 + tx < rows) dst[(size_t)(c0 + c) * rows + r0 + tx] = tile[tx][c];
+        if (a.copy[job]) {          // gather a strided block into a contiguous [rows][cols] matrix
+            for (int r = ty; r < 32; r += 8)
+                if (r0 + r < rows && c0 + tx < cols) dst[(size_t)(r0 + r) * cols + c0 + tx] = tile[r][tx];
+        } else {
+            for (int c = ty; c < 32; c += 8)
+                if (c0 + c < cols && r0 + tx < rows) dst[(size_t)(c0 + c) * rows + r0 + tx] = tile[tx][c];
+        }
         __syncthreads();
     }
 }
@@ -350,7 +356,7 @@ int transpose_batch(const float* src_base, float* dst_base, const TransposeJob* 
         for (int j = 0; j < a.n_jobs; ++j) {
             const TransposeJob& jb = jobs[j0 + j];
             a.src_off[j] = (int)jb.src_off; a.dst_off[j] = (int)jb.dst_off;
-            a.rows[j] = (short)jb.rows; a.cols[j] = (short)jb.cols; a.ld[j] = jb.ld;
+            a.rows[j] = (short)jb.rows; a.cols[j] = (short)jb.cols; a.ld[j] = jb.ld; a.copy[j] = (char)(jb.copy != 0);
             const int tiles = ceil_div(jb.rows, 32) * ceil_div(jb.cols, 32);
             if (tiles > max_tiles) max_tiles = tiles;
         }

@@ -41,7 +41,7 @@ int embed_backward(const float* type_f, int64_t n_nodes, const float* g_x, int n
                    cudaStream_t st);
 
 // dst[c*rows + r] = src[r*ld + c] for a batch of matrices (transposed weights for the forward node chain)
-struct TransposeJob { int64_t src_off, dst_off; int rows, cols, ld; };
+struct TransposeJob { int64_t src_off, dst_off; int rows, cols, ld; int copy; };   // copy != 0: strided -> contiguous, no transpose
 int transpose_batch(const float* src_base, float* dst_base, const TransposeJob* jobs_host, int n_jobs, cudaStream_t st);
 
 }  // namespace pamnet

@@ -107,6 +107,8 @@ namespace {
 struct HalfWs {
     // transposed weights (k-major) for the forward chain; offsets into Ws::wt
     float *x1T, *x2T, *resT[3][2], *outT[3], *projT;
+    float *projB;                           // [nP][D][D]: the per-node blocks of the edge-MLP weights, gathered contiguous
+                                            // for the backward chain (one bulk copy per stage instead of D strided ones)
     // saved activations, each [N, D] unless noted
     float *P;                               // [N, nP*D]
     float *z_x1, *x1, *h, *z_x2, *a_x2;
@@ -153,6 +155,7 @@ size_t ws_layout(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, void* bas
         for (int r = 0; r < 3; ++r) for (int s = 0; s < 2; ++s) h.resT[r][s] = take(D * D);
         for (int s = 0; s < 3; ++s) h.outT[s] = take(D * D);
         h.projT = take(nP_of(hh) * D * D);
+        h.projB = take(nP_of(hh) * D * D);
     }
     w.x0 = take(N * D);
     w.rbf_g = take(Eg * kNumRbf); w.rbf_l = take(El * kNumRbf); w.radial = take(El * kNumSbf);
@@ -268,10 +271,8 @@ void add_pre_bwd(Prog& p, const float* params, const HalfP& hp, const HalfWs& hw
     p.add(st_load(0, w.g_h, D, D));
     int cur = 0;
     for (int c = 0; c < nP; ++c) {
-        const float* Wc;
-        if (!is_local(hh)) Wc = params + hp.m.w + c * D;
-        else Wc = params + (c < 2 ? hp.m_ji.w : hp.m_kj.w) + (c & 1) * D;
-        ChainStage& s = p.add(st_gemm(kChainWide, cur ^ 1, Wc, 3 * D, nullptr, 0));
+        // W_c = block c of the edge-MLP weight ([out][in block]); the forward pass gathered it contiguous (projB)
+        ChainStage& s = p.add(st_gemm(kChainWide, cur ^ 1, hw.projB + (size_t)c * D * D, D, nullptr, 0));
         s.src_off = c * D; s.add_slot = cur;
         cur ^= 1;
     }
@@ -596,7 +597,10 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
         std::vector<TransposeJob> jobs;
         const float* ws_base = reinterpret_cast<const float*>(workspace);
         auto job = [&](int64_t src_off, int rows, int cols, int ld, float* dst) {
-            jobs.push_back(TransposeJob{src_off, (int64_t)(dst - ws_base), rows, cols, ld});
+            jobs.push_back(TransposeJob{src_off, (int64_t)(dst - ws_base), rows, cols, ld, 0});
+        };
+        auto gather = [&](int64_t src_off, int rows, int cols, int ld, float* dst) {
+            jobs.push_back(TransposeJob{src_off, (int64_t)(dst - ws_base), rows, cols, ld, 1});
         };
         for (int hh = 0; hh < H; ++hh) {
             const HalfP& hp = half_params(mp, hh);
@@ -610,6 +614,14 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
             } else {
                 job(hp.m_ji.w, D, 2 * D, 3 * D, hw.projT);
                 job(hp.m_kj.w, D, 2 * D, 3 * D, hw.projT + (size_t)2 * D * D);
+            }
+            {   // blocks for the backward chain (same launch; the weights of a step do not change before its backward)
+                for (int cblk = 0; cblk < nP_of(hh); ++cblk) {
+                    int64_t woff;
+                    if (!is_local(hh)) woff = hp.m.w + cblk * D;
+                    else woff = (cblk < 2 ? hp.m_ji.w : hp.m_kj.w) + (cblk & 1) * D;
+                    gather(woff, D, D, 3 * D, hw.projB + (size_t)cblk * D * D);
+                }
             }
         }
         PAMNET_TRY(transpose_batch(params, reinterpret_cast<float*>(workspace), jobs.data(), (int)jobs.size(), st));
