@@ -3,6 +3,8 @@
 // filled by the bulk-copy engine, the next stage's matrix in flight while the current one multiplies.
 #include "chain.cuh"
 
+#include <stdlib.h>
+
 namespace pamnet {
 
 // optional clock64 timeline of CTA 0 / thread 0 (-DPAMNET_TC_TRACE builds; tools/chain_trace.py): 8 stamps per stage
@@ -217,6 +219,12 @@ __global__ void __launch_bounds__(kChainKS * D / 2) chain_kernel(const ChainArgs
                 for (int i = 0; i < 2; ++i)
                     if (row0 + frow + i < n_rows) addg_v[i] = st.add_g[(size_t)(row0 + frow + i) * st.ld_add + fc];
             }
+            float zpost_v[2] = {0.f, 0.f};       // SiLU' operand of the NEXT stage's (fused) prologue
+            if (st.post_dst >= 0) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+                    if (row0 + frow + i < n_rows) zpost_v[i] = st.post_zmul[(size_t)(row0 + frow + i) * D + fc];
+            }
             CH_STAMP(si, 10);
             if (st.psrc >= 0) {
                 float* p = slot_ptr(st.psrc);
@@ -315,7 +323,18 @@ __global__ void __launch_bounds__(kChainKS * D / 2) chain_kernel(const ChainArgs
                     if (live && st.out_a) st.out_a[(size_t)(row0 + r) * st.ld_out + fc] = x[i];
                 }
                 CH_STAMP(si, 12);
-                if (st.dst >= 0) *reinterpret_cast<float2*>(slot_ptr(st.dst) + fc * R + frow) = make_float2(x[0], x[1]);
+                if (st.dst >= 0 && st.dst != st.post_dst)
+                    *reinterpret_cast<float2*>(slot_ptr(st.dst) + fc * R + frow) = make_float2(x[0], x[1]);
+                if (st.post_dst >= 0) {          // the next stage's prologue, on register values
+                    float y[2];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const bool live = row0 + frow + i < n_rows;
+                        y[i] = live ? x[i] * dsilu(zpost_v[i]) : 0.f;
+                        if (live && st.post_save) st.post_save[(size_t)(row0 + frow + i) * D + fc] = y[i];
+                    }
+                    *reinterpret_cast<float2*>(slot_ptr(st.post_dst) + fc * R + frow) = make_float2(y[0], y[1]);
+                }
             }
             CH_STAMP(si, 6);
             wcur ^= 1;
@@ -345,6 +364,17 @@ static int chain_launch_t(const ChainArgs& args, cudaStream_t st) {
         if (s.op == CH_DOT2 || s.op == CH_HEADS_BWD) bytes += 8.0 * args.n_rows + 8.0 * D;
     }
     ChainArgs a = args;
+    for (int i = 0; i < a.n_stages; ++i) { a.st[i].post_dst = -1; a.st[i].post_zmul = nullptr; a.st[i].post_save = nullptr; }
+    // prologue fusion (see ChainStage::post_dst): stage i + 1 = GEMM with a SiLU' prologue on exactly what stage i wrote
+    static int fuse = -1;
+    if (fuse < 0) { const char* e = getenv("PAMNET_CHAIN_FUSE"); fuse = (e && e[0] == '0') ? 0 : 1; }
+    for (int i = 0; fuse && i + 1 < a.n_stages; ++i) {
+        ChainStage& p = a.st[i];
+        ChainStage& c = a.st[i + 1];
+        if (p.op != CH_GEMM || c.op != CH_GEMM || c.psrc < 0 || p.dst < 0 || c.src != p.dst || c.src_off != 0) continue;
+        p.post_dst = c.psrc; p.post_zmul = c.zmul; p.post_save = c.save_src;
+        c.src = c.psrc; c.psrc = -1; c.zmul = nullptr; c.save_src = nullptr;
+    }
     for (int i = a.n_stages - 1, nxt = -1; i >= 0; --i) {
         a.st[i].next_gemm = nxt;
         if (a.st[i].op == CH_GEMM) nxt = i;

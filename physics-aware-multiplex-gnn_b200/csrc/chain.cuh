@@ -27,6 +27,11 @@ struct ChainStage {
     int width;          // LOAD: columns
     int ldw, ld_out, ld_add, ld_g;
     int next_gemm;      // index of the next CH_GEMM stage (-1: none); filled in by chain_launch
+    // filled in by chain_launch when the NEXT stage is a GEMM whose prologue (src * silu'(zmul) -> psrc, save_src) reads
+    // this stage's output: the multiplication then happens here, in the epilogue, on values that are still in registers
+    int post_dst;       // slot that receives out * silu'(post_zmul), -1 = none
+    const float* post_zmul;
+    float* post_save;
     const float* W;     // GEMM: [D(k)][D(n)] k-major (transposed weight in forward, weight itself in backward)
     const float* bias;
     const float* zmul;
