@@ -149,6 +149,21 @@ struct RowVec {
             }
         }
     }
+    // row[...] += v with fp32 reductions in L2 (order-free: callers accept run-to-run rounding differences)
+    __device__ __forceinline__ void atomic_add(float* __restrict__ row, int lane) const {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            float* p = row + (c * 32 + lane) * V;
+            if (V == 4) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[c * 4 + 0]), "f"(v[c * 4 + 1]),
+                             "f"(v[c * 4 + 2]), "f"(v[c * 4 + 3]) : "memory");
+            } else if (V == 2) {
+                asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v[c * 2 + 0]), "f"(v[c * 2 + 1]) : "memory");
+            } else {
+                if (active(lane)) atomicAdd(p, v[c]);
+            }
+        }
+    }
     __device__ __forceinline__ void store(float* __restrict__ row, int lane) const {
 #pragma unroll
         for (int c = 0; c < C; ++c) {

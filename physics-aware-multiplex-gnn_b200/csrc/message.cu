@@ -85,6 +85,10 @@ __global__ void __launch_bounds__(kMsgThreads) global_msg_bwd_kernel(const Globa
     }
     gz.store(a.gQT + (size_t)k * a.ldq, lane);
     gt.store(a.gQT + (size_t)k * a.ldq + D, lane);
+    if (a.g_P) {                     // z = Q_e + P_i[dst] + P_j[src]: grad z flows to both node rows
+        gz.atomic_add(a.g_P + (size_t)n * 2 * D, lane);
+        gz.atomic_add(a.g_P + (size_t)s * 2 * D + D, lane);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -195,6 +199,10 @@ __global__ void __launch_bounds__(kMsgThreads) local_msg_bwd_kernel(const LocalM
     gro.store(a.gQR + (size_t)k * a.ldq + 3 * D, lane);
     gs.store(a.g_s + (size_t)k * D, lane);
     gz.store(a.gQR + (size_t)k * a.ldq, lane);
+    if (a.g_P) {
+        gz.atomic_add(a.g_P + (size_t)n * 4 * D, lane);
+        gz.atomic_add(a.g_P + (size_t)j * 4 * D + D, lane);
+    }
     const int t0 = a.t_ptr[k], t1 = a.t_ptr[k + 1];
     for (int t = t0; t < t1; t += kUnroll) {
         RowVec<D> mn[kUnroll], zq[kUnroll];
@@ -258,6 +266,10 @@ __global__ void __launch_bounds__(kMsgThreads) local_trip_bwd_kernel(const Local
     }
     gz.store(a.gQR + (size_t)k * a.ldq + D, lane);
     gr.store(a.gQR + (size_t)k * a.ldq + 2 * D, lane);
+    if (a.g_P) {
+        gz.atomic_add(a.g_P + (size_t)i * 4 * D + 2 * D, lane);
+        gz.atomic_add(a.g_P + (size_t)j * 4 * D + 3 * D, lane);
+    }
 }
 
 // one warp per (node, task): task 2b = sum of gz_b over incoming slots, 2b+1 = over outgoing slots

@@ -24,6 +24,8 @@ struct GlobalMsgArgs {
     // backward
     const float* g_h;                // [N, D]
     float* gQT;                      // [E, ldq] at this layer's block: grad Q (= grad z) | grad Tt
+    float* g_P;                      // [N, 2D] zero-initialised, or null: grad of P accumulated here with fp32 reductions
+                                     // (replaces the node_grad_gather pass: one launch less on the critical path)
 };
 int global_msg_fwd(int dim, const GlobalMsgArgs& a, int n_edges, cudaStream_t st);
 int global_msg_bwd(int dim, const GlobalMsgArgs& a, int n_edges, cudaStream_t st);
@@ -44,6 +46,7 @@ struct LocalMsgArgs {
     float* h;
     // backward
     const float* g_h;
+    float* g_P;                      // [N, 4D] zero-initialised, or null (see GlobalMsgArgs::g_P)
     float* g_s;                      // [E, D]   grad of (m_ji + m_other)
     float* gQR;                      // [E, ldq] at this layer's block: grad z_ji | grad z_kj | grad R | grad Rout
     float* gzq;                      // [T, ldt] at this layer's block: grad of zq

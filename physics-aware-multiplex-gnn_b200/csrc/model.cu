@@ -11,6 +11,8 @@
 // turns the accumulated per-edge / per-triplet gradients into weight gradients with a few large GEMMs.
 #include "model.cuh"
 
+#include <stdlib.h>
+
 #include "basis.cuh"
 #include "chain.cuh"
 #include "gemm.cuh"
@@ -714,6 +716,16 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
     // accumulators of the per-edge / per-triplet embedding gradients, summed over layers with fp32 atomics
     if (sc.s4 != s2) PAMNET_TRY(sc.order(st, sc.s4));
     if (sc.s5 != s2 && sc.s5 != sc.s4) PAMNET_TRY(sc.order(st, sc.s5));
+    // grad of the per-node projections: deterministic CSR gather pass (default), or PAMNET_GATHER=atomic lets the message
+    // kernels accumulate it themselves with fp32 reductions in L2 (12 launches fewer; measured no faster: the
+    // reductions of one node's ~18 edges serialise in L2 for about as long as the gather kernel takes)
+    static int atomic_gp = -1;
+    if (atomic_gp < 0) { const char* e = getenv("PAMNET_GATHER"); atomic_gp = (e && strcmp(e, "atomic") == 0) ? 1 : 0; }
+    if (atomic_gp) {
+        for (int hh = 0; hh < H; ++hh)
+            PAMNET_CUDA(cudaMemsetAsync(w.half[hh].g_P, 0, sizeof(float) * N * nP_of(hh) * D, s2));
+        PAMNET_TRY(sc.order(s2, st));
+    }
     PAMNET_CUDA(cudaMemsetAsync(w.gz_eg, 0, sizeof(float) * Eg * D, s2));
     PAMNET_CUDA(cudaMemsetAsync(w.gz_el, 0, sizeof(float) * El * D, sc.s4));
     PAMNET_CUDA(cudaMemsetAsync(w.gz_s, 0, sizeof(float) * T * D, sc.s5));
@@ -921,6 +933,7 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
             memset(&a, 0, sizeof(a));
             a.n_nodes = (int)N; a.n_edges = (int)Eg; a.ptr = pl.g_ptr; a.src = pl.g_src; a.dst = pl.g_dst; a.P = hw.P;
             a.QT = w.QT + l * 2 * D; a.ldq = L * 2 * D; a.g_h = w.g_h; a.gQT = w.gQT + l * 2 * D;
+            a.g_P = atomic_gp ? hw.g_P : nullptr;
             PAMNET_TRY(global_msg_bwd(D, a, (int)Eg, st));
             ng.n_blocks = 1; ng.ptr = pl.g_ptr; ng.optr = pl.g_optr; ng.opos = pl.g_opos;
             ng.gz = w.gQT + l * 2 * D; ng.ldq = L * 2 * D;
@@ -932,12 +945,13 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
             a.P = hw.P; a.QR = w.QR + l * 4 * D; a.ldq = L * 4 * D; a.zq = w.zq2 + l * D; a.ldt = L * D;
             a.m_nb = hw.m_nb; a.msum = hw.msum; a.g_h = w.g_h; a.g_s = w.g_s;
             a.gQR = w.gQR + l * 4 * D; a.gzq = w.gzq2 + l * D;
+            a.g_P = atomic_gp ? hw.g_P : nullptr;
             PAMNET_TRY(local_msg_bwd(D, a, (int)T, st));
             PAMNET_TRY(local_trip_bwd(D, a, (int)T, st));
             ng.n_blocks = 2; ng.ptr = pl.l_ptr; ng.optr = pl.l_optr; ng.opos = pl.l_opos;
             ng.gz = w.gQR + l * 4 * D; ng.ldq = L * 4 * D;
         }
-        PAMNET_TRY(node_grad_gather(D, ng, is_local(hh) ? (int)El : (int)Eg, st));
+        if (!atomic_gp) PAMNET_TRY(node_grad_gather(D, ng, is_local(hh) ? (int)El : (int)Eg, st));
         PAMNET_TRY(sc.order(st, s3));
         PAMNET_TRY(node_wgrads(hh, hh + 1 < H ? hh + 1 : -1, hh, s3));
         // per-edge / per-triplet weight gradients of this half: everything they read is complete now

@@ -232,3 +232,69 @@ def test_c4_rna_batch8_large_graphs():
         if ref64 is not None:
             ok, e_new, e_ref = ladder_ok(grads[k], g32[k], ref64)
             assert ok, (k, e_new, e_ref)
+
+
+# ---- alternate execution paths must give the same numbers ------------------------------------------------------------
+def _run_subprocess_step(env):
+    """forward + backward of the QM9 golden model in a fresh process with `env` set; returns (out, one gradient)."""
+    import os, subprocess, sys, tempfile
+    code = r'''
+import sys, torch
+sys.path.insert(0, %r)
+from tests.helpers import load_golden, batch_of
+from pamnet_b200 import Config, PAMNet
+gold = load_golden("qm9_small_pamnet")
+m = PAMNet(Config(**gold["config"])); m.load_state_dict(gold["state_dict"]); m = m.cuda()
+b = batch_of(gold).to("cuda")
+out = m(b); (out - b.y).abs().mean().backward(); torch.cuda.synchronize()
+g = dict(m.named_parameters())["global_layer.0.mlp_m.0.0.weight"].grad
+torch.save({"out": out.detach().cpu(), "g": g.cpu(), "eg": m.last_plan.edge_index_g.cpu(), "el": m.last_plan.edge_index_l.cpu()}, sys.argv[1])
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.NamedTemporaryFile(suffix=".pt") as f:
+        subprocess.run([sys.executable, "-c", code, f.name], check=True, env={**os.environ, **env}, timeout=300)
+        return torch.load(f.name)
+
+
+_BASE_STEP = None
+
+
+@pytest.mark.parametrize("env", [{"PAMNET_STREAMS": "1"}, {"PAMNET_PDL": "0"}, {"PAMNET_PLAN": "stepwise"},
+                                 {"PAMNET_GATHER": "atomic"}, {"PAMNET_GEMM": "ffma"}, {"PAMNET_CHAIN_FUSE": "0"}])
+def test_alternate_paths_agree(env):
+    """Single-stream schedule, no programmatic dependent launch, the step-by-step front end, atomic projection
+    gradients, the FFMA GEMM and the unfused chain prologue: same graph bit for bit, same numbers to fp32 rounding."""
+    global _BASE_STEP
+    if _BASE_STEP is None:
+        _BASE_STEP = _run_subprocess_step({})
+    base = _BASE_STEP
+    alt = _run_subprocess_step(env)
+    assert torch.equal(base["eg"], alt["eg"]) and torch.equal(base["el"], alt["el"])
+    assert rel_err(alt["out"], base["out"]) < 2e-6
+    assert rel_err(alt["g"], base["g"]) < 1e-5
+
+
+def test_plan_build_grows_capacities():
+    """pamnet_plan_build with deliberately tiny capacities: returns 1 with the needed sizes, the retry succeeds and the
+    plan equals the one built step by step."""
+    import os
+    from pamnet_b200 import Config, PAMNet
+    from pamnet_b200.data import synthetic_qm9_batch, synthetic_rna_batch
+    for kind, cfgargs, batch in [("QM9", ("QM9", 32, 1, 5.0, 5.0), synthetic_qm9_batch(5, seed=2)),
+                                 ("rna", ("rna_native", 16, 1, 2.6, 20.0, "target_to_source"), synthetic_rna_batch(2, seed=2))]:
+        model = PAMNet(Config(*cfgargs)).cuda()
+        b = batch.to("cuda")
+        model._plan_caps = {"eg": 8, "el": 8, "base": 64, "trip": 64}
+        with torch.no_grad():
+            out = model(b)
+        fused = model.last_plan
+        assert model._plan_caps["eg"] >= fused.sizes.n_edges_g
+        os.environ["PAMNET_PLAN"] = "stepwise"
+        try:
+            with torch.no_grad():
+                out2 = model(b)
+        finally:
+            del os.environ["PAMNET_PLAN"]
+        step = model.last_plan
+        assert torch.equal(fused.edge_index_g, step.edge_index_g) and torch.equal(fused.edge_index_l, step.edge_index_l)
+        assert (fused.sizes.n_t2, fused.sizes.n_t1) == (step.sizes.n_t2, step.sizes.n_t1)
+        assert torch.equal(out, out2), kind
