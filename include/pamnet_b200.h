@@ -148,16 +148,25 @@ int pamnet_plan_build(const pamnet_config_t* cfg, const float* pos, const int64_
  * backward: grad_out [n_graphs] -> grad_params (flat, same layout as params; fully overwritten).
  * aux_stream: optional second stream (NULL = none): the x-independent GEMMs run on it, overlapped with the
  *             sequential layer loop on `stream`; both calls return with all their work ordered before later
- *             work on `stream`. */
+ *             work on `stream`.
+ * prepared_weights: optional (NULL = the forward call makes them itself, inside the workspace): a blob of
+ *             pamnet_prepared_weights_bytes(cfg) bytes filled by pamnet_prepare_weights(cfg, params, blob, aux_stream)
+ *             -- the k-major copies of the node-chain linears and the contiguous projection blocks, which depend on the
+ *             parameters only.  Issued on aux_stream BEFORE the graph is built, they run while the host waits for the
+ *             edge counts.  Pass the same blob to forward and backward of a step. */
 size_t pamnet_workspace_bytes(const pamnet_config_t* cfg, const pamnet_sizes_t* sz);
+size_t pamnet_prepared_weights_bytes(const pamnet_config_t* cfg);
+int pamnet_prepare_weights(const pamnet_config_t* cfg, const float* params, void* prepared_weights, void* stream);
 int pamnet_model_forward(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, const pamnet_sbf_consts_t* sbf,
                          const float* params, const float* node_in, const float* sign, const float* pos,
                          void* plan_base, void* plan_trip, void* workspace, size_t workspace_bytes,
-                         int32_t save_for_backward, float* out, void* stream, void* aux_stream);
+                         int32_t save_for_backward, float* out, void* stream, void* aux_stream,
+                         void* prepared_weights);
 int pamnet_model_backward(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, const pamnet_sbf_consts_t* sbf,
                           const float* params, const float* node_in, const float* sign, const float* pos,
                           void* plan_base, void* plan_trip, void* workspace, size_t workspace_bytes,
-                          const float* grad_out, float* grad_params, void* stream, void* aux_stream);
+                          const float* grad_out, float* grad_params, void* stream, void* aux_stream,
+                          void* prepared_weights);
 
 /* L1 / MSE loss + its gradient w.r.t. the prediction in one launch (main_qm9.py:108 F.l1_loss,
  * main_pdbbind.py MSE): loss_dev[0] = mean(|out-y|) or mean((out-y)^2); grad_out[g] = d loss / d out[g]. */

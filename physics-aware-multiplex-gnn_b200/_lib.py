@@ -49,8 +49,12 @@ SIGNATURES = {
     "pamnet_plan_count": (c_i32, [_PC, _PS, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "pamnet_plan_fill": (c_i32, [_PC, _PS, c_vp, c_vp, c_vp, c_vp]),
     "pamnet_workspace_bytes": (c_sz, [_PC, _PS]),
-    "pamnet_model_forward": (c_i32, [_PC, _PS, _PB, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_i32, c_vp, c_vp, c_vp]),
-    "pamnet_model_backward": (c_i32, [_PC, _PS, _PB, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp, c_vp, c_vp, c_vp]),
+    "pamnet_model_forward": (c_i32, [_PC, _PS, _PB, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_i32, c_vp, c_vp, c_vp,
+                                     c_vp]),
+    "pamnet_model_backward": (c_i32, [_PC, _PS, _PB, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp, c_vp, c_vp, c_vp,
+                                      c_vp]),
+    "pamnet_prepared_weights_bytes": (c_sz, [_PC]),
+    "pamnet_prepare_weights": (c_i32, [_PC, c_vp, c_vp, c_vp]),
     "pamnet_loss": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp]),
     "pamnet_scatter_add": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "pamnet_bessel_rbf": (c_i32, [c_vp, c_i64, c_vp, c_f32, c_vp, c_vp]),

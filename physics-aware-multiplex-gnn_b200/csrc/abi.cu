@@ -292,21 +292,28 @@ size_t pamnet_workspace_bytes(const pamnet_config_t* cfg, const pamnet_sizes_t* 
 int pamnet_model_forward(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, const pamnet_sbf_consts_t* sbf,
                          const float* params, const float* node_in, const float* sign, const float* pos,
                          void* plan_base, void* plan_trip, void* workspace, size_t workspace_bytes,
-                         int32_t save_for_backward, float* out, void* stream, void* aux_stream) {
+                         int32_t save_for_backward, float* out, void* stream, void* aux_stream,
+                         void* prepared_weights) {
     REQUIRE(cfg); REQUIRE(sz); REQUIRE(sbf); REQUIRE(params); REQUIRE(node_in); REQUIRE(pos); REQUIRE(plan_base);
     REQUIRE(plan_trip); REQUIRE(workspace); REQUIRE(out);
     (void)save_for_backward;
     return model_forward(*cfg, *sz, *sbf, params, node_in, sign, pos, plan_base, plan_trip, workspace,
-                         workspace_bytes, out, ST(stream), ST(aux_stream));
+                         workspace_bytes, out, ST(stream), ST(aux_stream), prepared_weights);
+}
+size_t pamnet_prepared_weights_bytes(const pamnet_config_t* cfg) { return cfg ? prepared_weights_bytes(*cfg) : 0; }
+int pamnet_prepare_weights(const pamnet_config_t* cfg, const float* params, void* prepared_weights, void* stream) {
+    REQUIRE(cfg); REQUIRE(params); REQUIRE(prepared_weights);
+    return prepare_weights(*cfg, params, prepared_weights, ST(stream));
 }
 int pamnet_model_backward(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, const pamnet_sbf_consts_t* sbf,
                           const float* params, const float* node_in, const float* sign, const float* pos,
                           void* plan_base, void* plan_trip, void* workspace, size_t workspace_bytes,
-                          const float* grad_out, float* grad_params, void* stream, void* aux_stream) {
+                          const float* grad_out, float* grad_params, void* stream, void* aux_stream,
+                          void* prepared_weights) {
     REQUIRE(cfg); REQUIRE(sz); REQUIRE(sbf); REQUIRE(params); REQUIRE(node_in); REQUIRE(pos); REQUIRE(plan_base);
     REQUIRE(plan_trip); REQUIRE(workspace); REQUIRE(grad_out); REQUIRE(grad_params);
     return model_backward(*cfg, *sz, *sbf, params, node_in, sign, pos, plan_base, plan_trip, workspace,
-                          workspace_bytes, grad_out, grad_params, ST(stream), ST(aux_stream));
+                          workspace_bytes, grad_out, grad_params, ST(stream), ST(aux_stream), prepared_weights);
 }
 
 int64_t pamnet_debug_ws_offset(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, const char* name, int32_t half) {

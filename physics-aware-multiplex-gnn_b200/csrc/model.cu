@@ -139,10 +139,14 @@ struct Ws {
 inline bool is_local(int hh) { return hh & 1; }
 inline int nP_of(int hh) { return is_local(hh) ? 4 : 2; }
 
-size_t ws_layout(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, void* base, Ws* out) {
+// `wbase` (optional): an external blob that holds the prepared-weights region (the first section of the layout,
+// which depends on the configuration only); `weights_bytes` (optional) receives that region's size.
+size_t ws_layout(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, void* base, Ws* out, void* wbase = nullptr,
+                 size_t* weights_bytes = nullptr) {
     size_t off = 0;
+    void* cur_base = wbase ? wbase : base;
     auto take = [&](int64_t n) {
-        float* p = base ? reinterpret_cast<float*>(static_cast<char*>(base) + off) : nullptr;
+        float* p = cur_base ? reinterpret_cast<float*>(static_cast<char*>(cur_base) + off) : nullptr;
         off += align_up(sizeof(float) * (size_t)(n > 0 ? n : 1));
         return p;
     };
@@ -159,6 +163,8 @@ size_t ws_layout(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, void* bas
         h.projT = take(nP_of(hh) * D * D);
         h.projB = take(nP_of(hh) * D * D);
     }
+    if (weights_bytes) *weights_bytes = off;
+    cur_base = base;
     w.x0 = take(N * D);
     w.rbf_g = take(Eg * kNumRbf); w.rbf_l = take(El * kNumRbf); w.radial = take(El * kNumSbf);
     w.sbf_ext = take(T * kSbfExt); w.w_ext = take(D * kSbfExt); w.gw_ext = take(D * kSbfExt);
@@ -363,14 +369,14 @@ struct Ctx {
 };
 
 int make_ctx(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pamnet_sbf_consts_t& sbf, void* plan_base,
-             void* plan_trip, void* workspace, size_t ws_bytes, Ctx* c) {
+             void* plan_trip, void* workspace, size_t ws_bytes, Ctx* c, void* prepared = nullptr) {
     PAMNET_TRY(build_param_layout(cfg, &c->mp));
     c->cfg = cfg; c->sz = sz;
     c->D = cfg.dim; c->L = cfg.n_layer; c->H = 2 * cfg.n_layer;
     c->N = sz.n_nodes; c->G = sz.n_graphs; c->Eg = sz.n_edges_g; c->El = sz.n_edges_l; c->T = sz.n_t2 + sz.n_t1;
     PAMNET_CHECK_ARG(c->N > 0 && c->G > 0, "empty batch (n_nodes=%lld, n_graphs=%lld)", (long long)c->N, (long long)c->G);
     PAMNET_CHECK_ARG(c->N < (1 << 30) && c->Eg * (int64_t)c->L * 2 * c->D < (1ll << 40), "batch too large");
-    const size_t need = ws_layout(cfg, sz, workspace, &c->w);
+    const size_t need = ws_layout(cfg, sz, workspace, &c->w, prepared);
     PAMNET_CHECK_ARG(ws_bytes >= need, "workspace too small: %zu < %zu", ws_bytes, need);
     plan_layout(sz, plan_base, plan_trip, &c->plan, nullptr, nullptr);
     make_sbf_tables(sbf, &c->tab);
@@ -380,6 +386,65 @@ int make_ctx(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pamnet_
 }  // namespace
 
 size_t workspace_bytes(const pamnet_config_t& cfg, const pamnet_sizes_t& sz) { return ws_layout(cfg, sz, nullptr, nullptr); }
+
+// ---------------------------------------------------------------------------------------------
+// prepared weights: k-major copies of every chain linear and the contiguous projection blocks of the backward chain.
+// They depend on the parameters only, so a caller may produce them on another stream while the graph is being built
+// (prepare_weights) and hand the blob to model_forward / model_backward; without it model_forward makes them itself.
+// ---------------------------------------------------------------------------------------------
+size_t prepared_weights_bytes(const pamnet_config_t& cfg) {
+    pamnet_sizes_t sz;
+    memset(&sz, 0, sizeof(sz));
+    size_t wb = 0;
+    ws_layout(cfg, sz, nullptr, nullptr, nullptr, &wb);
+    return wb;
+}
+
+namespace {
+int launch_weight_prep(const pamnet_config_t& cfg, const ModelP& mp, const Ws& w, const float* params, float* dst_base,
+                       cudaStream_t st) {
+    const int D = cfg.dim, H = 2 * cfg.n_layer;
+    std::vector<TransposeJob> jobs;
+    auto job = [&](int64_t src_off, int rows, int cols, int ld, float* dst) {
+        jobs.push_back(TransposeJob{src_off, (int64_t)(dst - dst_base), rows, cols, ld, 0});
+    };
+    auto gather = [&](int64_t src_off, int rows, int cols, int ld, float* dst) {
+        jobs.push_back(TransposeJob{src_off, (int64_t)(dst - dst_base), rows, cols, ld, 1});
+    };
+    for (int hh = 0; hh < H; ++hh) {
+        const HalfP& hp = half_params(mp, hh);
+        const HalfWs& hw = w.half[hh];
+        job(hp.x1.w, D, D, D, hw.x1T);
+        job(hp.x2.w, D, D, D, hw.x2T);
+        for (int r = 0; r < 3; ++r) for (int s = 0; s < 2; ++s) job(hp.res[r][s].w, D, D, D, hw.resT[r][s]);
+        for (int s = 0; s < 3; ++s) job(hp.out[s].w, D, D, D, hw.outT[s]);
+        if (!is_local(hh)) {
+            job(hp.m.w, D, 2 * D, 3 * D, hw.projT);                       // -> [2D, D]
+        } else {
+            job(hp.m_ji.w, D, 2 * D, 3 * D, hw.projT);
+            job(hp.m_kj.w, D, 2 * D, 3 * D, hw.projT + (size_t)2 * D * D);
+        }
+        // blocks for the backward chain (the weights of a step do not change before its backward)
+        for (int cblk = 0; cblk < nP_of(hh); ++cblk) {
+            int64_t woff;
+            if (!is_local(hh)) woff = hp.m.w + cblk * D;
+            else woff = (cblk < 2 ? hp.m_ji.w : hp.m_kj.w) + (cblk & 1) * D;
+            gather(woff, D, D, 3 * D, hw.projB + (size_t)cblk * D * D);
+        }
+    }
+    return transpose_batch(params, dst_base, jobs.data(), (int)jobs.size(), st);
+}
+}  // namespace
+
+int prepare_weights(const pamnet_config_t& cfg, const float* params, void* prepared, cudaStream_t st) {
+    ModelP mp;
+    PAMNET_TRY(build_param_layout(cfg, &mp));
+    pamnet_sizes_t sz;
+    memset(&sz, 0, sizeof(sz));
+    Ws w;
+    ws_layout(cfg, sz, prepared, &w, prepared);      // only the weight pointers of `w` are meaningful
+    return launch_weight_prep(cfg, mp, w, params, reinterpret_cast<float*>(prepared), st);
+}
 
 // byte offset of a named workspace buffer (test / debugging aid; -1 = unknown name)
 int64_t debug_ws_offset(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const char* name, int half) {
@@ -513,9 +578,10 @@ Sched make_sched(cudaStream_t st, cudaStream_t aux) {
 // ---------------------------------------------------------------------------------------------
 int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pamnet_sbf_consts_t& sbf,
                   const float* params, const float* node_in, const float* sign, const float* pos, void* plan_base,
-                  void* plan_trip, void* workspace, size_t ws_bytes, float* out, cudaStream_t st_user, cudaStream_t aux) {
+                  void* plan_trip, void* workspace, size_t ws_bytes, float* out, cudaStream_t st_user, cudaStream_t aux,
+                  void* prepared) {
     Ctx c;
-    PAMNET_TRY(make_ctx(cfg, sz, sbf, plan_base, plan_trip, workspace, ws_bytes, &c));
+    PAMNET_TRY(make_ctx(cfg, sz, sbf, plan_base, plan_trip, workspace, ws_bytes, &c, prepared));
     const int D = c.D, L = c.L, H = c.H;
     const int64_t N = c.N, Eg = c.Eg, El = c.El, T = c.T;
     const ModelP& mp = c.mp;
@@ -595,39 +661,8 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
     PAMNET_TRY(issue_group(0));
 
     // ================= main stream: node input, transposed chain weights, phase B
-    {
-        std::vector<TransposeJob> jobs;
-        const float* ws_base = reinterpret_cast<const float*>(workspace);
-        auto job = [&](int64_t src_off, int rows, int cols, int ld, float* dst) {
-            jobs.push_back(TransposeJob{src_off, (int64_t)(dst - ws_base), rows, cols, ld, 0});
-        };
-        auto gather = [&](int64_t src_off, int rows, int cols, int ld, float* dst) {
-            jobs.push_back(TransposeJob{src_off, (int64_t)(dst - ws_base), rows, cols, ld, 1});
-        };
-        for (int hh = 0; hh < H; ++hh) {
-            const HalfP& hp = half_params(mp, hh);
-            const HalfWs& hw = w.half[hh];
-            job(hp.x1.w, D, D, D, hw.x1T);
-            job(hp.x2.w, D, D, D, hw.x2T);
-            for (int r = 0; r < 3; ++r) for (int s = 0; s < 2; ++s) job(hp.res[r][s].w, D, D, D, hw.resT[r][s]);
-            for (int s = 0; s < 3; ++s) job(hp.out[s].w, D, D, D, hw.outT[s]);
-            if (!is_local(hh)) {
-                job(hp.m.w, D, 2 * D, 3 * D, hw.projT);                       // -> [2D, D]
-            } else {
-                job(hp.m_ji.w, D, 2 * D, 3 * D, hw.projT);
-                job(hp.m_kj.w, D, 2 * D, 3 * D, hw.projT + (size_t)2 * D * D);
-            }
-            {   // blocks for the backward chain (same launch; the weights of a step do not change before its backward)
-                for (int cblk = 0; cblk < nP_of(hh); ++cblk) {
-                    int64_t woff;
-                    if (!is_local(hh)) woff = hp.m.w + cblk * D;
-                    else woff = (cblk < 2 ? hp.m_ji.w : hp.m_kj.w) + (cblk & 1) * D;
-                    gather(woff, D, D, 3 * D, hw.projB + (size_t)cblk * D * D);
-                }
-            }
-        }
-        PAMNET_TRY(transpose_batch(params, reinterpret_cast<float*>(workspace), jobs.data(), (int)jobs.size(), st));
-    }
+    if (prepared) PAMNET_TRY(sc.order(s2, st));      // the caller produced them on the auxiliary stream
+    else PAMNET_TRY(launch_weight_prep(cfg, mp, w, params, reinterpret_cast<float*>(workspace), st));
     if (cfg.dataset == PAMNET_PDBBIND) {          // models.py:119
         GemmArgs a = gemm_zero(GEMM_NT, EPI_NONE, (int)N, D, kFeatPdb);
         a.nslots = 1;
@@ -697,10 +732,10 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
 int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pamnet_sbf_consts_t& sbf,
                    const float* params, const float* node_in, const float* sign, const float* pos, void* plan_base,
                    void* plan_trip, void* workspace, size_t ws_bytes, const float* grad_out, float* gp,
-                   cudaStream_t st_user, cudaStream_t aux) {
+                   cudaStream_t st_user, cudaStream_t aux, void* prepared) {
     (void)pos;
     Ctx c;
-    PAMNET_TRY(make_ctx(cfg, sz, sbf, plan_base, plan_trip, workspace, ws_bytes, &c));
+    PAMNET_TRY(make_ctx(cfg, sz, sbf, plan_base, plan_trip, workspace, ws_bytes, &c, prepared));
     const int D = c.D, L = c.L, H = c.H;
     const int64_t N = c.N, Eg = c.Eg, El = c.El, T = c.T;
     const ModelP& mp = c.mp;

@@ -35,11 +35,16 @@ int64_t debug_ws_offset(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, co
 
 int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pamnet_sbf_consts_t& sbf,
                   const float* params, const float* node_in, const float* sign, const float* pos, void* plan_base,
-                  void* plan_trip, void* workspace, size_t workspace_bytes, float* out, cudaStream_t st, cudaStream_t aux);
+                  void* plan_trip, void* workspace, size_t workspace_bytes, float* out, cudaStream_t st, cudaStream_t aux,
+                  void* prepared = nullptr);
 
 int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pamnet_sbf_consts_t& sbf,
                    const float* params, const float* node_in, const float* sign, const float* pos, void* plan_base,
                    void* plan_trip, void* workspace, size_t workspace_bytes, const float* grad_out, float* grad_params,
-                   cudaStream_t st, cudaStream_t aux);
+                   cudaStream_t st, cudaStream_t aux, void* prepared = nullptr);
+
+// k-major chain weights + contiguous projection blocks, produced ahead of model_forward (optional)
+size_t prepared_weights_bytes(const pamnet_config_t& cfg);
+int prepare_weights(const pamnet_config_t& cfg, const float* params, void* prepared, cudaStream_t st);
 
 }  // namespace pamnet

@@ -49,7 +49,7 @@ class _PAMNetFunction(torch.autograd.Function):
     routing 390 tensors through autograd costs more host time than the whole GPU step."""
 
     @staticmethod
-    def forward(ctx, mod, plan, node_in, sign, pos, flat):
+    def forward(ctx, mod, plan, node_in, sign, pos, flat, prepared):
         lib = _lib.load()
         dev = pos.device
         cfg, sz = mod._ccfg, plan.sizes
@@ -61,9 +61,10 @@ class _PAMNetFunction(torch.autograd.Function):
                                             _lib.ptr(sign), pos.data_ptr(), plan.base.data_ptr(),
                                             plan.trip.data_ptr(), ws.data_ptr(), ws_bytes, int(need_grad),
                                             out.data_ptr(), torch.cuda.current_stream().cuda_stream,
-                                            mod._aux_stream_ptr(dev)), "model_forward")
+                                            mod._aux_stream_ptr(dev), _lib.ptr(prepared)), "model_forward")
         if need_grad:
             ctx.mod, ctx.plan, ctx.ws, ctx.ws_bytes = mod, plan, ws, ws_bytes
+            ctx.prepared = prepared
             ctx.node_in, ctx.sign, ctx.pos = node_in, sign, pos
         return out
 
@@ -78,10 +79,11 @@ class _PAMNetFunction(torch.autograd.Function):
                                              plan.base.data_ptr(), plan.trip.data_ptr(), ctx.ws.data_ptr(),
                                              ctx.ws_bytes, grad_out.data_ptr(), target.data_ptr(),
                                              torch.cuda.current_stream().cuda_stream,
-                                             mod._aux_stream_ptr(grad_out.device)), "model_backward")
+                                             mod._aux_stream_ptr(grad_out.device), _lib.ptr(ctx.prepared)),
+                   "model_backward")
         ctx.ws = None
         mod._deliver_grads(target, direct)
-        return (None, None, None, None, None, None)
+        return (None, None, None, None, None, None, None)
 
 
 class _PAMNetBase(nn.Module):
@@ -321,9 +323,28 @@ class _PAMNetBase(nn.Module):
                 sign = torch.where(pos[:, 0] > 40.0, -1.0, 1.0).to(torch.float32).contiguous()   # models.py:122-125
             else:
                 node_in = xr[:, -1].contiguous()
+        prepared = self._prepare_weights(pos.device)      # on the auxiliary stream, overlapping the graph build
         plan = self._build_plan(pos, batch, int(n_graphs), el_in, max_nb)
         self.last_plan = plan
-        return _PAMNetFunction.apply(self, plan, node_in, sign, pos, self._flat)
+        return _PAMNetFunction.apply(self, plan, node_in, sign, pos, self._flat, prepared)
+
+    def _prepare_weights(self, dev):
+        """k-major chain weights + projection blocks (they depend on the parameters only) into a persistent blob,
+        issued on the auxiliary stream so that they run while the host waits for the edge counts of the graph build.
+        Returns None (model_forward then makes them itself) when there is no auxiliary stream."""
+        import os
+        aux_ptr = self._aux_stream_ptr(dev)
+        # Off by default: measured from Python (B200, batch 32) the extra call + stream wait cost more host latency at the
+        # start of the step (1.92 vs 1.89 ms/step) than the ~25 us of GPU time they take off the critical path.
+        if aux_ptr is None or os.environ.get("PAMNET_PREP", "0") != "1":
+            return None
+        lib = _lib.load()
+        buf = getattr(self, "_prepared", None)
+        if buf is None or buf.device != dev:
+            buf = self._prepared = torch.empty(lib.pamnet_prepared_weights_bytes(self._ccfg), dtype=torch.uint8, device=dev)
+        self._aux_stream.wait_stream(torch.cuda.current_stream())     # the parameters' last writer
+        _lib.check(lib.pamnet_prepare_weights(self._ccfg, self._flat.data_ptr(), buf.data_ptr(), aux_ptr), "prepare_weights")
+        return buf
 
     def _init_embeddings(self):
         stdv = math.sqrt(3)
