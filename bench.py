@@ -128,7 +128,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "10"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -206,12 +206,14 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing ("value") ----------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        step(dev_batch)
-    barrier()
+    # nvidia-smi needs ~0.1 s to deliver its first sample and a timed region is ~0.1-0.2 s: the sampler starts before
+    # the warm-up (already under load) and runs until the end of the end-to-end region
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step(dev_batch)
+    barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = _lib.launch_count()
     barrier()
@@ -223,7 +225,7 @@ def run_ours(args):
     barrier()
     launches = (_lib.launch_count() - launches0) // args.steps
     dev_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
-    clocks = sampler.stop() if rank == 0 else None
+    # (the clock sampler keeps running through the end-to-end timed region below: both are under load)
 
     # ---- end to end through the public API with host buffers ("e2e") ------------------------------------
     def e2e_step():
@@ -242,6 +244,7 @@ def run_ours(args):
     e1.record()
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
     h2d = sum(v.numel() * v.element_size() for v in host_batch.__dict__.values() if isinstance(v, torch.Tensor))
     d2h = 4 + 2 * 64    # loss scalar + the two count read-backs of the graph build
 
