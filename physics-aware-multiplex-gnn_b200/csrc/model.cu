@@ -593,28 +593,37 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
     if (st != st_user) PAMNET_TRY(sc.order(st_user, st));     // the plan and the inputs were produced on the caller's stream
     PAMNET_TRY(sc.order(st, s2));
 
-    // ================= auxiliary stream: phase A (models.py:180-188 and the x-independent halves of the layers)
-    PAMNET_TRY(rbf_forward(pl.dist_g, Eg, params + mp.freq_g, cfg.cutoff_g, w.rbf_g, s2));
-    {
+    // ================= auxiliary stream(s): phase A (models.py:180-188 and the x-independent halves of the layers).
+    // Two independent chains: the global-edge one (s2) and the local-edge / triplet one (sB, = s2 by default).
+    // Default: ONE auxiliary stream and everything of group 0 issued before the main stream's first kernels.
+    // PAMNET_FWD_SPLIT=1 runs the local / triplet chain on a second stream and issues it after the main stream's first
+    // kernels -- measured slower (1.96-2.03 vs 1.89-1.90 ms/step): the two chains then compete for the SMs the first
+    // node chains need.
+    static int fwd_split = -1;
+    if (fwd_split < 0) { const char* e = getenv("PAMNET_FWD_SPLIT"); fwd_split = (e && e[0] == '1') ? 1 : 0; }
+    cudaStream_t sB = fwd_split ? sc.s4 : s2;
+    if (sB != s2) PAMNET_TRY(sc.order(st, sB));
+    auto embed_global = [&]() -> int {
+        PAMNET_TRY(rbf_forward(pl.dist_g, Eg, params + mp.freq_g, cfg.cutoff_g, w.rbf_g, s2));
         GemmArgs a = gemm_zero(GEMM_NT, EPI_BIAS_SILU, (int)Eg, D, kNumRbf);
         a.nslots = 1;
         a.slot[0] = slot(w.rbf_g, kNumRbf, params + mp.rbf_g.w, kNumRbf, w.e_g, D, params + mp.rbf_g.b, w.z_eg);
-        PAMNET_TRY(gemm_launch(a, s2));
-    }
-    PAMNET_TRY(rbf_forward(pl.dist_l, El, params + mp.freq_l, cfg.cutoff_l, w.rbf_l, s2));
-    PAMNET_TRY(sbf_radial(c.tab, pl.dist_l, El, cfg.cutoff_l, w.radial, s2));
-    PAMNET_TRY(sbf_ext_forward(c.tab, pl, El, T, pos, w.radial, w.sbf_ext, s2));
-    PAMNET_TRY(sbf_weight_pack(D, cfg.simple ? nullptr : params + mp.sbf2.w, cfg.simple ? nullptr : params + mp.sbf2.b,
-                               params + mp.sbf1.w, params + mp.sbf1.b, w.w_ext, s2));
-    {
+        return gemm_launch(a, s2);
+    };
+    auto embed_local = [&]() -> int {
+        PAMNET_TRY(rbf_forward(pl.dist_l, El, params + mp.freq_l, cfg.cutoff_l, w.rbf_l, sB));
+        PAMNET_TRY(sbf_radial(c.tab, pl.dist_l, El, cfg.cutoff_l, w.radial, sB));
+        PAMNET_TRY(sbf_ext_forward(c.tab, pl, El, T, pos, w.radial, w.sbf_ext, sB));
+        PAMNET_TRY(sbf_weight_pack(D, cfg.simple ? nullptr : params + mp.sbf2.w, cfg.simple ? nullptr : params + mp.sbf2.b,
+                                   params + mp.sbf1.w, params + mp.sbf1.b, w.w_ext, sB));
         GemmArgs a = gemm_zero(GEMM_NT, EPI_BIAS_SILU, (int)El, D, kNumRbf);
         a.nslots = 1;
         a.slot[0] = slot(w.rbf_l, kNumRbf, params + mp.rbf_l.w, kNumRbf, w.e_l, D, params + mp.rbf_l.b, w.z_el);
-        PAMNET_TRY(gemm_launch(a, s2));
+        PAMNET_TRY(gemm_launch(a, sB));
         a.M = (int)T; a.K = kSbfExt;
         a.slot[0] = slot(w.sbf_ext, kSbfExt, w.w_ext, kSbfExt, w.s, D, nullptr, w.z_s);
-        PAMNET_TRY(gemm_launch(a, s2));
-    }
+        return gemm_launch(a, sB);
+    };
     // layers are grouped ([0,1), [1,3), [3,L) for L = 6): one batched GEMM launch per group and operand keeps the
     // tiles-per-launch high (a tensor-core tile has a ~15 us latency floor) while later groups overlap phase B
     std::vector<int> grp = layer_groups(L);
@@ -623,7 +632,7 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
     std::vector<int> group_of(L);
     for (int gi = 0; gi < ngrp; ++gi)
         for (int l = grp[gi]; l < grp[gi + 1]; ++l) group_of[l] = gi;
-    auto issue_group = [&](int gi) -> int {
+    auto issue_group_g = [&](int gi) -> int {
         const int l0 = grp[gi], l1 = grp[gi + 1];
         {   // global: Q | Tt = e_g [W_m,e ; W_e]^T (+ b_m)      (global_message_passing.py:52-56)
             const int ldq = L * 2 * D;
@@ -636,6 +645,10 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
             PAMNET_TRY(gemm_multi(gemm_zero(GEMM_NT, EPI_BIAS, (int)Eg, D, D), sl, s2));
             PAMNET_TRY(sc.record(s2, &ev_g[gi]));
         }
+        return 0;
+    };
+    auto issue_group_l = [&](int gi) -> int {
+        const int l0 = grp[gi], l1 = grp[gi + 1];
         {   // local: Qji | Qkj | R | Rout and the triplet gate MLP   (local_message_passing.py:46-53)
             const int ldq = L * 4 * D, ldt = L * D;
             std::vector<GemmSlot> sl, s1, s2v;
@@ -649,16 +662,19 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
                 s1.push_back(slot(w.s, D, params + hp.sbf[0].w, D, w.aq1 + l * D, ldt, params + hp.sbf[0].b, w.zq1 + l * D));
                 s2v.push_back(slot(w.aq1 + l * D, ldt, params + hp.sbf[1].w, D, w.zq2 + l * D, ldt, params + hp.sbf[1].b));
             }
-            PAMNET_TRY(gemm_multi(gemm_zero(GEMM_NT, EPI_BIAS, (int)El, D, D), sl, s2));
-            PAMNET_TRY(gemm_multi(gemm_zero(GEMM_NT, EPI_BIAS_SILU, (int)T, D, D), s1, s2));
-            PAMNET_TRY(gemm_multi(gemm_zero(GEMM_NT, EPI_BIAS, (int)T, D, D), s2v, s2));
-            PAMNET_TRY(sc.record(s2, &ev_l[gi]));
+            PAMNET_TRY(gemm_multi(gemm_zero(GEMM_NT, EPI_BIAS, (int)El, D, D), sl, sB));
+            PAMNET_TRY(gemm_multi(gemm_zero(GEMM_NT, EPI_BIAS_SILU, (int)T, D, D), s1, sB));
+            PAMNET_TRY(gemm_multi(gemm_zero(GEMM_NT, EPI_BIAS, (int)T, D, D), s2v, sB));
+            PAMNET_TRY(sc.record(sB, &ev_l[gi]));
         }
         return 0;
     };
-    // host issue order matters right after the plan sync: group 0 first, then the main stream's first kernels,
-    // then group gi+1 is issued just before the main stream works through the layers of group gi
-    PAMNET_TRY(issue_group(0));
+    // host issue order right after the plan sync: the global chain up to its first group, the main stream's first
+    // kernels, then the local chain; group gi+1 is issued just before the main stream works through group gi
+    PAMNET_TRY(embed_global());
+    if (!fwd_split) PAMNET_TRY(embed_local());
+    PAMNET_TRY(issue_group_g(0));
+    if (!fwd_split) PAMNET_TRY(issue_group_l(0));
 
     // ================= main stream: node input, transposed chain weights, phase B
     if (prepared) PAMNET_TRY(sc.order(s2, st));      // the caller produced them on the auxiliary stream
@@ -677,10 +693,17 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
         add_pre_fwd(p, params, half_params(mp, 0), w.half[0], 0, D, 2);
         PAMNET_TRY(chain_launch(D, p.a, st));
     }
+    if (fwd_split) {
+        PAMNET_TRY(embed_local());
+        PAMNET_TRY(issue_group_l(0));
+    }
     for (int hh = 0; hh < H; ++hh) {              // models.py:196-204
         const HalfWs& hw = w.half[hh];
         const int l = hh >> 1;
-        if (!is_local(hh) && l == grp[group_of[l]] && group_of[l] + 1 < ngrp) PAMNET_TRY(issue_group(group_of[l] + 1));
+        if (!is_local(hh) && l == grp[group_of[l]] && group_of[l] + 1 < ngrp) {
+            PAMNET_TRY(issue_group_g(group_of[l] + 1));
+            PAMNET_TRY(issue_group_l(group_of[l] + 1));
+        }
         if (!is_local(hh)) {
             if (l == grp[group_of[l]]) PAMNET_TRY(sc.wait(st, ev_g[group_of[l]]));
             GlobalMsgArgs a;
@@ -721,7 +744,8 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
     r.sign = cfg.dataset == PAMNET_PDBBIND ? sign : nullptr;
     r.gptr = pl.gptr; r.n2g = pl.n2g; r.att = w.att; r.out = w.out; r.node_val = w.node_val; r.pooled = out;
     PAMNET_TRY(readout_forward(r, st));
-    PAMNET_TRY(sc.order(s2, st));      // nothing of this call is still running on the auxiliary stream afterwards
+    PAMNET_TRY(sc.order(s2, st));      // nothing of this call is still running on the auxiliary streams afterwards
+    if (sB != s2) PAMNET_TRY(sc.order(sB, st));
     if (st != st_user) PAMNET_TRY(sc.order(st, st_user));
     return 0;
 }
