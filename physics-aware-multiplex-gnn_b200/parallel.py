@@ -28,6 +28,9 @@ def allreduce_gradients(model, group=None, average=True):
     world = dist.get_world_size(group)
     buf = flat_grad(model)
     if buf is not None:
+        if average and buf.is_cuda and dist.get_backend(group) == "nccl":
+            dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=group)      # averaged inside the collective: one launch
+            return
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
         if average:
             buf.mul_(1.0 / world)
