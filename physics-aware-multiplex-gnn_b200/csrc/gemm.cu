@@ -260,6 +260,15 @@ static int gemm_backend() {      // 0 = FFMA only, 1 = tensor cores where eligib
     return mode;
 }
 
+static int gemm_small_backend() {      // PAMNET_GEMM_SMALL=0 sends skinny problems to the FFMA tile kernel again
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("PAMNET_GEMM_SMALL");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on;
+}
+
 int gemm_launch(const GemmArgs& a, cudaStream_t st) {
     PAMNET_CHECK_ARG(a.nslots >= 1 && a.nslots <= kGemmMaxSlots, "gemm: nslots=%d", a.nslots);
     PAMNET_CHECK_ARG(a.nseg <= kGemmMaxSeg, "gemm: nseg=%d", a.nseg);
@@ -304,6 +313,14 @@ int gemm_launch(const GemmArgs& a, cudaStream_t st) {
             prof_end(st);
             PAMNET_LAUNCH_CHECK();
         }
+        return 0;
+    }
+    if (gemm_small_backend() && gemm_small_eligible(a)) {
+        prof_begin(KC_GEMM, bytes, st);
+        prof_flops(flops);
+        PAMNET_TRY(gemm_small_launch(a, st));
+        prof_end(st);
+        PAMNET_LAUNCH_CHECK();
         return 0;
     }
     // big tiles only when they still give >= 2 waves of CTAs on 148 SMs

@@ -54,6 +54,10 @@ bool gemm_tc_eligible(const GemmArgs& a);
 int gemm_tc_launch(const GemmArgs& a, cudaStream_t st);
 int tc_trace_read(long long* out, int n);
 
+// skinny problems (N <= 32 rows-kernel, M <= 32 weight gradients), gemm_small.cu
+bool gemm_small_eligible(const GemmArgs& a);
+int gemm_small_launch(const GemmArgs& a, cudaStream_t st);
+
 int mul_dsilu_launch(float* c, const float* z, int64_t n, cudaStream_t st);
 
 // out[c] += sum_r X[r*ld + c]  (bias gradients); out must be zero-initialised by the caller

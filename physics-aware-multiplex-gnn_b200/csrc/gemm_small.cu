@@ -1,0 +1,208 @@
+// Skinny GEMMs (gemm.cuh) for the dim = 16 / 32 models and the 16-wide basis layers: millions of rows against a
+// weight matrix of a few hundred floats.  These are HBM-bound streams -- a 64 x 64 FFMA tile wastes 3/4 of its lanes
+// on N = 16 and the tensor-core tile is 128 wide -- so:
+//  * NT / NN ("row kernel"): one thread per output row; the weight matrix sits in shared memory and is read by
+//    broadcast, the row is read once with 128-bit loads, bias / SiLU / SiLU' / z-output epilogues as in the other paths;
+//  * TN ("column kernel", weight gradients): a warp walks rows k, lane n owns output columns n, n + 32, ... for all
+//    M <= 32 output rows; A[k][:] is a broadcast load, B[k][:] a coalesced one; warps / CTAs combine with fp32 atomics.
+#include "gemm.cuh"
+
+namespace pamnet {
+
+constexpr int kSmallMaxK = 128, kSmallMaxN = 32, kSmallThreads = 128;
+constexpr int kSmallTnMaxM = 32, kSmallTnMaxN = 96;
+
+template <int NT_, int EPI>       // NT_ = register columns per thread (16 or 32)
+__global__ void __launch_bounds__(kSmallThreads) gemm_rows_kernel(const GemmArgs args) {
+    pdl_wait();
+    pdl_trigger();
+    __shared__ __align__(16) float Ws[kSmallMaxK * kSmallMaxN];      // [k][NT_]
+    const GemmSlot& sl = args.slot[blockIdx.z];
+    const int M = sl.m > 0 ? sl.m : args.M, N = args.N, K = args.K, mode = args.mode;
+    // weights -> shared memory as [k][n]
+    for (int i = threadIdx.x; i < K * NT_; i += kSmallThreads) {
+        const int k = i / NT_, n = i % NT_;
+        float v = 0.f;
+        if (n < N) {
+            if (mode == GEMM_NT) v = sl.B[(size_t)n * sl.ldb + k];
+            else if (args.nseg > 0) {
+                const int s = k / args.seg_len;
+                v = args.seg_B[s][(size_t)(k - s * args.seg_len) * args.seg_ldb[s] + n];
+            } else v = sl.B[(size_t)k * sl.ldb + n];
+        }
+        Ws[i] = v;
+    }
+    __syncthreads();
+    const int m = blockIdx.x * kSmallThreads + threadIdx.x;
+    if (m >= M) return;
+    float acc[NT_];
+#pragma unroll
+    for (int n = 0; n < NT_; ++n) acc[n] = 0.f;
+    const float* a = sl.A + (size_t)m * sl.lda;
+    const bool vec = ((reinterpret_cast<uintptr_t>(a) & 15) == 0) && (K % 4 == 0);
+    if (vec) {
+        for (int k = 0; k < K; k += 4) {
+            const float4 av = ld4(a + k);
+            const float ak[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float* w = Ws + (k + j) * NT_;
+#pragma unroll
+                for (int n = 0; n < NT_; ++n) acc[n] = fmaf(ak[j], w[n], acc[n]);
+            }
+        }
+    } else {
+        for (int k = 0; k < K; ++k) {
+            const float ak = a[k];
+            const float* w = Ws + k * NT_;
+#pragma unroll
+            for (int n = 0; n < NT_; ++n) acc[n] = fmaf(ak, w[n], acc[n]);
+        }
+    }
+    float* c = sl.C ? sl.C + (size_t)m * sl.ldc : nullptr;
+    if (EPI == EPI_NONE && args.ksplit > 1) {            // accumulate into a zero-initialised / shared output
+#pragma unroll
+        for (int n = 0; n < NT_; ++n) if (n < N) atomicAdd(c + n, acc[n]);
+        return;
+    }
+#pragma unroll
+    for (int n = 0; n < NT_; ++n) {
+        if (n >= N) break;
+        float v = acc[n];
+        if (EPI == EPI_BIAS || EPI == EPI_BIAS_SILU) {
+            if (sl.bias) v += sl.bias[n];
+            if (EPI == EPI_BIAS_SILU) {
+                if (sl.C2) sl.C2[(size_t)m * sl.ldc + n] = v;
+                v = silu(v);
+            }
+        } else if (EPI == EPI_MUL_DSILU) {
+            v *= dsilu(sl.Z[(size_t)m * sl.ldz + n]);
+        }
+        if (c) {
+            if (args.accumulate) v += c[n];
+            c[n] = v;
+        }
+    }
+}
+
+// weight gradient: C[m][n] (+)= sum_k A[k][m] B[k][n]; C2[m] += sum_k A[k][m].  Always combines with atomics: the
+// caller zero-initialises C (gemm_launch does it for plain-store launches).
+//   MT_ register rows per lane (16 or 32); NJ columns per lane (n = sub-lane + W j, W = 32 / RP lanes per row);
+//   RP rows walked side by side by the lane groups of a warp (2 when N <= 16, so that no lane idles).
+// kColsUnroll rows per lane group are loaded before any is multiplied: the loop is a stream of dependent-free loads.
+constexpr int kColsUnroll = 4;
+template <int MT_, int NJ, int RP>
+__global__ void __launch_bounds__(kSmallThreads) gemm_cols_kernel(const GemmArgs args, int rows_per_cta) {
+    pdl_wait();
+    pdl_trigger();
+    const GemmSlot& sl = args.slot[blockIdx.z];
+    const int M = sl.m > 0 ? sl.m : args.M, N = args.N, K = args.K;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int W = 32 / RP;
+    const int sub = lane % W, rp = lane / W;
+    float acc[MT_][NJ];
+#pragma unroll
+    for (int i = 0; i < MT_; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[i][j] = 0.f;
+    float asum[RP];                                    // column sums of A: rows m = sub + W r of this lane group's rows
+#pragma unroll
+    for (int r = 0; r < RP; ++r) asum[r] = 0.f;
+    const int k0 = blockIdx.x * rows_per_cta, k1 = min(K, k0 + rows_per_cta);
+    constexpr int kStep = (kSmallThreads / 32) * RP;   // rows between two consecutive rows of one lane group
+    for (int kb = k0 + warp * RP + rp; kb < k1; kb += kStep * kColsUnroll) {
+        float bv[kColsUnroll][NJ], am[kColsUnroll][RP], av[kColsUnroll][MT_];
+#pragma unroll
+        for (int u = 0; u < kColsUnroll; ++u) {
+            const int k = kb + u * kStep;
+            const bool live = k < k1;
+            const float* a = sl.A + (size_t)(live ? k : k0) * sl.lda;
+            const float* b = sl.B + (size_t)(live ? k : k0) * sl.ldb;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) bv[u][j] = (live && sub + W * j < N) ? b[sub + W * j] : 0.f;
+#pragma unroll
+            for (int r = 0; r < RP; ++r) am[u][r] = (live && sub + W * r < M) ? a[sub + W * r] : 0.f;
+#pragma unroll
+            for (int i = 0; i < MT_; ++i) av[u][i] = (live && i < M) ? a[i] : 0.f;      // broadcast loads
+        }
+#pragma unroll
+        for (int u = 0; u < kColsUnroll; ++u) {
+#pragma unroll
+            for (int r = 0; r < RP; ++r) asum[r] += am[u][r];
+#pragma unroll
+            for (int i = 0; i < MT_; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) acc[i][j] = fmaf(av[u][i], bv[u][j], acc[i][j]);
+        }
+    }
+    if (RP == 2) {                                     // fold the two lane groups
+#pragma unroll
+        for (int i = 0; i < MT_; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) acc[i][j] += __shfl_xor_sync(0xffffffffu, acc[i][j], 16);
+#pragma unroll
+        for (int r = 0; r < RP; ++r) asum[r] += __shfl_xor_sync(0xffffffffu, asum[r], 16);
+        if (rp != 0) return;
+    }
+#pragma unroll
+    for (int i = 0; i < MT_; ++i) {
+        if (i >= M) break;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+            if (sub + W * j < N && acc[i][j] != 0.f) atomicAdd(&sl.C[(size_t)i * sl.ldc + sub + W * j], acc[i][j]);
+    }
+    if (sl.C2) {
+#pragma unroll
+        for (int r = 0; r < RP; ++r)
+            if (sub + W * r < M && asum[r] != 0.f) atomicAdd(&sl.C2[sub + W * r], asum[r]);
+    }
+}
+
+bool gemm_small_eligible(const GemmArgs& a) {
+    if (a.mode == GEMM_TN) return a.M <= kSmallTnMaxM && a.N <= kSmallTnMaxN && !a.accumulate && a.epi == EPI_NONE;
+    if (a.N > kSmallMaxN || a.K > kSmallMaxK) return false;
+    if (a.ksplit > 1 && a.epi != EPI_NONE) return false;
+    return true;
+}
+
+int gemm_small_launch(const GemmArgs& a, cudaStream_t st) {
+    if (a.mode == GEMM_TN) {
+        if (a.ksplit <= 1) {         // plain-store semantics: zero the outputs, then accumulate
+            for (int i = 0; i < a.nslots; ++i) {
+                const int M = a.slot[i].m > 0 ? a.slot[i].m : a.M;
+                PAMNET_CUDA(cudaMemset2DAsync(a.slot[i].C, sizeof(float) * (size_t)a.slot[i].ldc, 0, sizeof(float) * a.N,
+                                              (size_t)M, st));
+            }
+        }
+        // enough CTAs to fill the GPU a few times over, at least 64 rows each
+        int ctas = ceil_div(a.K, 64);
+        const int cap = 8 * kNumSM / (a.nslots > 0 ? a.nslots : 1) + 1;
+        if (ctas > cap) ctas = cap;
+        const int rows = ceil_div(a.K, ctas);
+        dim3 grid(ceil_div(a.K, rows), 1, a.nslots);
+#define COLS_CASE(MT_) \
+        do { \
+            if (a.N <= 16) PAMNET_CUDA(launch_pdl(gemm_cols_kernel<MT_, 1, 2>, grid, dim3(kSmallThreads), 0, st, a, rows)); \
+            else if (a.N <= 32) PAMNET_CUDA(launch_pdl(gemm_cols_kernel<MT_, 1, 1>, grid, dim3(kSmallThreads), 0, st, a, rows)); \
+            else PAMNET_CUDA(launch_pdl(gemm_cols_kernel<MT_, kSmallTnMaxN / 32, 1>, grid, dim3(kSmallThreads), 0, st, a, rows)); \
+        } while (0)
+        if (a.M <= 16) COLS_CASE(16); else COLS_CASE(32);
+#undef COLS_CASE
+        return 0;
+    }
+    dim3 grid(ceil_div(a.M, kSmallThreads), 1, a.nslots);
+#define ROWS_CASE(NT_, EPI_) PAMNET_CUDA(launch_pdl(gemm_rows_kernel<NT_, EPI_>, grid, dim3(kSmallThreads), 0, st, a)); break
+#define ROWS_EPI(NT_)                                                   \
+    switch (a.epi) {                                                    \
+        case EPI_NONE: ROWS_CASE(NT_, EPI_NONE);                        \
+        case EPI_BIAS: ROWS_CASE(NT_, EPI_BIAS);                        \
+        case EPI_BIAS_SILU: ROWS_CASE(NT_, EPI_BIAS_SILU);              \
+        default: ROWS_CASE(NT_, EPI_MUL_DSILU);                         \
+    }
+    if (a.N <= 16) { ROWS_EPI(16) } else { ROWS_EPI(32) }
+#undef ROWS_EPI
+#undef ROWS_CASE
+    return 0;
+}
+
+}  // namespace pamnet
