@@ -65,22 +65,46 @@ __global__ void __launch_bounds__(kSmallThreads) gemm_rows_kernel(const GemmArgs
         for (int n = 0; n < NT_; ++n) if (n < N) atomicAdd(c + n, acc[n]);
         return;
     }
+    float* c2 = (EPI == EPI_BIAS_SILU && sl.C2) ? sl.C2 + (size_t)m * sl.ldc : nullptr;
+    const float* z = (EPI == EPI_MUL_DSILU) ? sl.Z + (size_t)m * sl.ldz : nullptr;
+    // rows are 64 / 128 B: 128-bit accesses when everything is aligned (a scalar store per column touches a different
+    // 32 B sector in every lane -- the first version of this kernel wrote at a quarter of the rate it read)
+    const bool v4 = (N % 4 == 0) && (!c || (reinterpret_cast<uintptr_t>(c) & 15) == 0) &&
+                    (!c2 || (reinterpret_cast<uintptr_t>(c2) & 15) == 0) && (!z || (reinterpret_cast<uintptr_t>(z) & 15) == 0);
 #pragma unroll
-    for (int n = 0; n < NT_; ++n) {
-        if (n >= N) break;
-        float v = acc[n];
-        if (EPI == EPI_BIAS || EPI == EPI_BIAS_SILU) {
-            if (sl.bias) v += sl.bias[n];
-            if (EPI == EPI_BIAS_SILU) {
-                if (sl.C2) sl.C2[(size_t)m * sl.ldc + n] = v;
-                v = silu(v);
+    for (int n0 = 0; n0 < NT_; n0 += 4) {
+        if (n0 >= N) break;
+        float v[4] = {acc[n0], acc[n0 + 1], acc[n0 + 2], acc[n0 + 3]};
+        float zz[4] = {0.f, 0.f, 0.f, 0.f}, old[4] = {0.f, 0.f, 0.f, 0.f};
+        if (z) {
+            if (v4) { const float4 t = ld4(z + n0); zz[0] = t.x; zz[1] = t.y; zz[2] = t.z; zz[3] = t.w; }
+            else for (int j = 0; j < 4; ++j) if (n0 + j < N) zz[j] = z[n0 + j];
+        }
+        if (c && args.accumulate) {
+            if (v4) { const float4 t = ld4(c + n0); old[0] = t.x; old[1] = t.y; old[2] = t.z; old[3] = t.w; }
+            else for (int j = 0; j < 4; ++j) if (n0 + j < N) old[j] = c[n0 + j];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (EPI == EPI_BIAS || EPI == EPI_BIAS_SILU) {
+                if (sl.bias && n0 + j < N) v[j] += sl.bias[n0 + j];
+            } else if (EPI == EPI_MUL_DSILU) {
+                v[j] *= dsilu(zz[j]);
             }
-        } else if (EPI == EPI_MUL_DSILU) {
-            v *= dsilu(sl.Z[(size_t)m * sl.ldz + n]);
+        }
+        if (c2) {
+            if (v4) st4(c2 + n0, make_float4(v[0], v[1], v[2], v[3]));
+            else for (int j = 0; j < 4; ++j) if (n0 + j < N) c2[n0 + j] = v[j];
+        }
+        if (EPI == EPI_BIAS_SILU) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = silu(v[j]);
         }
         if (c) {
-            if (args.accumulate) v += c[n];
-            c[n] = v;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] += old[j];
+            if (v4) st4(c + n0, make_float4(v[0], v[1], v[2], v[3]));
+            else for (int j = 0; j < 4; ++j) if (n0 + j < N) c[n0 + j] = v[j];
         }
     }
 }
@@ -90,16 +114,25 @@ __global__ void __launch_bounds__(kSmallThreads) gemm_rows_kernel(const GemmArgs
 //   MT_ register rows per lane (16 or 32); NJ columns per lane (n = sub-lane + W j, W = 32 / RP lanes per row);
 //   RP rows walked side by side by the lane groups of a warp (2 when N <= 16, so that no lane idles).
 // kColsUnroll rows per lane group are loaded before any is multiplied: the loop is a stream of dependent-free loads.
-constexpr int kColsUnroll = 4;
+// Accuracy: these reductions run over up to millions of rows with heavy cancellation (a 1185-way fp32 atomic
+// combine missed the 1e-5 parity bar on mlp_rbf_g.weight of the RNA checkpoint).  fp32 partial sums therefore cover
+// at most kColsFlush x kColsUnroll rows, are folded into a per-CTA fp64 tile in shared memory, and only
+// <= 4 x 148 per-CTA results meet in the fp32 output.
+constexpr int kColsUnroll = 4, kColsFlush = 8, kColsThreads = 256;
 template <int MT_, int NJ, int RP>
-__global__ void __launch_bounds__(kSmallThreads) gemm_cols_kernel(const GemmArgs args, int rows_per_cta) {
+__global__ void __launch_bounds__(kColsThreads) gemm_cols_kernel(const GemmArgs args, int rows_per_cta) {
     pdl_wait();
     pdl_trigger();
+    __shared__ double dacc[MT_ * 32 * NJ];             // [m][n], n < 32 NJ
+    __shared__ double dsum[32];
     const GemmSlot& sl = args.slot[blockIdx.z];
     const int M = sl.m > 0 ? sl.m : args.M, N = args.N, K = args.K;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int W = 32 / RP;
+    constexpr int W = 32 / RP, LDN = 32 * NJ;
     const int sub = lane % W, rp = lane / W;
+    for (int i = threadIdx.x; i < MT_ * LDN; i += kColsThreads) dacc[i] = 0.0;
+    if (threadIdx.x < 32) dsum[threadIdx.x] = 0.0;
+    __syncthreads();
     float acc[MT_][NJ];
 #pragma unroll
     for (int i = 0; i < MT_; ++i)
@@ -108,8 +141,23 @@ __global__ void __launch_bounds__(kSmallThreads) gemm_cols_kernel(const GemmArgs
     float asum[RP];                                    // column sums of A: rows m = sub + W r of this lane group's rows
 #pragma unroll
     for (int r = 0; r < RP; ++r) asum[r] = 0.f;
+    auto flush = [&]() {
+#pragma unroll
+        for (int i = 0; i < MT_; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                if (acc[i][j] != 0.f) atomicAdd(&dacc[i * LDN + sub + W * j], (double)acc[i][j]);
+                acc[i][j] = 0.f;
+            }
+#pragma unroll
+        for (int r = 0; r < RP; ++r) {
+            if (asum[r] != 0.f) atomicAdd(&dsum[sub + W * r], (double)asum[r]);
+            asum[r] = 0.f;
+        }
+    };
     const int k0 = blockIdx.x * rows_per_cta, k1 = min(K, k0 + rows_per_cta);
-    constexpr int kStep = (kSmallThreads / 32) * RP;   // rows between two consecutive rows of one lane group
+    constexpr int kStep = (kColsThreads / 32) * RP;    // rows between two consecutive rows of one lane group
+    int it = 0;
     for (int kb = k0 + warp * RP + rp; kb < k1; kb += kStep * kColsUnroll) {
         float bv[kColsUnroll][NJ], am[kColsUnroll][RP], av[kColsUnroll][MT_];
 #pragma unroll
@@ -134,27 +182,18 @@ __global__ void __launch_bounds__(kSmallThreads) gemm_cols_kernel(const GemmArgs
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) acc[i][j] = fmaf(av[u][i], bv[u][j], acc[i][j]);
         }
+        if (++it == kColsFlush) { flush(); it = 0; }
     }
-    if (RP == 2) {                                     // fold the two lane groups
-#pragma unroll
-        for (int i = 0; i < MT_; ++i)
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) acc[i][j] += __shfl_xor_sync(0xffffffffu, acc[i][j], 16);
-#pragma unroll
-        for (int r = 0; r < RP; ++r) asum[r] += __shfl_xor_sync(0xffffffffu, asum[r], 16);
-        if (rp != 0) return;
+    flush();
+    __syncthreads();
+    for (int i = threadIdx.x; i < M * N; i += kColsThreads) {
+        const int m = i / N, n = i % N;
+        const float v = (float)dacc[m * LDN + n];
+        if (v != 0.f) atomicAdd(&sl.C[(size_t)m * sl.ldc + n], v);
     }
-#pragma unroll
-    for (int i = 0; i < MT_; ++i) {
-        if (i >= M) break;
-#pragma unroll
-        for (int j = 0; j < NJ; ++j)
-            if (sub + W * j < N && acc[i][j] != 0.f) atomicAdd(&sl.C[(size_t)i * sl.ldc + sub + W * j], acc[i][j]);
-    }
-    if (sl.C2) {
-#pragma unroll
-        for (int r = 0; r < RP; ++r)
-            if (sub + W * r < M && asum[r] != 0.f) atomicAdd(&sl.C2[sub + W * r], asum[r]);
+    if (sl.C2 && threadIdx.x < M) {
+        const float v = (float)dsum[threadIdx.x];
+        if (v != 0.f) atomicAdd(&sl.C2[threadIdx.x], v);
     }
 }
 
@@ -174,17 +213,17 @@ int gemm_small_launch(const GemmArgs& a, cudaStream_t st) {
                                               (size_t)M, st));
             }
         }
-        // enough CTAs to fill the GPU a few times over, at least 64 rows each
-        int ctas = ceil_div(a.K, 64);
-        const int cap = 8 * kNumSM / (a.nslots > 0 ? a.nslots : 1) + 1;
+        // at most ~4 CTAs per SM over all slots (few fp32 partials meet in the output), at least 256 rows each
+        int ctas = ceil_div(a.K, 256);
+        const int cap = 4 * kNumSM / (a.nslots > 0 ? a.nslots : 1) + 1;
         if (ctas > cap) ctas = cap;
         const int rows = ceil_div(a.K, ctas);
         dim3 grid(ceil_div(a.K, rows), 1, a.nslots);
 #define COLS_CASE(MT_) \
         do { \
-            if (a.N <= 16) PAMNET_CUDA(launch_pdl(gemm_cols_kernel<MT_, 1, 2>, grid, dim3(kSmallThreads), 0, st, a, rows)); \
-            else if (a.N <= 32) PAMNET_CUDA(launch_pdl(gemm_cols_kernel<MT_, 1, 1>, grid, dim3(kSmallThreads), 0, st, a, rows)); \
-            else PAMNET_CUDA(launch_pdl(gemm_cols_kernel<MT_, kSmallTnMaxN / 32, 1>, grid, dim3(kSmallThreads), 0, st, a, rows)); \
+            if (a.N <= 16) PAMNET_CUDA(launch_pdl(gemm_cols_kernel<MT_, 1, 2>, grid, dim3(kColsThreads), 0, st, a, rows)); \
+            else if (a.N <= 32) PAMNET_CUDA(launch_pdl(gemm_cols_kernel<MT_, 1, 1>, grid, dim3(kColsThreads), 0, st, a, rows)); \
+            else PAMNET_CUDA(launch_pdl(gemm_cols_kernel<MT_, kSmallTnMaxN / 32, 1>, grid, dim3(kColsThreads), 0, st, a, rows)); \
         } while (0)
         if (a.M <= 16) COLS_CASE(16); else COLS_CASE(32);
 #undef COLS_CASE
