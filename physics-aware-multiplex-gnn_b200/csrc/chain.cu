@@ -73,7 +73,7 @@ struct ChainCfg {
 };
 
 template <int D>
-__global__ void __launch_bounds__(kChainKS * D / 2) chain_kernel(const ChainArgs args) {
+__global__ void __launch_bounds__(kChainKS * D / 2, 1) chain_kernel(const ChainArgs args) {
     using C = ChainCfg<D>;
     constexpr int R = C::R, NT = C::T, KL = C::KL;
     extern __shared__ __align__(16) float smem[];
@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(kChainKS * D / 2) chain_kernel(const ChainArgs
 
     const int n_stages = args.n_stages;
     for (int si = 0; si < n_stages; ++si) {
-        const ChainStage st = s_stage[si];                // register copy (independent shared-memory loads)
+        const ChainStage& st = s_stage[si];               // fields are read from shared memory where they are used (a
+                                                          // full register copy pushed the kernel over 128 registers)
         if (si == n_stages - 1) pdl_trigger();            // the next kernel's CTAs may start arriving
         CH_STAMP(si, 0);
         if (st.op == CH_LOAD) {
