@@ -1,6 +1,8 @@
 // Basis / embedding kernels (see basis.cuh).
 #include "basis.cuh"
 
+#include <stdlib.h>
+
 namespace pamnet {
 
 void make_sbf_tables(const pamnet_sbf_consts_t& c, SbfTables* t) {
@@ -214,6 +216,215 @@ int sbf_ext_forward(const SbfTables& tab, const Plan& plan, int64_t n_edges, int
     prof_begin(KC_BASIS, 0.0, st);
     sbf_ext_kernel<<<ceil_div(n_trip, 4), 128, 0, st>>>(tab, plan.l_src, plan.l_dst, plan.t_ptr, plan.t_split,
                                                         plan.t_gather, plan.t_owner, n_trip, pos, radial, sbf_ext);
+    prof_end(st);
+    PAMNET_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused spherical-basis embedding for the small-dim models (dim <= 32; the RNA config has 4 M triplet rows):
+// instead of materialising the [T, 88] extended operand (1.46 GB there, written once and read twice), the 42
+// features radial[gathered edge] * Y_l0(angle) are formed in registers and multiplied by the weight block of the
+// row's type (two-hop: mlp_sbf2, one-hop: mlp_sbf1; models.py:187-188) that sits in shared memory.  The seven
+// zonal values per row are kept ([T, 8]) for the weight-gradient pass, which recomputes the features the same way.
+// ---------------------------------------------------------------------------------------------
+constexpr int kYsphLd = 8;
+
+template <int DT>
+__global__ void __launch_bounds__(128) sbf_embed_fwd_kernel(const SbfTables tab, const int32_t* __restrict__ l_src,
+                                                            const int32_t* __restrict__ l_dst,
+                                                            const int32_t* __restrict__ t_ptr,
+                                                            const int32_t* __restrict__ t_split,
+                                                            const int32_t* __restrict__ t_gather,
+                                                            const int32_t* __restrict__ t_owner, int64_t n_trip,
+                                                            const float* __restrict__ pos, const float* __restrict__ radial,
+                                                            const float* __restrict__ w2, const float* __restrict__ b2,
+                                                            const float* __restrict__ w1, const float* __restrict__ b1,
+                                                            int dim, float* __restrict__ z_s, float* __restrict__ s_out,
+                                                            float* __restrict__ ysph) {
+    __shared__ float W[2][kNumSbf][DT];
+    __shared__ float Bv[2][DT];
+    for (int i = threadIdx.x; i < 2 * kNumSbf * DT; i += blockDim.x) {
+        const int ty = i / (kNumSbf * DT), c = (i / DT) % kNumSbf, d = i % DT;
+        const float* src = ty == 0 ? w2 : w1;
+        (&W[0][0][0])[i] = (src && d < dim) ? src[d * kNumSbf + c] : 0.f;
+    }
+    for (int i = threadIdx.x; i < 2 * DT; i += blockDim.x) {
+        const int ty = i / DT, d = i % DT;
+        const float* src = ty == 0 ? b2 : b1;
+        (&Bv[0][0])[i] = (src && d < dim) ? src[d] : 0.f;
+    }
+    __syncthreads();
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_trip) return;
+    const int k = t_owner[t], p = t_gather[t];
+    const int i = l_dst[k], j = l_src[k], o = l_src[p];
+    const bool two_hop = (t - t_ptr[k]) < t_split[k];
+    const double ct = two_hop ? cos_angle(pos, i, j, o) : cos_angle(pos, j, i, o);
+    float y[kNumSph];
+    zonal(tab, ct, y);
+    st4(ysph + t * kYsphLd, make_float4(y[0], y[1], y[2], y[3]));
+    st4(ysph + t * kYsphLd + 4, make_float4(y[4], y[5], y[6], 0.f));
+    const int ty = two_hop ? 0 : 1;
+    const float* r = radial + (size_t)p * kNumSbf;
+    float acc[DT];
+#pragma unroll
+    for (int d = 0; d < DT; ++d) acc[d] = 0.f;
+#pragma unroll
+    for (int l = 0; l < kNumSph; ++l) {
+#pragma unroll
+        for (int m = 0; m < kNumRad; ++m) {
+            const int c = l * kNumRad + m;
+            const float f = r[c] * y[l];
+            const float* w = &W[ty][c][0];
+#pragma unroll
+            for (int d = 0; d < DT; ++d) acc[d] = fmaf(f, w[d], acc[d]);
+        }
+    }
+    float* zr = z_s + t * dim;
+    float* sr = s_out + t * dim;
+#pragma unroll
+    for (int d0 = 0; d0 < DT; d0 += 4) {
+        if (d0 >= dim) break;
+        float v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = acc[d0 + q] + Bv[ty][d0 + q];
+        if (dim % 4 == 0) {
+            st4(zr + d0, make_float4(v[0], v[1], v[2], v[3]));
+            st4(sr + d0, make_float4(silu(v[0]), silu(v[1]), silu(v[2]), silu(v[3])));
+        } else {
+            for (int q = 0; q < 4; ++q)
+                if (d0 + q < dim) { zr[d0 + q] = v[q]; sr[d0 + q] = silu(v[q]); }
+        }
+    }
+}
+
+bool sbf_fused_enabled(int dim) {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("PAMNET_SBF_FUSED"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on && dim <= 32;
+}
+
+int sbf_embed_forward(const SbfTables& tab, const Plan& plan, int64_t n_trip, const float* pos, const float* radial,
+                      const float* w2, const float* b2, const float* w1, const float* b1, int dim, float* z_s, float* s,
+                      float* ysph, cudaStream_t st) {
+    if (n_trip == 0) return 0;
+    PAMNET_CHECK_ARG(dim <= 32, "sbf_embed_forward: dim=%d (<= 32)", dim);
+    prof_begin(KC_BASIS, 0.0, st);
+    const dim3 grid(ceil_div(n_trip, 128));
+    if (dim <= 16)
+        sbf_embed_fwd_kernel<16><<<grid, 128, 0, st>>>(tab, plan.l_src, plan.l_dst, plan.t_ptr, plan.t_split, plan.t_gather,
+                                                       plan.t_owner, n_trip, pos, radial, w2, b2, w1, b1, dim, z_s, s, ysph);
+    else
+        sbf_embed_fwd_kernel<32><<<grid, 128, 0, st>>>(tab, plan.l_src, plan.l_dst, plan.t_ptr, plan.t_split, plan.t_gather,
+                                                       plan.t_owner, n_trip, pos, radial, w2, b2, w1, b1, dim, z_s, s, ysph);
+    prof_end(st);
+    PAMNET_LAUNCH_CHECK();
+    return 0;
+}
+
+// weight gradients of mlp_sbf2 / mlp_sbf1: g_ext[d][col] = sum_t gz[t][d] * ext_t[col] over the 86 extended columns
+// (ext_t recomputed per row), accumulated like gemm_cols_kernel: fp32 over <= 32 rows, fp64 tile per CTA, one fp32
+// atomic per output and CTA straight into the parameter-gradient buffers.
+constexpr int kSbfWgThreads = 256, kSbfWgUnroll = 2, kSbfWgFlush = 16;
+template <int DT>
+__global__ void __launch_bounds__(kSbfWgThreads, (DT <= 16 ? 2 : 1)) sbf_embed_wgrad_kernel(const int32_t* __restrict__ t_ptr,
+                                                                        const int32_t* __restrict__ t_split,
+                                                                        const int32_t* __restrict__ t_gather,
+                                                                        const int32_t* __restrict__ t_owner,
+                                                                        int64_t n_trip, const float* __restrict__ radial,
+                                                                        const float* __restrict__ ysph,
+                                                                        const float* __restrict__ gz, int dim,
+                                                                        float* __restrict__ gw2, float* __restrict__ gb2,
+                                                                        float* __restrict__ gw1, float* __restrict__ gb1,
+                                                                        int rows_per_cta) {
+    constexpr int NJ = 3, LDN = 96;
+    __shared__ double dacc[DT * LDN];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < DT * LDN; i += kSbfWgThreads) dacc[i] = 0.0;
+    __syncthreads();
+    float acc[DT][NJ];
+#pragma unroll
+    for (int i = 0; i < DT; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[i][j] = 0.f;
+    auto flush = [&]() {
+#pragma unroll
+        for (int i = 0; i < DT; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                if (acc[i][j] != 0.f) atomicAdd(&dacc[i * LDN + lane + 32 * j], (double)acc[i][j]);
+                acc[i][j] = 0.f;
+            }
+    };
+    const int64_t k0 = (int64_t)blockIdx.x * rows_per_cta, k1 = min(n_trip, k0 + (int64_t)rows_per_cta);
+    constexpr int kStep = kSbfWgThreads / 32;
+    int it = 0;
+    for (int64_t kb = k0 + warp; kb < k1; kb += kStep * kSbfWgUnroll) {
+        float bv[kSbfWgUnroll][NJ], av[kSbfWgUnroll][DT];
+#pragma unroll
+        for (int u = 0; u < kSbfWgUnroll; ++u) {
+            const int64_t t = kb + u * kStep;
+            const bool live = t < k1;
+            const int64_t tt = live ? t : k0;
+            const int k = t_owner[tt], p = t_gather[tt];
+            const int ty = ((tt - t_ptr[k]) < t_split[k]) ? 0 : 1;
+            const float* r = radial + (size_t)p * kNumSbf;
+            const float* y = ysph + tt * kYsphLd;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int col = lane + 32 * j;
+                float v = 0.f;
+                if (live) {
+                    if (col < 2 * kNumSbf) {
+                        const int cty = col >= kNumSbf, cc = col - cty * kNumSbf;
+                        if (cty == ty) v = r[cc] * y[cc / kNumRad];
+                    } else if (col == 2 * kNumSbf + ty) {
+                        v = 1.f;
+                    }
+                }
+                bv[u][j] = v;
+            }
+            const float* a = gz + tt * dim;
+#pragma unroll
+            for (int i = 0; i < DT; ++i) av[u][i] = (live && i < dim) ? a[i] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < kSbfWgUnroll; ++u)
+#pragma unroll
+            for (int i = 0; i < DT; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) acc[i][j] = fmaf(av[u][i], bv[u][j], acc[i][j]);
+        if (++it == kSbfWgFlush) { flush(); it = 0; }
+    }
+    flush();
+    __syncthreads();
+    for (int i = threadIdx.x; i < dim * (2 * kNumSbf + 2); i += kSbfWgThreads) {
+        const int d = i / (2 * kNumSbf + 2), col = i % (2 * kNumSbf + 2);
+        const float v = (float)dacc[d * LDN + col];
+        if (v == 0.f) continue;
+        if (col < kNumSbf) { if (gw2) atomicAdd(&gw2[d * kNumSbf + col], v); }
+        else if (col < 2 * kNumSbf) atomicAdd(&gw1[d * kNumSbf + col - kNumSbf], v);
+        else if (col == 2 * kNumSbf) { if (gb2) atomicAdd(&gb2[d], v); }
+        else atomicAdd(&gb1[d], v);
+    }
+}
+
+int sbf_embed_wgrad(const Plan& plan, int64_t n_trip, const float* radial, const float* ysph, const float* gz, int dim,
+                    float* gw2, float* gb2, float* gw1, float* gb1, cudaStream_t st) {
+    if (n_trip == 0) return 0;
+    PAMNET_CHECK_ARG(dim <= 32, "sbf_embed_wgrad: dim=%d (<= 32)", dim);
+    int ctas = ceil_div(n_trip, 256);
+    if (ctas > 4 * kNumSM) ctas = 4 * kNumSM;
+    const int rows = ceil_div(n_trip, ctas);
+    const dim3 grid(ceil_div(n_trip, rows));
+    prof_begin(KC_BASIS, 0.0, st);
+    if (dim <= 16)
+        sbf_embed_wgrad_kernel<16><<<grid, kSbfWgThreads, 0, st>>>(plan.t_ptr, plan.t_split, plan.t_gather, plan.t_owner, n_trip,
+                                                                    radial, ysph, gz, dim, gw2, gb2, gw1, gb1, rows);
+    else
+        sbf_embed_wgrad_kernel<32><<<grid, kSbfWgThreads, 0, st>>>(plan.t_ptr, plan.t_split, plan.t_gather, plan.t_owner, n_trip,
+                                                                    radial, ysph, gz, dim, gw2, gb2, gw1, gb1, rows);
     prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;

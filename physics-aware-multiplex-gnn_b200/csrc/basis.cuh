@@ -29,6 +29,15 @@ int sbf_combine(const SbfTables& tab, const float* radial, const float* angle, c
 int sbf_ext_forward(const SbfTables& tab, const Plan& plan, int64_t n_edges, int64_t n_trip, const float* pos,
                     const float* radial, float* sbf_ext, cudaStream_t st);
 
+// fused small-dim path (dim <= 32): embedding straight from (radial, angle) without the [T, 88] operand, and its
+// weight gradient; ysph [T, 8] carries the zonal values from forward to backward
+bool sbf_fused_enabled(int dim);
+int sbf_embed_forward(const SbfTables& tab, const Plan& plan, int64_t n_trip, const float* pos, const float* radial,
+                      const float* w2, const float* b2, const float* w1, const float* b1, int dim, float* z_s, float* s,
+                      float* ysph, cudaStream_t st);
+int sbf_embed_wgrad(const Plan& plan, int64_t n_trip, const float* radial, const float* ysph, const float* gz, int dim,
+                    float* gw2, float* gb2, float* gw1, float* gb1, cudaStream_t st);
+
 // W_ext [D, 88] = [W_sbf2 | W_sbf1 | b_sbf2 | b_sbf1 | 0 0]; and the reverse scatter of its gradient
 int sbf_weight_pack(int dim, const float* w2, const float* b2, const float* w1, const float* b1, float* w_ext,
                     cudaStream_t st);

@@ -126,6 +126,7 @@ struct HalfWs {
 struct Ws {
     float* wt;
     float *x0, *rbf_g, *rbf_l, *radial, *sbf_ext, *w_ext, *gw_ext;
+    float* ysph;        // [T, 8] zonal values per triplet (fused small-dim spherical-basis path only)
     float *z_eg, *e_g, *z_el, *e_l, *z_s, *s;
     float *QT, *QR, *zq1, *aq1, *zq2;
     float *att, *out, *node_val;
@@ -167,7 +168,9 @@ size_t ws_layout(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, void* bas
     cur_base = base;
     w.x0 = take(N * D);
     w.rbf_g = take(Eg * kNumRbf); w.rbf_l = take(El * kNumRbf); w.radial = take(El * kNumSbf);
-    w.sbf_ext = take(T * kSbfExt); w.w_ext = take(D * kSbfExt); w.gw_ext = take(D * kSbfExt);
+    const bool sbf_fused = sbf_fused_enabled((int)D);
+    w.sbf_ext = take(sbf_fused ? 0 : T * kSbfExt); w.w_ext = take(D * kSbfExt); w.gw_ext = take(D * kSbfExt);
+    w.ysph = take(sbf_fused ? T * 8 : 0);
     w.z_eg = take(Eg * D); w.e_g = take(Eg * D); w.z_el = take(El * D); w.e_l = take(El * D);
     w.z_s = take(T * D); w.s = take(T * D);
     w.QT = take(Eg * L * 2 * D); w.QR = take(El * L * 4 * D);
@@ -613,13 +616,20 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
     auto embed_local = [&]() -> int {
         PAMNET_TRY(rbf_forward(pl.dist_l, El, params + mp.freq_l, cfg.cutoff_l, w.rbf_l, sB));
         PAMNET_TRY(sbf_radial(c.tab, pl.dist_l, El, cfg.cutoff_l, w.radial, sB));
-        PAMNET_TRY(sbf_ext_forward(c.tab, pl, El, T, pos, w.radial, w.sbf_ext, sB));
-        PAMNET_TRY(sbf_weight_pack(D, cfg.simple ? nullptr : params + mp.sbf2.w, cfg.simple ? nullptr : params + mp.sbf2.b,
-                                   params + mp.sbf1.w, params + mp.sbf1.b, w.w_ext, sB));
+        const bool fused = sbf_fused_enabled(D);
+        const float* w2 = cfg.simple ? nullptr : params + mp.sbf2.w;
+        const float* b2 = cfg.simple ? nullptr : params + mp.sbf2.b;
+        if (!fused) {
+            PAMNET_TRY(sbf_ext_forward(c.tab, pl, El, T, pos, w.radial, w.sbf_ext, sB));
+            PAMNET_TRY(sbf_weight_pack(D, w2, b2, params + mp.sbf1.w, params + mp.sbf1.b, w.w_ext, sB));
+        }
         GemmArgs a = gemm_zero(GEMM_NT, EPI_BIAS_SILU, (int)El, D, kNumRbf);
         a.nslots = 1;
         a.slot[0] = slot(w.rbf_l, kNumRbf, params + mp.rbf_l.w, kNumRbf, w.e_l, D, params + mp.rbf_l.b, w.z_el);
         PAMNET_TRY(gemm_launch(a, sB));
+        if (fused)      // small dims: features formed in registers, no [T, 88] operand (basis.cu)
+            return sbf_embed_forward(c.tab, pl, T, pos, w.radial, w2, b2, params + mp.sbf1.w, params + mp.sbf1.b, D, w.z_s,
+                                     w.s, w.ysph, sB);
         a.M = (int)T; a.K = kSbfExt;
         a.slot[0] = slot(w.sbf_ext, kSbfExt, w.w_ext, kSbfExt, w.s, D, nullptr, w.z_s);
         return gemm_launch(a, sB);
@@ -962,6 +972,9 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
     };
     auto embed_tail_sbf = [&](cudaStream_t s) -> int {      // SBF embeddings (models.py:187-188)
         PAMNET_TRY(mul_dsilu_launch(w.gz_s, w.z_s, T * D, s));
+        if (sbf_fused_enabled(D))
+            return sbf_embed_wgrad(pl, T, w.radial, w.ysph, w.gz_s, D, cfg.simple ? nullptr : gp + mp.sbf2.w,
+                                   cfg.simple ? nullptr : gp + mp.sbf2.b, gp + mp.sbf1.w, gp + mp.sbf1.b, s);
         PAMNET_CUDA(cudaMemsetAsync(w.gw_ext, 0, sizeof(float) * D * kSbfExt, s));
         GemmArgs cw = gemm_zero(GEMM_TN, EPI_NONE, D, kSbfExt, (int)T);
         cw.nslots = 1; cw.ksplit = pick_ksplit(T);
