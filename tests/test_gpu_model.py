@@ -260,10 +260,13 @@ _BASE_STEP = None
 
 @pytest.mark.parametrize("env", [{"PAMNET_STREAMS": "1"}, {"PAMNET_PDL": "0"}, {"PAMNET_PLAN": "stepwise"},
                                  {"PAMNET_GATHER": "atomic"}, {"PAMNET_GEMM": "ffma"}, {"PAMNET_CHAIN_FUSE": "0"},
-                                 {"PAMNET_PREP": "1"}, {"PAMNET_FWD_SPLIT": "1"}, {"PAMNET_GEMM_SMALL": "0"}])
+                                 {"PAMNET_PREP": "1"}, {"PAMNET_FWD_SPLIT": "1"}, {"PAMNET_GEMM_SMALL": "0"},
+                                 {"PAMNET_SBF_FUSED": "0"}])
 def test_alternate_paths_agree(env):
     """Single-stream schedule, no programmatic dependent launch, the step-by-step front end, atomic projection
-    gradients, the FFMA GEMM and the unfused chain prologue: same graph bit for bit, same numbers to fp32 rounding."""
+    gradients, the FFMA GEMM, the unfused chain prologue, ... (the golden model has dim = 32, so the
+    skinny-GEMM and fused spherical-basis paths are the defaults here): same graph bit for bit, same numbers to fp32
+    rounding."""
     global _BASE_STEP
     if _BASE_STEP is None:
         _BASE_STEP = _run_subprocess_step({})
