@@ -121,3 +121,39 @@ def test_synthetic_generator_contract():
     assert float(d.min()) >= 0.9 and float(d.max()) < 1.7
     b2 = synthetic_qm9_batch(32, seed=0)
     assert torch.equal(b.pos, b2.pos) and torch.equal(b.edge_index, b2.edge_index)
+
+
+def test_fused_optimizer_refuses_cpu_parameters_and_foreign_modules():
+    """pamnet_b200.FusedAdamEMA has no CPU path and only drives this package's flat-parameter modules."""
+    from pamnet_b200 import Config, PAMNet, FusedAdamEMA, PamnetError
+    model = PAMNet(Config("QM9", 16, 1, 5.0, 5.0))
+    with pytest.raises(PamnetError):
+        FusedAdamEMA(model, lr=1e-3)
+    with pytest.raises(TypeError):
+        FusedAdamEMA(torch.nn.Linear(4, 4), lr=1e-3)
+
+
+def test_optimizer_step_argument_checks_need_no_gpu():
+    """The C entry point validates sizes before touching memory (n must be a multiple of 4, step >= 1)."""
+    import ctypes
+    from pamnet_b200 import _lib
+    lib = _lib.load()
+    buf = (ctypes.c_float * 8)()
+    p = ctypes.addressof(buf)
+    rc = lib.pamnet_optimizer_step(p, p, p, p, None, 6, None, 0, 1, 1e-3, 0.9, 0.999, 1e-8, 0.0, 0.0, 0.0, 0, None, None)
+    assert rc < 0 and b"multiple of 4" in lib.pamnet_last_error()
+    rc = lib.pamnet_optimizer_step(p, p, p, p, None, 8, None, 0, 0, 1e-3, 0.9, 0.999, 1e-8, 0.0, 0.0, 0.0, 0, None, None)
+    assert rc < 0
+
+
+def test_plan_build_argument_checks_need_no_gpu():
+    import ctypes
+    from pamnet_b200 import _lib
+    lib = _lib.load()
+    cfg = _lib.Config(0, 16, 1, 0, 0, 5.0, 5.0)
+    assert lib.pamnet_plan_build_scratch_bytes(cfg, 100, 200, 1000) > 0
+    assert lib.pamnet_prepared_weights_bytes(cfg) > 0
+    need = (ctypes.c_int64 * 4)()
+    sz = _lib.Sizes(0, 0, 0, 0, 0, 0)
+    rc = lib.pamnet_plan_build(cfg, None, None, 10, 1, None, 0, 32, None, 0, None, 0, None, 0, None, 0, None, 0, sz, need, None)
+    assert rc < 0 and b"null pointer" in lib.pamnet_last_error()
