@@ -8,6 +8,7 @@
 
 #include "basis.cuh"
 #include "chain.cuh"
+#include "front_mol.cuh"
 #include "gemm.cuh"
 #include "graph.cuh"
 #include "message.cuh"
@@ -197,6 +198,11 @@ size_t build_scratch_layout(int kind, int64_t n, int64_t n_edges_in, int64_t cap
     if (out) *out = b;
     return off;
 }
+// PAMNET_FRONT=mol: per-molecule front end for QM9-shaped batches (read per call so that tests can switch it)
+bool front_mol_enabled() {
+    const char* e = getenv("PAMNET_FRONT");
+    return e && strcmp(e, "mol") == 0;
+}
 thread_local int64_t* g_host_counts = nullptr;      // pinned: the counters are read back between the build phases
 int read_counts(const int64_t* dev, cudaStream_t st) {
     if (!g_host_counts) PAMNET_CUDA(cudaMallocHost(reinterpret_cast<void**>(&g_host_counts), 8 * sizeof(int64_t)));
@@ -229,6 +235,50 @@ int pamnet_plan_build(const pamnet_config_t* cfg, const float* pos, const int64_
     cudaStream_t st = ST(stream);
     for (int i = 0; i < 4; ++i) need[i] = 0;
     PAMNET_CUDA(cudaMemsetAsync(b.counts, 0, 8 * sizeof(int64_t), st));
+
+    // ---- small-molecule batches: the whole front end as two launches and ONE read-back (front_mol.cuh) ------------
+    // Opt-in (PAMNET_FRONT=mol) until it has been confirmed on the GPU against the generic kernels below; batches it
+    // cannot take (molecules above the per-block capacities, bond lists not grouped by molecule) fall through.
+    if (kind == PAMNET_QM9 && front_mol_enabled() && n_graphs <= kMolGraphs && n_graphs <= n_nodes) {
+        MolArgs a;
+        memset(&a, 0, sizeof(a));
+        a.pos = pos; a.batch = batch; a.n_nodes = n_nodes; a.n_graphs = n_graphs;
+        a.ei_in = edge_index_in; a.n_edges_in = n_edges_in;
+        a.r2 = cfg->cutoff_g * cfg->cutoff_g; a.max_nb = max_nb;
+        a.g_dst_row = (cfg->flow == PAMNET_TARGET_TO_SOURCE) ? 0 : 1;
+        a.two_hop = cfg->simple ? 0 : 1;
+        a.mc_eg = b.deg_a; a.mc_el = b.ptr_a; a.mc_t2 = b.deg_b; a.mc_t1 = b.ptr_b;      // n_graphs <= n_nodes entries each
+        a.counts = reinterpret_cast<unsigned long long*>(b.counts);
+        PAMNET_TRY(mol_count(a, st));
+        PAMNET_TRY(read_counts(b.counts, st));
+        if (g_host_counts[5] == 0 && g_host_counts[4] == n_edges_in) {
+            pamnet_sizes_t sz;
+            memset(&sz, 0, sizeof(sz));
+            sz.n_nodes = n_nodes; sz.n_graphs = n_graphs;
+            sz.n_edges_g = g_host_counts[0]; sz.n_edges_l = g_host_counts[1];
+            sz.n_t2 = g_host_counts[2]; sz.n_t1 = g_host_counts[3];
+            size_t bb = 0, tb = 0;
+            plan_layout(sz, nullptr, nullptr, nullptr, &bb, &tb);
+            need[0] = sz.n_edges_g; need[1] = sz.n_edges_l; need[2] = (int64_t)bb; need[3] = (int64_t)tb;
+            if (sz.n_edges_g > cap_eg || sz.n_edges_l > cap_el || bb > cap_base || tb > cap_trip) return 1;
+            Plan p;
+            plan_layout(sz, plan_base, plan_trip, &p, nullptr, nullptr);
+            a.Eg = sz.n_edges_g; a.El = sz.n_edges_l;
+            a.eg_out = eg_buf;
+            a.el_out = (sz.n_edges_l == n_edges_in) ? nullptr : el_buf;      // nothing dropped: the caller's list is used in place
+            a.n2g = p.n2g; a.gptr = p.gptr;
+            a.g_ptr = p.g_ptr; a.g_src = p.g_src; a.g_dst = p.g_dst; a.g_eid = p.g_eid; a.g_optr = p.g_optr; a.g_opos = p.g_opos;
+            a.l_ptr = p.l_ptr; a.l_src = p.l_src; a.l_dst = p.l_dst; a.l_eid = p.l_eid; a.l_optr = p.l_optr; a.l_opos = p.l_opos;
+            a.t_split = p.t_split; a.t_cnt = p.t_cnt; a.t_ptr = p.t_ptr; a.tt_ptr = p.tt_ptr;
+            a.t_gather = p.t_gather; a.t_owner = p.t_owner; a.tt_t = p.tt_t;
+            a.t_angle = p.t_angle; a.dist_g = p.dist_g; a.dist_l = p.dist_l;
+            PAMNET_TRY(mol_fill(a, st));
+            *sizes_out = sz;
+            return 0;
+        }
+        for (int i = 0; i < 4; ++i) need[i] = 0;
+        PAMNET_CUDA(cudaMemsetAsync(b.counts, 0, 8 * sizeof(int64_t), st));
+    }
 
     // ---- phase 1: edge counts (models.py:110,115 / 128,131-136 / 143-157) ----------------------------------------
     if (kind == PAMNET_RNA) {
@@ -321,7 +371,8 @@ int64_t pamnet_debug_ws_offset(const pamnet_config_t* cfg, const pamnet_sizes_t*
     return debug_ws_offset(*cfg, *sz, name, half);
 }
 // plan arrays for tests: which = 0 g_ptr, 1 g_src, 2 g_eid, 3 l_ptr, 4 l_src, 5 l_dst, 6 l_eid, 7 t_ptr, 8 t_gather,
-// 9 t_owner, 10 t_split, 11 dist_g, 12 dist_l, 13 t_angle; returns the byte offset inside base (0..12) or trip blob
+// 9 t_owner, 10 t_split, 11 dist_g, 12 dist_l, 13 t_angle, 14 g_dst, 15 g_optr, 16 g_opos, 17 l_optr, 18 l_opos, 19 t_cnt,
+// 20 tt_ptr, 21 tt_t, 22 n2g, 23 gptr; returns the byte offset inside base (0..12) or trip blob
 int64_t pamnet_debug_plan_offset(const pamnet_sizes_t* sz, int32_t which, int32_t* in_trip) {
     if (!sz) return -1;
     Plan p;
@@ -329,9 +380,10 @@ int64_t pamnet_debug_plan_offset(const pamnet_sizes_t* sz, int32_t which, int32_
     char* t = reinterpret_cast<char*>(0x1000);
     plan_layout(*sz, b, t, &p, nullptr, nullptr);
     const void* tab[] = {p.g_ptr, p.g_src, p.g_eid, p.l_ptr, p.l_src, p.l_dst, p.l_eid, p.t_ptr, p.t_gather,
-                         p.t_owner, p.t_split, p.dist_g, p.dist_l, p.t_angle};
-    if (which < 0 || which > 13) return -1;
-    const bool trip = (which == 8 || which == 9 || which == 13);
+                         p.t_owner, p.t_split, p.dist_g, p.dist_l, p.t_angle,
+                         p.g_dst, p.g_optr, p.g_opos, p.l_optr, p.l_opos, p.t_cnt, p.tt_ptr, p.tt_t, p.n2g, p.gptr};
+    if (which < 0 || which > 23) return -1;
+    const bool trip = (which == 8 || which == 9 || which == 13 || which == 21);
     if (in_trip) *in_trip = trip;
     return (int64_t)(reinterpret_cast<const char*>(tab[which]) - (trip ? t : b));
 }

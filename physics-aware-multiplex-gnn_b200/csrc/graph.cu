@@ -7,6 +7,7 @@
 //   SparseTensor row gathers          models.py:68-98               -> incoming CSR walks (triplet_*, plan_*)
 // Canonical ordering and tie rules: oracle/graph_ops.py.
 #include "graph.cuh"
+#include "geom.cuh"
 
 namespace pamnet {
 
@@ -81,21 +82,6 @@ int scan_exclusive(const int32_t* in, int32_t* out, int64_t n, int64_t* total64,
 // ---------------------------------------------------------------------------------------------
 // graph segments from a non-decreasing batch vector
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int64_t lower_bound_i64(const int64_t* __restrict__ a, int64_t n, int64_t key) {
-    int64_t lo = 0, hi = n;
-    while (lo < hi) {
-        int64_t mid = (lo + hi) >> 1;
-        if (a[mid] < key) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
-// canonical squared distance: ((dx*dx)+(dy*dy))+(dz*dz), no FMA contraction (oracle/graph_ops.py:_d2_block)
-__device__ __forceinline__ float canon_d2(float ax, float ay, float az, float bx, float by, float bz) {
-    float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
-    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-}
-
 // One thread per query; the scan over the query's own graph reads pos[n] warp-uniformly for small molecules.
 template <bool FILL>
 __global__ void radius_kernel(const float* __restrict__ pos, const int64_t* __restrict__ batch, int64_t n_nodes,
@@ -268,12 +254,6 @@ int knn(const float* pos, const int64_t* batch, int64_t n_nodes, int k, int32_t*
     prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;
-}
-
-// edge length exactly as models.py:64-65 evaluates it on the API tensors: sqrt(sum((pos[i]-pos[j])^2))
-__device__ __forceinline__ float edge_len(const float* __restrict__ pos, int64_t a, int64_t b) {
-    float dx = pos[3 * a] - pos[3 * b], dy = pos[3 * a + 1] - pos[3 * b + 1], dz = pos[3 * a + 2] - pos[3 * b + 2];
-    return sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
 }
 
 template <bool FILL>
@@ -676,15 +656,6 @@ __global__ void plan_tcount_kernel(const int32_t* __restrict__ l_ptr, const int3
         atomicAdd(&totals[0], (unsigned long long)a);
         atomicAdd(&totals[1], (unsigned long long)b);
     }
-}
-
-__device__ __forceinline__ float bond_angle(const float* __restrict__ pos, int a, int b, int c) {
-    // models.py:165-177: u = pos[b]-pos[a], v = pos[c]-pos[b]; atan2(|u x v|, u.v)
-    const float ux = pos[3 * b] - pos[3 * a], uy = pos[3 * b + 1] - pos[3 * a + 1], uz = pos[3 * b + 2] - pos[3 * a + 2];
-    const float vx = pos[3 * c] - pos[3 * b], vy = pos[3 * c + 1] - pos[3 * b + 1], vz = pos[3 * c + 2] - pos[3 * b + 2];
-    const float dot = ux * vx + uy * vy + uz * vz;
-    const float cx = uy * vz - uz * vy, cy = uz * vx - ux * vz, cz = ux * vy - uy * vx;
-    return atan2f(sqrtf(cx * cx + cy * cy + cz * cz), dot);
 }
 
 // segment of slot k: first its two-hop entries (edges into the source j, minus the back edge), then its

@@ -44,4 +44,9 @@ int plan_count(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const int64
 int plan_fill(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const float* pos, void* plan_base, void* plan_trip,
               cudaStream_t st);
 
+// per-molecule front end (front_mol.cuh / front_mol.cu): count pass, then -- after the host has read the totals -- fill pass
+struct MolArgs;
+int mol_count(const MolArgs& a, cudaStream_t st);
+int mol_fill(const MolArgs& a, cudaStream_t st);
+
 }  // namespace pamnet

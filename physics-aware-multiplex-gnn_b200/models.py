@@ -41,6 +41,30 @@ class GraphPlan:
         self.sizes, self.base, self.trip = sizes, base, trip
         self.edge_index_g, self.edge_index_l = edge_index_g, edge_index_l
 
+    _ARRAYS = ("g_ptr", "g_src", "g_eid", "l_ptr", "l_src", "l_dst", "l_eid", "t_ptr", "t_gather", "t_owner", "t_split",
+               "dist_g", "dist_l", "t_angle", "g_dst", "g_optr", "g_opos", "l_optr", "l_opos", "t_cnt", "tt_ptr", "tt_t",
+               "n2g", "gptr")
+
+    def arrays(self):
+        """The plan's arrays as a dict of tensors (views of the two blobs) -- test / debugging aid; names and meaning:
+        csrc/graph.cuh:Plan."""
+        lib, sz = _lib.load(), self.sizes
+        n, g, eg, el, t = sz.n_nodes, sz.n_graphs, sz.n_edges_g, sz.n_edges_l, sz.n_t2 + sz.n_t1
+        count = {"g_ptr": n + 1, "g_optr": n + 1, "l_ptr": n + 1, "l_optr": n + 1, "n2g": n, "gptr": g + 1,
+                 "g_src": eg, "g_dst": eg, "g_eid": eg, "g_opos": eg, "dist_g": eg,
+                 "l_src": el, "l_dst": el, "l_eid": el, "l_opos": el, "dist_l": el, "t_split": el, "t_cnt": el,
+                 "t_ptr": el + 1, "tt_ptr": el + 1, "t_gather": t, "t_owner": t, "tt_t": t, "t_angle": t}
+        out = {}
+        for which, name in enumerate(self._ARRAYS):
+            in_trip = _lib.c_i32()
+            off = lib.pamnet_debug_plan_offset(sz, which, in_trip)
+            if off < 0:
+                raise _lib.PamnetError("plan array %s not available" % name)
+            blob = self.trip if in_trip.value else self.base
+            dtype = torch.float32 if name in ("dist_g", "dist_l", "t_angle") else torch.int32
+            out[name] = blob[off:off + 4 * count[name]].view(dtype)
+        return out
+
 
 class _PAMNetFunction(torch.autograd.Function):
     """One autograd node for the whole model.  Its only differentiable input is the flat parameter buffer; the

@@ -1,0 +1,151 @@
+"""Per-molecule front end (csrc/front_mol.cuh) checked on the CPU: the kernel body is compiled for the host with one
+"thread" per block (tests/host_emul/front_mol_host.cpp) and compared, bit for bit on every integer array, with the
+oracle's radius graph (oracle/graph_ops.py) and a numpy restatement of the plan (tests/plan_ref.py).  This validates the
+integer logic only; races between threads and device floating point are covered by the -m gpu test that compares
+the same kernels with the generic front end."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import graph_ops  # noqa: E402
+from pamnet_b200.data import synthetic_qm9_batch  # noqa: E402
+from tests import plan_ref  # noqa: E402
+
+INT_ARRAYS = ["n2g", "gptr", "g_ptr", "g_src", "g_dst", "g_eid", "g_optr", "g_opos", "l_ptr", "l_src", "l_dst", "l_eid",
+              "l_optr", "l_opos", "t_split", "t_cnt", "t_ptr", "tt_ptr", "t_gather", "t_owner", "tt_t"]
+FLT_ARRAYS = ["t_angle", "dist_g", "dist_l"]
+
+
+@pytest.fixture(scope="module")
+def host_lib(tmp_path_factory):
+    src = os.path.join(ROOT, "tests", "host_emul", "front_mol_host.cpp")
+    out = str(tmp_path_factory.mktemp("front_mol") / "front_mol_host.so")
+    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", "-o", out, src], check=True)
+    lib = C.CDLL(out)
+    lib.front_mol_host.restype = C.c_int
+    return lib
+
+
+def _run(lib, pos, batch, n_graphs, ei_in, r, max_nb, g_dst_row, two_hop):
+    pos = np.ascontiguousarray(pos, dtype=np.float32)
+    batch = np.ascontiguousarray(batch, dtype=np.int64)
+    ei_in = np.ascontiguousarray(ei_in, dtype=np.int64)
+    n, e_in = pos.shape[0], ei_in.shape[1]
+    mc = np.zeros(4 * n_graphs, dtype=np.int32)
+    counts = np.zeros(8, dtype=np.uint64)
+    r2 = np.float32(r) * np.float32(r)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    common = [p(pos), p(batch), C.c_int64(n), C.c_int64(n_graphs), p(ei_in), C.c_int64(e_in), C.c_float(r2),
+              C.c_int(max_nb), C.c_int(g_dst_row), C.c_int(two_hop), p(mc), p(counts)]
+    rc = lib.front_mol_host(C.c_int(0), *common, C.c_int64(0), C.c_int64(0), None, None, None, None)
+    assert rc == 0
+    eg_n, el_n, t2, t1, covered, flags = (int(v) for v in counts[:6])
+    res = {"counts": (eg_n, el_n, t2, t1), "covered": covered, "flags": flags}
+    if flags or covered != e_in:
+        return res
+    t = t2 + t1
+    sizes = {"n2g": n, "gptr": n_graphs + 1, "g_ptr": n + 1, "g_src": eg_n, "g_dst": eg_n, "g_eid": eg_n, "g_optr": n + 1,
+             "g_opos": eg_n, "l_ptr": n + 1, "l_src": el_n, "l_dst": el_n, "l_eid": el_n, "l_optr": n + 1, "l_opos": el_n,
+             "t_split": el_n, "t_cnt": el_n, "t_ptr": el_n + 1, "tt_ptr": el_n + 1, "t_gather": t, "t_owner": t, "tt_t": t,
+             "t_angle": t, "dist_g": eg_n, "dist_l": el_n}
+    ia = {k: np.full(max(sizes[k], 1), -7, dtype=np.int32) for k in INT_ARRAYS}
+    fa = {k: np.full(max(sizes[k], 1), np.nan, dtype=np.float32) for k in FLT_ARRAYS}
+    eg = np.full((2, max(eg_n, 1)), -7, dtype=np.int64)[:, :eg_n].copy() if eg_n else np.zeros((2, 0), dtype=np.int64)
+    el = np.full((2, el_n), -7, dtype=np.int64)
+    iptr = (C.c_void_p * len(INT_ARRAYS))(*[ia[k].ctypes.data for k in INT_ARRAYS])
+    fptr = (C.c_void_p * len(FLT_ARRAYS))(*[fa[k].ctypes.data for k in FLT_ARRAYS])
+    want_el = el_n != e_in
+    rc = lib.front_mol_host(C.c_int(1), *common, C.c_int64(eg_n), C.c_int64(el_n), p(eg), p(el) if want_el else None,
+                            iptr, fptr)
+    assert rc == 0
+    res.update({k: ia[k][:sizes[k]].astype(np.int64) for k in INT_ARRAYS})
+    res.update({k: fa[k][:sizes[k]] for k in FLT_ARRAYS})
+    res["eg"] = eg
+    res["el"] = el if want_el else ei_in
+    return res
+
+
+def _check(lib, pos, batch, n_graphs, ei_in, r=5.0, max_nb=1000, g_dst_row=1, two_hop=1):
+    got = _run(lib, pos, batch, n_graphs, ei_in, r, max_nb, g_dst_row, two_hop)
+    assert got["flags"] == 0 and got["covered"] == ei_in.shape[1]
+    tp, tb = torch.from_numpy(np.asarray(pos, dtype=np.float32)), torch.from_numpy(np.asarray(batch, dtype=np.int64))
+    row, col = graph_ops.radius_pairs(tp, tp, r, tb, tb, max_num_neighbors=max_nb)
+    eg_ref = graph_ops.drop_self_loops(torch.stack([row, col])).numpy()
+    el_ref = graph_ops.drop_self_loops(torch.from_numpy(np.asarray(ei_in, dtype=np.int64))).numpy()
+    assert np.array_equal(got["eg"], eg_ref)
+    assert np.array_equal(got["el"], el_ref)
+    ref = plan_ref.build_plan(pos, batch, n_graphs, eg_ref, el_ref, g_dst_row, bool(two_hop))
+    assert got["counts"] == (eg_ref.shape[1], el_ref.shape[1], ref["n_t2"], ref["n_t1"])
+    for k in INT_ARRAYS:
+        assert np.array_equal(got[k], ref[k]), k
+    assert np.array_equal(got["dist_g"], ref["dist_g"]) and np.array_equal(got["dist_l"], ref["dist_l"])
+    assert np.allclose(got["t_angle"], ref["t_angle"], rtol=0, atol=2e-6)
+    return got
+
+
+@pytest.mark.parametrize("g_dst_row,two_hop", [(1, 1), (0, 1), (1, 0)])
+def test_qm9_batches_match_plan_definition(host_lib, g_dst_row, two_hop):
+    for n_graphs, seed in [(32, 0), (5, 2), (1, 3)]:
+        b = synthetic_qm9_batch(n_graphs, seed=seed)
+        _check(host_lib, b.pos.numpy(), b.batch.numpy(), n_graphs, b.edge_index.numpy(), g_dst_row=g_dst_row,
+               two_hop=two_hop)
+
+
+def test_neighbour_cap_gives_asymmetric_graph(host_lib):
+    """max_num_neighbors below the neighbour count truncates per query (self counted), so the graph is not symmetric."""
+    b = synthetic_qm9_batch(6, seed=4)
+    for g_dst_row in (0, 1):
+        got = _check(host_lib, b.pos.numpy(), b.batch.numpy(), 6, b.edge_index.numpy(), max_nb=5, g_dst_row=g_dst_row)
+        fwd = set(map(tuple, got["eg"].T.tolist()))
+        assert any((c, r) not in fwd for r, c in fwd)
+
+
+def test_self_loops_duplicates_and_empty_molecules(host_lib):
+    """Bond list with self loops (filtered -> a new list is written), duplicate bonds, a molecule without bonds, a
+    single-atom molecule and a graph id without atoms."""
+    rng = np.random.default_rng(0)
+    sizes = [4, 1, 6, 0, 3]
+    pos = rng.normal(size=(sum(sizes), 3)).astype(np.float32) * 1.5
+    batch = np.concatenate([np.full(s, g) for g, s in enumerate(sizes)]).astype(np.int64)
+    ei = np.array([[0, 1, 1, 2, 2, 3, 0, 1, 1], [1, 0, 1, 1, 3, 2, 1, 2, 2]])              # molecule 0: loop 1-1, dup 0-1, dup 1-2
+    ei2 = np.array([[5, 6, 7, 8, 9, 10, 6, 9, 9], [6, 5, 8, 7, 10, 9, 6, 5, 9]])            # molecule 2 (atoms 5..10)
+    ei = np.concatenate([ei, ei2], axis=1)                                                   # molecules 1, 3, 4: no bonds
+    for g_dst_row in (0, 1):
+        got = _check(host_lib, pos, batch, len(sizes), ei, r=2.5, g_dst_row=g_dst_row)
+        assert got["el"].shape[1] == ei.shape[1] - 3
+    # nothing to filter and no bonds at all
+    _check(host_lib, pos, batch, len(sizes), np.zeros((2, 0), dtype=np.int64), r=2.5)
+
+
+def test_fallback_flags(host_lib):
+    """Inputs the per-molecule path must hand to the generic kernels: ungrouped or cross-molecule bond lists and
+    molecules above the per-block capacities."""
+    caps = (C.c_int * 4)()
+    host_lib.front_mol_caps(caps)
+    b = synthetic_qm9_batch(4, seed=1)
+    pos, batch, ei = b.pos.numpy(), b.batch.numpy(), b.edge_index.numpy()
+    perm = np.random.default_rng(0).permutation(ei.shape[1])
+    got = _run(host_lib, pos, batch, 4, ei[:, perm], 5.0, 1000, 1, 1)
+    assert got["flags"] != 0 or got["covered"] != ei.shape[1]
+    cross = ei.copy()
+    cross[1, 0] = pos.shape[0] - 1                      # first bond of molecule 0 now ends in the last molecule
+    got = _run(host_lib, pos, batch, 4, cross, 5.0, 1000, 1, 1)
+    assert got["flags"] & 2
+    n_big = caps[0] + 1
+    pos_big = np.random.default_rng(1).normal(size=(n_big, 3)).astype(np.float32) * 4
+    got = _run(host_lib, pos_big, np.zeros(n_big, dtype=np.int64), 1, np.zeros((2, 0), dtype=np.int64), 5.0, 1000, 1, 1)
+    assert got["flags"] & 1
+    # exactly at the atom capacity it is handled
+    pos_cap = pos_big[:caps[0]]
+    ring = np.arange(caps[0])
+    ei_ring = np.stack([np.concatenate([ring, (ring + 1) % caps[0]]), np.concatenate([(ring + 1) % caps[0], ring])])
+    order = np.lexsort((ei_ring[1], ei_ring[0]))
+    _check(host_lib, pos_cap, np.zeros(caps[0], dtype=np.int64), 1, ei_ring[:, order], r=3.0)
