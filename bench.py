@@ -190,13 +190,13 @@ def run_ours(args):
 
     import torch.nn.functional as F
 
-    def step(batch):
+    def step(batch, sync_grads=True):
         for p in params:             # == optimizer.zero_grad(set_to_none=True)
             p.grad = None
         out = model(batch)
         loss = F.l1_loss(out, batch.y)      # main_qm9.py:108
         loss.backward()
-        if world > 1:
+        if world > 1 and sync_grads:
             allreduce_gradients(model)
         return loss
 
@@ -256,6 +256,7 @@ def run_ours(args):
 
     if rank != 0:
         if world > 1:
+            dist.barrier()          # leave together with rank 0 (it still runs the collective-free profile pass)
             dist.destroy_process_group()
         return
 
@@ -281,14 +282,15 @@ def run_ours(args):
     }
 
     # ---- per-kernel-class event timing (separate pass; events perturb the step, so not the timed one) ----
+    # rank 0 only and WITHOUT the gradient all-reduce: the other ranks have left, a collective here would never return
     if not args.no_profile:
         for _ in range(2):
-            step(dev_batch)
+            step(dev_batch, sync_grads=False)
         torch.cuda.synchronize()
         nprof = 5
         _lib.profile_begin()
         for _ in range(nprof):
-            step(dev_batch)
+            step(dev_batch, sync_grads=False)
         prof = _lib.profile_end()
         tot_ms = sum(v[0] for v in prof.values())
         kernels = {k: {"ms_per_step": v[0] / nprof, "launches_per_step": v[1] / nprof, "share": v[0] / tot_ms,
@@ -331,13 +333,14 @@ def run_ours(args):
                                  "definition": "SURVEY.md 8(d) B_step / device ms_per_step"}
         line["kernels"] = kernels
 
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # reported at N = 1 only (the host cores are shared by all ranks)
         rate, steps, cores, t_step = time_cpu(cfg, args.batch_size, budget_s=15.0, warmup=1)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{steps} full steps of the same {args.batch_size}-molecule batch "
                                           f"({1e3 * t_step:.0f} ms/step), oracle port on torch CPU"}
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
