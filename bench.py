@@ -114,6 +114,8 @@ def workload_config(args, sizes):
          "l2": "flushed (256 MiB write) before every timed step"}
     if sizes:
         c["sizes"] = sizes
+    if os.environ.get("PAMNET_FRONT"):           # opt-in front end in effect
+        c["front_end"] = os.environ["PAMNET_FRONT"]
     return c
 
 
