@@ -173,7 +173,7 @@ int pamnet_plan_fill(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, const
 namespace {
 struct BuildScratch {
     int64_t* counts;
-    int32_t *deg_a, *ptr_a, *deg_b, *ptr_b, *keep, *pk, *nbr;
+    int32_t *deg_a, *ptr_a, *deg_b, *ptr_b, *keep, *pk, *nbr, *mol_rng;
     float* d2;
 };
 constexpr int kKnnK = 50;            // models.py:143
@@ -193,6 +193,7 @@ size_t build_scratch_layout(int kind, int64_t n, int64_t n_edges_in, int64_t cap
     b.ptr_b = static_cast<int32_t*>(take(sizeof(int32_t) * (n + 1)));
     b.keep = static_cast<int32_t*>(take(sizeof(int32_t) * ne));
     b.pk = static_cast<int32_t*>(take(sizeof(int32_t) * (ne + 1)));
+    b.mol_rng = static_cast<int32_t*>(take(kind == PAMNET_QM9 ? sizeof(int32_t) * 2 * (n + 2) : 0));   // front_mol.cuh range tables
     b.nbr = static_cast<int32_t*>(take(kind == PAMNET_RNA ? sizeof(int32_t) * n * kKnnK : 0));
     b.d2 = static_cast<float*>(take(kind == PAMNET_RNA ? sizeof(float) * n * kKnnK : 0));
     if (out) *out = b;
@@ -236,7 +237,7 @@ int pamnet_plan_build(const pamnet_config_t* cfg, const float* pos, const int64_
     for (int i = 0; i < 4; ++i) need[i] = 0;
     PAMNET_CUDA(cudaMemsetAsync(b.counts, 0, 8 * sizeof(int64_t), st));
 
-    // ---- small-molecule batches: the whole front end as two launches and ONE read-back (front_mol.cuh) ------------
+    // ---- small-molecule batches: the whole front end as three launches and ONE read-back (front_mol.cuh) ----------
     // Opt-in (PAMNET_FRONT=mol) until it has been confirmed on the GPU against the generic kernels below; batches it
     // cannot take (molecules above the per-block capacities, bond lists not grouped by molecule) fall through.
     if (kind == PAMNET_QM9 && front_mol_enabled() && n_graphs <= kMolGraphs && n_graphs <= n_nodes) {
@@ -247,6 +248,7 @@ int pamnet_plan_build(const pamnet_config_t* cfg, const float* pos, const int64_
         a.r2 = cfg->cutoff_g * cfg->cutoff_g; a.max_nb = max_nb;
         a.g_dst_row = (cfg->flow == PAMNET_TARGET_TO_SOURCE) ? 0 : 1;
         a.two_hop = cfg->simple ? 0 : 1;
+        a.gstart = b.mol_rng; a.estart = b.mol_rng + (n_nodes + 2);                      // n_graphs + 1 <= n_nodes + 1 entries each
         a.mc_eg = b.deg_a; a.mc_el = b.ptr_a; a.mc_t2 = b.deg_b; a.mc_t1 = b.ptr_b;      // n_graphs <= n_nodes entries each
         a.counts = reinterpret_cast<unsigned long long*>(b.counts);
         PAMNET_TRY(mol_count(a, st));

@@ -5,9 +5,11 @@
 //
 // Why it is legal: every edge and triplet stays inside one molecule, nodes are grouped by molecule
 // (non-decreasing batch vector), and PyG's collate groups data.edge_index by molecule as well.  Then the slots of all
-// per-edge arrays of a molecule are contiguous and start at the prefix sum of the earlier molecules' counts.  The count
-// pass verifies the grouping (every bond of the molecule's range joins two of its atoms, the ranges cover the list) and
-// the per-block capacities; anything else falls back to the generic kernels.
+// per-edge arrays of a molecule are contiguous and start at the prefix sum of the earlier molecules' counts.  Three
+// launches: pass 0 finds every molecule's atom and bond-list range and checks that both key sequences are non-decreasing;
+// pass 1 (one block per molecule) checks that every bond of the range joins two of its atoms and the per-block
+// capacities, and counts; the host reads the totals once; pass 2 fills.  Anything the checks reject falls back to the
+// generic kernels.
 //
 // The body is written as block-strided loops separated by barriers, with no warp intrinsics, so that the very same
 // source also compiles for the host with one "thread" per block (tests/host_emul): the CPU test suite checks the integer
@@ -55,6 +57,7 @@ struct MolArgs {
     int max_nb;                    // torch_cluster max_num_neighbors (self included, like radius_kernel)
     int g_dst_row;                 // row of edge_index_g that is the aggregation target (graph.cu:plan_count)
     int two_hop;                   // 0 for PAMNet_s
+    int32_t *gstart, *estart;      // [n_graphs + 1]: first atom / first bond-list entry of every molecule (mol_ranges_body)
     int32_t *mc_eg, *mc_el, *mc_t2, *mc_t1;     // per-molecule counts [n_graphs]
     unsigned long long* counts;    // [8]: E_g, E_l, T2, T1, covered bond-list entries, flags
     // ---- fill pass only ----
@@ -80,21 +83,38 @@ struct MolSmem {
     short ls_src[kMolEdges], ls_dst[kMolEdges];            // the same per CSR slot
     short t_n2[kMolEdges];
     short tg[kMolTrip];                                    // gathered slot per triplet
-    int a0, a1, lo, hi, n_kept, flag;
+    int a0, a1, lo, hi, n_kept, flag, bail;
     int eg_m, t2_m, t1_m;
     int og, ol, ot;
 };
 
-// first bond-list entry whose source atom belongs to a graph >= key (the list is grouped by molecule when valid)
-PAMNET_HD int64_t mol_edge_lower_bound(const MolArgs& A, int64_t key) {
-    int64_t lo = 0, hi = A.n_edges_in;
-    while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        const int64_t v = A.ei_in[mid];
-        const int64_t g = (v >= 0 && v < A.n_nodes) ? A.batch[v] : INT64_MAX;
-        if (g < key) lo = mid + 1; else hi = mid;
+// ---- pass 0: atom and bond-list ranges of every molecule (grid-stride over atoms and bonds, any grid size) ---------------
+// gstart[g] = first atom with batch >= g, estart[g] = first bond whose source atom belongs to a graph >= g; both need
+// non-decreasing keys (else kMolFlagGroup).  i runs to n inclusive so that the entries up to [n_graphs] get written.
+PAMNET_HD void mol_ranges_body(const MolArgs& A, int64_t gtid, int64_t gnt) {
+    const int64_t G = A.n_graphs;
+    for (int64_t i = gtid; i <= A.n_nodes; i += gnt) {
+        const int64_t prev = i == 0 ? -1 : A.batch[i - 1];
+        const int64_t cur = i == A.n_nodes ? G : A.batch[i];
+        if (cur < prev || cur < 0 || cur > G || (i < A.n_nodes && cur == G)) { pm_atomic_or64(&A.counts[5], kMolFlagGroup); continue; }
+        for (int64_t g = prev + 1; g <= cur; ++g) A.gstart[g] = (int32_t)i;
     }
-    return lo;
+    for (int64_t e = gtid; e <= A.n_edges_in; e += gnt) {
+        int64_t prev = -1, cur = G;
+        if (e > 0) {
+            const int64_t v = A.ei_in[e - 1];
+            prev = (v >= 0 && v < A.n_nodes) ? A.batch[v] : -2;
+        }
+        if (e < A.n_edges_in) {
+            const int64_t v = A.ei_in[e];
+            cur = (v >= 0 && v < A.n_nodes) ? A.batch[v] : -2;
+        }
+        if (prev == -2 || cur == -2 || cur < prev || cur > G || (e < A.n_edges_in && cur == G)) {
+            pm_atomic_or64(&A.counts[5], kMolFlagGroup);
+            continue;
+        }
+        for (int64_t g = prev + 1; g <= cur; ++g) A.estart[g] = (int32_t)e;
+    }
 }
 
 // exclusive scan of v[0..n) into out[0..n] (out[n] = total); a, b: scratch of n ints; v, a, b, out distinct
@@ -117,14 +137,15 @@ PAMNET_HD void mol_scan(const int* v, int n, int* a, int* b, int* out) {
 // API order.  Returns false (block-uniform) when the molecule cannot be handled; the flag is then already recorded.
 PAMNET_HD bool mol_setup(const MolArgs& A, MolSmem& s, int m) {
     if (PM_TID == 0) {
-        s.a0 = (int)lower_bound_i64(A.batch, A.n_nodes, m);
-        s.a1 = (int)lower_bound_i64(A.batch, A.n_nodes, (int64_t)m + 1);
-        s.lo = (int)mol_edge_lower_bound(A, m);
-        s.hi = (int)mol_edge_lower_bound(A, (int64_t)m + 1);
+        // pass 0 found the batch vector or the bond list not grouped: the range tables are incomplete, touch nothing
+        s.bail = A.counts[5] != 0;
+        s.a0 = s.bail ? 0 : A.gstart[m]; s.a1 = s.bail ? 0 : A.gstart[m + 1];
+        s.lo = s.bail ? 0 : A.estart[m]; s.hi = s.bail ? 0 : A.estart[m + 1];
         s.flag = 0; s.n_kept = 0; s.eg_m = 0; s.t2_m = 0; s.t1_m = 0; s.og = 0; s.ol = 0; s.ot = 0;
     }
     for (int i = PM_TID; i <= kMolAtoms; i += PM_NT) { s.l_in[i] = 0; s.l_out[i] = 0; }
     PM_SYNC();
+    if (s.bail) return false;
     const int a0 = s.a0, nA = s.a1 - s.a0, lo = s.lo, nE = s.hi - s.lo;
     if (nA > kMolAtoms || nE > kMolEdges) {
         if (PM_TID == 0) {

@@ -20,10 +20,15 @@ extern "C" int front_mol_host(int pass, const float* pos, const int64_t* batch, 
     a.mc_eg = mc; a.mc_el = mc + n_graphs; a.mc_t2 = mc + 2 * n_graphs; a.mc_t1 = mc + 3 * n_graphs;
     a.counts = counts;
     static MolSmem s;
+    static std::vector<int32_t> ranges;
     if (pass == 0) {
+        ranges.assign(2 * (n_graphs + 1), -12345);          // poison: an unwritten entry must never be used
+        a.gstart = ranges.data(); a.estart = ranges.data() + n_graphs + 1;
+        for (int64_t t = 0; t < 3; ++t) mol_ranges_body(a, 2 - t, 3);      // three "threads", any order
         for (int m = 0; m < n_graphs; ++m) mol_count_body(a, s, m);
         return 0;
     }
+    a.gstart = ranges.data(); a.estart = ranges.data() + n_graphs + 1;      // tables of the preceding count pass
     a.Eg = Eg; a.El = El; a.eg_out = eg_out; a.el_out = el_out;
     int32_t** p = iarr;
     a.n2g = p[0]; a.gptr = p[1]; a.g_ptr = p[2]; a.g_src = p[3]; a.g_dst = p[4]; a.g_eid = p[5]; a.g_optr = p[6];

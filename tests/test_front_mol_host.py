@@ -112,12 +112,12 @@ def test_self_loops_duplicates_and_empty_molecules(host_lib):
     """Bond list with self loops (filtered -> a new list is written), duplicate bonds, a molecule without bonds, a
     single-atom molecule and a graph id without atoms."""
     rng = np.random.default_rng(0)
-    sizes = [4, 1, 6, 0, 3]
+    sizes = [0, 4, 1, 6, 0, 3, 0]
     pos = rng.normal(size=(sum(sizes), 3)).astype(np.float32) * 1.5
     batch = np.concatenate([np.full(s, g) for g, s in enumerate(sizes)]).astype(np.int64)
-    ei = np.array([[0, 1, 1, 2, 2, 3, 0, 1, 1], [1, 0, 1, 1, 3, 2, 1, 2, 2]])              # molecule 0: loop 1-1, dup 0-1, dup 1-2
-    ei2 = np.array([[5, 6, 7, 8, 9, 10, 6, 9, 9], [6, 5, 8, 7, 10, 9, 6, 5, 9]])            # molecule 2 (atoms 5..10)
-    ei = np.concatenate([ei, ei2], axis=1)                                                   # molecules 1, 3, 4: no bonds
+    ei = np.array([[0, 1, 1, 2, 2, 3, 0, 1, 1], [1, 0, 1, 1, 3, 2, 1, 2, 2]])              # graph 1: loop 1-1, dup 0-1, dup 1-2
+    ei2 = np.array([[5, 6, 7, 8, 9, 10, 6, 9, 9], [6, 5, 8, 7, 10, 9, 6, 5, 9]])            # graph 3 (atoms 5..10)
+    ei = np.concatenate([ei, ei2], axis=1)                                                   # graphs 0, 2, 4, 5, 6: no bonds
     for g_dst_row in (0, 1):
         got = _check(host_lib, pos, batch, len(sizes), ei, r=2.5, g_dst_row=g_dst_row)
         assert got["el"].shape[1] == ei.shape[1] - 3
@@ -138,6 +138,10 @@ def test_fallback_flags(host_lib):
     cross = ei.copy()
     cross[1, 0] = pos.shape[0] - 1                      # first bond of molecule 0 now ends in the last molecule
     got = _run(host_lib, pos, batch, 4, cross, 5.0, 1000, 1, 1)
+    assert got["flags"] & 2
+    unsorted = batch.copy()
+    unsorted[[0, -1]] = unsorted[[-1, 0]]                # batch vector not non-decreasing
+    got = _run(host_lib, pos, unsorted, 4, ei, 5.0, 1000, 1, 1)
     assert got["flags"] & 2
     n_big = caps[0] + 1
     pos_big = np.random.default_rng(1).normal(size=(n_big, 3)).astype(np.float32) * 4
