@@ -121,6 +121,17 @@ int pamnet_plan_count(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, cons
 int pamnet_plan_fill(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, const float* pos, void* plan_base,
                      void* plan_trip, void* stream);
 
+/* Device-side collation -- replaces PyG's DataLoader collate + `data.to(device)` of
+ * main_qm9.py:59-60,103-104 for a dataset that is resident in device memory: concatenates x / pos / y of the chosen
+ * molecules, offsets each molecule's edge_index by the atoms before it and writes the graph id per atom, in one launch.
+ *   table [3, n_ids] int64 (device): molecule id | first atom of the molecule inside the batch | first bond inside the batch
+ *   dataset: node_ptr / edge_ptr [M + 1], x_all [sum n], pos_all [sum n, 3], ei_all [2, e_all] with atom ids relative to
+ *   the molecule (as every Data object stores them), y_all [M];  outputs: x [N], pos [N, 3], edge_index [2, n_edges],
+ *   batch [N], y [n_ids] with N / n_edges = the sums the host used for the offsets in `table`. */
+int pamnet_collate(const int64_t* table, int64_t n_ids, const int64_t* node_ptr, const int64_t* edge_ptr,
+                   const float* x_all, const float* pos_all, const int64_t* ei_all, int64_t e_all, const float* y_all,
+                   int64_t n_edges, float* x, float* pos, int64_t* edge_index, int64_t* batch, float* y, void* stream);
+
 /* The whole front end of PAMNet.forward (models.py:104-177: radius / kNN graph, self-loop and cutoff filters, the
  * destination-sorted plan, triplet lists, distances, angles) in ONE call.  The host must learn E_g, E_l and the triplet
  * counts to size the caller-owned buffers, so the call synchronises the stream two or three times internally (pinned

@@ -56,6 +56,7 @@ SIGNATURES = {
     "pamnet_prepared_weights_bytes": (c_sz, [_PC]),
     "pamnet_prepare_weights": (c_i32, [_PC, c_vp, c_vp, c_vp]),
     "pamnet_loss": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp]),
+    "pamnet_collate": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "pamnet_scatter_add": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "pamnet_bessel_rbf": (c_i32, [c_vp, c_i64, c_vp, c_f32, c_vp, c_vp]),
     "pamnet_sbf_radial": (c_i32, [_PB, c_vp, c_i64, c_f32, c_vp, c_vp]),

@@ -8,6 +8,7 @@
 
 #include "basis.cuh"
 #include "chain.cuh"
+#include "collate.cuh"
 #include "front_mol.cuh"
 #include "gemm.cuh"
 #include "graph.cuh"
@@ -464,6 +465,19 @@ int pamnet_loss(const float* out, const float* y, int64_t n, int32_t kind, float
                 void* stream) {
     REQUIRE(out); REQUIRE(y); REQUIRE(loss_dev); REQUIRE(grad_out);
     return loss_forward_backward(out, y, n, kind, loss_dev, grad_out, ST(stream));
+}
+
+int pamnet_collate(const int64_t* table, int64_t n_ids, const int64_t* node_ptr, const int64_t* edge_ptr,
+                   const float* x_all, const float* pos_all, const int64_t* ei_all, int64_t e_all, const float* y_all,
+                   int64_t n_edges, float* x, float* pos, int64_t* edge_index, int64_t* batch, float* y, void* stream) {
+    REQUIRE(table); REQUIRE(node_ptr); REQUIRE(edge_ptr); REQUIRE(x_all); REQUIRE(pos_all); REQUIRE(y_all);
+    REQUIRE(x); REQUIRE(pos); REQUIRE(batch); REQUIRE(y);
+    PAMNET_CHECK_ARG(n_edges == 0 || (ei_all && edge_index), "collate: %lld bonds but no edge lists", (long long)n_edges);
+    CollateArgs a;
+    a.table = table; a.n_ids = n_ids; a.node_ptr = node_ptr; a.edge_ptr = edge_ptr; a.x_all = x_all; a.pos_all = pos_all;
+    a.ei_all = ei_all; a.e_all = e_all; a.y_all = y_all; a.n_edges = n_edges; a.x = x; a.pos = pos;
+    a.edge_index = edge_index; a.batch = batch; a.y = y;
+    return collate(a, ST(stream));
 }
 
 int pamnet_scatter_add(const float* src, const int64_t* index, int64_t n_rows, int64_t width, int64_t dim_size,

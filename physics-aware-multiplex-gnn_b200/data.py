@@ -154,3 +154,90 @@ def synthetic_rna_batch(num_graphs=2, seed=0, min_atoms=200, max_atoms=400, spac
     return Batch(x=torch.from_numpy(np.concatenate(xs)),
                  batch=torch.from_numpy(np.concatenate(batch)),
                  y=torch.from_numpy(y))
+
+
+def molecules_of(batch):
+    """Split a collated QM9-shaped ``Batch`` back into per-molecule records (x [n], pos [n,3], edge_index [2,e] with atom
+    ids inside the molecule, y scalar) -- the form a dataset's ``Data`` objects have before the loader collates them."""
+    b = batch.batch.cpu().numpy()
+    x, pos = batch.x.cpu().numpy(), batch.pos.cpu().numpy()
+    ei, y = batch.edge_index.cpu().numpy(), batch.y.cpu().numpy()
+    n_graphs = int(y.shape[0])
+    starts = np.searchsorted(b, np.arange(n_graphs + 1), side="left")
+    eg = b[ei[0]] if ei.shape[1] else np.zeros(0, dtype=np.int64)
+    out = []
+    for g in range(n_graphs):
+        s, e = int(starts[g]), int(starts[g + 1])
+        sel = np.flatnonzero(eg == g)
+        out.append(types_ns(x=x[s:e].copy(), pos=pos[s:e].copy(), edge_index=ei[:, sel] - s, y=float(y[g])))
+    return out
+
+
+def types_ns(**kw):
+    import types
+    return types.SimpleNamespace(**kw)
+
+
+class DeviceDataset:
+    """QM9-shaped molecules resident in device memory; ``batch(ids)`` collates on the device in ONE kernel launch
+    (pamnet_collate) -- SURVEY.md 8(f) row 2.  Replaces the host-side collate of PyG's DataLoader plus ``data.to(device)``
+    (main_qm9.py:59-60,103-104): per batch the host sends only a [3, G] int64 table (molecule id, first atom and first
+    bond of the molecule inside the batch) instead of every field of every atom.
+
+    ``molecules``: sequence of records with ``x`` [n], ``pos`` [n, 3], ``edge_index`` [2, e] (atom ids inside the
+    molecule) and scalar ``y`` -- torch tensors or numpy arrays.  CUDA only: there is no CPU path."""
+
+    def __init__(self, molecules, device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            from . import _lib
+            raise _lib.PamnetError("DeviceDataset keeps the dataset in GPU memory: pass a CUDA device (no CPU fallback)")
+        arr = lambda v, dt: np.asarray(v.cpu() if isinstance(v, torch.Tensor) else v, dtype=dt)
+        xs = [arr(m.x, np.float32).reshape(-1) for m in molecules]
+        ps = [arr(m.pos, np.float32).reshape(-1, 3) for m in molecules]
+        es = [arr(m.edge_index, np.int64).reshape(2, -1) for m in molecules]
+        for k, (x, p, e) in enumerate(zip(xs, ps, es)):
+            if p.shape[0] != x.shape[0] or (e.size and (e.min() < 0 or e.max() >= x.shape[0])):
+                raise ValueError(f"molecule {k}: pos / edge_index do not match its {x.shape[0]} atoms")
+        self.n_atoms = np.array([x.shape[0] for x in xs], dtype=np.int64)
+        self.n_bonds = np.array([e.shape[1] for e in es], dtype=np.int64)
+        self.node_ptr_host = np.concatenate([[0], np.cumsum(self.n_atoms)]).astype(np.int64)
+        self.edge_ptr_host = np.concatenate([[0], np.cumsum(self.n_bonds)]).astype(np.int64)
+        to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+        self.device = device
+        self.x_all = to(np.concatenate(xs) if xs else np.zeros(0, np.float32))
+        self.pos_all = to(np.concatenate(ps) if ps else np.zeros((0, 3), np.float32))
+        self.ei_all = to(np.concatenate(es, axis=1) if es else np.zeros((2, 0), np.int64))
+        self.y_all = to(np.array([float(m.y) for m in molecules], dtype=np.float32))
+        self.node_ptr, self.edge_ptr = to(self.node_ptr_host), to(self.edge_ptr_host)
+
+    def __len__(self):
+        return int(self.n_atoms.shape[0])
+
+    def table(self, ids):
+        """Host side of a batch: the [3, G] table and the batch's atom / bond totals."""
+        ids = np.asarray(ids, dtype=np.int64).reshape(-1)
+        if ids.size == 0 or ids.min() < 0 or ids.max() >= len(self):
+            raise IndexError("molecule ids out of range")
+        na, nb = self.n_atoms[ids], self.n_bonds[ids]
+        n0 = np.concatenate([[0], np.cumsum(na)[:-1]])
+        e0 = np.concatenate([[0], np.cumsum(nb)[:-1]])
+        return np.stack([ids, n0, e0]).astype(np.int64), int(na.sum()), int(nb.sum())
+
+    def batch(self, ids):
+        from . import _lib
+        lib = _lib.load()
+        tab, n, e = self.table(ids)
+        g, dev = tab.shape[1], self.device
+        tab_dev = torch.from_numpy(tab).pin_memory().to(dev, non_blocking=True)
+        x = torch.empty(n, dtype=torch.float32, device=dev)
+        pos = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        ei = torch.empty((2, e), dtype=torch.int64, device=dev)
+        bvec = torch.empty(n, dtype=torch.int64, device=dev)
+        y = torch.empty(g, dtype=torch.float32, device=dev)
+        _lib.check(lib.pamnet_collate(tab_dev.data_ptr(), g, self.node_ptr.data_ptr(), self.edge_ptr.data_ptr(),
+                                      self.x_all.data_ptr(), self.pos_all.data_ptr(), self.ei_all.data_ptr(),
+                                      int(self.ei_all.shape[1]), self.y_all.data_ptr(), e, x.data_ptr(), pos.data_ptr(),
+                                      ei.data_ptr(), bvec.data_ptr(), y.data_ptr(),
+                                      torch.cuda.current_stream().cuda_stream), "collate")
+        return Batch(x=x, pos=pos, edge_index=ei, batch=bvec, y=y)
