@@ -1,11 +1,12 @@
 #!/bin/bash
-# First GPU call for the per-molecule front end (csrc/front_mol.cuh, PAMNET_FRONT=mol): parity against the generic
+# First GPU call for the two paths written without a GPU -- the per-molecule front end (csrc/front_mol.cuh, PAMNET_FRONT=mol)
+# and the device-side collation (csrc/collate.cuh): parity against the generic
 # graph kernels, then an A/B of the headline bench.  Run under gpurun from the repo root:
 #   gpurun --timeout 900 -- 'bash tools/front_mol_ab.sh'
 # Outputs land in gpurun_out/front_mol_*.{log,json}.  Make the switch the default only if the parity log is green.
 set -u
 mkdir -p gpurun_out
-PAMNET_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_front_mol.py -x -q -m gpu > gpurun_out/front_mol_parity.log 2>&1
+PAMNET_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_front_mol.py tests/test_collate_host.py -q -m gpu > gpurun_out/front_mol_parity.log 2>&1
 echo "parity rc=$?" >> gpurun_out/front_mol_parity.log
 tail -3 gpurun_out/front_mol_parity.log
 for rep in 1 2; do
