@@ -112,6 +112,7 @@ class _PAMNetFunction(torch.autograd.Function):
 
 class _PAMNetBase(nn.Module):
     _simple = False
+    _MAX_NB = 1000         # max_num_neighbors of the radius graph: models.py:110,128 (PAMNet), :301 (PAMNet_s: 500)
 
     # ---- flat parameter storage ---------------------------------------------------------------------
     def _setup_flat(self, config):
@@ -319,15 +320,14 @@ class _PAMNetBase(nn.Module):
         _lib.check(lib.pamnet_plan_fill(cfg, sz, pos.data_ptr(), base.data_ptr(), trip.data_ptr(), stream), "plan_fill")
         return GraphPlan(sz, base, trip, eg, el)
 
-    def _run(self, data, max_nb):
+    def _inputs(self, data):
+        """The tensors the C calls read, in the layout they expect (models.py:101-106,117-125,138-141)."""
         x_raw, batch = data.x, data.batch
         if not x_raw.is_cuda:
             raise _lib.PamnetError("pamnet_b200 runs on CUDA tensors only: move the model and the batch to a GPU "
                                    "(there is no CPU fallback)")
         if self._flat.device != x_raw.device:
             raise RuntimeError("model and data are on different devices")
-        if not self._aliased(full=False):      # e.g. EMA.assign swapped param.data (utils/ema.py:27)
-            self._flatten()
         kind = self._ccfg.dataset
         batch = batch.to(torch.int64).contiguous()
         n_graphs = getattr(data, "num_graphs", None)
@@ -347,8 +347,52 @@ class _PAMNetBase(nn.Module):
                 sign = torch.where(pos[:, 0] > 40.0, -1.0, 1.0).to(torch.float32).contiguous()   # models.py:122-125
             else:
                 node_in = xr[:, -1].contiguous()
-        prepared = self._prepare_weights(pos.device)      # on the auxiliary stream, overlapping the graph build
-        plan = self._build_plan(pos, batch, int(n_graphs), el_in, max_nb)
+        return batch, int(n_graphs), pos, node_in, sign, el_in
+
+    def prefetch(self, data, max_nb=None):
+        """Build the graph plan of ``data`` NOW on a side stream -- typically right after ``loss.backward()`` of the
+        previous batch, so that the front end of models.py:104-177 (which does not depend on the parameters) overlaps the
+        GPU work still queued for that step instead of preceding the first layer of the next one; ``model(data)`` on the
+        SAME object then starts from the attached plan.  The role a DataLoader worker plays for host-side
+        preprocessing.  Opt-in; without it ``forward`` builds the plan itself.  One batch can be pending at a time."""
+        cur = torch.cuda.current_stream()
+        side = getattr(self, "_side_stream", None)
+        if side is None or side.device != cur.device:
+            side = self._side_stream = torch.cuda.Stream(device=cur.device)
+        side.wait_stream(cur)                    # the batch (e.g. its H2D copy) was produced on the current stream
+        with torch.cuda.stream(side):
+            inputs = self._inputs(data)
+            batch, n_graphs, pos, node_in, sign, el_in = inputs
+            plan = self._build_plan(pos, batch, n_graphs, el_in, self._MAX_NB if max_nb is None else max_nb)
+            done = torch.cuda.Event()
+            done.record(side)
+        self._prefetched = (data, inputs, plan, done)
+
+    def _take_prefetched(self, data):
+        pre = getattr(self, "_prefetched", None)
+        if pre is None or pre[0] is not data:
+            return None
+        self._prefetched = None
+        _, inputs, plan, done = pre
+        cur = torch.cuda.current_stream()
+        cur.wait_event(done)
+        # these blocks came from the side stream's pool and are consumed on the current stream from here on
+        for t in (*inputs, plan.base, plan.trip, plan.edge_index_g, plan.edge_index_l):
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                t.record_stream(cur)
+        return inputs, plan
+
+    def _run(self, data, max_nb):
+        if not self._aliased(full=False):      # e.g. EMA.assign swapped param.data (utils/ema.py:27)
+            self._flatten()
+        pre = self._take_prefetched(data)
+        if pre is not None:
+            (batch, n_graphs, pos, node_in, sign, el_in), plan = pre
+            prepared = self._prepare_weights(pos.device)
+        else:
+            batch, n_graphs, pos, node_in, sign, el_in = self._inputs(data)
+            prepared = self._prepare_weights(pos.device)      # on the auxiliary stream, overlapping the graph build
+            plan = self._build_plan(pos, batch, n_graphs, el_in, max_nb)
         self.last_plan = plan
         return _PAMNetFunction.apply(self, plan, node_in, sign, pos, self._flat, prepared)
 
@@ -404,11 +448,12 @@ class PAMNet(_PAMNetBase):
         if _dataset_kind(self.dataset) < 0:
             raise ValueError("Invalid dataset. If you are using any dataset related to RNA 3D structure prediction, "
                              "be sure to use 'rna' as the first 3 characters of the dataset name.")
-        return self._run(data, max_nb=1000)
+        return self._run(data, max_nb=self._MAX_NB)
 
 
 class PAMNet_s(_PAMNetBase):
     _simple = True
+    _MAX_NB = 500
 
     def __init__(self, config: Config, num_spherical=7, num_radial=6, envelope_exponent=5):
         super(PAMNet_s, self).__init__()
@@ -434,4 +479,4 @@ class PAMNet_s(_PAMNetBase):
     def forward(self, data):
         if self.dataset != "QM9":
             raise ValueError("Invalid dataset. The current PAMNet_s is only for QM9 experiments.")
-        return self._run(data, max_nb=500)
+        return self._run(data, max_nb=self._MAX_NB)

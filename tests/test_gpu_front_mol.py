@@ -103,3 +103,47 @@ def test_generic_plan_matches_definition():
                 assert np.array_equal(v.numpy(), ref[k]), k
             else:
                 assert np.array_equal(v.numpy().astype(np.int64), ref[k]), k
+
+
+def test_prefetched_plan_gives_the_same_step():
+    """model.prefetch(batch) builds the plan on a side stream; forward + backward from it equal the inline path bit for
+    bit (gradients up to the summation order of the split-K atomics), a prefetch for another object is ignored, and it
+    composes with the per-molecule front end."""
+    from pamnet_b200 import Config, PAMNet
+    from pamnet_b200.data import synthetic_qm9_batch
+    torch.manual_seed(0)
+    model = PAMNet(Config("QM9", 64, 2, 5.0, 5.0)).cuda()
+    b = synthetic_qm9_batch(8, seed=7).to("cuda")
+    other = synthetic_qm9_batch(3, seed=8).to("cuda")
+
+    def run(batch, prefetch_of=None, front=None):
+        if front:
+            os.environ["PAMNET_FRONT"] = front
+        try:
+            for p in model.parameters():
+                p.grad = None
+            if prefetch_of is not None:
+                model.prefetch(prefetch_of)
+            out = model(batch)
+            (out - batch.y).abs().mean().backward()
+            torch.cuda.synchronize()
+            return out.detach().clone(), torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None]).clone()
+        finally:
+            os.environ.pop("PAMNET_FRONT", None)
+
+    def same_grads(a, c):       # split-K weight gradients meet in fp32 atomics: equal up to summation order
+        return torch.equal(a, c) or float((a - c).abs().max() / c.abs().max()) < 1e-6
+
+    out0, g0 = run(b)
+    out1, g1 = run(b, prefetch_of=b)
+    assert model._prefetched is None                                   # consumed
+    assert torch.equal(out0, out1) and same_grads(g1, g0)
+    out2, g2 = run(b, prefetch_of=other)                               # plan of another batch: not used for b
+    assert torch.equal(out0, out2) and same_grads(g2, g0)
+    out3, g3 = run(other)                                              # ... and still pending for `other`
+    assert model._prefetched is None and out3.shape[0] == 3
+    out4, g4 = run(b, prefetch_of=b, front="mol")
+    assert torch.equal(out0, out4) and same_grads(g4, g0)
+    for _ in range(20):                                                # back-to-back steps: buffers of the side stream's pool stay valid
+        out5, g5 = run(b, prefetch_of=b)
+        assert torch.equal(out0, out5) and same_grads(g5, g0)

@@ -13,6 +13,10 @@ for rep in 1 2; do
   timeout 300 python bench.py --steps 100 --warmup 5 --no-cpu-baseline > gpurun_out/front_mol_bench_generic_$rep.json 2> gpurun_out/front_mol_bench.err
   PAMNET_FRONT=mol timeout 300 python bench.py --steps 100 --warmup 5 --no-cpu-baseline > gpurun_out/front_mol_bench_mol_$rep.json 2>> gpurun_out/front_mol_bench.err
 done
+for rep in 1 2; do
+  timeout 300 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --prefetch > gpurun_out/front_mol_bench_prefetch_$rep.json 2>> gpurun_out/front_mol_bench.err
+  PAMNET_FRONT=mol timeout 300 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --prefetch > gpurun_out/front_mol_bench_prefetchmol_$rep.json 2>> gpurun_out/front_mol_bench.err
+done
 python - <<'PY'
 import glob, json
 for f in sorted(glob.glob("gpurun_out/front_mol_bench_*.json")):
