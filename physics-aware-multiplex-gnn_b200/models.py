@@ -349,35 +349,58 @@ class _PAMNetBase(nn.Module):
                 node_in = xr[:, -1].contiguous()
         return batch, int(n_graphs), pos, node_in, sign, el_in
 
-    def prefetch(self, data, max_nb=None):
+    def prefetch(self, data, max_nb=None, wait_current=None):
         """Build the graph plan of ``data`` NOW on a side stream -- typically right after ``loss.backward()`` of the
         previous batch, so that the front end of models.py:104-177 (which does not depend on the parameters) overlaps the
-        GPU work still queued for that step instead of preceding the first layer of the next one; ``model(data)`` on the
-        SAME object then starts from the attached plan.  The role a DataLoader worker plays for host-side
-        preprocessing.  Opt-in; without it ``forward`` builds the plan itself.  One batch can be pending at a time."""
-        cur = torch.cuda.current_stream()
+        GPU work still queued for that step instead of preceding the first layer of the next one.  Returns the batch to
+        call the model with: ``model(returned)`` on that SAME object starts from the attached plan.  The role a
+        DataLoader worker plays for host-side preprocessing.  Opt-in; without it ``forward`` builds the plan itself.
+        One batch can be pending at a time.
+
+        ``data`` on the host (pinned): it is copied to the model's device on the side stream as well, so neither the
+        copy nor the graph build waits for the backward queued on the current stream.  ``data`` already on the device:
+        by default the side stream first waits for the current stream (the batch may have been produced there, and then
+        nothing overlaps); pass ``wait_current=False`` when the batch is known to be complete."""
+        dev = self._flat.device
+        if dev.type != "cuda":
+            raise _lib.PamnetError("pamnet_b200 runs on CUDA only: move the model to a GPU (there is no CPU fallback)")
+        on_host = not data.x.is_cuda
+        if wait_current is None:
+            wait_current = not on_host
+        cur = torch.cuda.current_stream(dev)
         side = getattr(self, "_side_stream", None)
-        if side is None or side.device != cur.device:
-            side = self._side_stream = torch.cuda.Stream(device=cur.device)
-        side.wait_stream(cur)                    # the batch (e.g. its H2D copy) was produced on the current stream
+        if side is None or side.device != dev:
+            side = self._side_stream = torch.cuda.Stream(device=dev)
+        if wait_current:
+            side.wait_stream(cur)
         with torch.cuda.stream(side):
+            if on_host:
+                data = data.to(dev, non_blocking=True)
             inputs = self._inputs(data)
             batch, n_graphs, pos, node_in, sign, el_in = inputs
             plan = self._build_plan(pos, batch, n_graphs, el_in, self._MAX_NB if max_nb is None else max_nb)
             done = torch.cuda.Event()
             done.record(side)
-        self._prefetched = (data, inputs, plan, done)
+        self._prefetched = (data, inputs, plan, done, on_host)
+        return data
 
     def _take_prefetched(self, data):
         pre = getattr(self, "_prefetched", None)
         if pre is None or pre[0] is not data:
             return None
         self._prefetched = None
-        _, inputs, plan, done = pre
+        _, inputs, plan, done, copied = pre
         cur = torch.cuda.current_stream()
         cur.wait_event(done)
         # these blocks came from the side stream's pool and are consumed on the current stream from here on
-        for t in (*inputs, plan.base, plan.trip, plan.edge_index_g, plan.edge_index_l):
+        held = [*inputs, plan.base, plan.trip, plan.edge_index_g, plan.edge_index_l]
+        if copied:          # the batch itself was allocated on the side stream; the caller goes on using it (data.y in the loss)
+            fields = getattr(data, "__dict__", {})
+            held += list(fields.values())
+            store = fields.get("_store")
+            if hasattr(store, "values"):
+                held += list(store.values())
+        for t in held:
             if isinstance(t, torch.Tensor) and t.is_cuda:
                 t.record_stream(cur)
         return inputs, plan

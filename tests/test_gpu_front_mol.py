@@ -147,3 +147,15 @@ def test_prefetched_plan_gives_the_same_step():
     for _ in range(20):                                                # back-to-back steps: buffers of the side stream's pool stay valid
         out5, g5 = run(b, prefetch_of=b)
         assert torch.equal(out0, out5) and same_grads(g5, g0)
+    # host batch: copied to the device on the side stream too; the returned object is the one to call the model with
+    host = synthetic_qm9_batch(8, seed=7).pin_memory()
+    for _ in range(5):
+        for p in model.parameters():
+            p.grad = None
+        nb = model.prefetch(host)
+        assert nb.x.is_cuda and model._prefetched[0] is nb
+        out6 = model(nb)
+        (out6 - nb.y).abs().mean().backward()
+        torch.cuda.synchronize()
+        g6 = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None])
+        assert model._prefetched is None and torch.equal(out0, out6.detach()) and same_grads(g6, g0)

@@ -103,6 +103,8 @@ def test_cpu_tensors_fail_loudly_no_fallback():
         PAMNet(Config("QM9", 16, 1, 5.0, 5.0))(synthetic_qm9_batch(2))
     with pytest.raises(PamnetError):
         ops.radius_graph(torch.zeros(4, 3), torch.zeros(4, dtype=torch.long), 1.0)
+    with pytest.raises(PamnetError, match="CUDA"):                      # the opt-in plan prefetch has no CPU path either
+        PAMNet(Config("QM9", 16, 1, 5.0, 5.0)).prefetch(synthetic_qm9_batch(2))
 
 
 def test_synthetic_generator_contract():
