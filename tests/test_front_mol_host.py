@@ -153,3 +153,36 @@ def test_fallback_flags(host_lib):
     ei_ring = np.stack([np.concatenate([ring, (ring + 1) % caps[0]]), np.concatenate([(ring + 1) % caps[0], ring])])
     order = np.lexsort((ei_ring[1], ei_ring[0]))
     _check(host_lib, pos_cap, np.zeros(caps[0], dtype=np.int64), 1, ei_ring[:, order], r=3.0)
+
+
+def test_plan_definition_matches_reference_indices():
+    """tests/plan_ref.py (what the per-molecule front end is compared with) against the oracle's restatement of
+    PAMNet.indices (models.py:68-98, pinned to the verbatim reference by tests/test_oracle_vs_reference.py): per API bond
+    e the plan's segment of slot(e) lists, in order, exactly the reference's (idx_kj | idx_jj_pair) entries of e, and the
+    angles are those of models.py:165-177 on (idx_i, idx_j, idx_k) / (idx_i_pair, idx_j1_pair, idx_j2_pair)."""
+    b = synthetic_qm9_batch(6, seed=9)
+    pos, n = b.pos, b.pos.shape[0]
+    el = graph_ops.drop_self_loops(b.edge_index)
+    tp = b.pos
+    row, col = graph_ops.radius_pairs(tp, tp, 5.0, b.batch, b.batch, max_num_neighbors=1000)
+    eg = graph_ops.drop_self_loops(torch.stack([row, col]))
+    ref = plan_ref.build_plan(pos.numpy(), b.batch.numpy(), 6, eg.numpy(), el.numpy(), 1, True)
+    (idx_i, idx_j, idx_k, idx_kj, idx_ji, idx_i_p, idx_j1_p, idx_j2_p, idx_jj_p, idx_ji_p) = graph_ops.triplet_indices(el, n)
+    ang2 = graph_ops.bond_angle(pos, idx_i, idx_j, idx_k).numpy()
+    ang1 = graph_ops.bond_angle(pos, idx_i_p, idx_j1_p, idx_j2_p).numpy()
+    slot_of = np.empty(el.shape[1], dtype=np.int64)
+    slot_of[ref["l_eid"]] = np.arange(el.shape[1])
+    assert ref["n_t2"] == idx_kj.numel() and ref["n_t1"] == idx_jj_p.numel()
+    for e in range(el.shape[1]):
+        k = slot_of[e]
+        seg = np.arange(ref["t_ptr"][k], ref["t_ptr"][k + 1])
+        two, one = seg[:ref["t_split"][k]], seg[ref["t_split"][k]:]
+        sel2 = np.flatnonzero(idx_ji.numpy() == e)
+        sel1 = np.flatnonzero(idx_ji_p.numpy() == e)
+        assert np.array_equal(ref["l_eid"][ref["t_gather"][two]], idx_kj.numpy()[sel2])
+        assert np.array_equal(ref["l_eid"][ref["t_gather"][one]], idx_jj_p.numpy()[sel1])
+        assert np.all(ref["t_owner"][seg] == k)
+        assert np.allclose(ref["t_angle"][two], ang2[sel2], atol=2e-6) and np.allclose(ref["t_angle"][one], ang1[sel1], atol=2e-6)
+    # edge lengths as models.py:64-65 on the API lists (torch's sum may associate the three squares differently: 1 ulp)
+    assert np.allclose(ref["dist_l"], graph_ops.edge_lengths(el, pos).numpy()[ref["l_eid"]], atol=0, rtol=3e-7)
+    assert np.allclose(ref["dist_g"], graph_ops.edge_lengths(eg, pos).numpy()[ref["g_eid"]], atol=0, rtol=3e-7)
