@@ -75,6 +75,8 @@ def build_plan(pos, batch, n_graphs, edge_index_g, edge_index_l, g_dst_row, two_
     out["tt_ptr"] = np.concatenate([[0], np.cumsum(np.bincount(t_gather, minlength=n_l))]).astype(np.int64)
     tri = np.asarray(tri, dtype=np.int64).reshape(-1, 3)
     out["t_angle"] = _angle(pos, tri[:, 0], tri[:, 1], tri[:, 2])
+    # coincident atoms make a leg of the angle zero: atan2(0, +-0) is 0 or pi depending on the sign of the zero
+    out["t_angle_defined"] = (np.abs(pos[tri[:, 1]] - pos[tri[:, 0]]).sum(-1) > 0) & (np.abs(pos[tri[:, 2]] - pos[tri[:, 1]]).sum(-1) > 0)
     out["n_t2"] = int(out["t_split"].sum())
     out["n_t1"] = int(out["t_cnt"].sum() - out["t_split"].sum())
     return out
