@@ -25,6 +25,18 @@
 PAMNET_HD int pm_atomic_add(int* p, int v) { return atomicAdd(p, v); }
 PAMNET_HD void pm_atomic_add64(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }
 PAMNET_HD void pm_atomic_or64(unsigned long long* p, unsigned long long v) { atomicOr(p, v); }
+#elif defined(PM_HOST_THREADS)
+// host build with PM_HOST_THREADS real threads per block (tests/host_emul, run under ThreadSanitizer): the harness
+// provides the thread index and a barrier, the atomics are the compiler's
+extern thread_local int pm_host_tid;
+void pm_host_barrier();
+#define PM_TID pm_host_tid
+#define PM_NT PM_HOST_THREADS
+#define PM_SYNC() pm_host_barrier()
+#define PM_POPC(x) __builtin_popcountll(x)
+static inline int pm_atomic_add(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline void pm_atomic_add64(unsigned long long* p, unsigned long long v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline void pm_atomic_or64(unsigned long long* p, unsigned long long v) { __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 #else
 #define PM_TID 0
 #define PM_NT 1

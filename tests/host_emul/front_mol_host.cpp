@@ -1,9 +1,32 @@
-// Serial host emulation of the per-molecule front end: compiles csrc/front_mol.cuh with one "thread" per block
-// (PM_NT = 1, barriers are no-ops) so the CPU test suite can check its integer logic without a GPU.
+// Host emulation of the per-molecule front end: compiles csrc/front_mol.cuh with one "thread" per block (PM_NT = 1,
+// barriers are no-ops) so the CPU test suite can check its integer logic without a GPU -- or, with -DPM_HOST_THREADS=k
+// -fsanitize=thread -pthread, with k real threads per block and a pthread barrier, so that ThreadSanitizer reports any
+// pair of conflicting shared-memory accesses that no barrier separates.
 // Test infrastructure only -- never loaded by the package.  Build: g++ -O1 -ffp-contract=off -shared -fPIC.
 #include "../../physics-aware-multiplex-gnn_b200/csrc/front_mol.cuh"
 
 #include <vector>
+
+#ifdef PM_HOST_THREADS
+#include <pthread.h>
+
+#include <thread>
+thread_local int pm_host_tid = 0;
+static pthread_barrier_t g_barrier;
+void pm_host_barrier() { pthread_barrier_wait(&g_barrier); }
+// one block = PM_HOST_THREADS real threads running the same body
+template <class F>
+static void run_block(F body) {
+    pthread_barrier_init(&g_barrier, nullptr, PM_HOST_THREADS);
+    std::vector<std::thread> th;
+    for (int t = 0; t < PM_HOST_THREADS; ++t) th.emplace_back([=] { pm_host_tid = t; body(); });
+    for (auto& t : th) t.join();
+    pthread_barrier_destroy(&g_barrier);
+}
+#else
+template <class F>
+static void run_block(F body) { body(); }
+#endif
 
 using namespace pamnet;
 
@@ -25,7 +48,7 @@ extern "C" int front_mol_host(int pass, const float* pos, const int64_t* batch, 
         ranges.assign(2 * (n_graphs + 1), -12345);          // poison: an unwritten entry must never be used
         a.gstart = ranges.data(); a.estart = ranges.data() + n_graphs + 1;
         for (int64_t t = 0; t < 3; ++t) mol_ranges_body(a, 2 - t, 3);      // three "threads", any order
-        for (int m = 0; m < n_graphs; ++m) mol_count_body(a, s, m);
+        for (int m = 0; m < n_graphs; ++m) run_block([&a, m] { mol_count_body(a, s, m); });
         return 0;
     }
     a.gstart = ranges.data(); a.estart = ranges.data() + n_graphs + 1;      // tables of the preceding count pass
@@ -37,7 +60,7 @@ extern "C" int front_mol_host(int pass, const float* pos, const int64_t* batch, 
     a.t_owner = p[19]; a.tt_t = p[20];
     a.t_angle = farr[0]; a.dist_g = farr[1]; a.dist_l = farr[2];
     // blocks in reverse order: the result must not depend on the order the molecules are processed in
-    for (int m = (int)n_graphs - 1; m >= 0; --m) mol_fill_body(a, s, m);
+    for (int m = (int)n_graphs - 1; m >= 0; --m) run_block([&a, m] { mol_fill_body(a, s, m); });
     return 0;
 }
 
