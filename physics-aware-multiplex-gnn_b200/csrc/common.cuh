@@ -91,7 +91,15 @@ static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a
 // ---------------------------------------------------------------------------------------------
 // device math
 // ---------------------------------------------------------------------------------------------
+// Exact expf + IEEE division by default: ncu attributes 27 % of the global message kernel's stall samples and ~10 % of the
+// node chain's to this line (profiles/README.md section f).  -DPAMNET_FAST_SILU (build with PAMNET_FAST_SILU=1) switches
+// to ex2.approx + rcp.approx (~2 ulp per evaluation, relative error of __expf grows with |x|): an experiment for the next
+// round, to be kept only if the parity ladder of tests/helpers.py still holds.
+#ifdef PAMNET_FAST_SILU
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+#else
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+#endif
 // SiLU and its derivative (layers/basic.py:11-16): s(z)*(1 + z*(1-s(z)))
 __device__ __forceinline__ float silu(float z) { return z * sigmoidf_(z); }
 __device__ __forceinline__ float dsilu(float z) {
