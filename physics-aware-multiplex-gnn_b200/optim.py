@@ -82,6 +82,31 @@ class FusedAdamEMA(torch.optim.Optimizer):
             float(self.max_norm) if self.max_norm is not None else 0.0, float(decay), 1,
             self._sumsq.data_ptr(), torch.cuda.current_stream().cuda_stream), "optimizer_step")
 
+    # ---- checkpoint / resume: the moments and the EMA shadow live in flat buffers, not in Optimizer.state ----------
+    def state_dict(self):
+        sd = super().state_dict()
+        sd["pamnet_flat"] = {"exp_avg": self.exp_avg.detach().clone(), "exp_avg_sq": self.exp_avg_sq.detach().clone(),
+                             "shadow": None if self.shadow is None else self.shadow.detach().clone(),
+                             "num_steps": int(self.num_steps)}
+        return sd
+
+    @torch.no_grad()
+    def load_state_dict(self, state_dict):
+        sd = dict(state_dict)
+        flat = sd.pop("pamnet_flat", None)
+        super().load_state_dict(sd)
+        if flat is None:
+            raise KeyError("not a FusedAdamEMA state_dict (no 'pamnet_flat' entry)")
+        if flat["exp_avg"].numel() != self.exp_avg.numel():
+            raise ValueError("optimizer state belongs to a different model configuration")
+        self.exp_avg.copy_(flat["exp_avg"])
+        self.exp_avg_sq.copy_(flat["exp_avg_sq"])
+        if (flat["shadow"] is None) != (self.shadow is None):
+            raise ValueError("EMA shadow present in one of (checkpoint, optimizer) only")
+        if self.shadow is not None:
+            self.shadow.copy_(flat["shadow"])
+        self.num_steps = int(flat["num_steps"])
+
     def total_norm(self):
         """Gradient norm of the last step as clip_grad_norm_ returns it (device scalar, no synchronisation)."""
         return self._sumsq.sqrt().float()[0]

@@ -6,7 +6,7 @@
 # Outputs land in gpurun_out/front_mol_*.{log,json}.  Make the switch the default only if the parity log is green.
 set -u
 mkdir -p gpurun_out
-PAMNET_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_front_mol.py tests/test_collate_host.py -q -m gpu > gpurun_out/front_mol_parity.log 2>&1
+PAMNET_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_front_mol.py tests/test_collate_host.py tests/test_gpu_optim.py -q -m gpu > gpurun_out/front_mol_parity.log 2>&1
 echo "parity rc=$?" >> gpurun_out/front_mol_parity.log
 tail -3 gpurun_out/front_mol_parity.log
 for rep in 1 2; do
