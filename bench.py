@@ -34,6 +34,8 @@ def parse():
     ap.add_argument("--n-layer", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--fused-loss", action="store_true",
+                    help="opt-in: L1 loss and its gradient in one launch (pamnet_b200.ops.l1_loss) instead of F.l1_loss")
     ap.add_argument("--prefetch", action="store_true",
                     help="opt-in: build the NEXT step's graph plan on a side stream right after backward (model.prefetch); "
                          "every step still contains one H2D copy (e2e) and one front end")
@@ -117,6 +119,8 @@ def workload_config(args, sizes):
          "l2": "flushed (256 MiB write) before every timed step"}
     if sizes:
         c["sizes"] = sizes
+    if getattr(args, "fused_loss", False):
+        c["loss"] = "pamnet_b200.ops.l1_loss (value + gradient in one launch)"
     if getattr(args, "prefetch", False):
         c["prefetch"] = "next step's graph plan built on a side stream after backward (model.prefetch)"
     if os.environ.get("PAMNET_FRONT"):           # opt-in front end in effect
@@ -196,12 +200,13 @@ def run_ours(args):
     params = list(model.parameters())
 
     import torch.nn.functional as F
+    l1 = pamnet_b200.ops.l1_loss if args.fused_loss else F.l1_loss
 
     def step(batch, sync_grads=True, next_batch=None):
         for p in params:             # == optimizer.zero_grad(set_to_none=True)
             p.grad = None
         out = model(batch)
-        loss = F.l1_loss(out, batch.y)      # main_qm9.py:108
+        loss = l1(out, batch.y)             # main_qm9.py:108
         loss.backward()
         if next_batch is not None:          # --prefetch: the next step's front end overlaps this step's backward
             next_batch()

@@ -10,6 +10,7 @@ torch_scatter.scatter           local_message_passing.py:50,54 -> scatter
 BesselBasisLayer.forward        layers/basic.py:74-76          -> bessel_rbf
 SphericalBasisLayer.forward     layers/basic.py:107-116        -> spherical_basis
 nn.Linear (+SiLU)               layers/basic.py:19-22          -> linear
+F.l1_loss / MSE                 main_qm9.py:108, main_pdbbind.py -> l1_loss / mse_loss (loss + gradient in one launch)
 
 All tensors must live on a CUDA device; there is no CPU path.
 """
@@ -256,3 +257,37 @@ def gemm(mode, a, b, m, n, k, ksplit=1, want_dbias=False):
     _lib.check(lib.pamnet_gemm(mode, a.data_ptr(), a.shape[1], b.data_ptr(), b.shape[1], c.data_ptr(), n, m, n, k,
                                ksplit, _lib.ptr(dbias), _stream()), "gemm")
     return (c, dbias) if want_dbias else c
+
+
+class _FusedLoss(torch.autograd.Function):
+    """mean |out - y| (kind 0, F.l1_loss of main_qm9.py:108) or mean (out - y)^2 (kind 1, the MSE of main_pdbbind.py) with
+    its gradient in ONE launch (pamnet_loss); torch's own sequence is ~7 tiny launches between forward and backward."""
+
+    @staticmethod
+    def forward(ctx, out, y, kind):
+        _require_cuda(out, y)
+        if out.shape != y.shape:
+            raise ValueError(f"loss: prediction {tuple(out.shape)} and target {tuple(y.shape)} differ in shape")
+        o, t = _f32(out).reshape(-1), _f32(y).reshape(-1)
+        loss = torch.empty(1, dtype=torch.float32, device=o.device)
+        grad = torch.empty_like(o)
+        _lib.check(_lib.load().pamnet_loss(o.data_ptr(), t.data_ptr(), o.numel(), int(kind), loss.data_ptr(),
+                                           grad.data_ptr(), _stream()), "loss")
+        ctx.save_for_backward(grad)
+        ctx.shape = out.shape
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return (grad * g).view(ctx.shape), None, None
+
+
+def l1_loss(out, y):
+    """F.l1_loss(out, y) (mean reduction) with gradient w.r.t. ``out`` only (the target is data)."""
+    return _FusedLoss.apply(out, y, 0)
+
+
+def mse_loss(out, y):
+    """F.mse_loss(out, y) (mean reduction) with gradient w.r.t. ``out`` only."""
+    return _FusedLoss.apply(out, y, 1)

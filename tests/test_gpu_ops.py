@@ -171,3 +171,23 @@ def test_gemm_modes(ops, m, n, k, ksplit):
     c, db = ops.gemm(2, at.cuda(), bt.cuda(), m, n, k, ksplit=ksplit, want_dbias=True)
     assert err(c, at.double().T @ bt.double()) < tol
     assert err(db, at.double().sum(0)) < tol
+
+
+@pytest.mark.skipif(__import__("os").environ.get("PAMNET_TEST_EXPERIMENTAL", "") != "1",
+                    reason="written after the round's GPU budget was spent: set PAMNET_TEST_EXPERIMENTAL=1")
+def test_fused_losses_match_torch(ops):
+    """ops.l1_loss / ops.mse_loss (pamnet_loss: value and gradient in one launch) against F.l1_loss / F.mse_loss."""
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    for n in (1, 32, 1000):
+        y = torch.randn(n, device="cuda")
+        for fused, ref in ((ops.l1_loss, F.l1_loss), (ops.mse_loss, F.mse_loss)):
+            a = torch.randn(n, device="cuda", requires_grad=True)
+            b = a.detach().clone().requires_grad_(True)
+            la, lb = fused(a, y), ref(b, y)
+            (3.0 * la).backward()
+            (3.0 * lb).backward()
+            assert abs(float(la) - float(lb)) <= 1e-6 * max(1.0, abs(float(lb)))
+            assert torch.allclose(a.grad, b.grad, rtol=1e-6, atol=1e-9)
+    with pytest.raises(ValueError):
+        ops.l1_loss(torch.zeros(3, device="cuda"), torch.zeros(4, device="cuda"))

@@ -6,7 +6,7 @@
 # Outputs land in gpurun_out/front_mol_*.{log,json}.  Make the switch the default only if the parity log is green.
 set -u
 mkdir -p gpurun_out
-PAMNET_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_front_mol.py tests/test_collate_host.py tests/test_gpu_optim.py -q -m gpu > gpurun_out/front_mol_parity.log 2>&1
+PAMNET_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_front_mol.py tests/test_collate_host.py tests/test_gpu_optim.py tests/test_gpu_ops.py -q -m gpu > gpurun_out/front_mol_parity.log 2>&1
 echo "parity rc=$?" >> gpurun_out/front_mol_parity.log
 tail -3 gpurun_out/front_mol_parity.log
 for rep in 1 2; do
@@ -16,6 +16,7 @@ done
 for rep in 1 2; do
   timeout 300 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --prefetch > gpurun_out/front_mol_bench_prefetch_$rep.json 2>> gpurun_out/front_mol_bench.err
   PAMNET_FRONT=mol timeout 300 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --prefetch > gpurun_out/front_mol_bench_prefetchmol_$rep.json 2>> gpurun_out/front_mol_bench.err
+  PAMNET_FRONT=mol timeout 300 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --prefetch --fused-loss > gpurun_out/front_mol_bench_prefetchmolloss_$rep.json 2>> gpurun_out/front_mol_bench.err
 done
 python - <<'PY'
 import glob, json
