@@ -75,8 +75,6 @@ def test_device_dataset_needs_a_gpu():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("PAMNET_TEST_EXPERIMENTAL", "") != "1",
-                    reason="written after the round's GPU budget was spent: set PAMNET_TEST_EXPERIMENTAL=1")
 def test_device_dataset_batch_equals_loader_collate_gpu():
     from pamnet_b200 import Config, PAMNet
     ref = synthetic_qm9_batch(16, seed=2)

@@ -2,24 +2,21 @@
 plan array, both edge lists and the model output must be bit-identical; the generic plan is also checked against the numpy
 restatement of the plan definition (tests/plan_ref.py).
 
-The path was written after this round's GPU budget was spent: its integer logic is covered on the CPU
-(tests/test_front_mol_host.py), but it has not run on a device yet.  It is therefore opt-in (PAMNET_FRONT=mol) and these
-tests run only with PAMNET_TEST_EXPERIMENTAL=1 -- the first GPU call of the next round."""
+Its integer logic is also covered on the CPU (tests/test_front_mol_host.py).  Green on a B200 since round 2
+(gpurun_out/front_mol_parity.log); the per-molecule front end is the default for QM9-shaped batches, PAMNET_FRONT=generic
+selects the generic kernels."""
 import os
 
 import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PAMNET_TEST_EXPERIMENTAL", "") != "1",
-                                 reason="opt-in path not yet confirmed on a GPU: set PAMNET_TEST_EXPERIMENTAL=1")]
+pytestmark = [pytest.mark.gpu]
 
 
 def _plan(model, batch, front):
     old = os.environ.pop("PAMNET_FRONT", None)
-    if front:
-        os.environ["PAMNET_FRONT"] = front
+    os.environ["PAMNET_FRONT"] = front or "generic"
     try:
         with torch.no_grad():
             out = model(batch)
@@ -117,8 +114,7 @@ def test_prefetched_plan_gives_the_same_step():
     other = synthetic_qm9_batch(3, seed=8).to("cuda")
 
     def run(batch, prefetch_of=None, front=None):
-        if front:
-            os.environ["PAMNET_FRONT"] = front
+        os.environ["PAMNET_FRONT"] = front or "generic"
         try:
             for p in model.parameters():
                 p.grad = None

@@ -88,8 +88,6 @@ def test_lr_scheduler_drives_fused_optimizer_and_ema_swap():
     assert torch.isfinite(out_ema).all()
 
 
-@pytest.mark.skipif(__import__("os").environ.get("PAMNET_TEST_EXPERIMENTAL", "") != "1",
-                    reason="written after the round's GPU budget was spent: set PAMNET_TEST_EXPERIMENTAL=1")
 def test_optimizer_state_dict_round_trip_resumes():
     """Checkpoint / resume: moments, EMA shadow and step count travel through state_dict(); a resumed run continues
     exactly like the uninterrupted one."""
