@@ -7,11 +7,11 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpamnet_sm100.so")
-SOURCES = ["abi.cu", "graph.cu", "front_mol.cu", "collate.cu", "basis.cu", "gemm.cu", "gemm_tc.cu", "gemm_small.cu", "chain.cu", "message.cu", "readout.cu", "model.cu", "optim.cu"]
+SOURCES = ["abi.cu", "graph.cu", "front_mol.cu", "collate.cu", "basis.cu", "gemm.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_small.cu", "chain.cu", "chain_mma.cu", "message.cu", "readout.cu", "model.cu", "optim.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
-if os.environ.get("PAMNET_FAST_SILU") == "1":  # experiment: approximate exp / reciprocal in SiLU (csrc/common.cuh)
-    NVCC_FLAGS.append("-DPAMNET_FAST_SILU")
+if os.environ.get("PAMNET_SILU_MODE"):           # 0 exact / 1 fast reciprocal (default) / 2 + ex2.approx (csrc/common.cuh)
+    NVCC_FLAGS.append("-DPAMNET_SILU_MODE=" + str(int(os.environ["PAMNET_SILU_MODE"])))
 if os.environ.get("PAMNET_TC_TRACE"):          # in-kernel clock64 timeline of the tensor-core GEMM (debug builds)
     NVCC_FLAGS.append("-DPAMNET_TC_TRACE")
 

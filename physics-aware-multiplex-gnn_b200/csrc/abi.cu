@@ -4,6 +4,8 @@
 #include <stdlib.h>
 
 #include <atomic>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 #include "basis.cuh"
@@ -40,6 +42,27 @@ bool pdl_enabled() { return pdl_level() != 0; }
 // ---- launch counter + event profiler (single-threaded use: bench / tests) --------------------------
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// The attribute is per (function, device): remember which devices a kernel was configured on.  A mutex-protected table
+// instead of a function-local `static bool` (not thread-safe, and wrong for a second device in the same process).
+int func_smem_once(const void* func, size_t bytes) {
+    static std::mutex mu;
+    static std::vector<std::pair<const void*, unsigned>> done;     // (kernel, device bit mask)
+    int dev = 0;
+    PAMNET_CUDA(cudaGetDevice(&dev));
+    const unsigned bit = 1u << (dev & 31);
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& e : done)
+        if (e.first == func) {
+            if (e.second & bit) return 0;
+            PAMNET_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            e.second |= bit;
+            return 0;
+        }
+    PAMNET_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    done.emplace_back(func, bit);
+    return 0;
+}
 
 struct ProfRec { int cls; double bytes; cudaEvent_t e0, e1; cudaStream_t st; double flops; };
 static bool g_prof_on = false;

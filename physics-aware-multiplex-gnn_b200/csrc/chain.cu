@@ -14,7 +14,9 @@ __device__ long long g_chain_trace[16 * 16];
 #else
 #define CH_STAMP(si, i) do { } while (0)
 #endif
+int chain_mma_trace_read(long long* out, int n);
 int chain_trace_read(long long* out, int n) {
+    if (chain_mma_enabled(128)) return chain_mma_trace_read(out, n);
 #ifdef PAMNET_TC_TRACE
     PAMNET_CUDA(cudaMemcpyFromSymbol(out, g_chain_trace, sizeof(long long) * (n < 256 ? n : 256)));
     return 0;
@@ -346,14 +348,19 @@ __global__ void __launch_bounds__(kChainKS * D / 2, 1) chain_kernel(const ChainA
 }
 
 template <int D>
-static int chain_launch_t(const ChainArgs& args, cudaStream_t st) {
+static int chain_launch_t(const ChainArgs& a, double bytes, cudaStream_t st) {
     using C = ChainCfg<D>;
     const size_t smem = C::smem_floats * sizeof(float);
-    static bool configured = false;   // per-D instantiation; the attribute is per-function and idempotent
-    if (!configured) {
-        PAMNET_CUDA(cudaFuncSetAttribute(chain_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    PAMNET_TRY(func_smem_once(reinterpret_cast<const void*>(chain_kernel<D>), smem));
+    prof_begin(KC_CHAIN, bytes, st);
+    launch_pdl(chain_kernel<D>, dim3(ceil_div(a.n_rows, C::R)), dim3(C::T), smem, st, a);
+    prof_end(st);
+    PAMNET_LAUNCH_CHECK();
+    return 0;
+}
+
+// stage-table preprocessing shared by both interpreters: algorithmic bytes, prologue fusion, next-GEMM links
+static double chain_prepare(int D, const ChainArgs& args, ChainArgs* out) {
     double bytes = 0.0;
     for (int i = 0; i < args.n_stages; ++i) {
         const ChainStage& s = args.st[i];
@@ -364,7 +371,8 @@ static int chain_launch_t(const ChainArgs& args, cudaStream_t st) {
                                           (s.out_a ? 1 : 0) + (s.add_g ? 1 : 0));
         if (s.op == CH_DOT2 || s.op == CH_HEADS_BWD) bytes += 8.0 * args.n_rows + 8.0 * D;
     }
-    ChainArgs a = args;
+    ChainArgs& a = *out;
+    a = args;
     for (int i = 0; i < a.n_stages; ++i) { a.st[i].post_dst = -1; a.st[i].post_zmul = nullptr; a.st[i].post_save = nullptr; }
     // prologue fusion (see ChainStage::post_dst): stage i + 1 = GEMM with a SiLU' prologue on exactly what stage i wrote
     static int fuse = -1;
@@ -380,11 +388,7 @@ static int chain_launch_t(const ChainArgs& args, cudaStream_t st) {
         a.st[i].next_gemm = nxt;
         if (a.st[i].op == CH_GEMM) nxt = i;
     }
-    prof_begin(KC_CHAIN, bytes, st);
-    launch_pdl(chain_kernel<D>, dim3(ceil_div(args.n_rows, C::R)), dim3(C::T), smem, st, a);
-    prof_end(st);
-    PAMNET_LAUNCH_CHECK();
-    return 0;
+    return bytes;
 }
 
 int chain_launch(int dim, const ChainArgs& args, cudaStream_t st) {
@@ -396,11 +400,14 @@ int chain_launch(int dim, const ChainArgs& args, cudaStream_t st) {
             PAMNET_CHECK_ARG(s.dst != s.src && (s.psrc < 0 || s.dst != s.psrc) && s.dst != kChainWide,
                              "chain stage %d: output slot aliases its input", i);
     }
+    ChainArgs a;
+    const double bytes = chain_prepare(dim, args, &a);
+    if (chain_mma_enabled(dim)) return chain_mma_launch(dim, a, bytes, st);
     switch (dim) {
-        case 128: return chain_launch_t<128>(args, st);
-        case 64:  return chain_launch_t<64>(args, st);
-        case 32:  return chain_launch_t<32>(args, st);
-        case 16:  return chain_launch_t<16>(args, st);
+        case 128: return chain_launch_t<128>(a, bytes, st);
+        case 64:  return chain_launch_t<64>(a, bytes, st);
+        case 32:  return chain_launch_t<32>(a, bytes, st);
+        case 16:  return chain_launch_t<16>(a, bytes, st);
         default:
             set_error("chain: unsupported dim %d (16, 32, 64, 128)", dim);
             return -1;

@@ -52,4 +52,12 @@ struct ChainArgs {
 int chain_launch(int dim, const ChainArgs& args, cudaStream_t st);
 int chain_trace_read(long long* out, int n);
 
+// Tensor-core interpreter (chain_mma.cu; D = 64, 128 unless PAMNET_CHAIN=ffma).  Its GEMM stages read `W` as a
+// FRAGMENT IMAGE of the stage's A[m][k] matrix (m = output feature, k = input feature) produced by frag_batch; callers
+// (model.cu) pick the weight format with chain_mma_enabled(dim).
+bool chain_mma_enabled(int dim);
+int chain_mma_launch(int dim, const ChainArgs& prepared_args, double alg_bytes, cudaStream_t st);
+struct FragJob { int64_t src_off, dst_off; int ld; int trans; };   // trans 0: A[m][k] = src[m*ld+k]; 1: A[m][k] = src[k*ld+m]
+int frag_batch(const float* src_base, float* dst_base, int dim, const FragJob* jobs_host, int n_jobs, cudaStream_t st);
+
 }  // namespace pamnet

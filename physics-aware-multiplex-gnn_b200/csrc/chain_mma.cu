@@ -1,0 +1,434 @@
+// Tensor-core stage interpreter for the row-local node chains (chain.cuh), D >= 64.
+//
+// Same stage semantics as chain.cu (the FFMA interpreter, still used for D < 64 and with PAMNET_CHAIN=ffma); what
+// changes is how a D x D stage is multiplied.  A CTA still owns 8 rows and keeps the activations transposed in shared
+// memory ([k][8]), which is exactly the B operand of mma.m16n8k8 (N = the 8 rows).  The problem is computed as
+//     Y^T [D features x 8 rows] = A [D x D] * X^T [D x 8],        A[m][k] = the stage's weight matrix
+// Warp w owns features 16 w .. 16 w + 15: its A fragments for all D / 8 k-steps were laid out contiguously by the
+// weight-preparation kernel (frag_batch below), so a lane reads them with ONE conflict-free 128-bit shared-memory load per
+// k-step and every weight element is read from shared memory exactly once per stage (the FFMA kernel read the 64 KB
+// matrix twice and then exchanged 8 partial sums through shared memory: three barriers and ~1000 cycles of
+// exchange + reduce per stage).  fp32 accuracy comes from the 3xTF32 split done in REGISTERS: hi = rna_tf32(x),
+// lo = x - hi; products lo*hi + hi*lo + hi*hi accumulate in fp32 (same scheme as gemm_tc.cu, ~1e-6 relative).  The
+// accumulator fragment (features g, g + 8 x rows 2t, 2t + 1) goes straight through the stage epilogue in registers.
+//
+// Why not tcgen05 here: with 8 .. 16 rows per CTA the UMMA tile would be M = 128 features x N = rows, operands in
+// shared memory already split into tf32 planes -- 3 x 64 KB of operand reads and twice the L2 -> SM weight stream per
+// stage; the stage is bound by streaming 64 KB of weights into every SM, not by tensor throughput.
+#include "chain.cuh"
+
+#include <stdlib.h>
+
+namespace pamnet {
+// optional clock64 timeline of CTA 0 / thread 0 (-DPAMNET_TC_TRACE builds; tools/chain_trace.py): 8 stamps per stage
+#ifdef PAMNET_TC_TRACE
+__device__ long long g_chain_mma_trace[26 * 8];
+#define CM_STAMP(si, i) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (si) < 26) g_chain_mma_trace[(si) * 8 + (i)] = clock64(); } while (0)
+#else
+#define CM_STAMP(si, i) do { } while (0)
+#endif
+int chain_mma_trace_read(long long* out, int n) {
+#ifdef PAMNET_TC_TRACE
+    PAMNET_CUDA(cudaMemcpyFromSymbol(out, g_chain_mma_trace, sizeof(long long) * (n < 208 ? n : 208)));
+    return 0;
+#else
+    (void)out; (void)n;
+    set_error("built without PAMNET_TC_TRACE");
+    return -1;
+#endif
+}
+namespace {
+
+constexpr int kR = 8;     // rows per CTA = N of the MMA
+
+__device__ __forceinline__ unsigned smem_addr_(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init_(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr_(dst)), "l"(src), "r"(bytes), "r"(smem_addr_(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_(uint64_t* bar, unsigned parity) {
+    unsigned ok = 0;
+    for (unsigned spin = 0; !ok; ++spin) {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok) : "r"(smem_addr_(bar)), "r"(parity) : "memory");
+        if (spin > (1u << 24)) asm volatile("trap;");      // a protocol bug must not hang the GPU
+    }
+}
+
+// D (16x8, fp32) += A (16x8, tf32, row) * B (8x8, tf32, col)
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// x = hi + lo + O(2^-21 |x|): hi rounded to nearest tf32 with integer ops, lo exact in fp32 (the tensor core drops its
+// low mantissa bits: 2^-10 * 2^-11)
+__device__ __forceinline__ void split_tf32_(float x, uint32_t& hi, uint32_t& lo) {
+    hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+template <int D>
+struct MmaChainCfg {
+    static constexpr int WM = D / 16;                      // 16-feature M tiles
+    static constexpr int CW = 2 * WM;                      // consumer warps: (M tile, k half)
+    static constexpr int NC = CW * 32;                     // consumer threads
+    static constexpr int NT = NC + 32;                     // + the weight-producer warp
+    static constexpr int KS = D / 8;                       // k-steps per stage, KS / 2 per consumer warp
+    static constexpr size_t smem_floats = 2 * (size_t)D * D + (size_t)(kChainSlots + 4) * D * kR;
+};
+
+// Warp roles.  Consumer warp w = (M tile w % WM, k half w / WM) multiplies its 16 features x 8 rows over half of K; the
+// two warps of an M tile swap the accumulator halves they do NOT finish through shared memory (one named barrier per
+// pair) so that every thread ends up with 2 of the tile's elements: feature f0 + 8 (k half), rows 2 tq, 2 tq + 1.
+// The producer warp only walks the stage table in lockstep (same CTA barriers) and asks the bulk-copy engine for the
+// NEXT GEMM stage's fragment image at the start of every GEMM stage: the request (~230 cycles of one thread) used to sit
+// on thread 0's path to the multiply loop.
+template <int D>
+__global__ void __launch_bounds__(MmaChainCfg<D>::NT, 1) chain_mma_kernel(const ChainArgs args) {
+    using C = MmaChainCfg<D>;
+    constexpr int R = kR, NC = C::NC, NT = C::NT, KS = C::KS, WM = C::WM, CW = C::CW;
+    extern __shared__ __align__(16) float smem[];
+    float* wbuf = smem;                                   // [2][D * D]: fragment images of this and the next GEMM stage
+    float* slots = wbuf + 2 * D * D;                      // 3 x [D][R] transposed activations, then wide [4D][R]
+    auto slot_ptr = [&](int s) -> float* { return slots + s * D * R; };
+
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int n_rows = args.n_rows;
+    const int row0 = blockIdx.x * R;
+
+    __shared__ __align__(16) ChainStage s_stage[kChainMaxStages];
+    __shared__ __align__(8) uint64_t wbar[2];
+    __shared__ float s_red[2 * R * CW];
+    __shared__ __align__(8) float2 s_xch[CW * 32];
+    {
+        static_assert(sizeof(ChainStage) % 4 == 0, "word copy");
+        const int nwords = args.n_stages * (int)(sizeof(ChainStage) / 4);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(args.st);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(s_stage);
+        for (int i = t; i < nwords; i += NT) dst[i] = src[i];
+    }
+    if (t == 0) {
+        mbar_init_(&wbar[0], 1);
+        mbar_init_(&wbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int n_stages = args.n_stages;
+
+    if (warp == CW) {
+        // ---- producer warp: same CTA-barrier sequence as the consumers, nothing else ------------------------------
+        auto issue_weights = [&](int si, int buf) {           // one bulk copy: the image is contiguous
+            if (lane == 0) {
+                mbar_expect_tx_(&wbar[buf], (unsigned)(D * D * sizeof(float)));
+                bulk_g2s_(wbuf + buf * D * D, s_stage[si].W, (unsigned)(D * D * sizeof(float)), &wbar[buf]);
+            }
+        };
+        int wcur = 0;
+        {
+            int first = -1;
+            for (int i = 0; i < n_stages && first < 0; ++i)
+                if (s_stage[i].op == CH_GEMM) first = i;
+            if (first >= 0) issue_weights(first, 0);          // prepared weights: written before the predecessor started
+        }
+        for (int si = 0; si < n_stages; ++si) {
+            const int op = s_stage[si].op;
+            if (op == CH_GEMM) {
+                // buffer wcur ^ 1 was last read by the previous GEMM stage, whose trailing barrier this warp has passed
+                const int nxt = s_stage[si].next_gemm;
+                if (nxt >= 0) issue_weights(nxt, wcur ^ 1);
+                if (s_stage[si].psrc >= 0) __syncthreads();
+                wcur ^= 1;
+                __syncthreads();
+            } else {
+                __syncthreads();
+                if (op == CH_DOT2) __syncthreads();
+            }
+        }
+        return;
+    }
+
+    // ---- consumer warps ---------------------------------------------------------------------------------------------
+    const int g = lane >> 2, tq = lane & 3;
+    const int mt = warp % WM, kh = warp / WM;
+    const int f0 = 16 * mt + g;                           // fragment features f0, f0 + 8; rows 2 tq, 2 tq + 1
+    const int fe = f0 + 8 * kh;                           // the feature this thread finishes
+    const int r0 = 2 * tq;
+    const int er = t & (R - 1), ec = t / R;               // element-wise stages: (row, 4-column group), row fastest
+    constexpr int EC = NC / R;
+    const bool live0 = row0 + r0 < n_rows, live1 = row0 + r0 + 1 < n_rows;
+
+    unsigned wphase[2] = {0u, 0u};
+    float4 zpre = make_float4(0.f, 0.f, 0.f, 0.f);
+    int zpre_stage = -1;
+    int wcur = 0;
+    // Everything above touched only kernel parameters and prepared weights; from here on the predecessor's outputs are read.
+    pdl_wait();
+
+    for (int si = 0; si < n_stages; ++si) {
+        const ChainStage& st = s_stage[si];
+        if (si == n_stages - 1) pdl_trigger();
+        CM_STAMP(si, 0);
+        if (st.op == CH_LOAD) {
+            float* d = slot_ptr(st.dst);
+            const int w4 = st.width / 4;
+            const bool live = row0 + er < n_rows;
+            const float* g0 = st.g0; const float* g1 = st.g1; float* out_a = st.out_a;
+            const int ld_g = st.ld_g, ld_out = st.ld_out, add_slot = st.add_slot;
+            for (int c4 = ec; c4 < w4; c4 += EC) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live) {
+                    v = ld4(g0 + (size_t)(row0 + er) * ld_g + c4 * 4);
+                    if (g1) v = v + ld4(g1 + (size_t)(row0 + er) * ld_g + c4 * 4);
+                    if (add_slot >= 0) {
+                        const float* a = slot_ptr(add_slot) + (c4 * 4) * R + er;
+                        v = v + make_float4(a[0], a[R], a[2 * R], a[3 * R]);
+                    }
+                    if (out_a) st4(out_a + (size_t)(row0 + er) * ld_out + c4 * 4, v);
+                }
+                float* q = d + (c4 * 4) * R + er;
+                q[0] = v.x; q[R] = v.y; q[2 * R] = v.z; q[3 * R] = v.w;
+            }
+            __syncthreads();
+        } else if (st.op == CH_HEADS_BWD) {
+            float* d = slot_ptr(st.dst);
+            const bool live = row0 + er < n_rows;
+            const float ga = live ? st.g0[row0 + er] : 0.f, go = live ? st.g1[row0 + er] : 0.f;
+            const float* W = st.W; const float* Wo = st.bias;
+            for (int c4 = ec; c4 < D / 4; c4 += EC) {
+                const float4 w = ld4(W + c4 * 4), wo = ld4(Wo + c4 * 4);
+                float* q = d + (c4 * 4) * R + er;
+                q[0] = ga * w.x + go * wo.x; q[R] = ga * w.y + go * wo.y;
+                q[2 * R] = ga * w.z + go * wo.z; q[3 * R] = ga * w.w + go * wo.w;
+            }
+            __syncthreads();
+        } else if (st.op == CH_DOT2) {
+            const float* s = slot_ptr(st.src);
+            const float* W = st.W; const float* Wo = st.bias;
+            float a = 0.f, o = 0.f;
+            for (int cc = ec; cc < D; cc += EC) {
+                const float x = s[cc * R + er];
+                a = fmaf(x, W[cc], a);
+                o = fmaf(x, Wo[cc], o);
+            }
+            a += __shfl_xor_sync(0xffffffffu, a, 8);  o += __shfl_xor_sync(0xffffffffu, o, 8);
+            a += __shfl_xor_sync(0xffffffffu, a, 16); o += __shfl_xor_sync(0xffffffffu, o, 16);
+            if (lane < R) { s_red[(warp * R + lane) * 2] = a; s_red[(warp * R + lane) * 2 + 1] = o; }
+            __syncthreads();
+            if (t < R && row0 + t < n_rows) {
+                float sa = 0.f, so = 0.f;
+                for (int w = 0; w < CW; ++w) { sa += s_red[(w * R + t) * 2]; so += s_red[(w * R + t) * 2 + 1]; }
+                st.out_z[row0 + t] = sa;
+                st.out_a[row0 + t] = so + st.g0[0];
+            }
+            __syncthreads();
+        } else {  // CH_GEMM
+            // Stage fields copied to registers up front: `st` lives in shared memory and every global store may alias it
+            // as far as the compiler knows, so reading fields between the stores reloads them and serialises the
+            // independent element chains (ncu: 42 % of the first version's samples sat in the epilogue).
+            float* const out_z = st.out_z;
+            float* const out_a = st.out_a;
+            float* const post_save = st.post_save;
+            const float* const add_g = st.add_g;
+            const float* const bias = st.bias;
+            const int ld_out = st.ld_out, act = st.act, add_slot = st.add_slot, dst = st.dst, post_dst = st.post_dst;
+            const int psrc = st.psrc, nxt = st.next_gemm;
+            const float* in = slot_ptr(st.src) + st.src_off * R;
+            // epilogue operands requested now, consumed after the k-loop
+            const float bias_v = bias ? bias[fe] : 0.f;
+            float addg_v[2] = {0.f, 0.f}, zpost_v[2] = {0.f, 0.f};
+            if (add_g) {
+                const int ld_add = st.ld_add;
+                if (live0) addg_v[0] = add_g[(size_t)(row0 + r0) * ld_add + fe];
+                if (live1) addg_v[1] = add_g[(size_t)(row0 + r0 + 1) * ld_add + fe];
+            }
+            if (post_dst >= 0) {
+                const float* pz = st.post_zmul;
+                if (live0) zpost_v[0] = pz[(size_t)(row0 + r0) * D + fe];
+                if (live1) zpost_v[1] = pz[(size_t)(row0 + r0 + 1) * D + fe];
+            }
+            if (psrc >= 0) {          // prologue: src * SiLU'(zmul) -> psrc (and to global for the weight gradients)
+                float* p = slot_ptr(psrc);
+                const bool live = row0 + er < n_rows;
+                const float* zmul = st.zmul;
+                float* save_src = st.save_src;
+                for (int c4 = ec; c4 < D / 4; c4 += EC) {
+                    const float* gsrc = in + (c4 * 4) * R + er;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (live) {
+                        const float4 zz = (zpre_stage == si && c4 == ec) ? zpre : ld4(zmul + (size_t)(row0 + er) * D + c4 * 4);
+                        const float4 dz = dsilu4(zz);
+                        v = make_float4(gsrc[0] * dz.x, gsrc[R] * dz.y, gsrc[2 * R] * dz.z, gsrc[3 * R] * dz.w);
+                        if (save_src) st4(save_src + (size_t)(row0 + er) * D + c4 * 4, v);
+                    }
+                    float* q = p + (c4 * 4) * R + er;
+                    q[0] = v.x; q[R] = v.y; q[2 * R] = v.z; q[3 * R] = v.w;
+                }
+                in = p;
+            }
+            if (nxt >= 0 && s_stage[nxt].psrc >= 0 && ec < D / 4 && row0 + er < n_rows) {
+                zpre = ld4(s_stage[nxt].zmul + (size_t)(row0 + er) * D + ec * 4);
+                zpre_stage = nxt;
+            }
+            float2 addv = make_float2(0.f, 0.f);       // the residual slot was complete before this stage began
+            if (add_slot >= 0) addv = *reinterpret_cast<const float2*>(slot_ptr(add_slot) + fe * R + r0);
+            CM_STAMP(si, 1);
+            mbar_wait_(&wbar[wcur], wphase[wcur]);        // this stage's weights have landed
+            wphase[wcur] ^= 1u;
+            CM_STAMP(si, 2);
+            if (psrc >= 0) __syncthreads();               // prologue visible (otherwise the previous stage's trailing barrier covers the inputs)
+            CM_STAMP(si, 3);
+
+            // ---- multiply over this warp's half of K: 3 products per k-step, six independent accumulator chains ----
+            float acc_m[2][4], acc_x[2][4], acc_y[2][4];
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc_m[p][j] = acc_x[p][j] = acc_y[p][j] = 0.f;
+            const float4* wf = reinterpret_cast<const float4*>(wbuf + wcur * D * D) + ((size_t)mt * KS + kh * (KS / 2)) * 32 + lane;
+            const float* bp = in + (kh * (KS / 2) * 8 + tq) * R + g;
+#pragma unroll
+            for (int s = 0; s < KS / 2; ++s) {
+                const float4 av = wf[s * 32];
+                const float b0 = bp[(8 * s) * R], b1 = bp[(8 * s + 4) * R];
+                uint32_t ah[4], al[4], bh[2], bl[2];
+                split_tf32_(av.x, ah[0], al[0]); split_tf32_(av.y, ah[1], al[1]);
+                split_tf32_(av.z, ah[2], al[2]); split_tf32_(av.w, ah[3], al[3]);
+                split_tf32_(b0, bh[0], bl[0]); split_tf32_(b1, bh[1], bl[1]);
+                mma_tf32(acc_x[s & 1], al, bh);
+                mma_tf32(acc_y[s & 1], ah, bl);
+                mma_tf32(acc_m[s & 1], ah, bh);
+            }
+            float c[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)     // small terms first
+                c[j] = ((acc_x[0][j] + acc_x[1][j]) + (acc_y[0][j] + acc_y[1][j])) + (acc_m[0][j] + acc_m[1][j]);
+            CM_STAMP(si, 4);
+            // ---- swap halves with the partner warp (other k half of the same M tile): keep feature fe ----
+            {
+                const float2 give = kh ? make_float2(c[0], c[1]) : make_float2(c[2], c[3]);
+                s_xch[warp * 32 + lane] = give;
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + mt) : "memory");
+                const float2 got = s_xch[(warp ^ WM) * 32 + lane];     // WM is a power of two: partner = other k half
+                // fixed order (k half 0 + k half 1) -> deterministic
+                if (kh) { c[0] = got.x + c[2]; c[1] = got.y + c[3]; }
+                else    { c[0] = c[0] + got.x; c[1] = c[1] + got.y; }
+            }
+            // ---- epilogue: elements (feature fe, rows r0, r0 + 1), every operand already in registers ----
+            float x[2], z[2];
+            z[0] = c[0] + bias_v; z[1] = c[1] + bias_v;
+            x[0] = act ? silu(z[0]) : z[0];
+            x[1] = act ? silu(z[1]) : z[1];
+            x[0] = live0 ? (x[0] + addv.x) + addg_v[0] : 0.f;
+            x[1] = live1 ? (x[1] + addv.y) + addg_v[1] : 0.f;
+            if (x[0] == 12345.678f) CM_STAMP(si, 7);   // (forces the math to complete before the next stamp)
+            CM_STAMP(si, 5);
+            const size_t o0 = (size_t)(row0 + r0) * ld_out + fe;
+            if (out_z) {
+                if (live0) out_z[o0] = z[0];
+                if (live1) out_z[o0 + ld_out] = z[1];
+            }
+            if (out_a) {
+                if (live0) out_a[o0] = x[0];
+                if (live1) out_a[o0 + ld_out] = x[1];
+            }
+            if (dst >= 0 && dst != post_dst)
+                *reinterpret_cast<float2*>(slot_ptr(dst) + fe * R + r0) = make_float2(x[0], x[1]);
+            if (post_dst >= 0) {          // the next stage's prologue, on register values
+                const float y0 = live0 ? x[0] * dsilu(zpost_v[0]) : 0.f;
+                const float y1 = live1 ? x[1] * dsilu(zpost_v[1]) : 0.f;
+                if (post_save) {
+                    const size_t p0 = (size_t)(row0 + r0) * D + fe;
+                    if (live0) post_save[p0] = y0;
+                    if (live1) post_save[p0 + D] = y1;
+                }
+                *reinterpret_cast<float2*>(slot_ptr(post_dst) + fe * R + r0) = make_float2(y0, y1);
+            }
+            CM_STAMP(si, 6);
+            wcur ^= 1;
+            __syncthreads();
+        }
+        CM_STAMP(si, 7);
+    }
+}
+
+// A[m][k] of a D x D stage -> fragment image: float4 index (w * (D / 8) + s) * 32 + lane holds
+// { A[16w+g][8s+t], A[16w+g+8][8s+t], A[16w+g][8s+t+4], A[16w+g+8][8s+t+4] },  g = lane / 4, t = lane % 4
+constexpr int kFragJobs = 128;
+struct FragArgs {
+    int dim;
+    int src_off[kFragJobs], dst_off[kFragJobs], ld[kFragJobs];
+    char trans[kFragJobs];          // 0: A[m][k] = src[m * ld + k];  1: A[m][k] = src[k * ld + m]
+};
+__global__ void __launch_bounds__(256) frag_kernel(const float* __restrict__ src_base, float* __restrict__ dst_base,
+                                                   const FragArgs a) {
+    const int job = blockIdx.y, D = a.dim, ks = D / 8;
+    const float* src = src_base + a.src_off[job];
+    float4* dst = reinterpret_cast<float4*>(dst_base + a.dst_off[job]);
+    const int ld = a.ld[job];
+    const bool tr = a.trans[job] != 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D * D / 4; i += gridDim.x * blockDim.x) {
+        const int lane = i & 31, s = (i >> 5) % ks, w = (i >> 5) / ks;
+        const int m = 16 * w + (lane >> 2), k = 8 * s + (lane & 3);
+        auto A = [&](int mm, int kk) { return tr ? src[(size_t)kk * ld + mm] : src[(size_t)mm * ld + kk]; };
+        dst[i] = make_float4(A(m, k), A(m + 8, k), A(m, k + 4), A(m + 8, k + 4));
+    }
+}
+
+template <int D>
+int chain_mma_launch_t(const ChainArgs& a, double bytes, cudaStream_t st) {
+    using C = MmaChainCfg<D>;
+    const size_t smem = C::smem_floats * sizeof(float);
+    PAMNET_TRY(func_smem_once(reinterpret_cast<const void*>(chain_mma_kernel<D>), smem));
+    prof_begin(KC_CHAIN, bytes, st);
+    launch_pdl(chain_mma_kernel<D>, dim3(ceil_div(a.n_rows, kR)), dim3(C::NT), smem, st, a);
+    prof_end(st);
+    PAMNET_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+bool chain_mma_enabled(int dim) {
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("PAMNET_CHAIN"); mode = (e && strcmp(e, "ffma") == 0) ? 0 : 1; }
+    return mode == 1 && (dim == 128 || dim == 64);
+}
+
+int chain_mma_launch(int dim, const ChainArgs& a, double bytes, cudaStream_t st) {
+    switch (dim) {
+        case 128: return chain_mma_launch_t<128>(a, bytes, st);
+        case 64:  return chain_mma_launch_t<64>(a, bytes, st);
+        default:
+            set_error("chain_mma: unsupported dim %d (64, 128)", dim);
+            return -1;
+    }
+}
+
+int frag_batch(const float* src_base, float* dst_base, int dim, const FragJob* jobs, int n_jobs, cudaStream_t st) {
+    for (int j0 = 0; j0 < n_jobs; j0 += kFragJobs) {
+        FragArgs a;
+        a.dim = dim;
+        const int n = (n_jobs - j0 < kFragJobs) ? n_jobs - j0 : kFragJobs;
+        for (int j = 0; j < n; ++j) {
+            const FragJob& jb = jobs[j0 + j];
+            a.src_off[j] = (int)jb.src_off; a.dst_off[j] = (int)jb.dst_off; a.ld[j] = jb.ld; a.trans[j] = (char)(jb.trans != 0);
+        }
+        dim3 grid(ceil_div(dim * dim / 4, 256), n);
+        prof_begin(KC_BASIS, 0.0, st);
+        frag_kernel<<<grid, 256, 0, st>>>(src_base, dst_base, a);
+        prof_end(st);
+        PAMNET_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+}  // namespace pamnet

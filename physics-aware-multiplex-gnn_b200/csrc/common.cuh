@@ -59,6 +59,9 @@ void count_launch();
         if (_r != 0) return _r;     \
     } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device); thread-safe (abi.cu)
+int func_smem_once(const void* func, size_t bytes);
+
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // ---- programmatic dependent launch (PDL) ----------------------------------------------------------------------------
@@ -91,12 +94,19 @@ static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a
 // ---------------------------------------------------------------------------------------------
 // device math
 // ---------------------------------------------------------------------------------------------
-// Exact expf + IEEE division by default: ncu attributes 27 % of the global message kernel's stall samples and ~10 % of the
-// node chain's to this line (profiles/README.md section f).  -DPAMNET_FAST_SILU (build with PAMNET_FAST_SILU=1) switches
-// to ex2.approx + rcp.approx (~2 ulp per evaluation, relative error of __expf grows with |x|): an experiment for the next
-// round, to be kept only if the parity ladder of tests/helpers.py still holds.
-#ifdef PAMNET_FAST_SILU
+// sigmoid for SiLU / SiLU'.  PAMNET_SILU_MODE (build time, build.py):
+//   0  exact expf + IEEE division (round 1): ncu attributed 27 % of the global message kernel's stall samples and 22 %
+//      of the node chain's to this line -- the division alone is ~10 dependent instructions with a slow-path branch;
+//   1  (default) exact expf, reciprocal by MUFU.RCP (__fdividef, <= 2 ulp): one more ulp per evaluation;
+//   2  ex2.approx + MUFU.RCP (relative error of __expf grows with |x|).
+// The parity ladder of tests/helpers.py is the gate for the default.
+#ifndef PAMNET_SILU_MODE
+#define PAMNET_SILU_MODE 1
+#endif
+#if PAMNET_SILU_MODE == 2
 __device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+#elif PAMNET_SILU_MODE == 1
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + expf(-x)); }
 #else
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 #endif

@@ -251,11 +251,11 @@ int mul_dsilu_launch(float* c, const float* z, int64_t n, cudaStream_t st) {
     return 0;
 }
 
-static int gemm_backend() {      // 0 = FFMA only, 1 = tensor cores where eligible
+static int gemm_backend() {      // 0 = FFMA only, 1 = round-1 tcgen05 kernel (gemm_tc.cu), 2 = persistent TMA kernel (gemm_tc2.cu)
     static int mode = -1;
     if (mode < 0) {
         const char* e = getenv("PAMNET_GEMM");
-        mode = (e && strcmp(e, "ffma") == 0) ? 0 : 1;
+        mode = (e && strcmp(e, "ffma") == 0) ? 0 : (e && strcmp(e, "tc1") == 0) ? 1 : 2;
     }
     return mode;
 }
@@ -269,7 +269,31 @@ static int gemm_small_backend() {      // PAMNET_GEMM_SMALL=0 sends skinny probl
     return on;
 }
 
+static int gemm_launch_impl(const GemmArgs& a, cudaStream_t st, bool allow_tc2);
+
 int gemm_launch(const GemmArgs& a, cudaStream_t st) {
+    // Slots the TMA kernel cannot take (one-row slots of the merged node-level weight-gradient launch, unaligned
+    // operands) go through the other kernels in a second launch; everything else stays together.
+    if (gemm_backend() == 2 && a.nslots > 1 && a.nslots <= kGemmMaxSlots) {
+        int n_ok = 0;
+        for (int i = 0; i < a.nslots; ++i) n_ok += gemm_tc2_slot_ok(a, i) ? 1 : 0;
+        if (n_ok > 0 && n_ok < a.nslots) {
+            GemmArgs ok = a, rest = a;
+            ok.nslots = rest.nslots = 0;
+            for (int i = 0; i < a.nslots; ++i) {
+                if (gemm_tc2_slot_ok(a, i)) ok.slot[ok.nslots++] = a.slot[i];
+                else rest.slot[rest.nslots++] = a.slot[i];
+            }
+            if (gemm_tc2_eligible(ok)) {
+                PAMNET_TRY(gemm_launch_impl(ok, st, true));
+                return gemm_launch_impl(rest, st, false);
+            }
+        }
+    }
+    return gemm_launch_impl(a, st, true);
+}
+
+static int gemm_launch_impl(const GemmArgs& a, cudaStream_t st, bool allow_tc2) {
     PAMNET_CHECK_ARG(a.nslots >= 1 && a.nslots <= kGemmMaxSlots, "gemm: nslots=%d", a.nslots);
     PAMNET_CHECK_ARG(a.nseg <= kGemmMaxSeg, "gemm: nseg=%d", a.nseg);
     PAMNET_CHECK_ARG(a.nseg == 0 || (a.mode == GEMM_NN && a.seg_len % BK == 0 && a.nseg * a.seg_len == a.K),
@@ -282,7 +306,8 @@ int gemm_launch(const GemmArgs& a, cudaStream_t st) {
     const int ks = a.ksplit > 1 ? a.ksplit : 1;
     double flops = 0.0;
     for (int i = 0; i < a.nslots; ++i) flops += 2.0 * (a.slot[i].m > 0 ? a.slot[i].m : a.M) * (double)a.N * a.K;
-    if (gemm_backend() == 1 && gemm_tc_eligible(a)) {
+    const bool use_tc2 = gemm_backend() == 2 && allow_tc2 && gemm_tc2_eligible(a);
+    if (use_tc2 || (gemm_backend() >= 1 && gemm_tc_eligible(a))) {
         // The tensor core adds each MMA into the fp32 accumulator with truncation, so the error of one
         // accumulation chain grows linearly with its length (measured: 1e-5 relative at K = 1536).  Long
         // reductions are therefore split into <= 128-deep chains per CTA and combined with fp32 atomics
@@ -303,7 +328,12 @@ int gemm_launch(const GemmArgs& a, cudaStream_t st) {
         }
         prof_begin(KC_GEMM, bytes, st);
         prof_flops(flops);
-        PAMNET_TRY(gemm_tc_launch(b, st));
+        int rc2 = use_tc2 ? gemm_tc2_launch(b, st) : 1;
+        if (rc2 < 0) return rc2;
+        if (rc2 == 1) {       // not the TMA kernel (backend choice, or its tensor-map table is full)
+            PAMNET_CHECK_ARG(gemm_tc_eligible(b), "gemm: problem fits neither tensor-core kernel");
+            PAMNET_TRY(gemm_tc_launch(b, st));
+        }
         prof_end(st);
         PAMNET_LAUNCH_CHECK();
         if (long_nn && a.epi == EPI_MUL_DSILU) {

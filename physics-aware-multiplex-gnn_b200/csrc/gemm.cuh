@@ -40,6 +40,7 @@ struct GemmArgs {
     int accumulate;       // C += (plain read-modify-write; slots/tiles never overlap)
     int ksplit;           // > 1: split K across blockIdx.y, results combined with atomicAdd into C (EPI_NONE only)
     int nslots;           // blockIdx.z
+    int precision;        // 0 / 3: fp32-accurate (3xTF32 on the tensor-core paths); 1: single-pass TF32 (gemm_tc2 only, opt-in)
     // K segmentation (GEMM_NN only): K = nseg*seg_len, segment s multiplies B = seg_B[s] (leading dim seg_ldb[s])
     int nseg, seg_len;
     GemmSlot slot[kGemmMaxSlots];
@@ -53,6 +54,11 @@ int gemm_launch(const GemmArgs& args, cudaStream_t st);
 bool gemm_tc_eligible(const GemmArgs& a);
 int gemm_tc_launch(const GemmArgs& a, cudaStream_t st);
 int tc_trace_read(long long* out, int n);
+
+// persistent TMA-fed tcgen05 kernel (gemm_tc2.cu): the default tensor-core path; PAMNET_GEMM=tc1 selects gemm_tc.cu
+bool gemm_tc2_eligible(const GemmArgs& a);
+bool gemm_tc2_slot_ok(const GemmArgs& a, int slot);
+int gemm_tc2_launch(const GemmArgs& a, cudaStream_t st);
 
 // skinny problems (N <= 32 rows-kernel, M <= 32 weight gradients), gemm_small.cu
 bool gemm_small_eligible(const GemmArgs& a);

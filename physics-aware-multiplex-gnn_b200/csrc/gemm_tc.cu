@@ -440,11 +440,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const GemmArgs args
 
 template <int MODE, int EPI>
 int launch_tc(const GemmArgs& a, dim3 grid, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        PAMNET_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
-        configured = true;
-    }
+    PAMNET_TRY(func_smem_once(reinterpret_cast<const void*>(gemm_tc_kernel<MODE, EPI>), kTcSmem));
     if (pdl_level() == 1) PAMNET_CUDA(launch_pdl(gemm_tc_kernel<MODE, EPI>, grid, dim3(TC_THREADS), kTcSmem, st, a));
     else gemm_tc_kernel<MODE, EPI><<<grid, TC_THREADS, kTcSmem, st>>>(a);
     return 0;

@@ -107,10 +107,13 @@ int build_param_layout(const pamnet_config_t& cfg, ModelP* mp) {
 namespace {
 
 struct HalfWs {
-    // transposed weights (k-major) for the forward chain; offsets into Ws::wt
+    // prepared weights of the node chains.  FFMA interpreter: k-major (transposed) copies for the forward chain, projB =
+    // the per-node blocks of the edge-MLP weights gathered contiguous for the backward chain, every other backward
+    // stage reads the parameter itself (*B == nullptr).  Tensor-core interpreter (chain_mma.cu): fragment images of
+    // A = W (forward: *T) and A = W^T (backward: *B) for every stage.
     float *x1T, *x2T, *resT[3][2], *outT[3], *projT;
-    float *projB;                           // [nP][D][D]: the per-node blocks of the edge-MLP weights, gathered contiguous
-                                            // for the backward chain (one bulk copy per stage instead of D strided ones)
+    float *x1B, *x2B, *resB[3][2], *outB[3];
+    float *projB;                           // [nP][D][D]
     // saved activations, each [N, D] unless noted
     float *P;                               // [N, nP*D]
     float *z_x1, *x1, *h, *z_x2, *a_x2;
@@ -163,6 +166,11 @@ size_t ws_layout(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, void* bas
         for (int s = 0; s < 3; ++s) h.outT[s] = take(D * D);
         h.projT = take(nP_of(hh) * D * D);
         h.projB = take(nP_of(hh) * D * D);
+        if (chain_mma_enabled((int)D)) {
+            h.x1B = take(D * D); h.x2B = take(D * D);
+            for (int r = 0; r < 3; ++r) for (int s = 0; s < 2; ++s) h.resB[r][s] = take(D * D);
+            for (int s = 0; s < 3; ++s) h.outB[s] = take(D * D);
+        }
     }
     if (weights_bytes) *weights_bytes = off;
     cur_base = base;
@@ -288,7 +296,7 @@ void add_pre_bwd(Prog& p, const float* params, const HalfP& hp, const HalfWs& hw
         cur ^= 1;
     }
     // nP is even -> cur == 0 holds g_x1
-    ChainStage& s = p.add(st_gemm(cur, 2, params + hp.x1.w, D, nullptr, 0));
+    ChainStage& s = p.add(st_gemm(cur, 2, hw.x1B ? hw.x1B : params + hp.x1.w, D, nullptr, 0));
     s.psrc = cur; s.zmul = hw.z_x1; s.save_src = hw.gz_x1; s.add_g = w.g_resx; s.ld_add = D;
     s.out_a = g_x_out; s.ld_out = D;
 }
@@ -305,9 +313,10 @@ void add_heads_bwd(Prog& p, const float* params, const HalfP& hp, const HalfWs& 
         s.psrc = src; s.zmul = z; s.save_src = save;
         return s;
     };
-    bwd(0, 1, hw.z_o[2], hw.gz_o[2], params + hp.out[2].w);
-    bwd(1, 0, hw.z_o[1], hw.gz_o[1], params + hp.out[1].w);
-    { ChainStage& s = bwd(0, 1, hw.z_o[0], hw.gz_o[0], params + hp.out[0].w); s.out_a = hw.g_heads; s.ld_out = D; }
+    auto wb = [&](const float* image, int64_t off) { return image ? image : params + off; };
+    bwd(0, 1, hw.z_o[2], hw.gz_o[2], wb(hw.outB[2], hp.out[2].w));
+    bwd(1, 0, hw.z_o[1], hw.gz_o[1], wb(hw.outB[1], hp.out[1].w));
+    { ChainStage& s = bwd(0, 1, hw.z_o[0], hw.gz_o[0], wb(hw.outB[0], hp.out[0].w)); s.out_a = hw.g_heads; s.ld_out = D; }
 }
 
 // backward of add_post_fwd; expects grad wrt x_out (from the next half) in slot 2 when has_gx; writes g_h and g_resx
@@ -317,15 +326,16 @@ void add_post_bwd(Prog& p, const float* params, const HalfP& hp, const HalfWs& h
         s.psrc = psrc; s.zmul = z; s.save_src = save; s.add_slot = add_slot;
         return s;
     };
+    auto wb = [&](const float* image, int64_t off) { return image ? image : params + off; };
     { ChainStage& s = p.add(st_load(1, hw.g_heads, D, D)); s.add_slot = has_gx ? 2 : -1; }   // slot1 = g_r3
-    bwd(1, 0, 2, hw.z_B[2], hw.gz_B[2], params + hp.res[2][1].w, -1);
-    bwd(2, 2, 0, hw.z_A[2], hw.gz_A[2], params + hp.res[2][0].w, 1);                 // slot0 = g_r2
-    bwd(0, 1, 2, hw.z_B[1], hw.gz_B[1], params + hp.res[1][1].w, -1);
-    { ChainStage& s = bwd(2, 2, 1, hw.z_A[1], hw.gz_A[1], params + hp.res[1][0].w, 0);    // slot1 = g_r1
+    bwd(1, 0, 2, hw.z_B[2], hw.gz_B[2], wb(hw.resB[2][1], hp.res[2][1].w), -1);
+    bwd(2, 2, 0, hw.z_A[2], hw.gz_A[2], wb(hw.resB[2][0], hp.res[2][0].w), 1);                 // slot0 = g_r2
+    bwd(0, 1, 2, hw.z_B[1], hw.gz_B[1], wb(hw.resB[1][1], hp.res[1][1].w), -1);
+    { ChainStage& s = bwd(2, 2, 1, hw.z_A[1], hw.gz_A[1], wb(hw.resB[1][0], hp.res[1][0].w), 0);    // slot1 = g_r1
       s.out_a = w.g_resx; s.ld_out = D; }
-    bwd(1, 0, 2, hw.z_B[0], hw.gz_B[0], params + hp.res[0][1].w, -1);
-    bwd(2, 2, 0, hw.z_A[0], hw.gz_A[0], params + hp.res[0][0].w, 1);                 // slot0 = g_x2
-    { ChainStage& s = bwd(0, 0, 1, hw.z_x2, hw.gz_x2, params + hp.x2.w, -1);
+    bwd(1, 0, 2, hw.z_B[0], hw.gz_B[0], wb(hw.resB[0][1], hp.res[0][1].w), -1);
+    bwd(2, 2, 0, hw.z_A[0], hw.gz_A[0], wb(hw.resB[0][0], hp.res[0][0].w), 1);                 // slot0 = g_x2
+    { ChainStage& s = bwd(0, 0, 1, hw.z_x2, hw.gz_x2, wb(hw.x2B, hp.x2.w), -1);
       s.out_a = w.g_h; s.ld_out = D; }
 }
 
@@ -407,6 +417,29 @@ namespace {
 int launch_weight_prep(const pamnet_config_t& cfg, const ModelP& mp, const Ws& w, const float* params, float* dst_base,
                        cudaStream_t st) {
     const int D = cfg.dim, H = 2 * cfg.n_layer;
+    if (chain_mma_enabled(D)) {
+        // fragment images (chain_mma.cu): forward stages multiply by A = W ([out][in]), backward stages by A = W^T
+        std::vector<FragJob> fj;
+        auto img = [&](int64_t src_off, int ld, float* fwd, float* bwd) {
+            fj.push_back(FragJob{src_off, (int64_t)(fwd - dst_base), ld, 0});
+            fj.push_back(FragJob{src_off, (int64_t)(bwd - dst_base), ld, 1});
+        };
+        for (int hh = 0; hh < H; ++hh) {
+            const HalfP& hp = half_params(mp, hh);
+            const HalfWs& hw = w.half[hh];
+            img(hp.x1.w, D, hw.x1T, hw.x1B);
+            img(hp.x2.w, D, hw.x2T, hw.x2B);
+            for (int r = 0; r < 3; ++r) for (int s = 0; s < 2; ++s) img(hp.res[r][s].w, D, hw.resT[r][s], hw.resB[r][s]);
+            for (int s = 0; s < 3; ++s) img(hp.out[s].w, D, hw.outT[s], hw.outB[s]);
+            for (int cblk = 0; cblk < nP_of(hh); ++cblk) {      // per-node blocks of the edge-MLP weights ([D][3D])
+                int64_t woff;
+                if (!is_local(hh)) woff = hp.m.w + cblk * D;
+                else woff = (cblk < 2 ? hp.m_ji.w : hp.m_kj.w) + (cblk & 1) * D;
+                img(woff, 3 * D, hw.projT + (size_t)cblk * D * D, hw.projB + (size_t)cblk * D * D);
+            }
+        }
+        return frag_batch(params, dst_base, D, fj.data(), (int)fj.size(), st);
+    }
     std::vector<TransposeJob> jobs;
     auto job = [&](int64_t src_off, int rows, int cols, int ld, float* dst) {
         jobs.push_back(TransposeJob{src_off, (int64_t)(dst - dst_base), rows, cols, ld, 0});
