@@ -171,15 +171,41 @@ __global__ void __launch_bounds__(kChainKS * D / 2, 1) chain_kernel(const ChainA
             }
             __syncthreads();
         } else if (st.op == CH_HEADS_BWD) {
-            // grad of o3 from the two heads: g_att * W + g_out * W_out.weight
+            // grad of o3 from the two heads: g_att * W + g_out * W_out.weight.  Optionally (zmul = the saved o3 activations)
+            // also the heads' own weight gradients dW = o3^T g_att, dW_out = o3^T g_out, db_out = sum g_out: the CTA folds
+            // its 8 rows with shuffles and adds one partial per column to global memory (they used to be two one-row
+            // slots of the node-level weight-gradient GEMM launch).
             float* d = slot_ptr(st.dst);
             const bool live = row0 + er < n_rows;
             const float ga = live ? st.g0[row0 + er] : 0.f, go = live ? st.g1[row0 + er] : 0.f;
+            const float* W = st.W; const float* Wo = st.bias; const float* o3 = st.zmul;
+            float* gW = st.out_z; float* gWo = st.out_a; float* gbo = st.save_src;
             for (int c4 = ec; c4 < D / 4; c4 += NT / R) {
-                const float4 w = ld4(st.W + c4 * 4), wo = ld4(st.bias + c4 * 4);
+                const float4 w = ld4(W + c4 * 4), wo = ld4(Wo + c4 * 4);
                 float* q = d + (c4 * 4) * R + er;
                 q[0] = ga * w.x + go * wo.x; q[R] = ga * w.y + go * wo.y;
                 q[2 * R] = ga * w.z + go * wo.z; q[3 * R] = ga * w.w + go * wo.w;
+                if (o3) {
+                    const float4 a = live ? ld4(o3 + (size_t)(row0 + er) * D + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float pa[4] = {ga * a.x, ga * a.y, ga * a.z, ga * a.w}, po[4] = {go * a.x, go * a.y, go * a.z, go * a.w};
+#pragma unroll
+                    for (int o = 1; o < R; o <<= 1)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            pa[j] += __shfl_xor_sync(0xffffffffu, pa[j], o);
+                            po[j] += __shfl_xor_sync(0xffffffffu, po[j], o);
+                        }
+                    if (er == 0) {
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gW + c4 * 4), "f"(pa[0]), "f"(pa[1]), "f"(pa[2]), "f"(pa[3]) : "memory");
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gWo + c4 * 4), "f"(po[0]), "f"(po[1]), "f"(po[2]), "f"(po[3]) : "memory");
+                    }
+                }
+            }
+            if (o3 && gbo && ec == 0) {          // ec == 0: the 8 lanes t = 0..7
+                float sgo = go;
+#pragma unroll
+                for (int o = 1; o < R; o <<= 1) sgo += __shfl_xor_sync(0x000000ffu, sgo, o);
+                if (er == 0) atomicAdd(gbo, sgo);
             }
             __syncthreads();
         } else if (st.op == CH_DOT2) {
@@ -402,6 +428,9 @@ int chain_launch(int dim, const ChainArgs& args, cudaStream_t st) {
     }
     ChainArgs a;
     const double bytes = chain_prepare(dim, args, &a);
+    static int node_mlp = -1;      // PAMNET_NODE_MLP=tf32: single-pass TF32 node MLPs (opt-in reduced precision, configs[2])
+    if (node_mlp < 0) { const char* e = getenv("PAMNET_NODE_MLP"); node_mlp = (e && strcmp(e, "tf32") == 0) ? 1 : 0; }
+    a.precision = node_mlp;
     if (chain_mma_enabled(dim)) return chain_mma_launch(dim, a, bytes, st);
     switch (dim) {
         case 128: return chain_launch_t<128>(a, bytes, st);

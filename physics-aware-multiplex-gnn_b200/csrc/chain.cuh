@@ -46,6 +46,8 @@ struct ChainStage {
 struct ChainArgs {
     int n_rows;
     int n_stages;
+    int precision;      // 0: fp32-accurate (3xTF32 / FFMA); 1: single-pass TF32 (tensor-core interpreter only; chain_launch sets it
+                        // from PAMNET_NODE_MLP=tf32 -- the reduced-precision node-MLP path of BASELINE.json configs[2])
     ChainStage st[kChainMaxStages];
 };
 

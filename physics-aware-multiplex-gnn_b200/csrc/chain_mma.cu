@@ -199,15 +199,41 @@ __global__ void __launch_bounds__(MmaChainCfg<D>::NT, 1) chain_mma_kernel(const 
             }
             __syncthreads();
         } else if (st.op == CH_HEADS_BWD) {
+            // grad of o3 from the two heads: g_att * W + g_out * W_out.weight.  Optionally (zmul = the saved o3 activations)
+            // also the heads' own weight gradients dW = o3^T g_att, dW_out = o3^T g_out, db_out = sum g_out: the CTA folds
+            // its 8 rows with shuffles and adds one partial per column to global memory (they used to be two one-row
+            // slots of the node-level weight-gradient GEMM launch).
             float* d = slot_ptr(st.dst);
             const bool live = row0 + er < n_rows;
             const float ga = live ? st.g0[row0 + er] : 0.f, go = live ? st.g1[row0 + er] : 0.f;
-            const float* W = st.W; const float* Wo = st.bias;
+            const float* W = st.W; const float* Wo = st.bias; const float* o3 = st.zmul;
+            float* gW = st.out_z; float* gWo = st.out_a; float* gbo = st.save_src;
             for (int c4 = ec; c4 < D / 4; c4 += EC) {
                 const float4 w = ld4(W + c4 * 4), wo = ld4(Wo + c4 * 4);
                 float* q = d + (c4 * 4) * R + er;
                 q[0] = ga * w.x + go * wo.x; q[R] = ga * w.y + go * wo.y;
                 q[2 * R] = ga * w.z + go * wo.z; q[3 * R] = ga * w.w + go * wo.w;
+                if (o3) {
+                    const float4 a = live ? ld4(o3 + (size_t)(row0 + er) * D + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float pa[4] = {ga * a.x, ga * a.y, ga * a.z, ga * a.w}, po[4] = {go * a.x, go * a.y, go * a.z, go * a.w};
+#pragma unroll
+                    for (int o = 1; o < R; o <<= 1)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            pa[j] += __shfl_xor_sync(0xffffffffu, pa[j], o);
+                            po[j] += __shfl_xor_sync(0xffffffffu, po[j], o);
+                        }
+                    if (er == 0) {
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gW + c4 * 4), "f"(pa[0]), "f"(pa[1]), "f"(pa[2]), "f"(pa[3]) : "memory");
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gWo + c4 * 4), "f"(po[0]), "f"(po[1]), "f"(po[2]), "f"(po[3]) : "memory");
+                    }
+                }
+            }
+            if (o3 && gbo && ec == 0) {          // ec == 0: the 8 lanes t = 0..7
+                float sgo = go;
+#pragma unroll
+                for (int o = 1; o < R; o <<= 1) sgo += __shfl_xor_sync(0x000000ffu, sgo, o);
+                if (er == 0) atomicAdd(gbo, sgo);
             }
             __syncthreads();
         } else if (st.op == CH_DOT2) {
@@ -295,6 +321,16 @@ __global__ void __launch_bounds__(MmaChainCfg<D>::NT, 1) chain_mma_kernel(const 
                 for (int j = 0; j < 4; ++j) acc_m[p][j] = acc_x[p][j] = acc_y[p][j] = 0.f;
             const float4* wf = reinterpret_cast<const float4*>(wbuf + wcur * D * D) + ((size_t)mt * KS + kh * (KS / 2)) * 32 + lane;
             const float* bp = in + (kh * (KS / 2) * 8 + tq) * R + g;
+            if (args.precision == 1) {
+                // single-pass TF32: the tensor core reads the fp32 bit patterns and ignores the 13 low mantissa bits
+#pragma unroll
+                for (int s = 0; s < KS / 2; ++s) {
+                    const float4 av = wf[s * 32];
+                    const uint32_t a4[4] = {__float_as_uint(av.x), __float_as_uint(av.y), __float_as_uint(av.z), __float_as_uint(av.w)};
+                    const uint32_t b2[2] = {__float_as_uint(bp[(8 * s) * R]), __float_as_uint(bp[(8 * s + 4) * R])};
+                    mma_tf32(acc_m[s & 1], a4, b2);
+                }
+            } else
 #pragma unroll
             for (int s = 0; s < KS / 2; ++s) {
                 const float4 av = wf[s * 32];

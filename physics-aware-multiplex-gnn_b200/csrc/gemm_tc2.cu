@@ -18,7 +18,8 @@
 //     up to four 32-deep chunks ahead across tile boundaries;
 //   * precision 1 (GemmArgs::precision == 1, opt-in): single-pass TF32 straight from the TMA tiles, no converters
 //     (the reduced-precision node-MLP path of BASELINE.json configs[2]; >= bf16's 8-bit mantissa).
-// Warp roles (320 threads): 0 TMA producer, 1 MMA issuer + TMEM owner, 2-5 converters, 6-9 epilogue.
+// Warp roles (448 threads): 0 TMA producer, 1 MMA issuer + TMEM owner, 2-5 converters, 6-13 epilogue (two warps per
+// TMEM lane quarter, 64 columns each).
 #include "gemm.cuh"
 
 #include <cuda.h>
@@ -28,18 +29,37 @@
 #include <unordered_map>
 
 namespace pamnet {
+// optional clock64 timeline of CTA 0 (-DPAMNET_TC_TRACE; tools/gemm_trace.py).  Slots: 0 start, 1 setup done, 2 pdl_wait
+// passed; per chunk c < 12: 8+4c TMA issued, 9+4c converters saw the data, 10+4c converted, 11+4c MMAs issued;
+// per work item i < 4: 64+4i accumulator full (epilogue), 65+4i TMEM drained, 66+4i stores issued
+#ifdef PAMNET_TC_TRACE
+__device__ long long g_tc2_trace[96];
+#define T2_STAMP(i) do { if (blockIdx.x == 0 && (i) < 96) g_tc2_trace[(i)] = clock64(); } while (0)
+#else
+#define T2_STAMP(i) do { } while (0)
+#endif
+int tc2_trace_read(long long* out, int n) {
+#ifdef PAMNET_TC_TRACE
+    PAMNET_CUDA(cudaMemcpyFromSymbol(out, g_tc2_trace, sizeof(long long) * (n < 96 ? n : 96)));
+    return 0;
+#else
+    (void)out; (void)n;
+    set_error("built without PAMNET_TC_TRACE");
+    return -1;
+#endif
+}
 namespace {
 
 constexpr int TM = 128, TN = 128, TK = 32;
-constexpr int kRaw = 4, kLo = 2;                  // ring depths (32-deep chunks)
+constexpr int kRaw = 3, kLo = 2;                  // ring depths (32-deep chunks)
 constexpr int kTile = TM * TK * 4;                // 16 KB: one operand tile of one chunk
 constexpr int kStage = 2 * kTile;                 // A | B
-constexpr int kThreads = 320;
-constexpr int kConvWarp0 = 2, kConvThreads = 128, kEpiWarp0 = 6, kEpiThreads = 128;
+constexpr int kThreads = 448;
+constexpr int kConvWarp0 = 2, kConvThreads = 128, kEpiWarp0 = 6, kEpiWarps = 8, kEpiThreads = kEpiWarps * 32;
 constexpr int kStageLd = 36;                      // floats: row stride of the per-warp epilogue staging (conflict-free 128-bit)
 constexpr int kEpiStage = 32 * kStageLd * 4;      // bytes per epilogue warp
-constexpr size_t kSmem = 1024 /* alignment slack */ + (size_t)kRaw * kStage + (size_t)kLo * kStage + 4 * kEpiStage;
-constexpr int kTmemCols = 256;                    // two accumulators
+constexpr size_t kSmem = 1024 /* alignment slack */ + (size_t)kRaw * kStage + (size_t)kLo * kStage + kEpiWarps * kEpiStage;
+constexpr int kTmemCols = 512;                    // two buffers x (main | cross-term) accumulators of 128 columns
 
 struct Slot2 {
     const float* bias;
@@ -97,20 +117,25 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-    uint32_t r[32];
+// 32 lanes x 32 columns -> v[32] (thread = lane / row); the caller issues tcgen05.wait::ld before reading v
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+          "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]),
+          "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]),
+          "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
         : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// orders later uses of v[] after the tcgen05.wait::ld that precedes this (volatile asms keep their relative order; without
+// it the compiler may hoist register-only arithmetic on v[] above the wait)
+__device__ __forceinline__ void reg_fence32(float* v) {
+    asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]),
+                      "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]),
+                      "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]),
+                      "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31]));
 }
 __device__ __forceinline__ void red4(float* p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -118,7 +143,8 @@ __device__ __forceinline__ void red4(float* p, float a, float b, float c, float 
 __device__ __forceinline__ bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // lo part of the 3xTF32 split against the HARDWARE's hi = trunc_tf32(x): x - trunc(x) is exact in fp32 (<= 13
-// significant bits); rounding it to tf32 (instead of letting the tensor core truncate it too) keeps the split unbiased
+// significant bits); rounding it to tf32 here (instead of letting the tensor core truncate it too) keeps the split
+// unbiased: measured on the configs[1] parity ladder, worst gradient 0.28 of the limit with, 0.52 without
 __device__ __forceinline__ float lo_of(float x) {
     const float d = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
     return __uint_as_float((__float_as_uint(d) + 0x1000u) & 0xFFFFE000u);
@@ -173,6 +199,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
     __shared__ float s_colsum[TM];
 
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    if (t == 0) T2_STAMP(0);
     // SWIZZLE_128B tiles need 1024 B alignment
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     unsigned char* raw_ring = smem;                                   // [kRaw][A 16 KB | B 16 KB]
@@ -180,6 +207,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
     unsigned char* epi_stage = lo_ring + (size_t)kLo * kStage;        // [4 warps][32][kStageLd] floats
 
     const bool three = args.precision != 1;
+    const bool four = args.precision == 4;        // + A_lo * B_lo (hi = trunc leaves |lo| < 2^-10 |x|: the term is ~2^-22 |ab| rms)
     const bool a_mn = args.mode == GEMM_TN, b_mn = args.mode != GEMM_NT;
 
     if (t == 0) {
@@ -198,8 +226,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_s;
+    if (t == 0) T2_STAMP(1);
 
-    pdl_wait();          // operands (and zeroed split-K outputs) come from earlier kernels of the stream
+    pdl_wait();
+    if (t == 0) T2_STAMP(2);          // operands (and zeroed split-K outputs) come from earlier kernels of the stream
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -213,6 +243,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
                 for (int k0 = k_begin; k0 < k_end; k0 += TK, ++c) {
                     const int s = c % kRaw;
                     mbar_wait(&raw_free[s], ((c / kRaw) & 1) ^ 1);
+                    if (c < 12) T2_STAMP(8 + 4 * c);
                     mbar_expect_tx(&full_bar[s], kStage);
                     const uint32_t sa = smem_u32(raw_ring + (size_t)s * kStage), sb = sa + kTile;
                     const CUtensorMap* ma = &args.maps[sl.map_a];
@@ -255,15 +286,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
                 const int acc = it & 1;
                 mbar_wait(&acc_free[acc], ((it >> 1) & 1) ^ 1);          // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t d = tmem + (uint32_t)(acc * TN);
+                // The tensor core adds every MMA into the fp32 accumulator with truncation: the error of a chain grows with
+                // the number of accumulations and is biased (measured: the 48 accumulations of a 128-deep 3xTF32 chain put
+                // the weight gradients at 0.8 of the parity limit, 20 x the error of an FFMA GEMM).  The hi * hi products
+                // therefore get an accumulator of their own (16 accumulations per 128-deep chain); the cross terms, 2^-11
+                // of its magnitude, go to a second one and are added in the epilogue with round-to-nearest.
+                const uint32_t d = tmem + (uint32_t)(acc * 2 * TN), dx = d + TN;
                 bool first = true;
                 for (int k0 = k_begin; k0 < k_end; k0 += TK, ++c) {
                     const int s = c % kRaw, l = cc % kLo;
                     mbar_wait(&full_bar[s], (c / kRaw) & 1);             // TMA data landed
-                    if (use_conv) {
-                        mbar_wait(&conv_bar[l], (cc / kLo) & 1);         // acquire: the converters' st.shared
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
-                    }
+                    if (use_conv) mbar_wait(&conv_bar[l], (cc / kLo) & 1);   // acquire: the converters' (proxy-fenced) st.shared
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t ra = smem_u32(raw_ring + (size_t)s * kStage) >> 4, rb = ra + (kTile >> 4);
                     const uint32_t la = smem_u32(lo_ring + (size_t)l * kStage) >> 4, lb = la + (kTile >> 4);
@@ -272,15 +305,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
                         const uint64_t a_hi = da | ((ra + ks * a_step) & 0x3FFF), b_hi = db | ((rb + ks * b_step) & 0x3FFF);
                         if (three) {
                             const uint64_t a_lo = da | ((la + ks * a_step) & 0x3FFF), b_lo = db | ((lb + ks * b_step) & 0x3FFF);
-                            umma_tf32(d, a_lo, b_hi, idesc, first ? 0u : 1u);       // small terms first
-                            umma_tf32(d, a_hi, b_lo, idesc, 1u);
-                            umma_tf32(d, a_hi, b_hi, idesc, 1u);
+                            if (four) umma_tf32(dx, a_lo, b_lo, idesc, first ? 0u : 1u);
+                            umma_tf32(dx, a_lo, b_hi, idesc, (first && !four) ? 0u : 1u);
+                            umma_tf32(dx, a_hi, b_lo, idesc, 1u);
+                            umma_tf32(d, a_hi, b_hi, idesc, first ? 0u : 1u);
                         } else {
                             umma_tf32(d, a_hi, b_hi, idesc, first ? 0u : 1u);
                         }
                         first = false;
                     }
                     umma_commit(&raw_free[s]);
+                    if (c < 12) T2_STAMP(11 + 4 * c);
                     if (use_conv) { umma_commit(&lo_free[l]); ++cc; }
                 }
                 umma_commit(&acc_full[acc]);
@@ -308,6 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
             for (int k0 = k_begin; k0 < k_end; k0 += TK, ++c, ++cc) {
                 const int s = c % kRaw, l = cc % kLo;
                 mbar_wait(&full_bar[s], (c / kRaw) & 1);                 // TMA data landed
+                if (ct == 0 && c < 12) T2_STAMP(9 + 4 * c);
                 const float4* ra = reinterpret_cast<const float4*>(raw_ring + (size_t)s * kStage);
                 mbar_wait(&lo_free[l], ((cc / kLo) & 1) ^ 1);            // the MMAs of the chunk that last used this slot are done
                 if (three) {
@@ -327,7 +363,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
 #pragma unroll
                         for (int q = 0; q < 4; ++q) la[ct + 128 * (j + q)] = lo4(v[q]);
                     }
+                    // writer-side proxy fence: these generic-proxy stores are read by the tensor core (async proxy).  The
+                    // converters have nothing else in flight, so it only waits for the 16 stores above; executed by the
+                    // MMA thread instead it sat on the MMA issue path of every chunk (~400 cycles, clock64 trace).
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     mbar_arrive(&conv_bar[l]);
+                    if (ct == 0 && c < 12) T2_STAMP(10 + 4 * c);
                 } else {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -354,7 +395,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
         }
     } else {
         // ================= epilogue =================
-        const int q = warp & 3;                               // TMEM lane quarter this warp may read
+        // warp (q, half): TMEM lanes [32 q, +32) x columns [64 half, +64) of the tile
+        const int q = warp & 3, half = (warp - kEpiWarp0) >> 2;
         float* stg = reinterpret_cast<float*>(epi_stage + (size_t)(warp - kEpiWarp0) * kEpiStage);
         const int N = args.N, epi = args.epi;
         int it = 0;
@@ -377,6 +419,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
             const int acc = it & 1;
             mbar_wait(&acc_full[acc], (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (t == kEpiWarp0 * 32 && it < 4) T2_STAMP(64 + 4 * it);
             if (id == last_id) pdl_trigger();     // the next kernel of the stream may set itself up while the last tile is written back
             float* const C = sl.C;
             float* const C2 = sl.C2;
@@ -387,12 +430,27 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
                                (epi != EPI_MUL_DSILU || (al16(Z) && ldz % 4 == 0));
             const bool splitk = epi == EPI_NONE && args.ksplit > 1;
 #pragma unroll 1
-            for (int cb = 0; cb < TN / 32; ++cb) {
+            for (int cb = 2 * half; cb < 2 * half + 2; ++cb) {
                 float v[32];
-                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + cb * 32), v);
-                if (cb == TN / 32 - 1) {          // everything of this accumulator is in registers: hand it back
+                const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * TN + cb * 32);
+                if (three) {                      // main + cross-term accumulators: both loads in flight, one wait
+                    float vx[32];
+                    tmem_ld32_nowait(ta, v);
+                    tmem_ld32_nowait(ta + TN, vx);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    reg_fence32(v);
+                    reg_fence32(vx);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] += vx[i];
+                } else {
+                    tmem_ld32_nowait(ta, v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    reg_fence32(v);
+                }
+                if (cb == 2 * half + 1) {         // everything of this accumulator is in registers: hand it back
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     mbar_arrive(&acc_free[acc]);
+                    if (t == kEpiWarp0 * 32 && it < 4) T2_STAMP(65 + 4 * it);
                 }
                 __syncwarp();                      // previous block's readers are done with the staging buffer
 #pragma unroll
@@ -443,6 +501,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
                     else for (int j = 0; j < nv; ++j) C[ci + j] = x[j];
                 }
             }
+            if (t == kEpiWarp0 * 32 && it < 4) T2_STAMP(66 + 4 * it);
             ++it;
         }
     }
@@ -584,7 +643,9 @@ int gemm_tc2_launch(const GemmArgs& a, cudaStream_t st) {
     Args2 b;
     memset(&b, 0, sizeof(b));
     b.M = a.M; b.N = a.N; b.K = a.K; b.mode = a.mode; b.epi = a.epi; b.ksplit = a.ksplit > 1 ? a.ksplit : 1;
-    b.nslots = a.nslots; b.precision = a.precision == 1 ? 1 : 3; b.nseg = a.nseg; b.seg_len = a.seg_len;
+    static int n_prod = -1;       // PAMNET_TC2_PROD=3: drop the lo * lo product (see kernel)
+    if (n_prod < 0) { const char* e = getenv("PAMNET_TC2_PROD"); n_prod = (e && e[0] == '3') ? 3 : 4; }
+    b.nslots = a.nslots; b.precision = a.precision == 1 ? 1 : n_prod; b.nseg = a.nseg; b.seg_len = a.seg_len;
     b.tiles_m = ceil_div(a.M, TM); b.tiles_n = ceil_div(a.N, TN);
     b.total = b.nslots * b.ksplit * b.tiles_m * b.tiles_n;
     const bool a_mn = a.mode == GEMM_TN, b_mn = a.mode != GEMM_NT;

@@ -304,9 +304,11 @@ void add_pre_bwd(Prog& p, const float* params, const HalfP& hp, const HalfWs& hw
 // backward of add_heads_fwd: grad of the half's x output through the heads -> hw.g_heads (and the grad_z of mlp_out).
 // Depends only on the readout gradient, so all halves run up front, off the critical path.
 void add_heads_bwd(Prog& p, const float* params, const HalfP& hp, const HalfWs& hw, int D, const float* g_att,
-                   const float* g_out) {
+                   const float* g_out, float* gp) {
     ChainStage hb = stage_zero();
     hb.op = CH_HEADS_BWD; hb.dst = 0; hb.g0 = g_att; hb.g1 = g_out; hb.W = params + hp.W; hb.bias = params + hp.W_out.w;
+    // the heads' own weight gradients (global_message_passing.py:47-48): dW = o3^T g_att, dW_out = o3^T g_out, db_out = sum g_out
+    hb.zmul = hw.a_o[2]; hb.out_z = gp + hp.W; hb.out_a = gp + hp.W_out.w; hb.save_src = gp + hp.W_out.b;
     p.add(hb);
     auto bwd = [&](int src, int dst, const float* z, float* save, const float* W) -> ChainStage& {
         ChainStage& s = p.add(st_gemm(src, dst, W, D, nullptr, 0));
@@ -844,7 +846,7 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
     PAMNET_TRY(sc.order(st, s3));
     for (int hh = H - 1; hh >= 0; --hh) {
         Prog ph((int)N);
-        add_heads_bwd(ph, params, half_params(mp, hh), w.half[hh], D, w.g_att + (size_t)hh * N, w.g_out + (size_t)hh * N);
+        add_heads_bwd(ph, params, half_params(mp, hh), w.half[hh], D, w.g_att + (size_t)hh * N, w.g_out + (size_t)hh * N, gp);
         PAMNET_TRY(chain_launch(D, ph.a, s3));
         PAMNET_TRY(sc.record(s3, &ev_heads[hh]));
     }
@@ -853,7 +855,7 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
     // ONE launch per half for every weight gradient that is a [D, D] (or [1, D]) reduction over the nodes:
     //  * the post-chain of half `hh` (hh >= 0) and mlp_x1 of half `x1_half` (x1_half >= 0), whose grad_z a finished
     //    chain kernel has written;
-    //  * the two heads of half hh: dW = o3^T g_att, dW_out = o3^T g_out (+ bias) -- one-row slots (GemmSlot::m);
+    //  (the two heads' own gradients dW = o3^T g_att, dW_out = o3^T g_out are produced by the heads chain: add_heads_bwd)
     //  * the per-node halves of the edge MLPs of half `proj_half`: dW[:, cD:(c+1)D] = g_P_c^T x1.
     auto node_wgrads = [&](int hh, int x1_half, int proj_half, cudaStream_t s) -> int {
         std::vector<GemmSlot> sl;
@@ -875,11 +877,6 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
             lin(hw.gz_o[0], hw.r[2], hp.out[0]);
             lin(hw.gz_o[1], hw.a_o[0], hp.out[1]);
             lin(hw.gz_o[2], hw.a_o[1], hp.out[2]);
-            GemmSlot h1 = slot(w.g_att + (size_t)hh * N, 1, hw.a_o[2], D, gp + hp.W, D);
-            GemmSlot h2 = slot(w.g_out + (size_t)hh * N, 1, hw.a_o[2], D, gp + hp.W_out.w, D, nullptr, gp + hp.W_out.b);
-            h1.m = h2.m = 1;
-            sl.push_back(h1);
-            sl.push_back(h2);
         }
         if (proj_half >= 0) {
             const HalfWs& hw = w.half[proj_half];
