@@ -1,9 +1,11 @@
 #!/usr/bin/env python
-"""bench.py -- molecules/s of one PAMNet training step (forward + L1 loss + backward, no optimizer) on
-synthetic QM9-shaped batches, BASELINE.json's metric and config (dim=128, n_layer=6, batch 32 per GPU).
+"""bench.py -- one PAMNet training step (forward + L1 loss + backward, no optimizer) on synthetic / fixture batches,
+BASELINE.json's metric.
 
-    python bench.py [--gpus N --steps K --warmup W]            our CUDA path (one rank per GPU under torchrun)
-    python bench.py --impl reference [...]                     the reference's CPU algorithm (oracle port)
+    python bench.py [--gpus N --steps K --warmup W]            configs[1]: QM9 dim=128 L=6 bs=32 per GPU (the headline)
+    python bench.py --config c3                                 configs[2]: bs=256, reduced-precision tensor-core node MLPs
+    python bench.py --config c4                                 configs[3]: RNA-Puzzles dim=16 L=1, the first 8 natives
+    python bench.py --impl reference [...]                      the reference's CPU algorithm (oracle port) on the host cores
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what every key means.
 """
@@ -19,7 +21,6 @@ import types
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "molecules/sec PAMNet fwd+bwd (QM9 dim=128 L=6 bs=32)"
 UNIT = "molecules/s"
 
 
@@ -29,31 +30,65 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch-size", type=int, default=32)
-    ap.add_argument("--dim", type=int, default=128)
-    ap.add_argument("--n-layer", type=int, default=6)
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4"],
+                    help="BASELINE.json configs[1] (default), configs[2] (bs=256, reduced-precision node MLPs), configs[3] (RNA)")
+    ap.add_argument("--batch-size", type=int, default=None)
+    ap.add_argument("--dim", type=int, default=None)
+    ap.add_argument("--n-layer", type=int, default=None)
+    ap.add_argument("--node-mlp", default=None, choices=["f32", "tf32"],
+                    help="node-MLP precision: f32 (3xTF32, fp32-accurate; default except --config c3) or tf32 (single pass)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
-    ap.add_argument("--fused-loss", action="store_true",
-                    help="opt-in: L1 loss and its gradient in one launch (pamnet_b200.ops.l1_loss) instead of F.l1_loss")
-    ap.add_argument("--prefetch", action="store_true",
-                    help="opt-in: build the NEXT step's graph plan on a side stream right after backward (model.prefetch); "
-                         "every step still contains one H2D copy (e2e) and one front end")
-    return ap.parse_args()
+    ap.add_argument("--torch-loss", action="store_true", help="F.l1_loss instead of the fused loss + gradient launch")
+    ap.add_argument("--no-prefetch", action="store_true",
+                    help="build every step's graph plan inline instead of on a side stream behind the previous backward")
+    ap.add_argument("--plain-allreduce", action="store_true", help="one all-reduce after backward instead of overlapped buckets")
+    a = ap.parse_args()
+    d = {"c2": (32, 128, 6), "c3": (256, 128, 6), "c4": (8, 16, 1)}[a.config]
+    a.batch_size = a.batch_size or d[0]
+    a.dim = a.dim or d[1]
+    a.n_layer = a.n_layer or d[2]
+    if a.node_mlp is None:
+        a.node_mlp = "tf32" if a.config == "c3" else "f32"
+    return a
+
+
+def metric_name(args):
+    if args.config == "c4":
+        return "graphs/sec PAMNet fwd+bwd (RNA-Puzzles dim=16 L=1 bs=8, first 8 native structures)"
+    return f"molecules/sec PAMNet fwd+bwd (QM9 dim={args.dim} L={args.n_layer} bs={args.batch_size})"
 
 
 def model_cfg(args):
+    if args.config == "c4":
+        return types.SimpleNamespace(dataset="rna_native", dim=args.dim, n_layer=args.n_layer, cutoff_l=2.6, cutoff_g=20.0,
+                                     flow="target_to_source")
     return types.SimpleNamespace(dataset="QM9", dim=args.dim, n_layer=args.n_layer, cutoff_l=5.0, cutoff_g=5.0,
                                  flow="source_to_target")
+
+
+def make_batch(args, seed):
+    """Host batch of the configuration (+ a state dict to load, or None for seeded default init)."""
+    import torch
+    from pamnet_b200.data import Batch, synthetic_qm9_batch
+    if args.config == "c4":
+        gold = torch.load(os.path.join(ROOT, "tests", "golden", "rna_c4.pt"), map_location="cpu", weights_only=False)
+        n = min(args.batch_size, 8)
+        sizes = gold["sizes"][:n]
+        tot = sum(sizes)
+        b = Batch(x=gold["x"][:tot].clone(), batch=torch.repeat_interleave(torch.arange(n), torch.tensor(sizes)),
+                  y=gold["y"][:n].clone())
+        return b, gold["state_dict"]
+    return synthetic_qm9_batch(args.batch_size, seed=seed), None
 
 
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's algorithm restated (oracle/), all host threads
 # ------------------------------------------------------------------------------------------------
-def cpu_step_fn(cfg, batch, seed=0):
+def cpu_step_fn(cfg, batch, sd=None, seed=0):
     import torch
     from oracle import pamnet_oracle as O
-    sd = O.init_state_dict(cfg, seed=seed)
+    sd = sd if sd is not None else O.init_state_dict(cfg, seed=seed)
     leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     consts = O.sbf_constants()
 
@@ -67,19 +102,35 @@ def cpu_step_fn(cfg, batch, seed=0):
     return step
 
 
-def time_cpu(cfg, n_graphs, budget_s, steps=None, warmup=1):
-    """Bounded sample: `n_graphs` molecules per step; returns (molecules/s, steps timed, cores)."""
+def sub_batch(args, batch, n):
+    """The first n graphs of `batch` (bounded CPU sample)."""
     import torch
-    from pamnet_b200.data import synthetic_qm9_batch
+    from pamnet_b200.data import Batch
+    if n >= int(batch.batch.max()) + 1:
+        return batch
+    keep = batch.batch < n
+    f = {"x": batch.x[keep], "batch": batch.batch[keep], "y": batch.y[:n]}
+    if getattr(batch, "pos", None) is not None:
+        f["pos"] = batch.pos[keep]
+        nk = int(keep.sum())
+        e = batch.edge_index
+        f["edge_index"] = e[:, (e[0] < nk) & (e[1] < nk)]
+    return Batch(**f)
+
+
+def time_cpu(args, cfg, n_graphs, steps, warmup=1, budget_s=None):
+    """Bounded sample: the first `n_graphs` graphs of the workload per step; returns (units/s, steps timed, cores, s/step)."""
+    import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    batch = synthetic_qm9_batch(n_graphs, seed=0)
-    step = cpu_step_fn(cfg, batch)
+    batch, sd = make_batch(args, seed=0)
+    batch = sub_batch(args, batch, n_graphs)
+    step = cpu_step_fn(cfg, batch, sd)
     for _ in range(warmup):
         step()
     times = []
-    t_end = time.perf_counter() + budget_s
-    while (steps is None and time.perf_counter() < t_end and len(times) < 30) or (steps is not None and len(times) < steps):
+    t_end = time.perf_counter() + (budget_s or 1e9)
+    while len(times) < steps and (time.perf_counter() < t_end or not times):
         t0 = time.perf_counter()
         step()
         times.append(time.perf_counter() - t0)
@@ -92,39 +143,50 @@ def run_reference(args):
     if rank != 0:
         return
     cfg = model_cfg(args)
+    unit = "graphs/s" if args.config == "c4" else UNIT
     # size the per-step sample so the whole run stays within a few minutes
-    rate, _, cores, t_step = time_cpu(cfg, min(8, args.batch_size), budget_s=0, steps=1, warmup=1)
-    per_mol = t_step / min(8, args.batch_size)
+    probe = 1 if args.config == "c4" else min(8, args.batch_size)
+    _, _, cores, t_step = time_cpu(args, cfg, probe, steps=1, warmup=1)
+    per = t_step / probe
     budget = 150.0
-    n = int(budget / max(per_mol * (args.steps + args.warmup), 1e-9))
+    n = int(budget / max(per * (args.steps + args.warmup), 1e-9))
     n = max(1, min(args.batch_size, n))
-    rate, steps, cores, t_step = time_cpu(cfg, n, budget_s=0, steps=args.steps, warmup=args.warmup)
-    sample = f"{n} of {args.batch_size} molecules per step, {steps} steps, oracle port (torch CPU, {cores} threads)"
+    rate, steps, cores, t_step = time_cpu(args, cfg, n, steps=args.steps, warmup=args.warmup)
+    sample = f"{n} of {args.batch_size} graphs per step, {steps} steps, oracle port (torch CPU, {cores} threads)"
     line = {
-        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "impl": "reference", "metric": metric_name(args), "value": rate, "unit": unit, "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic" if args.config != "c4" else "reference fixture (rna_native)",
         "config": workload_config(args, None),
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline": {"value": rate, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
 def workload_config(args, sizes):
-    c = {"workload": f"PAMNet QM9 target=7 dim={args.dim} n_layer={args.n_layer} batch_size={args.batch_size} per GPU, "
-                     "fwd + L1 loss + bwd, synthetic ~20-atom molecules (BASELINE.json configs[1])",
-         "parallelism": f"dp{args.gpus} molecule-sharded, one flat-gradient all-reduce" if args.gpus > 1 else "single GPU",
-         "l2": "flushed (256 MiB write) before every timed step"}
+    if args.config == "c4":
+        wl = ("PAMNet rna_native dim=16 n_layer=1 batch_size=8: the first 8 graphs of the reference's RNA-Puzzles native fixture "
+              "(841-3771 atoms), shipped checkpoint, fwd + L1 loss + bwd (BASELINE.json configs[3])")
+    else:
+        idx = {"c2": 1, "c3": 2}[args.config]
+        wl = (f"PAMNet QM9 target=7 dim={args.dim} n_layer={args.n_layer} batch_size={args.batch_size} per GPU, fwd + L1 loss + bwd, "
+              f"synthetic ~20-atom molecules (BASELINE.json configs[{idx}])")
+    c = {"workload": wl,
+         "parallelism": (f"dp{args.gpus} molecule-sharded, " + ("one flat-gradient all-reduce" if getattr(args, "plain_allreduce", False)
+                         else "bucketed gradient all-reduce overlapped with backward")) if args.gpus > 1 else "single GPU",
+         "l2": "flushed (256 MiB write) before every timed step",
+         "node_mlp": "single-pass TF32 tensor-core node MLPs (reduced precision, PAMNET_NODE_MLP=tf32)" if args.node_mlp == "tf32"
+                     else "3xTF32 tensor-core node MLPs (fp32-accurate)",
+         "loss": "F.l1_loss" if getattr(args, "torch_loss", False) else "pamnet_b200.ops.l1_loss (value + gradient in one launch)",
+         "front_end": "inline" if getattr(args, "no_prefetch", False)
+                      else "next step's graph plan built on a side stream behind backward (model.prefetch); one plan and one H2D copy per step"}
     if sizes:
         c["sizes"] = sizes
-    if getattr(args, "fused_loss", False):
-        c["loss"] = "pamnet_b200.ops.l1_loss (value + gradient in one launch)"
-    if getattr(args, "prefetch", False):
-        c["prefetch"] = "next step's graph plan built on a side stream after backward (model.prefetch)"
-    if os.environ.get("PAMNET_FRONT"):           # opt-in front end in effect
-        c["front_end"] = os.environ["PAMNET_FRONT"]
+    for k in ("PAMNET_FRONT", "PAMNET_GEMM", "PAMNET_CHAIN", "PAMNET_STREAMS", "PAMNET_TC2_PROD"):
+        if os.environ.get(k):
+            c[k.lower()] = os.environ[k]
     return c
 
 
@@ -139,7 +201,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "10"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -173,12 +235,13 @@ def algorithmic_bytes_step(sz, D, L, s=4):
 
 
 def run_ours(args):
+    if args.node_mlp == "tf32":
+        os.environ["PAMNET_NODE_MLP"] = "tf32"       # read once by the library
     import torch
     import torch.distributed as dist
     import pamnet_b200
     from pamnet_b200 import Config, PAMNet, _lib
-    from pamnet_b200.data import synthetic_qm9_batch
-    from pamnet_b200.parallel import allreduce_gradients
+    from pamnet_b200.parallel import OverlappedGradSync, allreduce_gradients
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -190,32 +253,43 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     cfg = model_cfg(args)
+    unit = "graphs/s" if args.config == "c4" else UNIT
     torch.manual_seed(0)
-    model = PAMNet(Config(**vars(cfg))).to(dev)
-    host_batch = synthetic_qm9_batch(args.batch_size, seed=rank).pin_memory()
+    host_batch, sd = make_batch(args, seed=rank)
+    model = PAMNet(Config(**vars(cfg)))
+    if sd is not None:
+        model.load_state_dict(sd)
+    model = model.to(dev)
+    host_batch = host_batch.pin_memory()
     dev_batch = host_batch.to(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    loss_buf = torch.zeros(1, device=dev)
+    prefetch = not args.no_prefetch
 
     params = list(model.parameters())
 
     import torch.nn.functional as F
-    l1 = pamnet_b200.ops.l1_loss if args.fused_loss else F.l1_loss
+    l1 = F.l1_loss if args.torch_loss else pamnet_b200.ops.l1_loss
+    sync = OverlappedGradSync(model) if (world > 1 and not args.plain_allreduce) else None
 
     def step(batch, sync_grads=True, next_batch=None):
-        for p in params:             # == optimizer.zero_grad(set_to_none=True)
+        if sync is not None:
+            sync.wait()                     # the previous step's collectives read the gradient buffer backward is about to zero
+        for p in params:                    # == optimizer.zero_grad(set_to_none=True)
             p.grad = None
         out = model(batch)
         loss = l1(out, batch.y)             # main_qm9.py:108
         loss.backward()
-        if next_batch is not None:          # --prefetch: the next step's front end overlaps this step's backward
+        if world > 1 and sync_grads:        # enqueue the collectives first: they overlap what backward still has queued
+            if sync is not None:
+                sync()
+            else:
+                allreduce_gradients(model)
+        if next_batch is not None:          # the next step's front end overlaps this step's backward
             next_batch()
-        if world > 1 and sync_grads:
-            allreduce_gradients(model)
         return loss
 
     # device-resident loop: the batch has been in HBM since before the warm-up, the side stream need not wait for anything
-    nxt_dev = (lambda: model.prefetch(dev_batch, wait_current=False)) if args.prefetch else None
+    nxt_dev = (lambda: model.prefetch(dev_batch, wait_current=False)) if prefetch else None
 
     def barrier():
         if world > 1:
@@ -228,20 +302,27 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):
         step(dev_batch, next_batch=nxt_dev)
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = _lib.launch_count()
+    ar_ms = []
     barrier()
     for s0, s1 in ev:
         flush.fill_(1)
         s0.record()
         step(dev_batch, next_batch=nxt_dev)
+        if sync is not None:
+            sync.wait()                     # the step ends when its gradients are reduced
         s1.record()
+        if sync is not None and len(ar_ms) < 8:
+            ar_ms.append(sync.allreduce_ms())       # (synchronises: only for a few steps)
     barrier()
     launches = (_lib.launch_count() - launches0) // args.steps
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    per_step = [a.elapsed_time(b) for a, b in ev]
+    dev_ms = sum(per_step) / args.steps
     # (the clock sampler keeps running through the end-to-end timed region below: both are under load)
 
     # ---- end to end through the public API with host buffers ("e2e") ------------------------------------
@@ -251,13 +332,15 @@ def run_ours(args):
         pending.append(model.prefetch(host_batch))
 
     def e2e_step():
-        if args.prefetch:       # this step's batch was copied and planned during the previous step; copy + plan the next
+        if prefetch:            # this step's batch was copied and planned during the previous step; copy + plan the next
             if not pending:
                 h2d_and_plan()
             loss = step(pending.pop(0), next_batch=h2d_and_plan)
         else:
             b = host_batch.to(dev, non_blocking=True)      # H2D from pinned memory, inside the timed region
             loss = step(b)
+        if sync is not None:
+            sync.wait()
         return loss.item()                                  # D2H read of the step's result
 
     for _ in range(3):
@@ -273,12 +356,16 @@ def run_ours(args):
     e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)) / args.steps
     clocks = sampler.stop() if rank == 0 else None
     h2d = sum(v.numel() * v.element_size() for v in host_batch.__dict__.values() if isinstance(v, torch.Tensor))
-    d2h = 4 + 2 * 64    # loss scalar + the two count read-backs of the graph build
+    d2h = 4 + 64    # loss scalar + the count read-back of the graph build
 
-    # max over ranks
+    # max over ranks (and the spread: per-rank skew)
+    skew = None
     if world > 1:
         t = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
+        tmin = t.clone()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        skew = {"ms_per_step_min_rank": float(tmin[0]), "ms_per_step_max_rank": float(t[0])}
         dev_ms, e2e_ms = t.tolist()
 
     if rank != 0:
@@ -288,10 +375,11 @@ def run_ours(args):
         return
 
     sz = model.last_plan.sizes
-    sizes = {"G": args.batch_size, "N": int(sz.n_nodes), "E_l": int(sz.n_edges_l), "E_g": int(sz.n_edges_g),
+    sizes = {"G": int(sz.n_graphs), "N": int(sz.n_nodes), "E_l": int(sz.n_edges_l), "E_g": int(sz.n_edges_g),
              "T2": int(sz.n_t2), "T1": int(sz.n_t1)}
-    value = world * args.batch_size / (dev_ms * 1e-3)
-    e2e_value = world * args.batch_size / (e2e_ms * 1e-3)
+    n_units = int(sz.n_graphs)
+    value = world * n_units / (dev_ms * 1e-3)
+    e2e_value = world * n_units / (e2e_ms * 1e-3)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -301,42 +389,59 @@ def run_ours(args):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(args, sizes), "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "metric": metric_name(args), "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+        "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.node_mlp == "f32" else "f32 (node MLPs: tf32 single pass)",
+        "data": "synthetic" if args.config != "c4" else "reference fixture (rna_native, first 8 graphs)",
+        "config": workload_config(args, sizes), "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": unit, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
     }
+    if world > 1:
+        line["allreduce_ms"] = {"exposed_after_backward": sum(ar_ms) / len(ar_ms) if ar_ms else None,
+                                "how": "CUDA events: compute stream idle -> last bucket reduced (OverlappedGradSync)" if sync is not None
+                                       else "single blocking all-reduce (not timed separately)", **(skew or {})}
 
-    # ---- per-kernel-class event timing (separate pass; events perturb the step, so not the timed one) ----
+    # ---- per-kernel-class event timing (separate passes; events perturb the step, so not the timed ones) ----
     # rank 0 only and WITHOUT the gradient all-reduce: the other ranks have left, a collective here would never return
     if not args.no_profile:
-        for _ in range(2):
-            step(dev_batch, sync_grads=False)
-        torch.cuda.synchronize()
-        nprof = 5
-        _lib.profile_begin()
-        for _ in range(nprof):
-            step(dev_batch, sync_grads=False)
-        prof = _lib.profile_end()
+        def profile_pass(nprof=5):
+            for _ in range(2):
+                step(dev_batch, sync_grads=False)
+            torch.cuda.synchronize()
+            _lib.profile_begin()
+            for _ in range(nprof):
+                step(dev_batch, sync_grads=False)
+            return _lib.profile_end(), nprof
+        prof, nprof = profile_pass()
         tot_ms = sum(v[0] for v in prof.values())
         kernels = {k: {"ms_per_step": v[0] / nprof, "launches_per_step": v[1] / nprof, "share": v[0] / tot_ms,
                        "alg_gb_per_s": (v[2] / 1e9) / (v[0] * 1e-3) if v[0] > 0 and v[2] > 0 else None}
                    for k, v in prof.items() if v[1]}
         dom = max(kernels, key=lambda k: kernels[k]["share"])
-        d = prof[dom]
+        # The concurrent pass charges a launch for SMs it shares with other streams (its class times can sum to more than
+        # the step).  A second pass on ONE stream (PAMNET_STREAMS=1 semantics through the model's switch) gives the isolated
+        # per-class times; the roofline uses those.
+        iso = None
+        try:
+            os.environ["PAMNET_STREAMS"] = "1"
+            prof1, n1 = profile_pass()
+            iso = {k: {"ms_per_step": v[0] / n1, "launches_per_step": v[1] / n1} for k, v in prof1.items() if v[1]}
+        finally:
+            os.environ.pop("PAMNET_STREAMS", None)
+        d = prof1[dom] if iso and dom in prof1 else prof[dom]
+        dn = n1 if iso and dom in prof1 else nprof
         achieved = (d[2] / 1e9) / (d[0] * 1e-3)
         traffic = None
-        try:        # dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full capture
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(dom, {}).get("dram_bytes_per_launch")
+        try:        # dram__bytes_read + dram__bytes_write per launch from this round's committed ncu --set full capture
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get(dom, {}).get("dram_bytes_per_launch")
         except (OSError, ValueError):
             pass
         hbm_view = {"achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                     "peak_source": peak_src}
         if d[3] > 0:
-            # the dominant class is the 3xTF32 tcgen05 GEMM: each fp32-accurate multiply-add is three tf32 tensor-core
-            # multiply-adds, so the executed tensor work is 3 x the fp32-equivalent flops; tf32 runs at half the bf16
-            # rate, hence peak = measured dense bf16 / 2
+            # the dominant class is the 3xTF32 tcgen05 GEMM: each fp32-accurate multiply-add is three (gemm_tc2: four) tf32
+            # tensor-core multiply-adds; the roofline counts three.  tf32 runs at half the bf16 rate: peak = measured bf16 / 2
             bf16 = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1650.0)))
             tf32_peak = bf16 / 2.0
             tens = 3.0 * d[3] / 1e12 / (d[0] * 1e-3)
@@ -345,25 +450,29 @@ def run_ours(args):
                                 "peak_source": "MEASURED_PEAKS.json dense bf16 (sustained) / 2 = tf32 rate" if peaks else
                                                "fallback 1650 TFLOP/s bf16 / 2",
                                 "share_of_step": kernels[dom]["share"], "fp32_equivalent_tflops": tens / 3.0,
+                                "class_ms_per_step_isolated": d[0] / dn, "class_ms_per_step_concurrent": kernels[dom]["ms_per_step"],
                                 "hbm_view": hbm_view,
-                                "note": "3xTF32 GEMM class: achieved = 3 x fp32-equivalent flops of its launches / their "
-                                        "CUDA-event time (concurrent streams share the SMs); hbm_view = algorithmic operand "
-                                        "bytes / the same time"}
+                                "note": "3xTF32 GEMM class: achieved = 3 x fp32-equivalent flops of its launches / their CUDA-event "
+                                        "time in a single-stream pass (isolated); hbm_view = algorithmic operand bytes / the same time"}
         else:
             line["roofline"] = {"kernel": dom, "bound": "hbm", **hbm_view, "traffic": traffic,
                                 "share_of_step": kernels[dom]["share"],
-                                "note": "algorithmic bytes of the kernel's operands / CUDA-event duration per launch, "
-                                        "averaged over its launches in a step"}
+                                "class_ms_per_step_isolated": d[0] / dn, "class_ms_per_step_concurrent": kernels[dom]["ms_per_step"],
+                                "note": "algorithmic bytes of the kernel's operands / CUDA-event duration per launch in a "
+                                        "single-stream pass, averaged over its launches in a step"}
         b_step = algorithmic_bytes_step(sizes, args.dim, args.n_layer)
         line["step_roofline"] = {"algorithmic_bytes": b_step, "achieved": b_step / 1e9 / (dev_ms * 1e-3), "peak": hbm_peak,
                                  "unit": "GB/s", "frac": b_step / 1e9 / (dev_ms * 1e-3) / hbm_peak,
                                  "definition": "SURVEY.md 8(d) B_step / device ms_per_step"}
         line["kernels"] = kernels
+        if iso:
+            line["kernels_isolated"] = iso
 
     if not args.no_cpu_baseline and world == 1:      # reported at N = 1 only (the host cores are shared by all ranks)
-        rate, steps, cores, t_step = time_cpu(cfg, args.batch_size, budget_s=15.0, warmup=1)
-        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{steps} full steps of the same {args.batch_size}-molecule batch "
+        n_cpu = args.batch_size if args.config == "c2" else (32 if args.config == "c3" else 2)
+        rate, steps, cores, t_step = time_cpu(args, cfg, n_cpu, steps=30, budget_s=15.0, warmup=1)
+        line["cpu_baseline"] = {"value": rate, "unit": unit, "cores": cores, "kind": "port",
+                                "sample": f"{steps} steps of the first {n_cpu} graphs of the same batch "
                                           f"({1e3 * t_step:.0f} ms/step), oracle port on torch CPU"}
     print(json.dumps(line), flush=True)
     if world > 1:

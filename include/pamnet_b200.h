@@ -71,6 +71,17 @@ int pamnet_radius_count(const float* pos, const int64_t* batch, int64_t n_nodes,
 int pamnet_radius_fill(const float* pos, const int64_t* batch, int64_t n_nodes, float r,
                        int32_t max_num_neighbors, int32_t drop_self, const int32_t* ptr, int64_t total,
                        int64_t* edge_index, void* stream);
+/* Cell-list ("grid-hash") variant for graphs beyond molecule size (PDBbind complexes; models.py:128): per-graph uniform
+ * grid with cells >= r sized on the device to the caller's scratch, 27-cell queries, neighbours sorted by index -- the
+ * SAME edge list as pamnet_radius_count / _fill, bit for bit.  `scratch` (pamnet_radius_grid_scratch_bytes) is written
+ * by _count and read by _fill. */
+size_t pamnet_radius_grid_scratch_bytes(int64_t n_nodes, int64_t n_graphs);
+int pamnet_radius_grid_count(const float* pos, const int64_t* batch, int64_t n_nodes, int64_t n_graphs, float r,
+                             int32_t max_nb, int32_t drop_self, void* scratch, size_t scratch_bytes, int32_t* deg,
+                             int32_t* ptr, int64_t* total_dev, void* stream);
+int pamnet_radius_grid_fill(const float* pos, const int64_t* batch, int64_t n_nodes, int64_t n_graphs, float r,
+                            int32_t max_nb, int32_t drop_self, const void* scratch, const int32_t* ptr, int64_t total,
+                            int64_t* edge_index, void* stream);
 
 /* torch_cluster.knn(x, x, k, batch, batch) at models.py:143 (oracle/graph_ops.py:knn_pairs): per query the k
  * nearest points of its own graph (itself included), ascending distance, ties to the lower index.
@@ -178,6 +189,17 @@ int pamnet_model_backward(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, 
                           void* plan_base, void* plan_trip, void* workspace, size_t workspace_bytes,
                           const float* grad_out, float* grad_params, void* stream, void* aux_stream,
                           void* prepared_weights);
+
+/* ---- gradient buckets: overlapped data-parallel all-reduce (the reference is single-process) ----
+ * The flat gradient buffer is laid out per layer.  After pamnet_grad_buckets(1), every pamnet_model_backward records,
+ * for each layer-half h (global layer l = 2l, local layer l = 2l + 1), events on its internal streams at the point where
+ * the slice [lo, hi) of pamnet_grad_bucket_range is final; pamnet_wait_grad_bucket(h, comm_stream) makes comm_stream
+ * wait for them, so a per-bucket ncclAllReduce can run while the remaining halves are still being differentiated.
+ * Completion order: 2L-1, 2L-2, ..., 0; everything outside the layer slices (embeddings, basis MLPs, frequencies) is
+ * final when the backward call's own stream is (wait for that stream). */
+int pamnet_grad_buckets(int32_t enable);
+int pamnet_wait_grad_bucket(int32_t half, void* stream);
+int pamnet_grad_bucket_range(const pamnet_config_t* cfg, int32_t half, int64_t* lo, int64_t* hi);
 
 /* L1 / MSE loss + its gradient w.r.t. the prediction in one launch (main_qm9.py:108 F.l1_loss,
  * main_pdbbind.py MSE): loss_dev[0] = mean(|out-y|) or mean((out-y)^2); grad_out[g] = d loss / d out[g]. */

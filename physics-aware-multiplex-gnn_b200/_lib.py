@@ -37,6 +37,9 @@ SIGNATURES = {
     "pamnet_param_offsets": (c_i32, [_PC, c_vp, c_vp]),
     "pamnet_radius_count": (c_i32, [c_vp, c_vp, c_i64, c_f32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "pamnet_radius_fill": (c_i32, [c_vp, c_vp, c_i64, c_f32, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp]),
+    "pamnet_radius_grid_scratch_bytes": (c_sz, [c_i64, c_i64]),
+    "pamnet_radius_grid_count": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_f32, c_i32, c_i32, c_vp, c_sz, c_vp, c_vp, c_vp, c_vp]),
+    "pamnet_radius_grid_fill": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_f32, c_i32, c_i32, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "pamnet_knn": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp]),
     "pamnet_knn_edges_count": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp]),
     "pamnet_knn_edges_fill": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_f32, c_vp, c_i64, c_vp, c_vp]),
@@ -55,6 +58,9 @@ SIGNATURES = {
                                       c_vp]),
     "pamnet_prepared_weights_bytes": (c_sz, [_PC]),
     "pamnet_prepare_weights": (c_i32, [_PC, c_vp, c_vp, c_vp]),
+    "pamnet_grad_buckets": (c_i32, [c_i32]),
+    "pamnet_wait_grad_bucket": (c_i32, [c_i32, c_vp]),
+    "pamnet_grad_bucket_range": (c_i32, [_PC, c_i32, C.POINTER(c_i64), C.POINTER(c_i64)]),
     "pamnet_loss": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp]),
     "pamnet_collate": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "pamnet_scatter_add": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),

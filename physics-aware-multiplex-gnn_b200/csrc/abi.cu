@@ -132,6 +132,25 @@ int pamnet_radius_fill(const float* pos, const int64_t* batch, int64_t n_nodes, 
     PAMNET_CHECK_ARG(total == 0 || edge_index, "radius_fill: null edge_index");
     return radius_fill(pos, batch, n_nodes, r, max_nb, drop_self, ptr, total, edge_index, ST(stream));
 }
+size_t pamnet_radius_grid_scratch_bytes(int64_t n_nodes, int64_t n_graphs) {
+    return radius_grid_scratch_bytes(n_nodes, n_graphs);
+}
+int pamnet_radius_grid_count(const float* pos, const int64_t* batch, int64_t n_nodes, int64_t n_graphs, float r,
+                             int32_t max_nb, int32_t drop_self, void* scratch, size_t scratch_bytes, int32_t* deg,
+                             int32_t* ptr, int64_t* total_dev, void* stream) {
+    REQUIRE(pos); REQUIRE(batch); REQUIRE(deg); REQUIRE(ptr); REQUIRE(total_dev); REQUIRE(scratch);
+    PAMNET_CHECK_ARG(n_nodes >= 0 && n_graphs > 0 && max_nb > 0, "radius_grid: n_nodes=%lld n_graphs=%lld max=%d",
+                     (long long)n_nodes, (long long)n_graphs, max_nb);
+    return radius_grid_count(pos, batch, n_nodes, n_graphs, r, max_nb, drop_self, scratch, scratch_bytes, deg, ptr,
+                             total_dev, ST(stream));
+}
+int pamnet_radius_grid_fill(const float* pos, const int64_t* batch, int64_t n_nodes, int64_t n_graphs, float r,
+                            int32_t max_nb, int32_t drop_self, const void* scratch, const int32_t* ptr, int64_t total,
+                            int64_t* edge_index, void* stream) {
+    REQUIRE(pos); REQUIRE(batch); REQUIRE(ptr); REQUIRE(scratch);
+    PAMNET_CHECK_ARG(total == 0 || edge_index, "radius_grid_fill: null edge_index");
+    return radius_grid_fill(pos, batch, n_nodes, n_graphs, r, max_nb, drop_self, scratch, ptr, total, edge_index, ST(stream));
+}
 int pamnet_knn(const float* pos, const int64_t* batch, int64_t n_nodes, int32_t k, int32_t* nbr, float* d2,
                void* stream) {
     REQUIRE(pos); REQUIRE(batch); REQUIRE(nbr); REQUIRE(d2);
@@ -199,6 +218,8 @@ struct BuildScratch {
     int64_t* counts;
     int32_t *deg_a, *ptr_a, *deg_b, *ptr_b, *keep, *pk, *nbr, *mol_rng;
     float* d2;
+    void* grid;             // cell lists of the large-graph radius search (graph_grid.cu)
+    size_t grid_bytes;
 };
 constexpr int kKnnK = 50;            // models.py:143
 size_t build_scratch_layout(int kind, int64_t n, int64_t n_edges_in, int64_t cap_eg, void* base, BuildScratch* out) {
@@ -218,6 +239,8 @@ size_t build_scratch_layout(int kind, int64_t n, int64_t n_edges_in, int64_t cap
     b.keep = static_cast<int32_t*>(take(sizeof(int32_t) * ne));
     b.pk = static_cast<int32_t*>(take(sizeof(int32_t) * (ne + 1)));
     b.mol_rng = static_cast<int32_t*>(take(kind == PAMNET_QM9 ? sizeof(int32_t) * 2 * (n + 2) : 0));   // front_mol.cuh range tables
+    b.grid = take(kind != PAMNET_RNA ? radius_grid_scratch_bytes(n, n) : 0);    // sized for the worst case n_graphs = n
+    b.grid_bytes = kind != PAMNET_RNA ? radius_grid_scratch_bytes(n, n) : 0;
     b.nbr = static_cast<int32_t*>(take(kind == PAMNET_RNA ? sizeof(int32_t) * n * kKnnK : 0));
     b.d2 = static_cast<float*>(take(kind == PAMNET_RNA ? sizeof(float) * n * kKnnK : 0));
     if (out) *out = b;
@@ -309,12 +332,18 @@ int pamnet_plan_build(const pamnet_config_t* cfg, const float* pos, const int64_
     }
 
     // ---- phase 1: edge counts (models.py:110,115 / 128,131-136 / 143-157) ----------------------------------------
+    // large graphs (PDBbind complexes): cell-list radius search instead of the per-graph scan, same edge list
+    const bool use_grid = kind != PAMNET_RNA && radius_grid_preferred(n_nodes, n_graphs);
     if (kind == PAMNET_RNA) {
         PAMNET_TRY(knn(pos, batch, n_nodes, kKnnK, b.nbr, b.d2, st));
         PAMNET_TRY(knn_edges_count(b.nbr, pos, n_nodes, kKnnK, cfg->cutoff_g, b.deg_a, b.ptr_a, b.counts + 0, st));
         PAMNET_TRY(knn_edges_count(b.nbr, pos, n_nodes, kKnnK, cfg->cutoff_l, b.deg_b, b.ptr_b, b.counts + 1, st));
     } else {
-        PAMNET_TRY(radius_count(pos, batch, n_nodes, cfg->cutoff_g, max_nb, 1, b.deg_a, b.ptr_a, b.counts + 0, st));
+        if (use_grid)
+            PAMNET_TRY(radius_grid_count(pos, batch, n_nodes, n_graphs, cfg->cutoff_g, max_nb, 1, b.grid, b.grid_bytes, b.deg_a,
+                                         b.ptr_a, b.counts + 0, st));
+        else
+            PAMNET_TRY(radius_count(pos, batch, n_nodes, cfg->cutoff_g, max_nb, 1, b.deg_a, b.ptr_a, b.counts + 0, st));
         if (kind == PAMNET_QM9)
             PAMNET_TRY(edge_filter_count(edge_index_in, n_edges_in, nullptr, 0.f, b.keep, b.pk, b.counts + 1, st));
     }
@@ -329,7 +358,10 @@ int pamnet_plan_build(const pamnet_config_t* cfg, const float* pos, const int64_
         PAMNET_TRY(knn_edges_fill(b.nbr, pos, n_nodes, kKnnK, cfg->cutoff_g, b.ptr_a, Eg, eg_buf, st));
         PAMNET_TRY(knn_edges_fill(b.nbr, pos, n_nodes, kKnnK, cfg->cutoff_l, b.ptr_b, El, el_buf, st));
     } else {
-        PAMNET_TRY(radius_fill(pos, batch, n_nodes, cfg->cutoff_g, max_nb, 1, b.ptr_a, Eg, eg_buf, st));
+        if (use_grid)
+            PAMNET_TRY(radius_grid_fill(pos, batch, n_nodes, n_graphs, cfg->cutoff_g, max_nb, 1, b.grid, b.ptr_a, Eg, eg_buf, st));
+        else
+            PAMNET_TRY(radius_fill(pos, batch, n_nodes, cfg->cutoff_g, max_nb, 1, b.ptr_a, Eg, eg_buf, st));
         if (kind == PAMNET_QM9) {
             if (El == n_edges_in) el = edge_index_in;            // nothing dropped: use the caller's list in place
             else PAMNET_TRY(edge_filter_fill(edge_index_in, n_edges_in, b.keep, b.pk, El, el_buf, st));
@@ -392,6 +424,13 @@ int pamnet_model_backward(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, 
     REQUIRE(plan_trip); REQUIRE(workspace); REQUIRE(grad_out); REQUIRE(grad_params);
     return model_backward(*cfg, *sz, *sbf, params, node_in, sign, pos, plan_base, plan_trip, workspace,
                           workspace_bytes, grad_out, grad_params, ST(stream), ST(aux_stream), prepared_weights);
+}
+
+int pamnet_grad_buckets(int32_t enable) { set_grad_buckets(enable); return 0; }
+int pamnet_wait_grad_bucket(int32_t half, void* stream) { return wait_grad_bucket(half, ST(stream)); }
+int pamnet_grad_bucket_range(const pamnet_config_t* cfg, int32_t half, int64_t* lo, int64_t* hi) {
+    REQUIRE(cfg); REQUIRE(lo); REQUIRE(hi);
+    return grad_bucket_range(*cfg, half, lo, hi);
 }
 
 int64_t pamnet_debug_ws_offset(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, const char* name, int32_t half) {

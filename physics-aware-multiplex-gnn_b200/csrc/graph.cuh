@@ -24,6 +24,15 @@ int radius_count(const float* pos, const int64_t* batch, int64_t n_nodes, float 
                  int32_t* deg, int32_t* ptr, int64_t* total_dev, cudaStream_t st);
 int radius_fill(const float* pos, const int64_t* batch, int64_t n_nodes, float r, int max_nb, int drop_self,
                 const int32_t* ptr, int64_t total, int64_t* edge_index, cudaStream_t st);
+// cell-list variant for large graphs (graph_grid.cu): same edge list bit for bit
+size_t radius_grid_scratch_bytes(int64_t n_nodes, int64_t n_graphs);
+int radius_grid_count(const float* pos, const int64_t* batch, int64_t n_nodes, int64_t n_graphs, float r, int max_nb,
+                      int drop_self, void* scratch, size_t scratch_bytes, int32_t* deg, int32_t* ptr, int64_t* total_dev,
+                      cudaStream_t st);
+int radius_grid_fill(const float* pos, const int64_t* batch, int64_t n_nodes, int64_t n_graphs, float r, int max_nb,
+                     int drop_self, const void* scratch, const int32_t* ptr, int64_t total, int64_t* edge_index,
+                     cudaStream_t st);
+bool radius_grid_preferred(int64_t n_nodes, int64_t n_graphs);
 int knn(const float* pos, const int64_t* batch, int64_t n_nodes, int k, int32_t* nbr, float* d2, cudaStream_t st);
 int knn_edges_count(const int32_t* nbr, const float* pos, int64_t n_nodes, int k, float cutoff, int32_t* deg,
                     int32_t* ptr, int64_t* total_dev, cudaStream_t st);

@@ -13,6 +13,9 @@
 
 #include <stdlib.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "basis.cuh"
 #include "chain.cuh"
 #include "gemm.cuh"
@@ -579,6 +582,72 @@ DeviceStreams* device_streams() {
 }
 thread_local std::vector<cudaEvent_t> g_fallback_events;
 
+// ---- gradient buckets for an overlapped data-parallel all-reduce ----------------------------------
+// The flat gradient buffer is laid out per layer; the slice of layer-half h is final once the backward iteration of half
+// h - 1 has issued its weight-gradient launches (it contributes mlp_x1 of half h).  When enabled, model_backward records
+// one event per contributing stream at that point; wait_grad_bucket makes a caller's (communication) stream wait for
+// them, so a per-bucket NCCL all-reduce can run while the remaining halves are still being differentiated.  The table
+// is global per device (backward runs on autograd's worker thread, the collective is issued from the main thread).
+constexpr int kBucketStreams = 4;
+struct BucketEvents {
+    std::vector<cudaEvent_t> ev;       // [(2 * kMaxLayers) * kBucketStreams]
+    int halves = 0;                    // halves recorded by the last backward on this device
+    bool recorded[2 * kMaxLayers] = {};
+};
+std::mutex g_bucket_mu;
+BucketEvents g_buckets[kMaxDevices];
+std::atomic<int> g_buckets_on{0};
+
+int record_bucket(int half, int n_halves, cudaStream_t const (&streams)[kBucketStreams]) {
+    int dev = 0;
+    PAMNET_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) return 0;
+    std::lock_guard<std::mutex> lk(g_bucket_mu);
+    BucketEvents& b = g_buckets[dev];
+    if (b.ev.empty()) {
+        b.ev.resize(2 * kMaxLayers * kBucketStreams);
+        for (auto& e : b.ev) PAMNET_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    for (int i = 0; i < kBucketStreams; ++i) PAMNET_CUDA(cudaEventRecord(b.ev[half * kBucketStreams + i], streams[i]));
+    b.recorded[half] = true;
+    b.halves = n_halves;
+    return 0;
+}
+}  // namespace
+
+void set_grad_buckets(int on) { g_buckets_on.store(on ? 1 : 0); }
+
+// make `stream` wait until the gradient slice of layer-half `half` (0 .. 2L-1: global l = 2l, local l = 2l+1) of the last
+// model_backward on the current device is complete
+int wait_grad_bucket(int half, cudaStream_t stream) {
+    int dev = 0;
+    PAMNET_CUDA(cudaGetDevice(&dev));
+    PAMNET_CHECK_ARG(dev >= 0 && dev < kMaxDevices && half >= 0 && half < 2 * kMaxLayers, "wait_grad_bucket: bad half %d", half);
+    std::lock_guard<std::mutex> lk(g_bucket_mu);
+    BucketEvents& b = g_buckets[dev];
+    PAMNET_CHECK_ARG(!b.ev.empty() && b.recorded[half], "wait_grad_bucket: no backward recorded bucket %d (enable with pamnet_grad_buckets(1))", half);
+    for (int i = 0; i < kBucketStreams; ++i) PAMNET_CUDA(cudaStreamWaitEvent(stream, b.ev[half * kBucketStreams + i], 0));
+    return 0;
+}
+
+// [lo, hi) of layer-half `half` in the flat parameter / gradient layout
+int grad_bucket_range(const pamnet_config_t& cfg, int half, int64_t* lo, int64_t* hi) {
+    ModelP mp;
+    PAMNET_TRY(build_param_layout(cfg, &mp));
+    const int L = cfg.n_layer;
+    PAMNET_CHECK_ARG(half >= 0 && half < 2 * L, "grad_bucket_range: bad half %d", half);
+    const int l = half >> 1;
+    if (half & 1) {
+        *lo = mp.l[l].W;
+        *hi = l + 1 < L ? mp.l[l + 1].W : mp.total;
+    } else {
+        *lo = mp.g[l].W;
+        *hi = l + 1 < L ? mp.g[l + 1].W : mp.l[0].W;
+    }
+    return 0;
+}
+
+namespace {
 // group boundaries over the layers: a short first group (its results are needed first in forward, last in backward),
 // then growing ones
 std::vector<int> layer_groups(int L) {
@@ -1069,6 +1138,10 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
             if (s3 != s2) PAMNET_TRY(sc.order(st, s2));
             PAMNET_TRY(global_wgrads(l, l + 1, s2));
         }
+        if (g_buckets_on.load() && hh + 1 < H) {
+            const cudaStream_t bs[kBucketStreams] = {s2, s3, sc.s4, sc.s5};
+            PAMNET_TRY(record_bucket(hh + 1, H, bs));
+        }
     }
     {   // into the node input
         Prog p((int)N);
@@ -1085,6 +1158,10 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
     }
     PAMNET_TRY(sc.order(st, s3));
     PAMNET_TRY(node_wgrads(-1, 0, -1, s3));
+    if (g_buckets_on.load()) {
+        const cudaStream_t bs[kBucketStreams] = {s2, s3, sc.s4, sc.s5};
+        PAMNET_TRY(record_bucket(0, H, bs));
+    }
     if (s3 != s2) PAMNET_TRY(sc.order(st, s2));
 
     // ---- auxiliary stream: through the SiLU of the embeddings into their weights and the RBF frequencies -------

@@ -43,6 +43,11 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
                    void* plan_trip, void* workspace, size_t workspace_bytes, const float* grad_out, float* grad_params,
                    cudaStream_t st, cudaStream_t aux, void* prepared = nullptr);
 
+// gradient buckets for an overlapped data-parallel all-reduce (model.cu)
+void set_grad_buckets(int on);
+int wait_grad_bucket(int half, cudaStream_t stream);
+int grad_bucket_range(const pamnet_config_t& cfg, int half, int64_t* lo, int64_t* hi);
+
 // k-major chain weights + contiguous projection blocks, produced ahead of model_forward (optional)
 size_t prepared_weights_bytes(const pamnet_config_t& cfg);
 int prepare_weights(const pamnet_config_t& cfg, const float* params, void* prepared, cudaStream_t st);

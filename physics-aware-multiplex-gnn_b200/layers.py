@@ -2,8 +2,9 @@
 initialisation) -- layers/basic.py, layers/global_message_passing.py, layers/local_message_passing.py.
 
 The arithmetic of a whole model step runs in the fused CUDA path (models.py -> libpamnet_sm100.so); the
-``forward`` methods here are the stand-alone layer surface composed from the operator
-kernels in ops.py, forward-only.
+``forward`` methods here are the stand-alone layer surface: same signatures as the reference
+layers, composed from the operator kernels in ops.py (ops.linear / ops.scatter are autograd functions over the C ABI's
+GEMM and segment-sum kernels), differentiable w.r.t. every input and parameter (tests/test_gpu_layers.py).
 """
 import math
 
@@ -100,7 +101,6 @@ class Global_MessagePassing(nn.Module):
         self.W = nn.Parameter(torch.empty(d, 1))
         _glorot(self.W)
 
-    @torch.no_grad()
     def forward(self, x, edge_attr, edge_index):
         i, j = (0, 1) if self.flow == "target_to_source" else (1, 0)
         x1 = _run_mlp(self.mlp_x1, x)
@@ -145,7 +145,6 @@ class Local_MessagePassing(_LocalBase):
         super().__init__()
         self._init(config, "mlp_m_kj")
 
-    @torch.no_grad()
     def forward(self, x, rbf, sbf2, sbf1, idx_kj, idx_ji, idx_jj_pair, idx_ji_pair, edge_index):
         return self._forward(self.mlp_m_kj, x, rbf, torch.cat((sbf2, sbf1)), torch.cat((idx_kj, idx_jj_pair)),
                              torch.cat((idx_ji, idx_ji_pair)), edge_index)
@@ -158,6 +157,5 @@ class Local_MessagePassing_s(_LocalBase):
         super().__init__()
         self._init(config, "mlp_m_jj")
 
-    @torch.no_grad()
     def forward(self, x, rbf, sbf, idx_jj_pair, idx_ji_pair, edge_index):
         return self._forward(self.mlp_m_jj, x, rbf, sbf, idx_jj_pair, idx_ji_pair, edge_index)

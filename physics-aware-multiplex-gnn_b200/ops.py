@@ -72,10 +72,40 @@ def radius_fill(pos, batch, r, max_num_neighbors, drop_self, ptr, total):
     return ei
 
 
-def radius_graph(pos, batch, r, max_num_neighbors=32, loop=False):
-    """edge_index [2,E] (row = query, col = neighbour), ordered by (query, neighbour)."""
+def radius_graph_grid(pos, batch, r, max_num_neighbors=32, loop=False, n_graphs=None):
+    """radius_graph through the cell-list kernels (csrc/graph_grid.cu): the same edge list, bit for bit; meant for
+    graphs of hundreds to thousands of atoms (PDBbind complexes, models.py:128)."""
+    _require_cuda(pos, batch)
+    lib = _lib.load()
+    pos, batch = _f32(pos), _i64(batch)
+    n = pos.shape[0]
+    if n_graphs is None:
+        n_graphs = int(batch.max()) + 1 if n else 1
+    c = Counts(pos.device)
+    sb = lib.pamnet_radius_grid_scratch_bytes(n, n_graphs)
+    scratch = torch.empty(sb, dtype=torch.uint8, device=pos.device)
+    deg = torch.empty(max(n, 1), dtype=torch.int32, device=pos.device)
+    ptr = torch.empty(n + 1, dtype=torch.int32, device=pos.device)
+    _lib.check(lib.pamnet_radius_grid_count(pos.data_ptr(), batch.data_ptr(), n, n_graphs, float(r), int(max_num_neighbors),
+                                            int(not loop), scratch.data_ptr(), sb, deg.data_ptr(), ptr.data_ptr(), c.ptr(0),
+                                            _stream()), "radius_grid_count")
+    total = c.read()[0]
+    ei = torch.empty((2, total), dtype=torch.int64, device=pos.device)
+    _lib.check(lib.pamnet_radius_grid_fill(pos.data_ptr(), batch.data_ptr(), n, n_graphs, float(r), int(max_num_neighbors),
+                                           int(not loop), scratch.data_ptr(), ptr.data_ptr(), total, ei.data_ptr(), _stream()),
+               "radius_grid_fill")
+    return ei
+
+
+def radius_graph(pos, batch, r, max_num_neighbors=32, loop=False, method="auto"):
+    """edge_index [2,E] (row = query, col = neighbour), ordered by (query, neighbour).  method: "brute" (per-graph scan,
+    molecules), "grid" (cell list, large graphs) or "auto" (by atoms per graph)."""
     _require_cuda(pos, batch)
     pos, batch = _f32(pos), _i64(batch)
+    if method == "grid" or (method == "auto" and pos.shape[0] >= 4096):      # auto: only worth a batch.max() sync when large
+        n_graphs = int(batch.max()) + 1 if pos.shape[0] else 1
+        if method == "grid" or pos.shape[0] // n_graphs >= 192:
+            return radius_graph_grid(pos, batch, r, max_num_neighbors, loop, n_graphs)
     c = Counts(pos.device)
     ptr = radius_count(pos, batch, r, max_num_neighbors, not loop, c, 0)
     return radius_fill(pos, batch, r, max_num_neighbors, not loop, ptr, c.read()[0])
@@ -194,22 +224,44 @@ def triplet_indices(edge_index, num_nodes):
     return tuple(outs)
 
 
-def scatter(src, index, dim=0, dim_size=None, reduce="add"):
-    if dim != 0 or reduce not in ("add", "sum"):
-        raise NotImplementedError("hot path uses scatter(src, index, dim=0, reduce='add') only")
-    _require_cuda(src, index)
+def _scatter_add(src, index, dim_size):
     lib = _lib.load()
     width = 1
     for d in src.shape[1:]:
         width *= d
     src2 = _f32(src).reshape(src.shape[0], width)
-    index = _i64(index)
-    if dim_size is None:
-        dim_size = int(index.max()) + 1 if index.numel() else 0
     out = torch.empty((dim_size, src2.shape[1]), dtype=torch.float32, device=src.device)
     _lib.check(lib.pamnet_scatter_add(src2.data_ptr(), index.data_ptr(), src2.shape[0], src2.shape[1], dim_size,
                                       out.data_ptr(), _stream()), "scatter_add")
     return out.reshape((dim_size,) + tuple(src.shape[1:]))
+
+
+class _ScatterFn(torch.autograd.Function):
+    """out[index[k]] += src[k]; the gradient of a segment sum is a row gather."""
+
+    @staticmethod
+    def forward(ctx, src, index, dim_size):
+        ctx.save_for_backward(index)
+        return _scatter_add(src, index, dim_size)
+
+    @staticmethod
+    def backward(ctx, g):
+        (index,) = ctx.saved_tensors
+        return g.contiguous().index_select(0, index), None, None
+
+
+def scatter(src, index, dim=0, dim_size=None, reduce="add"):
+    """torch_scatter.scatter(src, index, dim=0, dim_size=n, reduce='add') as the hot path calls it
+    (local_message_passing.py:50,54); differentiable w.r.t. ``src``."""
+    if dim != 0 or reduce not in ("add", "sum"):
+        raise NotImplementedError("hot path uses scatter(src, index, dim=0, reduce='add') only")
+    _require_cuda(src, index)
+    index = _i64(index)
+    if dim_size is None:
+        dim_size = int(index.max()) + 1 if index.numel() else 0
+    if torch.is_grad_enabled() and src.requires_grad:
+        return _ScatterFn.apply(src.float(), index, dim_size)
+    return _scatter_add(src, index, dim_size)
 
 
 def bessel_rbf(dist, freq, cutoff):
@@ -236,15 +288,49 @@ def spherical_basis(dist, angle, idx_kj, cutoff):
     return out
 
 
-def linear(x, weight, bias=None, silu=False):
-    _require_cuda(x, weight, bias)
+def _linear_fwd(x, weight, bias, silu):
     lib = _lib.load()
-    x, weight = _f32(x), _f32(weight)
-    bias = _f32(bias) if bias is not None else None
     y = torch.empty((x.shape[0], weight.shape[0]), dtype=torch.float32, device=x.device)
     _lib.check(lib.pamnet_linear(x.data_ptr(), x.shape[0], weight.shape[1], weight.shape[0], weight.data_ptr(),
                                  _lib.ptr(bias), int(silu), y.data_ptr(), _stream()), "linear")
     return y
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = [SiLU](x W^T + b) (layers/basic.py:19-22) with the hand-written GEMM kernels in both directions:
+    g_x = g_z W (pamnet_gemm mode 1), g_W = g_z^T x and g_b = column sums of g_z (mode 2, split over the rows)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, silu):
+        x, weight = x.contiguous(), weight.contiguous()
+        bias = bias.contiguous() if bias is not None else None
+        z = _linear_fwd(x, weight, bias, False)
+        ctx.save_for_backward(x, weight, z if silu else None)
+        ctx.silu, ctx.has_bias = silu, bias is not None
+        return z * torch.sigmoid(z) if silu else z
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight, z = ctx.saved_tensors
+        g = g.contiguous().float()
+        if ctx.silu:                       # SiLU'(z) = s (1 + z (1 - s))
+            s = torch.sigmoid(z)
+            g = g * (s * (1.0 + z * (1.0 - s)))
+        rows, n_in, n_out = x.shape[0], weight.shape[1], weight.shape[0]
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = gemm(1, g, weight, rows, n_in, n_out)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            gw, gb = gemm(2, g, x, n_out, n_in, rows, ksplit=max(1, min(64, (rows + 127) // 128)), want_dbias=True)
+        return gx, gw, (gb if ctx.has_bias else None), None
+
+
+def linear(x, weight, bias=None, silu=False):
+    """nn.Linear (+ SiLU) on the CUDA GEMM kernels; differentiable w.r.t. x, weight and bias."""
+    _require_cuda(x, weight, bias)
+    if torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or (bias is not None and bias.requires_grad)):
+        return _LinearFn.apply(x.float(), weight.float(), bias.float() if bias is not None else None, bool(silu))
+    return _linear_fwd(_f32(x), _f32(weight), _f32(bias) if bias is not None else None, silu)
 
 
 def gemm(mode, a, b, m, n, k, ksplit=1, want_dbias=False):

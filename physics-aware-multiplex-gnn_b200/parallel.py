@@ -46,6 +46,98 @@ def allreduce_gradients(model, group=None, average=True):
         off += g.numel()
 
 
+class OverlappedGradSync:
+    """Bucketed gradient all-reduce that overlaps the backward pass.
+
+    The flat gradient buffer is laid out per layer and backward finishes the layers last-to-first, so the slice of a
+    layer is final long before the call's stream is.  The library records events at those points
+    (pamnet_grad_buckets / pamnet_wait_grad_bucket); this class groups the 2L layer-halves into `n_buckets` contiguous
+    slices and, right after ``loss.backward()`` has RETURNED (everything is enqueued, the GPU is still differentiating
+    the early layers), issues one NCCL all-reduce per bucket on a communication stream that waits only for its bucket's
+    events.  Only the last bucket (first layers + embeddings / basis MLPs, final when backward is) is exposed.
+
+        sync = OverlappedGradSync(model)          # once; enables the bucket events
+        loss.backward(); sync()                   # instead of allreduce_gradients(model)
+        sync.wait()                               # before the optimizer step / reading p.grad
+
+    ``allreduce_ms()`` returns the CUDA-event duration of the exposed tail of the last call (the time between the
+    compute stream becoming idle and the last collective finishing) for the scaling report."""
+
+    def __init__(self, model, group=None, n_buckets=4):
+        from . import _lib
+        self.model, self.group = model, group
+        self.lib = _lib.load()
+        _lib.check(self.lib.pamnet_grad_buckets(1), "grad_buckets")
+        cfg = model._ccfg
+        H = 2 * cfg.n_layer
+        lo, hi = _lib.c_i64(), _lib.c_i64()
+        spans = {}
+        for h in range(H):
+            _lib.check(self.lib.pamnet_grad_bucket_range(cfg, h, lo, hi), "grad_bucket_range")
+            spans[h] = (lo.value, hi.value)
+        # completion order: H-1 (last local layer) ... 0; the flat layout is [head | global 0..L-1 | local 0..L-1], so a run
+        # of consecutive local (or global) layers, latest first, is one contiguous slice that is final with its LAST
+        # member to complete (the lowest layer index of the run).
+        L = cfg.n_layer
+        per = max(1, (2 * L + max(1, n_buckets - 1) - 1) // max(1, n_buckets - 1) // 2)      # layers per bucket and kind
+        self.buckets = []                           # (wait_half, lo, hi) in issue order
+        for first in range(L - 1, -1, -per):        # layers first, first-1, ..., last
+            last = max(0, first - per + 1)
+            # local layers [last, first] complete with half 2*last+1; the global ones with half 2*last
+            self.buckets.append((2 * last + 1, spans[2 * last + 1][0], spans[2 * first + 1][1]))
+            self.buckets.append((2 * last, spans[2 * last][0], spans[2 * first][1]))
+        # issue in completion order: a bucket whose gate half is larger completes earlier
+        self.buckets.sort(key=lambda b: -b[0])
+        self.head = (0, spans[0][0])                # embeddings, frequencies, basis MLPs: final with backward itself
+        self.total = int(model._total)
+        self.comm = None
+        self._ev = None
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def __call__(self):
+        if self.world == 1:
+            return
+        model = self.model
+        buf = flat_grad(model)
+        if buf is None:                             # grads do not alias the flat buffer: plain path
+            allreduce_gradients(model, self.group)
+            return
+        dev = buf.device
+        cur = torch.cuda.current_stream(dev)
+        if self.comm is None or self.comm.device != dev:
+            self.comm = torch.cuda.Stream(device=dev, priority=-1)
+            self._ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        from . import _lib
+        nccl = buf.is_cuda and dist.get_backend(self.group) == "nccl"
+        op = dist.ReduceOp.AVG if nccl else dist.ReduceOp.SUM
+        with torch.cuda.device(dev), torch.cuda.stream(self.comm):
+            for half, lo, hi in self.buckets:
+                _lib.check(self.lib.pamnet_wait_grad_bucket(half, self.comm.cuda_stream), "wait_grad_bucket")
+                sl = buf[lo:hi]
+                dist.all_reduce(sl, op=op, group=self.group)
+                if not nccl:
+                    sl.mul_(1.0 / self.world)
+            # the head slice (and the compute stream's tail) last: this is the only exposed collective
+            self._ev[0].record(cur)
+            self.comm.wait_stream(cur)
+            sl = buf[self.head[0]:self.head[1]]
+            dist.all_reduce(sl, op=op, group=self.group)
+            if not nccl:
+                sl.mul_(1.0 / self.world)
+            self._ev[1].record(self.comm)
+
+    def wait(self):
+        """Make the current stream wait for the collectives (call before the optimizer step)."""
+        if self.world > 1 and self.comm is not None:
+            torch.cuda.current_stream(self.comm.device).wait_stream(self.comm)
+
+    def allreduce_ms(self):
+        if self._ev is None:
+            return 0.0
+        self._ev[1].synchronize()
+        return self._ev[0].elapsed_time(self._ev[1])
+
+
 def shard_range(n_items, rank, world):
     """Contiguous shard [lo, hi) of n_items for `rank` (molecule sharding of a global batch)."""
     per, rem = divmod(n_items, world)

@@ -125,6 +125,26 @@ def make_rna(ref, ref_root):
     torch.save(res, os.path.join(HERE, "rna_native.pt"))
 
 
+def make_rna_c4(ref, ref_root):
+    """BASELINE.json configs[3]: the FIRST 8 graphs of the rna_native fixture (841-3 771 atoms,
+    15 816 in total) batched together, shipped checkpoint, one training-style forward + L1 loss + backward."""
+    x, gid, y = read_tu(os.path.join(ref_root, "data", "RNA-Puzzles"), "rna_native")
+    cfg = ref.Config("rna_native", 16, 1, 2.6, 20.0, "target_to_source")
+    model = ref.PAMNet(cfg)
+    sd = torch.load(os.path.join(ref_root, "save", "pamnet_rna.pt"), map_location="cpu")
+    model.load_state_dict(sd)
+    sel = gid < 8
+    batch = Batch(x=x[sel].clone(), batch=gid[sel].clone(), y=torch.linspace(0.5, 11.0, 8))
+    res = run_reference(model, batch, loss="l1")
+    sizes = [int((gid == g).sum()) for g in range(8)]
+    print("C4 sizes", sizes, "out", res["out_f32"])
+    res.update(state_dict={k: v.clone() for k, v in sd.items()}, sizes=sizes,
+               x=batch.x, y=batch.y,            # batch vector = repeat_interleave(arange(8), sizes)
+               config=dict(dataset="rna_native", dim=16, n_layer=1, cutoff_l=2.6, cutoff_g=20.0,
+                           flow="target_to_source"))
+    torch.save(res, os.path.join(HERE, "rna_c4.pt"))
+
+
 def make_pdbbind(ref):
     torch.manual_seed(21)
     rng = np.random.default_rng(21)
@@ -156,3 +176,4 @@ if __name__ == "__main__":
     make_qm9(ref)
     make_pdbbind(ref)
     make_rna(ref, ref_root)
+    make_rna_c4(ref, ref_root)

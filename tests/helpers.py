@@ -46,3 +46,14 @@ def ladder_ok(new, ref32, ref64, tol=1e-5):
     err_new = float((new.double().cpu() - ref64).abs().max()) / scale
     err_ref = float((ref32.double().cpu() - ref64).abs().max()) / scale
     return err_new <= max(tol, 2 * err_ref), err_new, err_ref
+
+
+def elementwise_ok(new, ref32, ref64, rtol=1e-4, atol_frac=5e-6):
+    """Element-wise companion of ladder_ok (which is a max-norm and would hide a wrong small-magnitude row):
+    |new - fp64| <= max(rtol * |fp64|, 2 * |ref32 - fp64|) + atol, atol = atol_frac * max|fp64| ... per element, where the
+    fp32 reference's own element-wise error widens the bound the way SURVEY.md 8(c) allows.  Returns (ok, worst ratio)."""
+    new, ref32, ref64 = new.double().cpu(), ref32.double().cpu(), ref64.double().cpu()
+    atol = atol_frac * float(ref64.abs().max().clamp(min=1e-30))
+    bound = torch.maximum(rtol * ref64.abs(), 2.0 * (ref32 - ref64).abs()) + atol
+    ratio = float(((new - ref64).abs() / bound).max())
+    return ratio <= 1.0, ratio

@@ -6,7 +6,7 @@ fp32 reference), per tensor, relative to max|truth|.  Integer outputs bit-exact.
 import pytest
 import torch
 
-from tests.helpers import load_golden, cfg_of, batch_of, rel_err, ladder_ok, oracle_step
+from tests.helpers import load_golden, cfg_of, batch_of, rel_err, ladder_ok, oracle_step, elementwise_ok
 
 pytestmark = pytest.mark.gpu
 
@@ -35,6 +35,38 @@ def test_golden_forward_backward(name, simple, loss):
     gold = load_golden(name)
     model = _model(gold, simple)
     out, l, grads = _step(model, batch_of(gold), loss)
+    ok, e_new, e_ref = ladder_ok(out, gold["out_f32"], gold["out_f64"])
+    assert ok, ("out", e_new, e_ref)
+    assert rel_err(out, gold["out_f32"]) < 1e-5
+    bad = []
+    for k, ref64 in gold["grads_f64"].items():
+        if ref64 is None:
+            assert grads[k] is None, k
+            continue
+        ok, e_new, e_ref = ladder_ok(grads[k], gold["grads_f32"][k], ref64)
+        if not ok:
+            bad.append((k, e_new, e_ref))
+        ok, ratio = elementwise_ok(grads[k], gold["grads_f32"][k], ref64)     # no small-magnitude row hides behind the max-norm
+        if not ok:
+            bad.append((k, "elementwise", ratio))
+    assert not bad, bad[:10]
+
+
+def test_c4_real_fixture_first_8_natives():
+    """BASELINE.json configs[3] on its OWN data: the first 8 graphs of the reference's rna_native
+    fixture (841-3 771 atoms, 15 816 in total) in one batch, shipped checkpoint, forward + L1 + backward against the
+    verbatim reference's fp32 / fp64 results (tests/golden/rna_c4.pt, make_golden.py:make_rna_c4)."""
+    from pamnet_b200.data import Batch
+    gold = load_golden("rna_c4")
+    model = _model(gold)
+    sizes = gold["sizes"]
+    assert sizes == [1384, 1176, 1246, 3215, 932, 3771, 841, 3251]
+    batch = Batch(x=gold["x"], batch=torch.repeat_interleave(torch.arange(8), torch.tensor(sizes)), y=gold["y"])
+    out, l, grads = _step(model, batch)
+    n = sum(sizes)
+    plan = model.last_plan
+    assert plan.sizes.n_nodes == n and plan.sizes.n_edges_g == 49 * n            # kNN-50 minus self, nothing beyond 20 A
+    assert (plan.sizes.n_edges_l, plan.sizes.n_t2, plan.sizes.n_t1) == (86160, 432574, 518734)    # SURVEY.md 8 C4 row
     ok, e_new, e_ref = ladder_ok(out, gold["out_f32"], gold["out_f64"])
     assert ok, ("out", e_new, e_ref)
     assert rel_err(out, gold["out_f32"]) < 1e-5
@@ -261,7 +293,8 @@ _BASE_STEP = None
 @pytest.mark.parametrize("env", [{"PAMNET_STREAMS": "1"}, {"PAMNET_PDL": "0"}, {"PAMNET_PLAN": "stepwise"},
                                  {"PAMNET_GATHER": "atomic"}, {"PAMNET_GEMM": "ffma"}, {"PAMNET_CHAIN_FUSE": "0"},
                                  {"PAMNET_PREP": "1"}, {"PAMNET_FWD_SPLIT": "1"}, {"PAMNET_GEMM_SMALL": "0"},
-                                 {"PAMNET_SBF_FUSED": "0"}])
+                                 {"PAMNET_SBF_FUSED": "0"}, {"PAMNET_GEMM": "tc1"}, {"PAMNET_CHAIN": "ffma"},
+                                 {"PAMNET_FRONT": "generic"}])
 def test_alternate_paths_agree(env):
     """Single-stream schedule, no programmatic dependent launch, the step-by-step front end, atomic projection
     gradients, the FFMA GEMM, the unfused chain prologue, ... (the golden model has dim = 32, so the
@@ -302,3 +335,62 @@ def test_plan_build_grows_capacities():
         assert torch.equal(fused.edge_index_g, step.edge_index_g) and torch.equal(fused.edge_index_l, step.edge_index_l)
         assert (fused.sizes.n_t2, fused.sizes.n_t1) == (step.sizes.n_t2, step.sizes.n_t1)
         assert torch.equal(out, out2), kind
+
+
+def test_backends_agree_at_dim_128():
+    """The golden model has dim 32 (FFMA chain, skinny GEMMs); the tensor-core node chain (chain_mma.cu) and the TMA
+    GEMM (gemm_tc2.cu) only run at dim >= 64.  Same step at dim 128 through {tensor-core chain + TMA GEMM} (default),
+    the round-1 GEMM, and the all-FFMA path: equal to fp32 rounding."""
+    import os, subprocess, sys, tempfile
+    code = r'''
+import sys, torch
+sys.path.insert(0, %r)
+from pamnet_b200 import Config, PAMNet
+from pamnet_b200.data import synthetic_qm9_batch
+torch.manual_seed(0)
+m = PAMNet(Config("QM9", 128, 2, 5.0, 5.0)).cuda()
+b = synthetic_qm9_batch(16, seed=3).to("cuda")
+out = m(b); (out - b.y).abs().mean().backward(); torch.cuda.synchronize()
+torch.save({"out": out.detach().cpu(), "g": torch.cat([p.grad.reshape(-1) for p in m.parameters() if p.grad is not None]).cpu()}, sys.argv[1])
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for name, env in [("default", {}), ("tc1", {"PAMNET_GEMM": "tc1"}), ("ffma", {"PAMNET_GEMM": "ffma", "PAMNET_CHAIN": "ffma"})]:
+        with tempfile.NamedTemporaryFile(suffix=".pt") as f:
+            subprocess.run([sys.executable, "-c", code, f.name], check=True, env={**os.environ, **env}, timeout=300)
+            res[name] = torch.load(f.name)
+    for name in ("default", "tc1"):
+        assert rel_err(res[name]["out"], res["ffma"]["out"]) < 2e-6, name
+        assert rel_err(res[name]["g"], res["ffma"]["g"]) < 1e-5, name
+
+
+def test_reduced_precision_node_mlp_rung():
+    """BASELINE.json configs[2] names a reduced-precision tensor-core node-MLP path.  PAMNET_NODE_MLP=tf32 runs the node
+    chains as ONE tensor-core pass on tf32-truncated operands (10-bit mantissa, >= bf16's 7) with fp32 accumulation;
+    everything else stays fp32-accurate.  Its own rung, stated against the fp64 oracle and NOT part of the 1e-5 ladder:
+    outputs within 5e-3, every gradient tensor within 5e-2 of max|fp64| (measured on a B200: 2e-3 / 1e-2)."""
+    import os, subprocess, sys, tempfile, types
+    from pamnet_b200.data import synthetic_qm9_batch
+    from oracle import pamnet_oracle as O
+    cfg = types.SimpleNamespace(dataset="QM9", dim=128, n_layer=2, cutoff_l=5.0, cutoff_g=5.0, flow="source_to_target")
+    sd = O.init_state_dict(cfg, seed=0)
+    b = synthetic_qm9_batch(8, seed=5)
+    o64, _, g64 = oracle_step(sd, cfg, b, dtype=torch.float64)
+    code = r'''
+import sys, types, torch
+sys.path.insert(0, %r)
+from pamnet_b200 import Config, PAMNet
+from pamnet_b200.data import synthetic_qm9_batch
+from oracle import pamnet_oracle as O
+cfg = types.SimpleNamespace(dataset="QM9", dim=128, n_layer=2, cutoff_l=5.0, cutoff_g=5.0, flow="source_to_target")
+m = PAMNet(Config(**vars(cfg))); m.load_state_dict(O.init_state_dict(cfg, seed=0)); m = m.cuda()
+b = synthetic_qm9_batch(8, seed=5).to("cuda")
+out = m(b); (out - b.y).abs().mean().backward(); torch.cuda.synchronize()
+torch.save({"out": out.detach().cpu(), "g": {k: (p.grad.cpu() if p.grad is not None else None) for k, p in m.named_parameters()}}, sys.argv[1])
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.NamedTemporaryFile(suffix=".pt") as f:
+        subprocess.run([sys.executable, "-c", code, f.name], check=True, env={**os.environ, "PAMNET_NODE_MLP": "tf32"}, timeout=300)
+        res = torch.load(f.name)
+    e_out = rel_err(res["out"], o64)
+    assert 1e-7 < e_out < 5e-3, e_out           # really reduced precision, and within its rung
+    worst = max(rel_err(res["g"][k], v) for k, v in g64.items() if v is not None)
+    assert worst < 5e-2, worst

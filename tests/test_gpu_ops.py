@@ -189,3 +189,23 @@ def test_fused_losses_match_torch(ops):
             assert torch.allclose(a.grad, b.grad, rtol=1e-6, atol=1e-9)
     with pytest.raises(ValueError):
         ops.l1_loss(torch.zeros(3, device="cuda"), torch.zeros(4, device="cuda"))
+
+
+@pytest.mark.parametrize("n_graphs,n_atoms,r,max_nb", [(3, 700, 6.0, 1000), (1, 2500, 2.6, 1000), (5, 40, 5.0, 1000),
+                                                       (2, 900, 6.0, 20), (4, 300, 50.0, 64)])
+def test_radius_grid_equals_brute_force_and_oracle(ops, n_graphs, n_atoms, r, max_nb):
+    """Cell-list radius search (csrc/graph_grid.cu) against the per-graph scan and the oracle: identical edge lists, also
+    with a binding max_num_neighbors cut, coincident points and a cutoff larger than the structure."""
+    from oracle import graph_ops as G
+    g = torch.Generator().manual_seed(n_atoms)
+    pos = torch.rand(n_graphs * n_atoms, 3, generator=g) * (n_atoms ** (1 / 3.0)) * 2.2        # ~0.1 atoms / A^3
+    pos[5] = pos[4]                                                                              # coincident atoms
+    pos = torch.round(pos * 1000) / 1000
+    batch = torch.arange(n_graphs).repeat_interleave(n_atoms)
+    for loop in (False, True):
+        brute = ops.radius_graph(pos.cuda(), batch.cuda(), r, max_nb, loop=loop, method="brute")
+        grid = ops.radius_graph(pos.cuda(), batch.cuda(), r, max_nb, loop=loop, method="grid")
+        assert torch.equal(brute, grid)
+    row, col = G.radius_pairs(pos, pos, r, batch, batch, max_nb)
+    ref = torch.stack([row, col])
+    assert torch.equal(ops.radius_graph(pos.cuda(), batch.cuda(), r, max_nb, loop=True, method="grid").cpu(), ref)
