@@ -42,7 +42,9 @@ def parse():
     ap.add_argument("--torch-loss", action="store_true", help="F.l1_loss instead of the fused loss + gradient launch")
     ap.add_argument("--no-prefetch", action="store_true",
                     help="build every step's graph plan inline instead of on a side stream behind the previous backward")
-    ap.add_argument("--plain-allreduce", action="store_true", help="one all-reduce after backward instead of overlapped buckets")
+    ap.add_argument("--allreduce", default="native", choices=["native", "buckets", "plain"],
+                    help="N > 1: native = library-owned NCCL all-reduce issued bucket by bucket inside backward (default); "
+                         "buckets = the same buckets from Python (OverlappedGradSync); plain = one all-reduce after backward")
     a = ap.parse_args()
     d = {"c2": (32, 128, 6), "c3": (256, 128, 6), "c4": (8, 16, 1)}[a.config]
     a.batch_size = a.batch_size or d[0]
@@ -174,8 +176,10 @@ def workload_config(args, sizes):
         wl = (f"PAMNet QM9 target=7 dim={args.dim} n_layer={args.n_layer} batch_size={args.batch_size} per GPU, fwd + L1 loss + bwd, "
               f"synthetic ~20-atom molecules (BASELINE.json configs[{idx}])")
     c = {"workload": wl,
-         "parallelism": (f"dp{args.gpus} molecule-sharded, " + ("one flat-gradient all-reduce" if getattr(args, "plain_allreduce", False)
-                         else "bucketed gradient all-reduce overlapped with backward")) if args.gpus > 1 else "single GPU",
+         "parallelism": (f"dp{args.gpus} molecule-sharded, " + {"plain": "one flat-gradient all-reduce after backward",
+                         "buckets": "bucketed gradient all-reduce issued from Python, overlapped with backward",
+                         "native": "bucketed ncclAllReduce issued by the library inside backward (two-layer buckets, head last)"}[
+                         getattr(args, "allreduce", "native")]) if args.gpus > 1 else "single GPU",
          "l2": "flushed (256 MiB write) before every timed step",
          "node_mlp": "single-pass TF32 tensor-core node MLPs (reduced precision, PAMNET_NODE_MLP=tf32)" if args.node_mlp == "tf32"
                      else "3xTF32 tensor-core node MLPs (fp32-accurate)",
@@ -241,7 +245,7 @@ def run_ours(args):
     import torch.distributed as dist
     import pamnet_b200
     from pamnet_b200 import Config, PAMNet, _lib
-    from pamnet_b200.parallel import OverlappedGradSync, allreduce_gradients
+    from pamnet_b200.parallel import NativeGradSync, OverlappedGradSync, allreduce_gradients
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -269,7 +273,8 @@ def run_ours(args):
 
     import torch.nn.functional as F
     l1 = F.l1_loss if args.torch_loss else pamnet_b200.ops.l1_loss
-    sync = OverlappedGradSync(model) if (world > 1 and not args.plain_allreduce) else None
+    sync = OverlappedGradSync(model) if (world > 1 and args.allreduce == "buckets") else None
+    native = NativeGradSync(model) if (world > 1 and args.allreduce == "native") else None
 
     def step(batch, sync_grads=True, next_batch=None):
         if sync is not None:
@@ -282,7 +287,7 @@ def run_ours(args):
         if world > 1 and sync_grads:        # enqueue the collectives first: they overlap what backward still has queued
             if sync is not None:
                 sync()
-            else:
+            elif native is None:            # (native: the all-reduce happened inside backward)
                 allreduce_gradients(model)
         if next_batch is not None:          # the next step's front end overlaps this step's backward
             next_batch()
@@ -400,10 +405,13 @@ def run_ours(args):
     if world > 1:
         line["allreduce_ms"] = {"exposed_after_backward": sum(ar_ms) / len(ar_ms) if ar_ms else None,
                                 "how": "CUDA events: compute stream idle -> last bucket reduced (OverlappedGradSync)" if sync is not None
-                                       else "single blocking all-reduce (not timed separately)", **(skew or {})}
+                                       else ("issued inside backward by the library (not timed separately)" if native is not None
+                                             else "single blocking all-reduce (not timed separately)"), **(skew or {})}
 
     # ---- per-kernel-class event timing (separate passes; events perturb the step, so not the timed ones) ----
     # rank 0 only and WITHOUT the gradient all-reduce: the other ranks have left, a collective here would never return
+    if native is not None:
+        native.enable(False)                # rank 0 is alone from here on
     if not args.no_profile:
         def profile_pass(nprof=5):
             for _ in range(2):

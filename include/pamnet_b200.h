@@ -201,6 +201,19 @@ int pamnet_grad_buckets(int32_t enable);
 int pamnet_wait_grad_bucket(int32_t half, void* stream);
 int pamnet_grad_bucket_range(const pamnet_config_t* cfg, int32_t half, int64_t* lo, int64_t* hi);
 
+/* ---- library-owned gradient all-reduce (data parallelism without Python between the buckets) ----
+ * pamnet_comm_unique_id fills a 128-byte ncclUniqueId on one rank; the host side broadcasts it (torch.distributed) and
+ * every rank calls pamnet_comm_init(id, rank, world) with its device current.  From then on pamnet_model_backward
+ * averages the gradients over the ranks itself: one ncclAllReduce per two-layer bucket on a communication stream as
+ * soon as the bucket's weight gradients have been issued, the head of the buffer last; the caller's stream waits for
+ * the last one, so `grad_params` holds the averaged gradient when the call's work completes.  pamnet_comm_enable(0)
+ * bypasses the collective (single-rank passes), pamnet_comm_destroy releases the communicator.  NCCL is resolved with
+ * dlopen("libnccl.so.2") at run time; without it these calls fail and everything else works. */
+int pamnet_comm_unique_id(void* out128);
+int pamnet_comm_init(const void* id128, int32_t rank, int32_t world);
+int pamnet_comm_enable(int32_t on);
+int pamnet_comm_destroy(void);
+
 /* L1 / MSE loss + its gradient w.r.t. the prediction in one launch (main_qm9.py:108 F.l1_loss,
  * main_pdbbind.py MSE): loss_dev[0] = mean(|out-y|) or mean((out-y)^2); grad_out[g] = d loss / d out[g]. */
 int pamnet_loss(const float* out, const float* y, int64_t n, int32_t kind /*0 = L1, 1 = MSE*/, float* loss_dev,

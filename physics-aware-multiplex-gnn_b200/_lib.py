@@ -58,6 +58,10 @@ SIGNATURES = {
                                       c_vp]),
     "pamnet_prepared_weights_bytes": (c_sz, [_PC]),
     "pamnet_prepare_weights": (c_i32, [_PC, c_vp, c_vp, c_vp]),
+    "pamnet_comm_unique_id": (c_i32, [c_vp]),
+    "pamnet_comm_init": (c_i32, [c_vp, c_i32, c_i32]),
+    "pamnet_comm_enable": (c_i32, [c_i32]),
+    "pamnet_comm_destroy": (c_i32, []),
     "pamnet_grad_buckets": (c_i32, [c_i32]),
     "pamnet_wait_grad_bucket": (c_i32, [c_i32, c_vp]),
     "pamnet_grad_bucket_range": (c_i32, [_PC, c_i32, C.POINTER(c_i64), C.POINTER(c_i64)]),

@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpamnet_sm100.so")
-SOURCES = ["abi.cu", "graph.cu", "graph_grid.cu", "front_mol.cu", "collate.cu", "basis.cu", "gemm.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_small.cu", "chain.cu", "chain_mma.cu", "message.cu", "readout.cu", "model.cu", "optim.cu"]
+SOURCES = ["abi.cu", "comm.cu", "graph.cu", "graph_grid.cu", "front_mol.cu", "collate.cu", "basis.cu", "gemm.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_small.cu", "chain.cu", "chain_mma.cu", "message.cu", "readout.cu", "model.cu", "optim.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 if os.environ.get("PAMNET_SILU_MODE"):           # 0 exact / 1 fast reciprocal (default) / 2 + ex2.approx (csrc/common.cuh)
@@ -51,7 +51,7 @@ def build(force=False, verbose=False):
     with ThreadPoolExecutor(max_workers=8) as ex:
         list(ex.map(run, jobs))
     if jobs or not os.path.exists(LIB):
-        run([_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"])
+        run([_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-ldl"])
     return LIB
 
 

@@ -11,6 +11,7 @@
 #include "basis.cuh"
 #include "chain.cuh"
 #include "collate.cuh"
+#include "comm.cuh"
 #include "front_mol.cuh"
 #include "gemm.cuh"
 #include "graph.cuh"
@@ -425,6 +426,11 @@ int pamnet_model_backward(const pamnet_config_t* cfg, const pamnet_sizes_t* sz, 
     return model_backward(*cfg, *sz, *sbf, params, node_in, sign, pos, plan_base, plan_trip, workspace,
                           workspace_bytes, grad_out, grad_params, ST(stream), ST(aux_stream), prepared_weights);
 }
+
+int pamnet_comm_unique_id(void* out128) { REQUIRE(out128); return comm_unique_id(out128); }
+int pamnet_comm_init(const void* id128, int32_t rank, int32_t world) { REQUIRE(id128); return comm_init(id128, rank, world); }
+int pamnet_comm_enable(int32_t on) { return comm_enable(on); }
+int pamnet_comm_destroy(void) { return comm_destroy(); }
 
 int pamnet_grad_buckets(int32_t enable) { set_grad_buckets(enable); return 0; }
 int pamnet_wait_grad_bucket(int32_t half, void* stream) { return wait_grad_bucket(half, ST(stream)); }

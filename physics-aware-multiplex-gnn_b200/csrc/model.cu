@@ -18,6 +18,7 @@
 
 #include "basis.cuh"
 #include "chain.cuh"
+#include "comm.cuh"
 #include "gemm.cuh"
 #include "graph.cuh"
 #include "message.cuh"
@@ -882,6 +883,7 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
     Sched sc = make_sched(st_user, aux);
     cudaStream_t st = sc.st, s2 = sc.s2, s3 = sc.s3;
 
+    const bool native_comm = comm_active() && sc.dual;     // gradient all-reduce issued from here, bucket by bucket
     if (st != st_user) PAMNET_TRY(sc.order(st_user, st));
     PAMNET_CUDA(cudaMemsetAsync(gp, 0, sizeof(float) * mp.total, st));
     PAMNET_TRY(sc.order(st, s2));      // gradients zeroed (split-K GEMMs accumulate into them) before s2 / s3 start
@@ -1142,6 +1144,21 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
             const cudaStream_t bs[kBucketStreams] = {s2, s3, sc.s4, sc.s5};
             PAMNET_TRY(record_bucket(hh + 1, H, bs));
         }
+        // library-owned collective: layers [l, l + 1] of the kind that just completed (half hh + 1), once both are final
+        if (native_comm && hh + 1 < H) {
+            const int hc = hh + 1, lc = hc >> 1;
+            const bool pair_done = (lc % 2 == 0);      // buckets of two layers [lc, lc + 1]: lc + 1 completed earlier
+            if (pair_done) {
+                const int l_hi = (lc + 1 < L) ? lc + 1 : lc;
+                const HalfP* lo_p = (hc & 1) ? &mp.l[lc] : &mp.g[lc];
+                int64_t lo = lo_p->W, hi;
+                if (hc & 1) hi = l_hi + 1 < L ? mp.l[l_hi + 1].W : mp.total;
+                else hi = l_hi + 1 < L ? mp.g[l_hi + 1].W : mp.l[0].W;
+                cudaStream_t cs = comm_stream();
+                for (cudaStream_t s : {s2, s3, sc.s4, sc.s5}) PAMNET_TRY(sc.order(s, cs));
+                PAMNET_TRY(comm_allreduce_avg(gp + lo, hi - lo));
+            }
+        }
     }
     {   // into the node input
         Prog p((int)N);
@@ -1170,6 +1187,17 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
     if (s3 != s2) PAMNET_TRY(sc.order(s3, st));
     if (sc.s4 != s2) PAMNET_TRY(sc.order(sc.s4, st));
     if (sc.s5 != s2 && sc.s5 != sc.s4) PAMNET_TRY(sc.order(sc.s5, st));
+    if (native_comm) {
+        // head of the buffer (embeddings, frequencies, basis MLPs: final with everything else) together with global
+        // layers [0, 1], which complete with the last node-level weight gradients and are contiguous with it: ONE
+        // exposed collective instead of two
+        const int l_hi = 1 < L ? 1 : 0;
+        const int64_t hi = l_hi + 1 < L ? mp.g[l_hi + 1].W : mp.l[0].W;
+        cudaStream_t cs = comm_stream();
+        PAMNET_TRY(sc.order(st, cs));
+        PAMNET_TRY(comm_allreduce_avg(gp, hi));
+        PAMNET_TRY(sc.order(cs, st));
+    }
     if (st != st_user) PAMNET_TRY(sc.order(st, st_user));
     return 0;
 }

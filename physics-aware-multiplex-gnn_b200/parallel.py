@@ -138,6 +138,51 @@ class OverlappedGradSync:
         return self._ev[0].elapsed_time(self._ev[1])
 
 
+class NativeGradSync:
+    """Gradient averaging INSIDE ``loss.backward()``: the library owns an NCCL communicator (pamnet_comm_*) and
+    model_backward enqueues one all-reduce per two-layer bucket on its communication stream as backward produces them
+    (csrc/comm.cuh).  Nothing to call per step -- after ``backward()`` the gradients are the rank average.
+
+        sync = NativeGradSync(model)      # once per process, after dist.init_process_group and torch.cuda.set_device
+        ...
+        sync.close()
+
+    The unique id travels over the default torch.distributed group (any backend)."""
+
+    def __init__(self, model, group=None):
+        import ctypes
+        from . import _lib
+        self.lib = _lib.load()
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.active = False
+        if self.world == 1:
+            return
+        rank = dist.get_rank(group)
+        dev = model._flat.device
+        buf = (ctypes.c_ubyte * 128)()
+        if rank == 0:
+            _lib.check(self.lib.pamnet_comm_unique_id(buf), "comm_unique_id")
+        t = torch.tensor(list(buf), dtype=torch.uint8, device=dev if dist.get_backend(group) == "nccl" else "cpu")
+        dist.broadcast(t, src=0, group=group)
+        raw = bytes(t.cpu().tolist())
+        cbuf = (ctypes.c_ubyte * 128).from_buffer_copy(raw)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.pamnet_comm_init(cbuf, rank, self.world), "comm_init")
+        self.dev = dev
+        self.active = True
+
+    def enable(self, on=True):
+        if self.active:
+            with torch.cuda.device(self.dev):
+                self.lib.pamnet_comm_enable(1 if on else 0)
+
+    def close(self):
+        if self.active:
+            with torch.cuda.device(self.dev):
+                self.lib.pamnet_comm_destroy()
+            self.active = False
+
+
 def shard_range(n_items, rank, world):
     """Contiguous shard [lo, hi) of n_items for `rank` (molecule sharding of a global batch)."""
     per, rem = divmod(n_items, world)

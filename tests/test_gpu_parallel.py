@@ -1,6 +1,7 @@
 """GPU, world_size 2 over NCCL (skipped with fewer than two devices): the data-parallel step equals the single-GPU step
-on the concatenated batch -- for the one-collective path (allreduce_gradients) and for
-the bucketed all-reduce that overlaps backward (OverlappedGradSync)."""
+on the concatenated batch -- for the one-collective path (allreduce_gradients), for
+the bucketed all-reduce issued from Python (OverlappedGradSync) and for the library-owned NCCL communicator that averages
+the buckets inside backward (NativeGradSync, csrc/comm.cu)."""
 import os
 
 import pytest
@@ -22,7 +23,7 @@ def _worker(rank, world, port, q):
         import pamnet_b200
         from pamnet_b200 import Config, PAMNet
         from pamnet_b200.data import synthetic_qm9_batch
-        from pamnet_b200.parallel import OverlappedGradSync, allreduce_gradients
+        from pamnet_b200.parallel import NativeGradSync, OverlappedGradSync, allreduce_gradients
         torch.manual_seed(0)
         model = PAMNet(Config("QM9", 128, 3, 5.0, 5.0)).cuda()
         shards = [synthetic_qm9_batch(6, seed=10 + r) for r in range(world)]
@@ -48,6 +49,16 @@ def _worker(rank, world, port, q):
         torch.cuda.synchronize()
         res["overlap"] = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None]).cpu()
         res["exposed_ms"] = sync.allreduce_ms()
+        native = NativeGradSync(model)                     # library-owned communicator: averaged inside backward
+        for _ in range(3):
+            local_step()
+        torch.cuda.synchronize()
+        res["native"] = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None]).cpu()
+        native.enable(False)
+        local_step()
+        torch.cuda.synchronize()
+        res["native_off"] = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None]).cpu()
+        native.close()
         if rank == 0:
             # single-GPU reference: the same shards, equal-size -> mean over ranks of per-rank means == mean over all graphs
             for p in model.parameters():
@@ -78,7 +89,9 @@ def test_two_gpu_step_equals_single_gpu_step():
     single = res[0]["single"]
     scale = float(single.abs().max())
     for r in (0, 1):
-        for kind in ("plain", "overlap"):
+        for kind in ("plain", "overlap", "native"):
             err = float((res[r][kind] - single).abs().max()) / scale
             assert err < 1e-5, (r, kind, err)                  # summation order of the collective / split-K atomics only
     assert torch.equal(res[0]["overlap"], res[1]["overlap"])    # both ranks hold the same averaged gradient
+    assert torch.equal(res[0]["native"], res[1]["native"])
+    assert not torch.equal(res[0]["native_off"], res[1]["native_off"])     # bypassed: each rank keeps its own gradient
