@@ -76,29 +76,37 @@ __device__ __forceinline__ void split_tf32_(float x, uint32_t& hi, uint32_t& lo)
     lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
-template <int D>
+template <int D, bool TP>
 struct MmaChainCfg {
     static constexpr int WM = D / 16;                      // 16-feature M tiles
-    static constexpr int CW = 2 * WM;                      // consumer warps: (M tile, k half)
+    static constexpr int CW = TP ? WM : 2 * WM;            // consumer warps: M tile (x k half in the latency variant)
     static constexpr int NC = CW * 32;                     // consumer threads
     static constexpr int NT = NC + 32;                     // + the weight-producer warp
-    static constexpr int KS = D / 8;                       // k-steps per stage, KS / 2 per consumer warp
-    static constexpr size_t smem_floats = 2 * (size_t)D * D + (size_t)(kChainSlots + 4) * D * kR;
+    static constexpr int KS = D / 8;                       // k-steps per stage
+    static constexpr int NBUF = TP ? 1 : 2;                // weight buffers
+    static constexpr size_t smem_floats = (size_t)NBUF * D * D + (size_t)(kChainSlots + 4) * D * kR;
 };
 
-// Warp roles.  Consumer warp w = (M tile w % WM, k half w / WM) multiplies its 16 features x 8 rows over half of K; the
-// two warps of an M tile swap the accumulator halves they do NOT finish through shared memory (one named barrier per
-// pair) so that every thread ends up with 2 of the tile's elements: feature f0 + 8 (k half), rows 2 tq, 2 tq + 1.
+// Two variants of one kernel.
+//  * latency (TP = false; up to ~2 waves of 8-row CTAs, the batch-32 case): consumer warp w = (M tile w % WM, k half
+//    w / WM) multiplies its 16 features x 8 rows over half of K; the two warps of an M tile swap the accumulator halves
+//    they do NOT finish through shared memory (one named barrier per pair) so that every thread ends up with 2 of the
+//    tile's elements.  Weights are double-buffered: the next stage's image streams in behind the current multiply.
+//  * throughput (TP = true; thousands of rows, configs[2]): one warp per M tile over all of K, 4 elements per thread,
+//    ONE weight buffer and <= 112 registers so that TWO CTAs share an SM: a stage is ~1500 cycles of tensor pipe and
+//    ~1600 cycles of everything else (clock64 trace), and the co-resident CTA's multiply fills the other half.
 // The producer warp only walks the stage table in lockstep (same CTA barriers) and asks the bulk-copy engine for the
-// NEXT GEMM stage's fragment image at the start of every GEMM stage: the request (~230 cycles of one thread) used to sit
-// on thread 0's path to the multiply loop.
-template <int D>
-__global__ void __launch_bounds__(MmaChainCfg<D>::NT, 1) chain_mma_kernel(const ChainArgs args) {
-    using C = MmaChainCfg<D>;
-    constexpr int R = kR, NC = C::NC, NT = C::NT, KS = C::KS, WM = C::WM, CW = C::CW;
+// NEXT GEMM stage's fragment image: the request (~230 cycles of one thread) used to sit on thread 0's path to the
+// multiply loop.
+template <int D, bool TP>
+__global__ void __launch_bounds__(MmaChainCfg<D, TP>::NT, TP ? 2 : 1) chain_mma_kernel(const ChainArgs args) {
+    using C = MmaChainCfg<D, TP>;
+    constexpr int R = kR, NC = C::NC, NT = C::NT, KS = C::KS, WM = C::WM, CW = C::CW, NBUF = C::NBUF;
+    constexpr int KSW = TP ? KS : KS / 2;                 // k-steps per consumer warp
+    constexpr int NE = TP ? 4 : 2;                        // finished elements per thread
     extern __shared__ __align__(16) float smem[];
-    float* wbuf = smem;                                   // [2][D * D]: fragment images of this and the next GEMM stage
-    float* slots = wbuf + 2 * D * D;                      // 3 x [D][R] transposed activations, then wide [4D][R]
+    float* wbuf = smem;                                   // [NBUF][D * D]: fragment images of this (and the next) GEMM stage
+    float* slots = wbuf + NBUF * D * D;                   // 3 x [D][R] transposed activations, then wide [4D][R]
     auto slot_ptr = [&](int s) -> float* { return slots + s * D * R; };
 
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -108,7 +116,7 @@ __global__ void __launch_bounds__(MmaChainCfg<D>::NT, 1) chain_mma_kernel(const 
     __shared__ __align__(16) ChainStage s_stage[kChainMaxStages];
     __shared__ __align__(8) uint64_t wbar[2];
     __shared__ float s_red[2 * R * CW];
-    __shared__ __align__(8) float2 s_xch[CW * 32];
+    __shared__ __align__(8) float2 s_xch[TP ? 1 : CW * 32];
     {
         static_assert(sizeof(ChainStage) % 4 == 0, "word copy");
         const int nwords = args.n_stages * (int)(sizeof(ChainStage) / 4);
@@ -142,12 +150,14 @@ __global__ void __launch_bounds__(MmaChainCfg<D>::NT, 1) chain_mma_kernel(const 
         for (int si = 0; si < n_stages; ++si) {
             const int op = s_stage[si].op;
             if (op == CH_GEMM) {
-                // buffer wcur ^ 1 was last read by the previous GEMM stage, whose trailing barrier this warp has passed
                 const int nxt = s_stage[si].next_gemm;
-                if (nxt >= 0) issue_weights(nxt, wcur ^ 1);
+                // two buffers: buffer wcur ^ 1 was last read by the previous GEMM stage, whose trailing barrier this warp
+                // has passed; one buffer: it is free only after THIS stage's trailing barrier
+                if (NBUF == 2 && nxt >= 0) issue_weights(nxt, wcur ^ 1);
                 if (s_stage[si].psrc >= 0) __syncthreads();
-                wcur ^= 1;
+                if (NBUF == 2) wcur ^= 1;
                 __syncthreads();
+                if (NBUF == 1 && nxt >= 0) issue_weights(nxt, 0);
             } else {
                 __syncthreads();
                 if (op == CH_DOT2) __syncthreads();
@@ -158,13 +168,15 @@ __global__ void __launch_bounds__(MmaChainCfg<D>::NT, 1) chain_mma_kernel(const 
 
     // ---- consumer warps ---------------------------------------------------------------------------------------------
     const int g = lane >> 2, tq = lane & 3;
-    const int mt = warp % WM, kh = warp / WM;
+    const int mt = warp % WM, kh = TP ? 0 : warp / WM;
     const int f0 = 16 * mt + g;                           // fragment features f0, f0 + 8; rows 2 tq, 2 tq + 1
-    const int fe = f0 + 8 * kh;                           // the feature this thread finishes
+    const int fe = f0 + 8 * kh;                           // latency variant: the feature this thread finishes
     const int r0 = 2 * tq;
+    // finished element e: feature fe_(e), row r0 + (e & 1)
+    auto fe_ = [&](int e) { return TP ? f0 + 8 * (e >> 1) : fe; };
     const int er = t & (R - 1), ec = t / R;               // element-wise stages: (row, 4-column group), row fastest
     constexpr int EC = NC / R;
-    const bool live0 = row0 + r0 < n_rows, live1 = row0 + r0 + 1 < n_rows;
+    const bool live_r[2] = {row0 + r0 < n_rows, row0 + r0 + 1 < n_rows};
 
     unsigned wphase[2] = {0u, 0u};
     float4 zpre = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -269,17 +281,22 @@ __global__ void __launch_bounds__(MmaChainCfg<D>::NT, 1) chain_mma_kernel(const 
             const int psrc = st.psrc, nxt = st.next_gemm;
             const float* in = slot_ptr(st.src) + st.src_off * R;
             // epilogue operands requested now, consumed after the k-loop
-            const float bias_v = bias ? bias[fe] : 0.f;
-            float addg_v[2] = {0.f, 0.f}, zpost_v[2] = {0.f, 0.f};
+            float bias_v[NE / 2], addg_v[NE], zpost_v[NE];
+#pragma unroll
+            for (int e = 0; e < NE; ++e) { addg_v[e] = 0.f; zpost_v[e] = 0.f; }
+#pragma unroll
+            for (int h = 0; h < NE / 2; ++h) bias_v[h] = bias ? bias[fe_(2 * h)] : 0.f;
             if (add_g) {
                 const int ld_add = st.ld_add;
-                if (live0) addg_v[0] = add_g[(size_t)(row0 + r0) * ld_add + fe];
-                if (live1) addg_v[1] = add_g[(size_t)(row0 + r0 + 1) * ld_add + fe];
+#pragma unroll
+                for (int e = 0; e < NE; ++e)
+                    if (live_r[e & 1]) addg_v[e] = add_g[(size_t)(row0 + r0 + (e & 1)) * ld_add + fe_(e)];
             }
             if (post_dst >= 0) {
                 const float* pz = st.post_zmul;
-                if (live0) zpost_v[0] = pz[(size_t)(row0 + r0) * D + fe];
-                if (live1) zpost_v[1] = pz[(size_t)(row0 + r0 + 1) * D + fe];
+#pragma unroll
+                for (int e = 0; e < NE; ++e)
+                    if (live_r[e & 1]) zpost_v[e] = pz[(size_t)(row0 + r0 + (e & 1)) * D + fe_(e)];
             }
             if (psrc >= 0) {          // prologue: src * SiLU'(zmul) -> psrc (and to global for the weight gradients)
                 float* p = slot_ptr(psrc);
@@ -304,8 +321,16 @@ __global__ void __launch_bounds__(MmaChainCfg<D>::NT, 1) chain_mma_kernel(const 
                 zpre = ld4(s_stage[nxt].zmul + (size_t)(row0 + er) * D + ec * 4);
                 zpre_stage = nxt;
             }
-            float2 addv = make_float2(0.f, 0.f);       // the residual slot was complete before this stage began
-            if (add_slot >= 0) addv = *reinterpret_cast<const float2*>(slot_ptr(add_slot) + fe * R + r0);
+            float addv[NE];                            // the residual slot was complete before this stage began
+#pragma unroll
+            for (int e = 0; e < NE; ++e) addv[e] = 0.f;
+            if (add_slot >= 0) {
+#pragma unroll
+                for (int h = 0; h < NE / 2; ++h) {
+                    const float2 a2 = *reinterpret_cast<const float2*>(slot_ptr(add_slot) + fe_(2 * h) * R + r0);
+                    addv[2 * h] = a2.x; addv[2 * h + 1] = a2.y;
+                }
+            }
             CM_STAMP(si, 1);
             mbar_wait_(&wbar[wcur], wphase[wcur]);        // this stage's weights have landed
             wphase[wcur] ^= 1u;
@@ -319,20 +344,20 @@ __global__ void __launch_bounds__(MmaChainCfg<D>::NT, 1) chain_mma_kernel(const 
             for (int p = 0; p < 2; ++p)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc_m[p][j] = acc_x[p][j] = acc_y[p][j] = 0.f;
-            const float4* wf = reinterpret_cast<const float4*>(wbuf + wcur * D * D) + ((size_t)mt * KS + kh * (KS / 2)) * 32 + lane;
-            const float* bp = in + (kh * (KS / 2) * 8 + tq) * R + g;
+            const float4* wf = reinterpret_cast<const float4*>(wbuf + wcur * D * D) + ((size_t)mt * KS + kh * KSW) * 32 + lane;
+            const float* bp = in + (kh * KSW * 8 + tq) * R + g;
             if (args.precision == 1) {
                 // single-pass TF32: the tensor core reads the fp32 bit patterns and ignores the 13 low mantissa bits
 #pragma unroll
-                for (int s = 0; s < KS / 2; ++s) {
+                for (int s = 0; s < KSW; ++s) {
                     const float4 av = wf[s * 32];
                     const uint32_t a4[4] = {__float_as_uint(av.x), __float_as_uint(av.y), __float_as_uint(av.z), __float_as_uint(av.w)};
                     const uint32_t b2[2] = {__float_as_uint(bp[(8 * s) * R]), __float_as_uint(bp[(8 * s + 4) * R])};
                     mma_tf32(acc_m[s & 1], a4, b2);
                 }
             } else
-#pragma unroll
-            for (int s = 0; s < KS / 2; ++s) {
+#pragma unroll (TP ? 8 : KSW)
+            for (int s = 0; s < KSW; ++s) {
                 const float4 av = wf[s * 32];
                 const float b0 = bp[(8 * s) * R], b1 = bp[(8 * s + 4) * R];
                 uint32_t ah[4], al[4], bh[2], bl[2];
@@ -348,8 +373,8 @@ __global__ void __launch_bounds__(MmaChainCfg<D>::NT, 1) chain_mma_kernel(const 
             for (int j = 0; j < 4; ++j)     // small terms first
                 c[j] = ((acc_x[0][j] + acc_x[1][j]) + (acc_y[0][j] + acc_y[1][j])) + (acc_m[0][j] + acc_m[1][j]);
             CM_STAMP(si, 4);
-            // ---- swap halves with the partner warp (other k half of the same M tile): keep feature fe ----
-            {
+            // ---- latency variant: swap halves with the partner warp (other k half of the same M tile), keep feature fe ----
+            if (!TP) {
                 const float2 give = kh ? make_float2(c[0], c[1]) : make_float2(c[2], c[3]);
                 s_xch[warp * 32 + lane] = give;
                 asm volatile("bar.sync %0, 64;" ::"r"(1 + mt) : "memory");
@@ -358,38 +383,46 @@ __global__ void __launch_bounds__(MmaChainCfg<D>::NT, 1) chain_mma_kernel(const 
                 if (kh) { c[0] = got.x + c[2]; c[1] = got.y + c[3]; }
                 else    { c[0] = c[0] + got.x; c[1] = c[1] + got.y; }
             }
-            // ---- epilogue: elements (feature fe, rows r0, r0 + 1), every operand already in registers ----
-            float x[2], z[2];
-            z[0] = c[0] + bias_v; z[1] = c[1] + bias_v;
-            x[0] = act ? silu(z[0]) : z[0];
-            x[1] = act ? silu(z[1]) : z[1];
-            x[0] = live0 ? (x[0] + addv.x) + addg_v[0] : 0.f;
-            x[1] = live1 ? (x[1] + addv.y) + addg_v[1] : 0.f;
+            // ---- epilogue: NE elements (feature fe_(e), row r0 + (e & 1)), every operand already in registers ----
+            float x[NE], z[NE];
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                z[e] = c[e] + bias_v[e >> 1];
+                x[e] = act ? silu(z[e]) : z[e];
+                x[e] = live_r[e & 1] ? (x[e] + addv[e]) + addg_v[e] : 0.f;
+            }
             if (x[0] == 12345.678f) CM_STAMP(si, 7);   // (forces the math to complete before the next stamp)
             CM_STAMP(si, 5);
-            const size_t o0 = (size_t)(row0 + r0) * ld_out + fe;
             if (out_z) {
-                if (live0) out_z[o0] = z[0];
-                if (live1) out_z[o0 + ld_out] = z[1];
+#pragma unroll
+                for (int e = 0; e < NE; ++e)
+                    if (live_r[e & 1]) out_z[(size_t)(row0 + r0 + (e & 1)) * ld_out + fe_(e)] = z[e];
             }
             if (out_a) {
-                if (live0) out_a[o0] = x[0];
-                if (live1) out_a[o0 + ld_out] = x[1];
+#pragma unroll
+                for (int e = 0; e < NE; ++e)
+                    if (live_r[e & 1]) out_a[(size_t)(row0 + r0 + (e & 1)) * ld_out + fe_(e)] = x[e];
             }
-            if (dst >= 0 && dst != post_dst)
-                *reinterpret_cast<float2*>(slot_ptr(dst) + fe * R + r0) = make_float2(x[0], x[1]);
+            if (dst >= 0 && dst != post_dst) {
+#pragma unroll
+                for (int h = 0; h < NE / 2; ++h)
+                    *reinterpret_cast<float2*>(slot_ptr(dst) + fe_(2 * h) * R + r0) = make_float2(x[2 * h], x[2 * h + 1]);
+            }
             if (post_dst >= 0) {          // the next stage's prologue, on register values
-                const float y0 = live0 ? x[0] * dsilu(zpost_v[0]) : 0.f;
-                const float y1 = live1 ? x[1] * dsilu(zpost_v[1]) : 0.f;
+                float y[NE];
+#pragma unroll
+                for (int e = 0; e < NE; ++e) y[e] = live_r[e & 1] ? x[e] * dsilu(zpost_v[e]) : 0.f;
                 if (post_save) {
-                    const size_t p0 = (size_t)(row0 + r0) * D + fe;
-                    if (live0) post_save[p0] = y0;
-                    if (live1) post_save[p0 + D] = y1;
+#pragma unroll
+                    for (int e = 0; e < NE; ++e)
+                        if (live_r[e & 1]) post_save[(size_t)(row0 + r0 + (e & 1)) * D + fe_(e)] = y[e];
                 }
-                *reinterpret_cast<float2*>(slot_ptr(post_dst) + fe * R + r0) = make_float2(y0, y1);
+#pragma unroll
+                for (int h = 0; h < NE / 2; ++h)
+                    *reinterpret_cast<float2*>(slot_ptr(post_dst) + fe_(2 * h) * R + r0) = make_float2(y[2 * h], y[2 * h + 1]);
             }
             CM_STAMP(si, 6);
-            wcur ^= 1;
+            if (NBUF == 2) wcur ^= 1;
             __syncthreads();
         }
         CM_STAMP(si, 7);
@@ -419,16 +452,24 @@ __global__ void __launch_bounds__(256) frag_kernel(const float* __restrict__ src
     }
 }
 
-template <int D>
+template <int D, bool TP>
 int chain_mma_launch_t(const ChainArgs& a, double bytes, cudaStream_t st) {
-    using C = MmaChainCfg<D>;
+    using C = MmaChainCfg<D, TP>;
     const size_t smem = C::smem_floats * sizeof(float);
-    PAMNET_TRY(func_smem_once(reinterpret_cast<const void*>(chain_mma_kernel<D>), smem));
+    PAMNET_TRY(func_smem_once(reinterpret_cast<const void*>(chain_mma_kernel<D, TP>), smem));
     prof_begin(KC_CHAIN, bytes, st);
-    launch_pdl(chain_mma_kernel<D>, dim3(ceil_div(a.n_rows, kR)), dim3(C::NT), smem, st, a);
+    launch_pdl(chain_mma_kernel<D, TP>, dim3(ceil_div(a.n_rows, kR)), dim3(C::NT), smem, st, a);
     prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;
+}
+
+// throughput variant (two CTAs per SM) from ~2 waves of 8-row CTAs on; PAMNET_CHAIN_TP=0 / 1 forces either
+bool chain_throughput(int n_rows) {
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("PAMNET_CHAIN_TP"); mode = e ? (e[0] == '1' ? 1 : 0) : 2; }
+    if (mode != 2) return mode == 1;
+    return n_rows > 2 * kNumSM * kR;
 }
 
 }  // namespace
@@ -441,8 +482,8 @@ bool chain_mma_enabled(int dim) {
 
 int chain_mma_launch(int dim, const ChainArgs& a, double bytes, cudaStream_t st) {
     switch (dim) {
-        case 128: return chain_mma_launch_t<128>(a, bytes, st);
-        case 64:  return chain_mma_launch_t<64>(a, bytes, st);
+        case 128: return chain_throughput(a.n_rows) ? chain_mma_launch_t<128, true>(a, bytes, st) : chain_mma_launch_t<128, false>(a, bytes, st);
+        case 64:  return chain_throughput(a.n_rows) ? chain_mma_launch_t<64, true>(a, bytes, st) : chain_mma_launch_t<64, false>(a, bytes, st);
         default:
             set_error("chain_mma: unsupported dim %d (64, 128)", dim);
             return -1;
