@@ -312,6 +312,9 @@ def run_ours(args):
         step(dev_batch, next_batch=nxt_dev)
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    import gc
+    gc.collect()
+    gc.disable()                # a collector pause inside a 1.5 ms step is host jitter, not kernel time (re-enabled after the timed regions)
     launches0 = _lib.launch_count()
     ar_ms = []
     barrier()
@@ -359,6 +362,7 @@ def run_ours(args):
     e1.record()
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)) / args.steps
+    gc.enable()
     clocks = sampler.stop() if rank == 0 else None
     h2d = sum(v.numel() * v.element_size() for v in host_batch.__dict__.values() if isinstance(v, torch.Tensor))
     d2h = 4 + 64    # loss scalar + the count read-back of the graph build
@@ -401,6 +405,7 @@ def run_ours(args):
         "config": workload_config(args, sizes), "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": unit, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
+        "ms_per_step_stats": {"median": sorted(per_step)[len(per_step) // 2], "min": min(per_step), "max": max(per_step)},
     }
     if world > 1:
         line["allreduce_ms"] = {"exposed_after_backward": sum(ar_ms) / len(ar_ms) if ar_ms else None,

@@ -399,7 +399,10 @@ static double chain_prepare(int D, const ChainArgs& args, ChainArgs* out) {
     }
     ChainArgs& a = *out;
     a = args;
-    for (int i = 0; i < a.n_stages; ++i) { a.st[i].post_dst = -1; a.st[i].post_zmul = nullptr; a.st[i].post_save = nullptr; }
+    for (int i = 0; i < a.n_stages; ++i) {
+        a.st[i].post_dst = -1;
+        if (a.st[i].op < CH_GMSG_FWD) { a.st[i].post_zmul = nullptr; a.st[i].post_save = nullptr; }   // (gather stages keep their CSR pointers there)
+    }
     // prologue fusion (see ChainStage::post_dst): stage i + 1 = GEMM with a SiLU' prologue on exactly what stage i wrote
     static int fuse = -1;
     if (fuse < 0) { const char* e = getenv("PAMNET_CHAIN_FUSE"); fuse = (e && e[0] == '0') ? 0 : 1; }

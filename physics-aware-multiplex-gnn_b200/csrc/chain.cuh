@@ -11,7 +11,14 @@
 
 namespace pamnet {
 
-enum ChainOp : int { CH_LOAD = 0, CH_GEMM = 1, CH_DOT2 = 2, CH_HEADS_BWD = 3 };
+enum ChainOp : int {
+    CH_LOAD = 0, CH_GEMM = 1, CH_DOT2 = 2, CH_HEADS_BWD = 3,
+    // Gather stages (tensor-core interpreter only): the node-level segment sums that used to be separate launches in front
+    // of a chain, run as the chain's loading stage -- one launch and one [N, D] round trip less per half.
+    CH_GMSG_FWD = 4,     // h[n] = x1[n] + sum_{k in in(n)} SiLU(P_i[n] + P_j[src k] + Q[k]) * Tt[k]   (global_message_passing.py:52-56,38)
+    CH_LMSG_FWD = 5,     // h[n] = x1[n] + sum_{k in in(n)} msum[k] * Rout[k]                          (local_message_passing.py:53-54)
+    CH_GATHER_BWD = 6,   // g_P[n][task] = sum of the per-edge gradient blocks over n's incoming / outgoing slots (wide slot)
+};
 
 constexpr int kChainMaxStages = 26;
 constexpr int kChainSlots = 3;      // D-wide slots 0..2; slot 3 is the wide (4D) staging slot
@@ -30,17 +37,21 @@ struct ChainStage {
     // filled in by chain_launch when the NEXT stage is a GEMM whose prologue (src * silu'(zmul) -> psrc, save_src) reads
     // this stage's output: the multiplication then happens here, in the epilogue, on values that are still in registers
     int post_dst;       // slot that receives out * silu'(post_zmul), -1 = none
-    const float* post_zmul;
-    float* post_save;
+    union { const float* post_zmul; const int32_t* o_ptr; };   // (gather stages: outgoing CSR, see below)
+    union { float* post_save; const int32_t* o_pos; };
     const float* W;     // GEMM: [D(k)][D(n)] k-major (transposed weight in forward, weight itself in backward)
     const float* bias;
-    const float* zmul;
-    float* save_src;    // prologue result written to global (grad wrt pre-activation, for weight gradients)
+    union { const float* zmul; const int32_t* i_ptr; };         // (gather stages: incoming CSR)
+    union { float* save_src; const int32_t* i_src; };           // prologue result written to global (grad wrt pre-activation, for weight gradients)
     float* out_z;       // pre-activation written to global
     float* out_a;       // final value written to global
     const float* add_g; // global tensor added to the output after the activation
     const float* g0;    // LOAD: source; HEADS_BWD: grad_att [N]; DOT2: pointer to W_out.bias
     const float* g1;    // LOAD: optional second addend; HEADS_BWD: grad_out [N]
+    // gather stages (always stage 0 of a chain): i_ptr / i_src = CSR of the nodes' incoming slots and the source node per
+    // slot, o_ptr / o_pos = outgoing CSR and the slot of the k-th outgoing edge (unions above); GMSG_FWD: g0 = P [N, 2D],
+    // g1 = x1, W = Q|Tt rows (ldw); LMSG_FWD: g0 = msum [E, D], g1 = x1, W = Rout rows (ldw); GATHER_BWD: W = per-edge
+    // gradient rows (ldw), width = n_blocks * 2 * D, out_a = g_P
 };
 
 struct ChainArgs {

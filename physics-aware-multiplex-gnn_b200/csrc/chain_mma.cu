@@ -87,6 +87,129 @@ struct MmaChainCfg {
     static constexpr size_t smem_floats = (size_t)NBUF * D * D + (size_t)(kChainSlots + 4) * D * kR;
 };
 
+// ---- gather stages (kept out of line: their row registers must not constrain the GEMM stage's allocation) ----------
+template <int D, int CW>
+__device__ __noinline__ void gmsg_fwd_stage(const ChainStage& st, float* slots, int row0, int n_rows, int warp, int lane,
+                                            int er, int ec) {
+    constexpr int R = kR, EC = CW * 32 / R;
+    auto slot_ptr = [&](int s) -> float* { return slots + s * D * R; };
+            // Two warps per node when there are 16 consumer warps (each takes every other incoming edge), one otherwise;
+            // a lane owns 4 (D = 128) / 2 (D = 64) columns, every row access is one coalesced request, kU rows in flight.
+            constexpr int kU = 2, WPN = CW / R;                    // WPN = warps per node (2 or 1); kU x 3 rows in flight per warp
+            float* part = slot_ptr(kChainWide);                  // [WPN][R][D] partial sums (the wide slot is free in forward chains)
+            const int r = warp % R, wsub = warp / R;
+            const int n = row0 + r;
+            RowVec<D> acc;
+            acc.zero();
+            if (n < n_rows) {
+                const float* P = st.g0; const float* QT = st.W; const int ldq = st.ldw;
+                const int32_t* srcs = st.i_src;
+                RowVec<D> pi;
+                pi.load(P + (size_t)n * 2 * D, lane);
+                const int e0 = st.i_ptr[n], e1 = st.i_ptr[n + 1];
+                for (int k = e0 + wsub; k < e1; k += WPN * kU) {
+                    RowVec<D> pj[kU], q[kU], tt[kU];
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) {
+                        const int kk = k + u * WPN;
+                        if (kk < e1) {
+                            pj[u].load(P + (size_t)srcs[kk] * 2 * D + D, lane);
+                            q[u].load(QT + (size_t)kk * ldq, lane);
+                            tt[u].load(QT + (size_t)kk * ldq + D, lane);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < kU; ++u)
+                        if (k + u * WPN < e1) {
+#pragma unroll
+                            for (int i = 0; i < RowVec<D>::C * RowVec<D>::V; ++i) acc.v[i] += silu(pi.v[i] + pj[u].v[i] + q[u].v[i]) * tt[u].v[i];
+                        }
+                }
+            }
+            acc.store(part + ((size_t)wsub * R + r) * D, lane);
+            __syncthreads();
+            {   // combine (fixed order), + x1, -> slot (transposed) and global h
+                float* d = slot_ptr(st.dst);
+                const bool live = row0 + er < n_rows;
+                const float* x1 = st.g1; float* out_a = st.out_a;
+                for (int c4 = ec; c4 < D / 4; c4 += EC) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (live) {
+                        v = ld4(x1 + (size_t)(row0 + er) * D + c4 * 4);
+#pragma unroll
+                        for (int ws = 0; ws < WPN; ++ws) v = v + ld4(part + ((size_t)ws * R + er) * D + c4 * 4);
+                        if (out_a) st4(out_a + (size_t)(row0 + er) * D + c4 * 4, v);
+                    }
+                    float* qd = d + (c4 * 4) * R + er;
+                    qd[0] = v.x; qd[R] = v.y; qd[2 * R] = v.z; qd[3 * R] = v.w;
+                }
+            }
+            __syncthreads();
+}
+
+template <int D, int CW>
+__device__ __noinline__ void gather_stage(const ChainStage& st, float* slots, int row0, int n_rows, int warp, int lane) {
+    constexpr int R = kR;
+    auto slot_ptr = [&](int s) -> float* { return slots + s * D * R; };
+            // one warp per (node, task): LMSG_FWD has one task per node (h = x1 + sum msum * Rout), GATHER_BWD 2 * n_blocks
+            // (block b of the per-edge gradient rows over incoming / outgoing slots); results go straight to the slot
+            constexpr int kU = 2;
+            const bool fwd = st.op == CH_LMSG_FWD;
+            const int ntask = fwd ? 1 : st.width / D;
+            float* d = slot_ptr(st.dst);
+            const float* rows = st.W; const int ldr = st.ldw;
+            float* out_a = st.out_a; const int ld_out = fwd ? D : st.width;
+            for (int item = warp; item < R * ntask; item += CW) {
+                const int r = item % R, task = item / R;
+                const int n = row0 + r;
+                RowVec<D> s;
+                s.zero();
+                if (n < n_rows) {
+                    if (fwd) {
+                        const float* msum = st.g0;
+                        s.load(st.g1 + (size_t)n * D, lane);
+                        for (int k = st.i_ptr[n], k1 = st.i_ptr[n + 1]; k < k1; k += kU) {
+                            RowVec<D> ms[kU], ro[kU];
+#pragma unroll
+                            for (int u = 0; u < kU; ++u)
+                                if (k + u < k1) { ms[u].load(msum + (size_t)(k + u) * D, lane); ro[u].load(rows + (size_t)(k + u) * ldr, lane); }
+#pragma unroll
+                            for (int u = 0; u < kU; ++u)
+                                if (k + u < k1) {
+#pragma unroll
+                                    for (int i = 0; i < RowVec<D>::C * RowVec<D>::V; ++i) s.v[i] += ms[u].v[i] * ro[u].v[i];
+                                }
+                        }
+                    } else {
+                        const int b = task >> 1;
+                        const bool outgoing = task & 1;
+                        const int32_t* ptr = outgoing ? st.o_ptr : st.i_ptr;
+                        const int32_t* opos = st.o_pos;
+                        for (int k = ptr[n], k1 = ptr[n + 1]; k < k1; k += kU) {
+                            RowVec<D> v[kU];
+#pragma unroll
+                            for (int u = 0; u < kU; ++u)
+                                if (k + u < k1) v[u].load(rows + (size_t)(outgoing ? opos[k + u] : k + u) * ldr + b * D, lane);
+#pragma unroll
+                            for (int u = 0; u < kU; ++u)
+                                if (k + u < k1) {
+#pragma unroll
+                                    for (int i = 0; i < RowVec<D>::C * RowVec<D>::V; ++i) s.v[i] += v[u].v[i];
+                                }
+                        }
+                    }
+                    if (out_a) s.store(out_a + (size_t)n * ld_out + task * D, lane);
+                }
+                // transposed slot: column c of this task -> d[(task * D + c) * R + r]
+#pragma unroll
+                for (int cc = 0; cc < RowVec<D>::C; ++cc)
+#pragma unroll
+                    for (int vv = 0; vv < RowVec<D>::V; ++vv)
+                        d[(size_t)(task * D + (cc * 32 + lane) * RowVec<D>::V + vv) * R + r] = s.v[cc * RowVec<D>::V + vv];
+            }
+            __syncthreads();
+}
+
 // Two variants of one kernel.
 //  * latency (TP = false; up to ~2 waves of 8-row CTAs, the batch-32 case): consumer warp w = (M tile w % WM, k half
 //    w / WM) multiplies its 16 features x 8 rows over half of K; the two warps of an M tile swap the accumulator halves
@@ -160,7 +283,7 @@ __global__ void __launch_bounds__(MmaChainCfg<D, TP>::NT, TP ? 2 : 1) chain_mma_
                 if (NBUF == 1 && nxt >= 0) issue_weights(nxt, 0);
             } else {
                 __syncthreads();
-                if (op == CH_DOT2) __syncthreads();
+                if (op == CH_DOT2 || op == CH_GMSG_FWD) __syncthreads();
             }
         }
         return;
@@ -185,7 +308,13 @@ __global__ void __launch_bounds__(MmaChainCfg<D, TP>::NT, TP ? 2 : 1) chain_mma_
     // Everything above touched only kernel parameters and prepared weights; from here on the predecessor's outputs are read.
     pdl_wait();
 
-    for (int si = 0; si < n_stages; ++si) {
+    // A gather stage is always stage 0: it runs before the stage loop, out of line, so that its row registers and the call
+    // do not touch the loop's register allocation (inside the loop the call sites cost 144 B of spills and 60 % of the
+    // kernel's speed).
+    int si0 = 0;
+    if (s_stage[0].op == CH_GMSG_FWD) { gmsg_fwd_stage<D, CW>(s_stage[0], slots, row0, n_rows, warp, lane, er, ec); si0 = 1; }
+    else if (s_stage[0].op == CH_LMSG_FWD || s_stage[0].op == CH_GATHER_BWD) { gather_stage<D, CW>(s_stage[0], slots, row0, n_rows, warp, lane); si0 = 1; }
+    for (int si = si0; si < n_stages; ++si) {
         const ChainStage& st = s_stage[si];
         if (si == n_stages - 1) pdl_trigger();
         CM_STAMP(si, 0);

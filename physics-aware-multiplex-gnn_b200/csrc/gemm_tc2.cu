@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[kRaw], raw_free[kRaw], conv_bar[kLo], lo_free[kLo], acc_full[2], acc_free[2];
     __shared__ uint32_t tmem_base_s;
-    __shared__ float s_colsum[TM];
+    __shared__ float s_colsum[4][TM];        // per converter warp: column sums of A (bias gradient)
 
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     if (t == 0) T2_STAMP(0);
@@ -221,7 +221,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
                      "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (t < TM) s_colsum[t] = 0.f;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -380,16 +379,29 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
                 }
             }
             if (do_bias) {
-                // fold the 8 threads per (block, chunk) in shared memory, then one atomic per column
-                const int lc = ((((ct & 7) >> 1) ^ ((ct >> 3) & 3)) << 1) | (ct & 1);
+                // Thread ct holds 16 partial column sums (4 blocks x its logical chunk lc).  Within a warp the four lanes
+                // that share lc differ in k-row % 4 (lane bits 3-4) and, through the swizzle, in their physical 32-byte
+                // chunk (lane bits 1-2): two xor-butterfly steps (masks 8|2 and 16|4) fold them; lanes 0-7 then hold the
+                // warp's sums for lc = lane.  (The first version did 16 shared-memory atomics per thread onto 128
+                // addresses: 20 % of the kernel's stall samples in the ncu capture of a weight-gradient launch.)
 #pragma unroll
-                for (int b = 0; b < 4; ++b)
+                for (int i = 0; i < 16; ++i) {
+                    asum[i] += __shfl_xor_sync(0xffffffffu, asum[i], 10);
+                    asum[i] += __shfl_xor_sync(0xffffffffu, asum[i], 20);
+                }
+                const int cw = ct >> 5, cl = ct & 31;
+                if (cl < 8) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) { atomicAdd(&s_colsum[32 * b + 4 * lc + e], asum[4 * b + e]); asum[4 * b + e] = 0.f; }
+                    for (int b = 0; b < 4; ++b)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) s_colsum[cw][32 * b + 4 * cl + e] = asum[4 * b + e];
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) asum[i] = 0.f;
                 asm volatile("bar.sync 1, %0;" ::"n"(kConvThreads) : "memory");
                 const int M = sl.m > 0 ? sl.m : args.M;
-                if (w.m0 + ct < M) atomicAdd(&sl.C2[w.m0 + ct], s_colsum[ct]);    // C2 is zero-initialised by the caller
-                s_colsum[ct] = 0.f;
+                if (w.m0 + ct < M)      // C2 is zero-initialised by the caller
+                    atomicAdd(&sl.C2[w.m0 + ct], (s_colsum[0][ct] + s_colsum[1][ct]) + (s_colsum[2][ct] + s_colsum[3][ct]));
                 asm volatile("bar.sync 1, %0;" ::"n"(kConvThreads) : "memory");
             }
         }

@@ -143,6 +143,13 @@ struct Ws {
     float *gQT, *gQR, *gzq2, *gzq1, *gz_s, *gz_eg, *gz_el, *g_rbf_g, *g_rbf_l;
 };
 
+// PAMNET_GATHER_FUSE=0: node-level segment sums as their own launches again (the round-1 schedule)
+inline bool gather_fusion_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("PAMNET_GATHER_FUSE"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on == 1;
+}
+
 // half index hh = 2*l (global layer l) or 2*l+1 (local layer l)
 inline bool is_local(int hh) { return hh & 1; }
 inline int nP_of(int hh) { return is_local(hh) ? 4 : 2; }
@@ -252,8 +259,10 @@ void add_pre_fwd(Prog& p, const float* params, const HalfP& hp, const HalfWs& hw
 }
 
 // forward update block (global_message_passing.py:39-44); leaves x_out in slot 1 (and in hw.r[2])
-void add_post_fwd(Prog& p, const float* params, const HalfP& hp, const HalfWs& hw, int D, const float* res_x) {
-    p.add(st_load(0, hw.h, D, D));
+void add_post_fwd(Prog& p, const float* params, const HalfP& hp, const HalfWs& hw, int D, const float* res_x,
+                  const ChainStage* gather = nullptr) {
+    if (gather) p.add(*gather);            // the half's node-level segment sum as the chain's loading stage (writes hw.h too)
+    else p.add(st_load(0, hw.h, D, D));
     { ChainStage& s = p.add(st_gemm(0, 1, hw.x2T, D, params + hp.x2.b, 1)); s.out_z = hw.z_x2; s.out_a = hw.a_x2; s.ld_out = D; }
     int cur = 1;                                    // slot holding the Res input
     for (int r = 0; r < 3; ++r) {
@@ -288,9 +297,10 @@ void add_heads_fwd(Prog& p, const float* params, const HalfP& hp, const HalfWs& 
 // backward of add_pre_fwd for half hh: g_x1 = g_h + g_P . W_proj ; g_x = (g_x1 * SiLU'(z_x1)) . W_x1 + g_resx
 // result in slot 2 (and in `g_x_out` if non-null)
 void add_pre_bwd(Prog& p, const float* params, const HalfP& hp, const HalfWs& hw, int hh, int D, const Ws& w,
-                 float* g_x_out) {
+                 float* g_x_out, const ChainStage* gather = nullptr) {
     const int nP = nP_of(hh);
-    p.add(st_load(kChainWide, hw.g_P, nP * D, nP * D));
+    if (gather) p.add(*gather);            // grad of P gathered from the per-edge gradients right here (writes hw.g_P too)
+    else p.add(st_load(kChainWide, hw.g_P, nP * D, nP * D));
     p.add(st_load(0, w.g_h, D, D));
     int cur = 0;
     for (int c = 0; c < nP; ++c) {
@@ -812,6 +822,9 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
         PAMNET_TRY(embed_local());
         PAMNET_TRY(issue_group_l(0));
     }
+    // node-level segment sums run as the loading stage of the chain that consumes them (tensor-core interpreter only)
+    const bool fuse_gather = chain_mma_enabled(D) && gather_fusion_enabled();
+    ChainStage gstage;
     for (int hh = 0; hh < H; ++hh) {              // models.py:196-204
         const HalfWs& hw = w.half[hh];
         const int l = hh >> 1;
@@ -825,7 +838,13 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
             memset(&a, 0, sizeof(a));
             a.n_nodes = (int)N; a.n_edges = (int)Eg; a.ptr = pl.g_ptr; a.src = pl.g_src; a.dst = pl.g_dst; a.P = hw.P;
             a.QT = w.QT + l * 2 * D; a.ldq = L * 2 * D; a.x1 = hw.x1; a.h = hw.h;
-            PAMNET_TRY(global_msg_fwd(D, a, (int)Eg, st));
+            if (fuse_gather) {
+                gstage = stage_zero();
+                gstage.op = CH_GMSG_FWD; gstage.dst = 0; gstage.g0 = hw.P; gstage.g1 = hw.x1; gstage.W = a.QT; gstage.ldw = a.ldq;
+                gstage.i_ptr = pl.g_ptr; gstage.i_src = pl.g_src; gstage.out_a = hw.h;
+            } else {
+                PAMNET_TRY(global_msg_fwd(D, a, (int)Eg, st));
+            }
         } else {
             if (l == grp[group_of[l]]) PAMNET_TRY(sc.wait(st, ev_l[group_of[l]]));
             LocalMsgArgs a;
@@ -836,11 +855,17 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
             a.x1 = hw.x1; a.m_nb = hw.m_nb; a.msum = hw.msum; a.h = hw.h;
             PAMNET_TRY(local_edge_fwd(D, a, st));
             PAMNET_TRY(local_trip_fwd(D, a, (int)T, st));
-            PAMNET_TRY(local_msg_fwd(D, a, (int)T, st));
+            if (fuse_gather) {
+                gstage = stage_zero();
+                gstage.op = CH_LMSG_FWD; gstage.dst = 0; gstage.g0 = hw.msum; gstage.g1 = hw.x1; gstage.W = a.QR + 3 * D; gstage.ldw = a.ldq;
+                gstage.i_ptr = pl.l_ptr; gstage.out_a = hw.h;
+            } else {
+                PAMNET_TRY(local_msg_fwd(D, a, (int)T, st));
+            }
         }
         Prog p((int)N);
         const float* res_x = hh == 0 ? w.x0 : w.half[hh - 1].r[2];
-        add_post_fwd(p, params, half_params(mp, hh), hw, D, res_x);
+        add_post_fwd(p, params, half_params(mp, hh), hw, D, res_x, fuse_gather ? &gstage : nullptr);
         if (hh + 1 < H) add_pre_fwd(p, params, half_params(mp, hh + 1), w.half[hh + 1], hh + 1, D, 1);
         PAMNET_TRY(chain_launch(D, p.a, st));
         {   // readout heads of this half, concurrently with the next half
@@ -1086,6 +1111,8 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
     };
 
     // ---- main stream: phase B reversed; auxiliary stream: weight gradients as soon as their inputs exist --------
+    const bool fuse_gather = chain_mma_enabled(D) && gather_fusion_enabled() && !atomic_gp;
+    ChainStage gstage = stage_zero();
     for (int hh = H - 1; hh >= 0; --hh) {
         const HalfWs& hw = w.half[hh];
         const HalfP& hp = half_params(mp, hh);
@@ -1093,7 +1120,8 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
         {
             Prog p((int)N);
             const bool has_gx = hh + 1 < H;   // the last layer's x output is unused (models.py:201-204)
-            if (has_gx) add_pre_bwd(p, params, half_params(mp, hh + 1), w.half[hh + 1], hh + 1, D, w, nullptr);
+            if (has_gx) add_pre_bwd(p, params, half_params(mp, hh + 1), w.half[hh + 1], hh + 1, D, w, nullptr,
+                                    fuse_gather ? &gstage : nullptr);      // gstage: half hh + 1's gather, set up below last iteration
             add_post_bwd(p, params, hp, hw, D, w, has_gx);
             PAMNET_TRY(sc.wait(st, ev_heads[hh]));
             PAMNET_TRY(chain_launch(D, p.a, st));
@@ -1124,9 +1152,19 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
             ng.n_blocks = 2; ng.ptr = pl.l_ptr; ng.optr = pl.l_optr; ng.opos = pl.l_opos;
             ng.gz = w.gQR + l * 4 * D; ng.ldq = L * 4 * D;
         }
-        if (!atomic_gp) PAMNET_TRY(node_grad_gather(D, ng, is_local(hh) ? (int)El : (int)Eg, st));
+        if (fuse_gather) {
+            // the gather of this half's per-edge gradients into grad P runs as the loading stage of the NEXT chain launch
+            // (which consumes it); the projection weight gradients that read grad P follow that launch
+            gstage = stage_zero();
+            gstage.op = CH_GATHER_BWD; gstage.dst = kChainWide; gstage.width = 2 * ng.n_blocks * D;
+            gstage.W = ng.gz; gstage.ldw = ng.ldq; gstage.i_ptr = ng.ptr; gstage.o_ptr = ng.optr; gstage.o_pos = ng.opos;
+            gstage.out_a = hw.g_P;
+        } else if (!atomic_gp) {
+            PAMNET_TRY(node_grad_gather(D, ng, is_local(hh) ? (int)El : (int)Eg, st));
+        }
         PAMNET_TRY(sc.order(st, s3));
-        PAMNET_TRY(node_wgrads(hh, hh + 1 < H ? hh + 1 : -1, hh, s3));
+        if (fuse_gather) PAMNET_TRY(node_wgrads(hh, hh + 1 < H ? hh + 1 : -1, hh + 1 < H ? hh + 1 : -1, s3));
+        else PAMNET_TRY(node_wgrads(hh, hh + 1 < H ? hh + 1 : -1, hh, s3));
         // per-edge / per-triplet weight gradients of this half: everything they read is complete now
         if (is_local(hh)) {
             if (sc.s4 != s3) PAMNET_TRY(sc.order(st, sc.s4));
@@ -1162,7 +1200,7 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
     }
     {   // into the node input
         Prog p((int)N);
-        add_pre_bwd(p, params, half_params(mp, 0), w.half[0], 0, D, w, w.g_x0);
+        add_pre_bwd(p, params, half_params(mp, 0), w.half[0], 0, D, w, w.g_x0, fuse_gather ? &gstage : nullptr);
         PAMNET_TRY(chain_launch(D, p.a, st));
     }
     if (cfg.dataset == PAMNET_PDBBIND) {
@@ -1174,7 +1212,7 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
         PAMNET_TRY(embed_backward(node_in, N, w.g_x0, mp.n_embed, D, gp + mp.emb, st));
     }
     PAMNET_TRY(sc.order(st, s3));
-    PAMNET_TRY(node_wgrads(-1, 0, -1, s3));
+    PAMNET_TRY(node_wgrads(-1, 0, fuse_gather ? 0 : -1, s3));
     if (g_buckets_on.load()) {
         const cudaStream_t bs[kBucketStreams] = {s2, s3, sc.s4, sc.s5};
         PAMNET_TRY(record_bucket(0, H, bs));
