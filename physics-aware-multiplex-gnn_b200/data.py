@@ -235,9 +235,10 @@ class DeviceDataset:
         ei = torch.empty((2, e), dtype=torch.int64, device=dev)
         bvec = torch.empty(n, dtype=torch.int64, device=dev)
         y = torch.empty(g, dtype=torch.float32, device=dev)
-        _lib.check(lib.pamnet_collate(tab_dev.data_ptr(), g, self.node_ptr.data_ptr(), self.edge_ptr.data_ptr(),
-                                      self.x_all.data_ptr(), self.pos_all.data_ptr(), self.ei_all.data_ptr(),
-                                      int(self.ei_all.shape[1]), self.y_all.data_ptr(), e, x.data_ptr(), pos.data_ptr(),
-                                      ei.data_ptr(), bvec.data_ptr(), y.data_ptr(),
-                                      torch.cuda.current_stream().cuda_stream), "collate")
+        with torch.cuda.device(dev):            # the library launches on the current device
+            _lib.check(lib.pamnet_collate(tab_dev.data_ptr(), g, self.node_ptr.data_ptr(), self.edge_ptr.data_ptr(),
+                                          self.x_all.data_ptr(), self.pos_all.data_ptr(), self.ei_all.data_ptr(),
+                                          int(self.ei_all.shape[1]), self.y_all.data_ptr(), e, x.data_ptr(), pos.data_ptr(),
+                                          ei.data_ptr(), bvec.data_ptr(), y.data_ptr(),
+                                          torch.cuda.current_stream(dev).cuda_stream), "collate")
         return Batch(x=x, pos=pos, edge_index=ei, batch=bvec, y=y)

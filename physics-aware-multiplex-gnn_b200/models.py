@@ -81,11 +81,14 @@ class _PAMNetFunction(torch.autograd.Function):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         out = torch.empty(sz.n_graphs, dtype=torch.float32, device=dev)
         need_grad = ctx.needs_input_grad[5]
-        _lib.check(lib.pamnet_model_forward(cfg, sz, sbf_consts_struct(), flat.data_ptr(), node_in.data_ptr(),
-                                            _lib.ptr(sign), pos.data_ptr(), plan.base.data_ptr(),
-                                            plan.trip.data_ptr(), ws.data_ptr(), ws_bytes, int(need_grad),
-                                            out.data_ptr(), torch.cuda.current_stream().cuda_stream,
-                                            mod._aux_stream_ptr(dev), _lib.ptr(prepared)), "model_forward")
+        # the library launches on the CURRENT device and owns per-device streams: make the tensors' device current
+        # (a model on cuda:1 while cuda:0 is current would otherwise run on device 0 with device-1 pointers)
+        with torch.cuda.device(dev):
+            _lib.check(lib.pamnet_model_forward(cfg, sz, sbf_consts_struct(), flat.data_ptr(), node_in.data_ptr(),
+                                                _lib.ptr(sign), pos.data_ptr(), plan.base.data_ptr(),
+                                                plan.trip.data_ptr(), ws.data_ptr(), ws_bytes, int(need_grad),
+                                                out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream,
+                                                mod._aux_stream_ptr(dev), _lib.ptr(prepared)), "model_forward")
         if need_grad:
             ctx.mod, ctx.plan, ctx.ws, ctx.ws_bytes = mod, plan, ws, ws_bytes
             ctx.prepared = prepared
@@ -96,21 +99,37 @@ class _PAMNetFunction(torch.autograd.Function):
     def backward(ctx, grad_out):
         lib = _lib.load()
         mod, plan = ctx.mod, ctx.plan
+        if ctx.ws is None:
+            raise RuntimeError("pamnet_b200: backward through the same forward a second time (retain_graph=True) is not "
+                               "supported -- the step's workspace is released after the first backward; run forward again")
         grad_out = grad_out.contiguous().float()
         target, direct = mod._grad_target()
-        _lib.check(lib.pamnet_model_backward(mod._ccfg, plan.sizes, sbf_consts_struct(), mod._flat.data_ptr(),
-                                             ctx.node_in.data_ptr(), _lib.ptr(ctx.sign), ctx.pos.data_ptr(),
-                                             plan.base.data_ptr(), plan.trip.data_ptr(), ctx.ws.data_ptr(),
-                                             ctx.ws_bytes, grad_out.data_ptr(), target.data_ptr(),
-                                             torch.cuda.current_stream().cuda_stream,
-                                             mod._aux_stream_ptr(grad_out.device), _lib.ptr(ctx.prepared)),
-                   "model_backward")
+        dev = grad_out.device
+        with torch.cuda.device(dev):
+            _lib.check(lib.pamnet_model_backward(mod._ccfg, plan.sizes, sbf_consts_struct(), mod._flat.data_ptr(),
+                                                 ctx.node_in.data_ptr(), _lib.ptr(ctx.sign), ctx.pos.data_ptr(),
+                                                 plan.base.data_ptr(), plan.trip.data_ptr(), ctx.ws.data_ptr(),
+                                                 ctx.ws_bytes, grad_out.data_ptr(), target.data_ptr(),
+                                                 torch.cuda.current_stream(dev).cuda_stream,
+                                                 mod._aux_stream_ptr(dev), _lib.ptr(ctx.prepared)),
+                       "model_backward")
         ctx.ws = None
         mod._deliver_grads(target, direct)
         return (None, None, None, None, None, None, None)
 
 
 class _PAMNetBase(nn.Module):
+    """Shared machinery of PAMNet / PAMNet_s.
+
+    Autograd contract (differs from a plain nn.Module): the module's parameters are views of one
+    flat buffer and the whole model is ONE autograd node whose backward writes the gradients straight into the matching
+    flat gradient buffer and attaches ``p.grad`` views.  Consequences:
+      * ``loss.backward()`` (optionally after ``zero_grad``) is the supported way to obtain parameter gradients;
+        ``torch.autograd.grad(loss, model.parameters())`` and ``backward(inputs=...)`` do not see the parameters, and
+        parameter hooks do not fire -- so ``torch.nn.parallel.DistributedDataParallel`` would silently skip its
+        all-reduce: wrapping is refused (use pamnet_b200.parallel instead);
+      * a second backward through the same forward (retain_graph=True) raises;
+      * grad tensors kept from an earlier step alias the flat buffer and are overwritten by the next backward."""
     _simple = False
     _MAX_NB = 1000         # max_num_neighbors of the radius graph: models.py:110,128 (PAMNet), :301 (PAMNet_s: 500)
 
@@ -204,18 +223,21 @@ class _PAMNetBase(nn.Module):
         self._gflat = None
 
     def _aliased(self, full=True):
-        """Do the parameters still alias the flat buffer?  (utils/ema.py:27,32 swap param.data wholesale.)
-        full=False checks the first, the last and a rotating window of 16 parameters; every 64th call is full."""
+        """Do the parameters still alias the flat buffer?  (utils/ema.py:27,32 swap param.data wholesale; a partial weight
+        load may replace single tensors.)  All ~390 pointers are compared on every call (~55 us of host time; the round-1
+        rotating window could miss a replaced tensor for up to 63 steps); `full` is kept for callers of the old signature.
+        Replaced Parameter OBJECTS (load_state_dict(assign=True)) are picked up by load_state_dict below."""
         base = self._flat.data_ptr()
-        pl, offs = self._param_list, self._offsets
-        if not full:
-            self._alias_tick += 1
-            if self._alias_tick % 64:
-                n = len(pl)
-                lo = (self._alias_tick * 16) % n
-                idx = [0, n - 1] + [(lo + i) % n for i in range(16)]
-                return all(pl[i][1].data_ptr() == base + 4 * offs[i] for i in idx)
-        return all(p.data_ptr() == base + 4 * off for (_, p), off in zip(pl, offs))
+        return all(p.data_ptr() == base + 4 * off for (_, p), off in zip(self._param_list, self._offsets))
+
+    def load_state_dict(self, state_dict, *args, **kwargs):
+        out = super().load_state_dict(state_dict, *args, **kwargs)
+        if getattr(self, "_param_list", None):
+            cur = list(self.named_parameters())
+            if any(a is not b for (_, a), (_, b) in zip(self._param_list, cur)):      # assign=True replaced the Parameters
+                self._param_list = cur
+                self._flatten()
+        return out
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
@@ -245,7 +267,7 @@ class _PAMNetBase(nn.Module):
         base_b, trip_b = _lib.c_sz(), _lib.c_sz()
         need = (_lib.c_i64 * 4)()
         sz = _lib.Sizes(n, n_graphs, 0, 0, 0, 0)
-        stream = torch.cuda.current_stream().cuda_stream
+        stream = torch.cuda.current_stream(dev).cuda_stream
         for attempt in range(4):
             guess = _lib.Sizes(n, n_graphs, caps["eg"], caps["el"], 4 * caps["el"], 4 * caps["el"])
             _lib.check(lib.pamnet_plan_bytes(cfg, guess, base_b, trip_b), "plan_bytes")
@@ -256,10 +278,11 @@ class _PAMNetBase(nn.Module):
             trip = torch.empty(caps["trip"], dtype=torch.uint8, device=dev)
             sb = lib.pamnet_plan_build_scratch_bytes(cfg, n, e_in, caps["eg"])
             scratch = torch.empty(sb, dtype=torch.uint8, device=dev)
-            rc = lib.pamnet_plan_build(cfg, pos.data_ptr(), batch.data_ptr(), n, n_graphs, _lib.ptr(el_in), e_in,
-                                       int(max_nb), eg_buf.data_ptr(), caps["eg"], el_buf.data_ptr(), caps["el"],
-                                       base.data_ptr(), caps["base"], trip.data_ptr(), caps["trip"],
-                                       scratch.data_ptr(), sb, sz, need, stream)
+            with torch.cuda.device(dev):
+                rc = lib.pamnet_plan_build(cfg, pos.data_ptr(), batch.data_ptr(), n, n_graphs, _lib.ptr(el_in), e_in,
+                                           int(max_nb), eg_buf.data_ptr(), caps["eg"], el_buf.data_ptr(), caps["el"],
+                                           base.data_ptr(), caps["base"], trip.data_ptr(), caps["trip"],
+                                           scratch.data_ptr(), sb, sz, need, stream)
             if rc == 0:
                 break
             if rc != 1:
@@ -390,7 +413,7 @@ class _PAMNetBase(nn.Module):
             return None
         self._prefetched = None
         _, inputs, plan, done, copied = pre
-        cur = torch.cuda.current_stream()
+        cur = torch.cuda.current_stream(self._flat.device)
         cur.wait_event(done)
         # these blocks came from the side stream's pool and are consumed on the current stream from here on
         held = [*inputs, plan.base, plan.trip, plan.edge_index_g, plan.edge_index_l]
@@ -433,8 +456,9 @@ class _PAMNetBase(nn.Module):
         buf = getattr(self, "_prepared", None)
         if buf is None or buf.device != dev:
             buf = self._prepared = torch.empty(lib.pamnet_prepared_weights_bytes(self._ccfg), dtype=torch.uint8, device=dev)
-        self._aux_stream.wait_stream(torch.cuda.current_stream())     # the parameters' last writer
-        _lib.check(lib.pamnet_prepare_weights(self._ccfg, self._flat.data_ptr(), buf.data_ptr(), aux_ptr), "prepare_weights")
+        self._aux_stream.wait_stream(torch.cuda.current_stream(dev))     # the parameters' last writer
+        with torch.cuda.device(dev):
+            _lib.check(lib.pamnet_prepare_weights(self._ccfg, self._flat.data_ptr(), buf.data_ptr(), aux_ptr), "prepare_weights")
         return buf
 
     def _init_embeddings(self):

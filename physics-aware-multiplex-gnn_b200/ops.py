@@ -25,9 +25,19 @@ def _stream():
 
 
 def _require_cuda(*ts):
+    """CUDA tensors on the CURRENT device: the operator calls enqueue on torch's current stream and the library launches on
+    the current device, so a tensor of another GPU would be addressed from the wrong device."""
+    cur = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise _lib.PamnetError("pamnet_b200 ops run on CUDA tensors only (no CPU fallback)")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise _lib.PamnetError(f"pamnet_b200 ops: tensor on cuda:{t.device.index} but cuda:{cur} is the current device; "
+                                   f"call inside `with torch.cuda.device({t.device.index}):`")
 
 
 def _f32(t):

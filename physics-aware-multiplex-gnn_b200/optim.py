@@ -34,14 +34,30 @@ class FusedAdamEMA(torch.optim.Optimizer):
         self.shadow = flat.detach().clone() if self.ema_decay is not None else None
         self._original = None
         self._sumsq = torch.zeros(1, dtype=torch.float64, device=flat.device)
-        skip = []
-        for (_, p), off, used in zip(model._param_list, model._offsets, model._param_used):
-            if not (used and p.requires_grad):          # torch.optim skips parameters whose .grad is None
-                skip += [off, off + p.numel()]
-        if len(skip) > 8:
-            raise ValueError("more than 4 gradient-free tensors: not a reference PAMNet configuration")
-        self._skip = (_lib.c_i64 * max(len(skip), 1))(*skip)
-        self._n_skip = len(skip) // 2
+        self._skip, self._n_skip = None, 0
+        self._skip_ranges()
+
+    def _skip_ranges(self):
+        """[begin, end) element ranges the kernel must leave untouched: tensors without a gradient RIGHT NOW (grad is None,
+        requires_grad False, or unused on this dataset) -- torch.optim.Adam skips exactly those.  Re-evaluated every step
+        (a later requires_grad change or a step without a preceding backward is honoured); adjacent tensors are merged."""
+        m = self.model
+        ranges = []
+        for (_, p), off, used in zip(m._param_list, m._offsets, m._param_used):
+            if used and p.requires_grad and p.grad is not None:
+                continue
+            end = off + p.numel()
+            if ranges and off - ranges[-1][1] < 64:       # padding between tensors (128 B alignment) carries no parameter
+                ranges[-1][1] = end
+            else:
+                ranges.append([off, end])
+        if len(ranges) > 4:
+            raise ValueError("more than 4 separate gradient-free parameter ranges: the fused step supports the reference "
+                             "configurations (unused init_linear / embeddings) and frozen contiguous blocks only")
+        flat = [x for r in ranges for x in r]
+        self._skip = (_lib.c_i64 * max(len(flat), 1))(*flat)
+        self._n_skip = len(ranges)
+        return ranges
 
     def _flat_grad(self):
         """The flat gradient buffer, valid when every p.grad is the view backward attached (the normal case after
@@ -49,11 +65,9 @@ class FusedAdamEMA(torch.optim.Optimizer):
         m = self.model
         views = m._grad_views()
         for (_, p), v, used in zip(m._param_list, views, m._param_used):
-            if not (used and p.requires_grad):
+            if not (used and p.requires_grad) or p.grad is None:
                 continue
-            if p.grad is None:
-                v.zero_()
-            elif p.grad is not v:
+            if p.grad is not v:
                 v.copy_(p.grad)
         return m._gflat
 
@@ -67,6 +81,9 @@ class FusedAdamEMA(torch.optim.Optimizer):
         flat = m._flat
         if self.exp_avg.device != flat.device:
             raise RuntimeError("the model moved to another device after the optimizer was built")
+        ranges = self._skip_ranges()
+        if len(ranges) == 1 and ranges[0][0] == 0 and ranges[0][1] >= m._offsets[-1] + m._param_list[-1][1].numel():
+            return None                      # no parameter has a gradient (step without backward): torch.optim.Adam does nothing
         g = self._flat_grad()
         group = self.param_groups[0]
         beta1, beta2 = group["betas"]
@@ -75,12 +92,13 @@ class FusedAdamEMA(torch.optim.Optimizer):
         if self.shadow is not None:             # utils/ema.py:14
             decay = min(self.ema_decay, (1.0 + num_updates) / (10.0 + num_updates))
         lib = _lib.load()
-        _lib.check(lib.pamnet_optimizer_step(
-            flat.data_ptr(), g.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
-            _lib.ptr(self.shadow), flat.numel(), self._skip, self._n_skip, self.num_steps, float(group["lr"]),
-            float(beta1), float(beta2), float(group["eps"]), float(group["weight_decay"]),
-            float(self.max_norm) if self.max_norm is not None else 0.0, float(decay), 1,
-            self._sumsq.data_ptr(), torch.cuda.current_stream().cuda_stream), "optimizer_step")
+        with torch.cuda.device(flat.device):            # the library launches on the current device
+            _lib.check(lib.pamnet_optimizer_step(
+                flat.data_ptr(), g.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                _lib.ptr(self.shadow), flat.numel(), self._skip, self._n_skip, self.num_steps, float(group["lr"]),
+                float(beta1), float(beta2), float(group["eps"]), float(group["weight_decay"]),
+                float(self.max_norm) if self.max_norm is not None else 0.0, float(decay), 1,
+                self._sumsq.data_ptr(), torch.cuda.current_stream(flat.device).cuda_stream), "optimizer_step")
 
     # ---- checkpoint / resume: the moments and the EMA shadow live in flat buffers, not in Optimizer.state ----------
     def state_dict(self):
@@ -94,11 +112,14 @@ class FusedAdamEMA(torch.optim.Optimizer):
     def load_state_dict(self, state_dict):
         sd = dict(state_dict)
         flat = sd.pop("pamnet_flat", None)
-        super().load_state_dict(sd)
+        # validate BEFORE touching any state: a rejected checkpoint must leave param_groups as they were
         if flat is None:
             raise KeyError("not a FusedAdamEMA state_dict (no 'pamnet_flat' entry)")
         if flat["exp_avg"].numel() != self.exp_avg.numel():
             raise ValueError("optimizer state belongs to a different model configuration")
+        if (flat["shadow"] is None) != (self.shadow is None):
+            raise ValueError("EMA shadow present in one of (checkpoint, optimizer) only")
+        super().load_state_dict(sd)
         self.exp_avg.copy_(flat["exp_avg"])
         self.exp_avg_sq.copy_(flat["exp_avg_sq"])
         if (flat["shadow"] is None) != (self.shadow is None):

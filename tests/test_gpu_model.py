@@ -394,3 +394,15 @@ torch.save({"out": out.detach().cpu(), "g": {k: (p.grad.cpu() if p.grad is not N
     assert 1e-7 < e_out < 5e-3, e_out           # really reduced precision, and within its rung
     worst = max(rel_err(res["g"][k], v) for k, v in g64.items() if v is not None)
     assert worst < 5e-2, worst
+
+
+def test_second_backward_raises_clearly():
+    """The step's workspace is released after backward: a second backward through the same forward is an explicit error
+    (not an AttributeError), as documented in _PAMNetBase."""
+    gold = load_golden("qm9_small_pamnet")
+    model = _model(gold)
+    b = batch_of(gold).to("cuda")
+    loss = (model(b) - b.y).abs().mean()
+    loss.backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="second time"):
+        loss.backward()

@@ -115,3 +115,24 @@ def test_optimizer_state_dict_round_trip_resumes():
     assert rel(opt_b.shadow, opt_a.shadow) < 1e-6 and rel(opt_b.exp_avg_sq, opt_a.exp_avg_sq) < 1e-5
     with pytest.raises(KeyError):
         opt_b.load_state_dict(torch.optim.Adam(model_b.parameters()).state_dict())
+
+
+def test_step_without_backward_is_a_no_op_and_frozen_block_is_skipped():
+    """torch.optim.Adam skips parameters whose grad is None: a step() without a preceding backward changes nothing, and a
+    block frozen AFTER the optimizer was built (requires_grad False) keeps its values while the rest updates."""
+    from pamnet_b200 import FusedAdamEMA, synthetic_qm9_batch
+    model, _ = _pair()
+    batch = synthetic_qm9_batch(4, seed=1).to("cuda")
+    opt = FusedAdamEMA(model, lr=1e-2, max_norm=1000.0, ema_decay=0.9)
+    before = model._flat.detach().clone()
+    opt.zero_grad(set_to_none=True)
+    opt.step()
+    assert torch.equal(model._flat.detach(), before) and opt.num_steps == 0
+    for p in model.global_layer[0].parameters():
+        p.requires_grad_(False)
+    frozen = {k: p.detach().clone() for k, p in model.global_layer[0].named_parameters()}
+    torch.nn.functional.l1_loss(model(batch), batch.y).backward()
+    opt.step()
+    for k, p in model.global_layer[0].named_parameters():
+        assert torch.equal(p.detach(), frozen[k]), k
+    assert not torch.equal(model._flat.detach(), before)          # everything else moved
