@@ -57,6 +57,8 @@ struct ChainStage {
 struct ChainArgs {
     int n_rows;
     int n_stages;
+    int small_footprint; // 1: run the two-CTAs-per-SM variant whatever the row count (chains off the critical path: the readout
+                         // heads run beside the layer loop, and 78 + 78 one-per-SM CTAs do not fit on 148 SMs)
     int precision;      // 0: fp32-accurate (3xTF32 / FFMA); 1: single-pass TF32 (tensor-core interpreter only; chain_launch sets it
                         // from PAMNET_NODE_MLP=tf32 -- the reduced-precision node-MLP path of BASELINE.json configs[2])
     ChainStage st[kChainMaxStages];

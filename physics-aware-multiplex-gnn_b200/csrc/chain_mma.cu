@@ -611,8 +611,8 @@ bool chain_mma_enabled(int dim) {
 
 int chain_mma_launch(int dim, const ChainArgs& a, double bytes, cudaStream_t st) {
     switch (dim) {
-        case 128: return chain_throughput(a.n_rows) ? chain_mma_launch_t<128, true>(a, bytes, st) : chain_mma_launch_t<128, false>(a, bytes, st);
-        case 64:  return chain_throughput(a.n_rows) ? chain_mma_launch_t<64, true>(a, bytes, st) : chain_mma_launch_t<64, false>(a, bytes, st);
+        case 128: return (a.small_footprint || chain_throughput(a.n_rows)) ? chain_mma_launch_t<128, true>(a, bytes, st) : chain_mma_launch_t<128, false>(a, bytes, st);
+        case 64:  return (a.small_footprint || chain_throughput(a.n_rows)) ? chain_mma_launch_t<64, true>(a, bytes, st) : chain_mma_launch_t<64, false>(a, bytes, st);
         default:
             set_error("chain_mma: unsupported dim %d (64, 128)", dim);
             return -1;

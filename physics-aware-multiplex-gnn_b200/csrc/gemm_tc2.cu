@@ -694,7 +694,15 @@ int gemm_tc2_launch(const GemmArgs& a, cudaStream_t st) {
         d.map_a = ia; d.map_b = ib;
     }
     PAMNET_TRY(func_smem_once(reinterpret_cast<const void*>(gemm_tc2_kernel), kSmem));
-    const int grid = b.total < gemm_tc2_max_ctas() ? b.total : gemm_tc2_max_ctas();
+    // Work items per CTA: a persistent CTA holds its SM (216 KB of shared memory) for its whole list, and the layer loop's
+    // chain kernels need 78 free SMs every ~25 us.  PAMNET_GEMM_TPC=n caps the list (several waves of short-lived CTAs);
+    // measured: no difference at batch 32 (1.53-1.58 ms/step for 1, 2, 4, unlimited), 7.37 vs 6.41 ms/step at batch 256 for
+    // 2 vs unlimited -> unlimited by default.
+    static int tpc = -1;
+    if (tpc < 0) { const char* e = getenv("PAMNET_GEMM_TPC"); tpc = e ? atoi(e) : 0; if (tpc < 1) tpc = 1 << 20; }
+    int grid = b.total < gemm_tc2_max_ctas() ? b.total : gemm_tc2_max_ctas();
+    const int by_tpc = ceil_div(b.total, tpc);
+    if (by_tpc > grid) grid = by_tpc;
     if (pdl_level() == 1) PAMNET_CUDA(launch_pdl(gemm_tc2_kernel, dim3(grid), dim3(kThreads), kSmem, st, b));
     else gemm_tc2_kernel<<<grid, kThreads, kSmem, st>>>(b);
     return 0;

@@ -150,6 +150,13 @@ inline bool gather_fusion_enabled() {
     return on == 1;
 }
 
+// PAMNET_HEADS_SMALL=0: head chains as one-CTA-per-SM launches again
+inline int heads_small_footprint() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("PAMNET_HEADS_SMALL"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on;
+}
+
 // half index hh = 2*l (global layer l) or 2*l+1 (local layer l)
 inline bool is_local(int hh) { return hh & 1; }
 inline int nP_of(int hh) { return is_local(hh) ? 4 : 2; }
@@ -872,6 +879,7 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
             PAMNET_TRY(sc.order(st, sc.s3));
             Prog ph((int)N);
             add_heads_fwd(ph, params, half_params(mp, hh), hw, D, w.att + (size_t)hh * N, w.out + (size_t)hh * N);
+            ph.a.small_footprint = heads_small_footprint();
             PAMNET_TRY(chain_launch(D, ph.a, sc.s3));
         }
     }
@@ -943,6 +951,7 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
     for (int hh = H - 1; hh >= 0; --hh) {
         Prog ph((int)N);
         add_heads_bwd(ph, params, half_params(mp, hh), w.half[hh], D, w.g_att + (size_t)hh * N, w.g_out + (size_t)hh * N, gp);
+        ph.a.small_footprint = heads_small_footprint();
         PAMNET_TRY(chain_launch(D, ph.a, s3));
         PAMNET_TRY(sc.record(s3, &ev_heads[hh]));
     }
@@ -1169,14 +1178,19 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
         if (is_local(hh)) {
             if (sc.s4 != s3) PAMNET_TRY(sc.order(st, sc.s4));
             if (sc.s5 != sc.s4) PAMNET_TRY(sc.order(st, sc.s5));
-            PAMNET_TRY(local_wgrads(l, l + 1, sc.s4, sc.s5));
+            // two layers per batched launch (the per-edge gradient buffers hold all layers side by side): half the launches,
+            // twice the tiles per launch; layer l + 1 simply waits for layer l.  Per layer when a caller consumes the
+            // per-half bucket events (their contract is "final after the next half's iteration").
+            if (g_buckets_on.load()) PAMNET_TRY(local_wgrads(l, l + 1, sc.s4, sc.s5));
+            else if (l % 2 == 0) PAMNET_TRY(local_wgrads(l, l + 2 < L ? l + 2 : L, sc.s4, sc.s5));
             if (l == 0) {                        // last local half: both local families are complete
                 PAMNET_TRY(embed_tail_local(sc.s4));
                 PAMNET_TRY(embed_tail_sbf(sc.s5));
             }
         } else {
             if (s3 != s2) PAMNET_TRY(sc.order(st, s2));
-            PAMNET_TRY(global_wgrads(l, l + 1, s2));
+            if (g_buckets_on.load()) PAMNET_TRY(global_wgrads(l, l + 1, s2));
+            else if (l % 2 == 0) PAMNET_TRY(global_wgrads(l, l + 2 < L ? l + 2 : L, s2));
         }
         if (g_buckets_on.load() && hh + 1 < H) {
             const cudaStream_t bs[kBucketStreams] = {s2, s3, sc.s4, sc.s5};
