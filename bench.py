@@ -185,7 +185,7 @@ def workload_config(args, sizes):
                      else "3xTF32 tensor-core node MLPs (fp32-accurate)",
          "loss": "F.l1_loss" if getattr(args, "torch_loss", False) else "pamnet_b200.ops.l1_loss (value + gradient in one launch)",
          "front_end": "inline" if getattr(args, "no_prefetch", False)
-                      else "next step's graph plan built on a side stream behind backward (model.prefetch); one plan and one H2D copy per step"}
+                      else "next step's H2D copy + graph plan on a side stream from a prefetch worker thread (model.prefetch_async), overlapping this step's backward; one plan and one H2D copy per step"}
     if sizes:
         c["sizes"] = sizes
     for k in ("PAMNET_FRONT", "PAMNET_GEMM", "PAMNET_CHAIN", "PAMNET_STREAMS", "PAMNET_TC2_PROD"):
@@ -279,9 +279,10 @@ def run_ours(args):
     def step(batch, sync_grads=True, next_batch=None):
         if sync is not None:
             sync.wait()                     # the previous step's collectives read the gradient buffer backward is about to zero
-        for p in params:                    # == optimizer.zero_grad(set_to_none=True)
-            p.grad = None
+        model.zero_grad()                   # optimizer.zero_grad() of main_qm9.py:106 (the module's O(1) form: grads stay attached, backward overwrites)
         out = model(batch)
+        if next_batch is not None:          # the next step's front end: started on the prefetch worker while this thread
+            next_batch()                    # enqueues the loss and the backward pass
         loss = l1(out, batch.y)             # main_qm9.py:108
         loss.backward()
         if world > 1 and sync_grads:        # enqueue the collectives first: they overlap what backward still has queued
@@ -289,12 +290,16 @@ def run_ours(args):
                 sync()
             elif native is None:            # (native: the all-reduce happened inside backward)
                 allreduce_gradients(model)
-        if next_batch is not None:          # the next step's front end overlaps this step's backward
-            next_batch()
         return loss
 
     # device-resident loop: the batch has been in HBM since before the warm-up, the side stream need not wait for anything
-    nxt_dev = (lambda: model.prefetch(dev_batch, wait_current=False)) if prefetch else None
+    fut_dev = []
+    nxt_dev = (lambda: fut_dev.append(model.prefetch_async(dev_batch, wait_current=False))) if prefetch else None
+
+    def dev_step():
+        if fut_dev:
+            fut_dev.pop(0).result()         # the plan requested during the previous step (same batch object every step)
+        return step(dev_batch, next_batch=nxt_dev)
 
     def barrier():
         if world > 1:
@@ -309,7 +314,7 @@ def run_ours(args):
         sampler.start()
     warmup = max(args.warmup, 3)
     for _ in range(warmup):
-        step(dev_batch, next_batch=nxt_dev)
+        dev_step()
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     import gc
@@ -321,7 +326,7 @@ def run_ours(args):
     for s0, s1 in ev:
         flush.fill_(1)
         s0.record()
-        step(dev_batch, next_batch=nxt_dev)
+        dev_step()
         if sync is not None:
             sync.wait()                     # the step ends when its gradients are reduced
         s1.record()
@@ -336,14 +341,17 @@ def run_ours(args):
     # ---- end to end through the public API with host buffers ("e2e") ------------------------------------
     pending = []
 
-    def h2d_and_plan():         # H2D copy from pinned memory + graph plan of the next batch, both on the side stream
-        pending.append(model.prefetch(host_batch))
+    if fut_dev:
+        fut_dev.pop(0).result()
+
+    def h2d_and_plan():         # H2D copy from pinned memory + graph plan of the next batch: prefetch worker, side stream
+        pending.append(model.prefetch_async(host_batch))
 
     def e2e_step():
         if prefetch:            # this step's batch was copied and planned during the previous step; copy + plan the next
             if not pending:
                 h2d_and_plan()
-            loss = step(pending.pop(0), next_batch=h2d_and_plan)
+            loss = step(pending.pop(0).result(), next_batch=h2d_and_plan)
         else:
             b = host_batch.to(dev, non_blocking=True)      # H2D from pinned memory, inside the timed region
             loss = step(b)

@@ -179,16 +179,43 @@ class _PAMNetBase(nn.Module):
                             for (_, p), off in zip(self._param_list, self._offsets)]
         return self._gviews
 
+    def _views_attached(self):
+        """O(1) check that the gradient views are (still) attached: first, middle and last parameter that receive one."""
+        idx = getattr(self, "_sentinels", None)
+        if idx is None:
+            live = [i for i, ((_, p), used) in enumerate(zip(self._param_list, self._param_used)) if used and p.requires_grad]
+            idx = self._sentinels = (live[0], live[len(live) // 2], live[-1]) if live else ()
+        views = self._gviews
+        return views is not None and all(self._param_list[i][1].grad is views[i] for i in idx)
+
+    def zero_grad(self, set_to_none=True):
+        """``optimizer.zero_grad()`` of main_qm9.py:106 for this module, without touching 390 tensors: when the gradients
+        are the views backward attached, they STAY attached and the next backward overwrites the flat buffer (the per-step
+        loops ``p.grad = None`` + re-attach cost ~0.2 ms of host time, and the step is host-bound).  Until that backward,
+        ``p.grad`` shows the previous step's values instead of None; ``torch.optim.Optimizer.zero_grad`` (which sets None)
+        keeps working and takes the ordinary path."""
+        if set_to_none and self._gflat is not None and self._views_attached():
+            self._overwrite_next = True
+            return
+        self._overwrite_next = False
+        super().zero_grad(set_to_none)
+
     def _grad_target(self):
         """Where backward should write: straight into the flat gradient buffer when no parameter holds a
-        gradient yet (after zero_grad(set_to_none=True)), otherwise into a scratch buffer that is then added."""
+        gradient yet (after zero_grad), otherwise into a scratch buffer that is then added."""
         self._grad_views()
+        if getattr(self, "_overwrite_next", False) and self._views_attached():
+            return self._gflat, True
+        self._overwrite_next = False
         if all(p.grad is None for _, p in self._param_list):
             return self._gflat, True
         return torch.empty_like(self._gflat), False
 
     def _deliver_grads(self, target, direct):
         views = self._grad_views()
+        if direct and getattr(self, "_overwrite_next", False):
+            self._overwrite_next = False          # the views were attached all along
+            return
         if direct:
             for (_, p), v, used in zip(self._param_list, views, self._param_used):
                 if used and p.requires_grad:
@@ -221,6 +248,9 @@ class _PAMNetBase(nn.Module):
                 p.data = flat[off:off + p.numel()].view(p.shape)
         self._flat = flat.requires_grad_(True)     # the single differentiable input of _PAMNetFunction
         self._gflat = None
+        self._gviews = None
+        self._overwrite_next = False
+        self._sentinels = None
 
     def _aliased(self, full=True):
         """Do the parameters still alias the flat buffer?  (utils/ema.py:27,32 swap param.data wholesale; a partial weight
@@ -406,6 +436,38 @@ class _PAMNetBase(nn.Module):
             done.record(side)
         self._prefetched = (data, inputs, plan, done, on_host)
         return data
+
+    def prefetch_async(self, data, max_nb=None, wait_current=None):
+        """``prefetch`` on a worker thread: returns a handle at once; ``handle.result()`` is the batch to call the model
+        with.  The plan build contains one small device-to-host read-back (the edge / triplet counts the buffer sizes
+        depend on) and ~0.2 ms of host work; on the caller's thread that sits between ``backward()`` and the next
+        ``forward()`` of a step whose host enqueue time equals its GPU time, on a worker it overlaps the enqueue of
+        ``backward()`` (ctypes and torch release the GIL inside their calls).  Start it right after ``model(batch)``
+        returned, collect it before the next ``model(...)``: what a ``DataLoader(num_workers=1)`` does for host-side
+        preprocessing.  One request may be in flight at a time."""
+        import concurrent.futures
+        pool = getattr(self, "_prefetch_pool", None)
+        if pool is None:
+            pool = self._prefetch_pool = concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix="pamnet-prefetch")
+        dev = self._flat.device
+        cur = torch.cuda.current_stream(dev)
+        on_host = not data.x.is_cuda
+        if wait_current is None:
+            wait_current = not on_host
+        ready = None
+        if wait_current:                      # "current stream" means the CALLER's: capture its state here, not on the worker
+            ready = torch.cuda.Event()
+            ready.record(cur)
+
+        def work():
+            with torch.cuda.device(dev):
+                if ready is not None:
+                    side = getattr(self, "_side_stream", None)
+                    if side is None or side.device != dev:
+                        side = self._side_stream = torch.cuda.Stream(device=dev)
+                    side.wait_event(ready)
+                return self.prefetch(data, max_nb=max_nb, wait_current=False)
+        return pool.submit(work)
 
     def _take_prefetched(self, data):
         pre = getattr(self, "_prefetched", None)
