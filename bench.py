@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--torch-loss", action="store_true", help="F.l1_loss instead of the fused loss + gradient launch")
     ap.add_argument("--no-prefetch", action="store_true",
                     help="build every step's graph plan inline instead of on a side stream behind the previous backward")
+    ap.add_argument("--vary", type=int, default=1,
+                    help="visit K distinct synthetic batches round-robin (different atom / edge / triplet counts every step, as "
+                         "an epoch does) instead of re-running one batch")
     ap.add_argument("--allreduce", default="native", choices=["native", "buckets", "plain"],
                     help="N > 1: native = library-owned NCCL all-reduce issued bucket by bucket inside backward (default); "
                          "buckets = the same buckets from Python (OverlappedGradSync); plain = one all-reduce after backward")
@@ -186,6 +189,8 @@ def workload_config(args, sizes):
          "loss": "F.l1_loss" if getattr(args, "torch_loss", False) else "pamnet_b200.ops.l1_loss (value + gradient in one launch)",
          "front_end": "inline" if getattr(args, "no_prefetch", False)
                       else "next step's H2D copy + graph plan on a side stream from a prefetch worker thread (model.prefetch_async), overlapping this step's backward; one plan and one H2D copy per step"}
+    if getattr(args, "vary", 1) > 1:
+        c["batches"] = f"{args.vary} distinct batches visited round-robin (sizes below: the last one)"
     if sizes:
         c["sizes"] = sizes
     for k in ("PAMNET_FRONT", "PAMNET_GEMM", "PAMNET_CHAIN", "PAMNET_STREAMS", "PAMNET_TC2_PROD"):
@@ -260,12 +265,17 @@ def run_ours(args):
     unit = "graphs/s" if args.config == "c4" else UNIT
     torch.manual_seed(0)
     host_batch, sd = make_batch(args, seed=rank)
+    # --vary K: K distinct batches (different atom / edge / triplet counts) visited round-robin, as an epoch does
+    host_pool = [host_batch] + [make_batch(args, seed=1000 * (i + 1) + rank)[0] for i in range(max(args.vary, 1) - 1)]
     model = PAMNet(Config(**vars(cfg)))
     if sd is not None:
         model.load_state_dict(sd)
     model = model.to(dev)
-    host_batch = host_batch.pin_memory()
-    dev_batch = host_batch.to(dev)
+    host_pool = [b.pin_memory() for b in host_pool]
+    host_batch = host_pool[0]
+    dev_pool = [b.to(dev) for b in host_pool]
+    dev_batch = dev_pool[0]
+    turn = {"dev": 0, "e2e": 0}
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     prefetch = not args.no_prefetch
 
@@ -294,12 +304,17 @@ def run_ours(args):
 
     # device-resident loop: the batch has been in HBM since before the warm-up, the side stream need not wait for anything
     fut_dev = []
-    nxt_dev = (lambda: fut_dev.append(model.prefetch_async(dev_batch, wait_current=False))) if prefetch else None
+
+    def plan_next_dev():
+        fut_dev.append(model.prefetch_async(dev_pool[(turn["dev"] + 1) % len(dev_pool)], wait_current=False))
+    nxt_dev = plan_next_dev if prefetch else None
 
     def dev_step():
         if fut_dev:
-            fut_dev.pop(0).result()         # the plan requested during the previous step (same batch object every step)
-        return step(dev_batch, next_batch=nxt_dev)
+            fut_dev.pop(0).result()         # the plan requested during the previous step
+        loss = step(dev_pool[turn["dev"] % len(dev_pool)], next_batch=nxt_dev)
+        turn["dev"] += 1
+        return loss
 
     def barrier():
         if world > 1:
@@ -345,7 +360,8 @@ def run_ours(args):
         fut_dev.pop(0).result()
 
     def h2d_and_plan():         # H2D copy from pinned memory + graph plan of the next batch: prefetch worker, side stream
-        pending.append(model.prefetch_async(host_batch))
+        pending.append(model.prefetch_async(host_pool[turn["e2e"] % len(host_pool)]))
+        turn["e2e"] += 1
 
     def e2e_step():
         if prefetch:            # this step's batch was copied and planned during the previous step; copy + plan the next
@@ -353,7 +369,8 @@ def run_ours(args):
                 h2d_and_plan()
             loss = step(pending.pop(0).result(), next_batch=h2d_and_plan)
         else:
-            b = host_batch.to(dev, non_blocking=True)      # H2D from pinned memory, inside the timed region
+            b = host_pool[turn["e2e"] % len(host_pool)].to(dev, non_blocking=True)      # H2D from pinned memory, inside the timed region
+            turn["e2e"] += 1
             loss = step(b)
         if sync is not None:
             sync.wait()

@@ -493,7 +493,10 @@ int embed_forward(const float* type_f, int64_t n_nodes, const float* emb, int n_
     return 0;
 }
 
-// one block per (type, 32-column tile): 8 node-strided partial sums per column, combined in fixed order
+// one block per (type, 32-column tile, node chunk): 8 node-strided partial sums per column, combined in fixed order; with
+// more than one chunk (large graphs: the RNA batch has 15 816 nodes and 3 types x 16 columns -- three blocks scanning
+// every node took 238 us) the chunks meet in fp32 atomics on the zero-initialised gradient
+constexpr int kEmbChunk = 2048;
 __global__ void __launch_bounds__(256) embed_bwd_kernel(const float* __restrict__ type_f, int64_t n_nodes,
                                                         const float* __restrict__ g_x, int dim,
                                                         float* __restrict__ g_emb) {
@@ -501,22 +504,25 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const float* __restrict_
     const int ty = blockIdx.y;
     const int cl = threadIdx.x & 31, part = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
+    const int64_t n0 = (int64_t)blockIdx.z * kEmbChunk, n1 = min(n_nodes, n0 + kEmbChunk);
     float s = 0.f;
     if (c < dim)
-        for (int64_t n = part; n < n_nodes; n += 8)
+        for (int64_t n = n0 + part; n < n1; n += 8)
             if ((int)type_f[n] == ty) s += g_x[n * dim + c];
     red[part][cl] = s;
     __syncthreads();
     if (part == 0 && c < dim) {
         float tot = 0.f;
         for (int p = 0; p < 8; ++p) tot += red[p][cl];
-        g_emb[(size_t)ty * dim + c] = tot;
+        if (gridDim.z == 1) g_emb[(size_t)ty * dim + c] = tot;
+        else atomicAdd(&g_emb[(size_t)ty * dim + c], tot);
     }
 }
 
+// g_emb must be zero on entry when n_nodes > kEmbChunk (model_backward zeroes the whole gradient buffer first)
 int embed_backward(const float* type_f, int64_t n_nodes, const float* g_x, int n_embed, int dim, float* g_emb,
                    cudaStream_t st) {
-    dim3 grid(ceil_div(dim, 32), n_embed);
+    dim3 grid(ceil_div(dim, 32), n_embed, ceil_div(n_nodes > 0 ? n_nodes : 1, kEmbChunk));
     prof_begin(KC_BASIS, 0.0, st);
     embed_bwd_kernel<<<grid, 256, 0, st>>>(type_f, n_nodes, g_x, dim, g_emb);
     prof_end(st);

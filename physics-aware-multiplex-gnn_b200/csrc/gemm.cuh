@@ -59,6 +59,7 @@ int tc_trace_read(long long* out, int n);
 bool gemm_tc2_eligible(const GemmArgs& a);
 bool gemm_tc2_slot_ok(const GemmArgs& a, int slot);
 int gemm_tc2_launch(const GemmArgs& a, cudaStream_t st);
+void gemm_set_stable_range(const float* lo, size_t n_floats);    // parameter buffer of the model call in progress (this thread)
 
 // skinny problems (N <= 32 rows-kernel, M <= 32 weight gradients), gemm_small.cu
 bool gemm_small_eligible(const GemmArgs& a);

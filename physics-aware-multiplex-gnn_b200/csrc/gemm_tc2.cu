@@ -59,6 +59,7 @@ constexpr int kConvWarp0 = 2, kConvThreads = 128, kEpiWarp0 = 6, kEpiWarps = 8, 
 constexpr int kStageLd = 36;                      // floats: row stride of the per-warp epilogue staging (conflict-free 128-bit)
 constexpr int kEpiStage = 32 * kStageLd * 4;      // bytes per epilogue warp
 constexpr size_t kSmem = 1024 /* alignment slack */ + (size_t)kRaw * kStage + (size_t)kLo * kStage + kEpiWarps * kEpiStage;
+constexpr int kInline = 34;                       // by-value tensor maps per launch (4.3 KB)
 constexpr int kTmemCols = 512;                    // two buffers x (main | cross-term) accumulators of 128 columns
 
 struct Slot2 {
@@ -78,7 +79,8 @@ struct Args2 {
     int total;                                    // work items: nslots * ksplit * tiles_m * tiles_n
     int seg_map[kGemmMaxSeg];
     Slot2 slot[kGemmMaxSlots];
-    const CUtensorMap* maps;                      // device table of tensor maps (see MapTable); slots hold indices
+    const CUtensorMap* maps;                      // device table of tensor maps for STABLE operands (parameters); index >= 0
+    CUtensorMap inl[kInline];                     // maps of this launch's other operands, by value; index -(i + 1)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -245,18 +247,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc2_kernel(const __grid_cons
                     if (c < 12) T2_STAMP(8 + 4 * c);
                     mbar_expect_tx(&full_bar[s], kStage);
                     const uint32_t sa = smem_u32(raw_ring + (size_t)s * kStage), sb = sa + kTile;
-                    const CUtensorMap* ma = &args.maps[sl.map_a];
+                    const CUtensorMap* ma = sl.map_a >= 0 ? &args.maps[sl.map_a] : &args.inl[-1 - sl.map_a];
                     if (!a_mn) {
                         tma_load_2d(sa, ma, k0, w.m0, &full_bar[s]);
                     } else {
 #pragma unroll
                         for (int b = 0; b < 4; ++b) tma_load_2d(sa + b * 4096, ma, w.m0 + 32 * b, k0, &full_bar[s]);
                     }
-                    const CUtensorMap* mb = &args.maps[sl.map_b];
+                    const CUtensorMap* mb = sl.map_b >= 0 ? &args.maps[sl.map_b] : &args.inl[-1 - sl.map_b];
                     int kb = k0;
                     if (args.nseg > 0) {
                         const int sg = k0 / args.seg_len;
-                        mb = &args.maps[args.seg_map[sg]];
+                        const int mi = args.seg_map[sg];
+                        mb = mi >= 0 ? &args.maps[mi] : &args.inl[-1 - mi];
                         kb = k0 - sg * args.seg_len;
                     }
                     if (!b_mn) {
@@ -540,11 +543,15 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// Device-resident table of tensor maps, one per CUDA device.  A map depends on (address, shape, box, swizzle) only, so
-// entries are written once (host encode + copy on a private stream, completed before the call returns) and never
-// modified: kernels receive the table pointer and indices, which keeps the launch parameters small (the first version
-// passed up to 72 maps = 9 KB by value and paid ~4 us of host time per launch).  When the table is full, new operands
-// fall back to the round-1 kernel (the caller checks gemm_tc2_launch's return value).
+// Tensor maps.  A map depends on (address, shape, box, swizzle) only.
+//  * STABLE operands -- anything inside the flat parameter buffer registered with gemm_set_stable_range (the weights: the
+//    same addresses every step) -- live in a device-resident table, one per CUDA device: written once (host encode + copy
+//    on a private stream, completed before the call returns), never modified; kernels receive the table pointer + index.
+//  * every other operand (activations, gradients: workspace addresses and shapes change with every batch) travels BY VALUE
+//    in the launch parameters (up to kInline per launch; the encoded maps are cached on the host by key, so a fixed-shape
+//    loop does not even re-encode).  A table entry for them would cost an upload + stream synchronisation per new
+//    (address, shape) -- hundreds per step as soon as batch shapes vary.
+// When a launch needs more by-value maps than kInline, or the table is full, the caller falls back to the round-1 kernel.
 constexpr int kTableCap = 1 << 15;
 constexpr int kMaxDev = 16;
 struct MapKey {
@@ -569,6 +576,39 @@ struct MapTable {
 };
 std::mutex g_map_mu;
 MapTable g_tables[kMaxDev];
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_host_maps;      // encoded maps of non-stable operands (host only)
+thread_local const float* g_stable_lo = nullptr;
+thread_local const float* g_stable_hi = nullptr;
+
+int encode_map(const float* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer, int swz32, CUtensorMap* out) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return -1; }
+    const cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
+    const cuuint32_t box[2] = {32u, (cuuint32_t)box_outer};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          swz32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for [%lld x %lld] ld %lld", (int)r, (long long)outer, (long long)inner, (long long)ld);
+        return -1;
+    }
+    return 0;
+}
+
+// encoded map of a non-stable operand (host cache, bounded)
+int host_map(const float* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer, int swz32, CUtensorMap* out) {
+    const MapKey key{ptr, inner, outer, ld, box_outer, swz32};
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    auto it = g_host_maps.find(key);
+    if (it != g_host_maps.end()) { *out = it->second; return 0; }
+    if (encode_map(ptr, inner, outer, ld, box_outer, swz32, out) != 0) return -1;
+    if (g_host_maps.size() > (1u << 14)) g_host_maps.clear();
+    g_host_maps.emplace(key, *out);
+    return 0;
+}
 
 // row-major fp32 [outer][inner] with leading dimension ld; box {32 inner, box_outer rows}, zero OOB fill; swz32: the
 // 32-byte-atom 128 B swizzle of the MN-major operand layout, else the plain 128 B swizzle.  Returns the table index
@@ -591,20 +631,7 @@ int map_index(const float* ptr, int64_t inner, int64_t outer, int64_t ld, int bo
     auto it = t.index.find(key);
     if (it != t.index.end()) return it->second;
     if (t.used >= kTableCap) return -2;
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return -1; }
-    const cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-    const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
-    const cuuint32_t box[2] = {32u, (cuuint32_t)box_outer};
-    const cuuint32_t estr[2] = {1u, 1u};
-    const CUresult r = fn(t.pinned, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          swz32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed (%d) for [%lld x %lld] ld %lld", (int)r, (long long)outer, (long long)inner, (long long)ld);
-        return -1;
-    }
+    if (encode_map(ptr, inner, outer, ld, box_outer, swz32, t.pinned) != 0) return -1;
     const int idx = t.used;
     if (cudaMemcpyAsync(t.dev + idx, t.pinned, sizeof(CUtensorMap), cudaMemcpyHostToDevice, t.copy_stream) != cudaSuccess ||
         cudaStreamSynchronize(t.copy_stream) != cudaSuccess) {
@@ -619,6 +646,12 @@ int map_index(const float* ptr, int64_t inner, int64_t outer, int64_t ld, int bo
 bool tma_ok(const float* p, int ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && ld % 4 == 0 && p != nullptr; }
 
 }  // namespace
+
+// [lo, lo + n) = the flat parameter buffer of the model call in progress on this host thread (model_forward / _backward)
+void gemm_set_stable_range(const float* lo, size_t n_floats) {
+    g_stable_lo = lo;
+    g_stable_hi = lo ? lo + n_floats : nullptr;
+}
 
 int gemm_tc2_max_ctas() {
     static int v = -1;
@@ -661,24 +694,30 @@ int gemm_tc2_launch(const GemmArgs& a, cudaStream_t st) {
     b.tiles_m = ceil_div(a.M, TM); b.tiles_n = ceil_div(a.N, TN);
     b.total = b.nslots * b.ksplit * b.tiles_m * b.tiles_n;
     const bool a_mn = a.mode == GEMM_TN, b_mn = a.mode != GEMM_NT;
-    // the last lookup of an operand is remembered: slots of a batched launch mostly share one of their operands
-    const float* last_p[2] = {nullptr, nullptr};
-    int last_i[2] = {0, 0};
-    int64_t last_shape[2][3] = {{0, 0, 0}, {0, 0, 0}};
-    auto map_of = [&](int which, const float* p, int64_t inner, int64_t outer, int64_t ld, int box, int swz32) -> int {
-        if (p == last_p[which] && inner == last_shape[which][0] && outer == last_shape[which][1] && ld == last_shape[which][2])
-            return last_i[which];
-        const int idx = map_index(p, inner, outer, ld, box, swz32, &b.maps);
-        if (idx >= 0) {
-            last_p[which] = p; last_i[which] = idx;
-            last_shape[which][0] = inner; last_shape[which][1] = outer; last_shape[which][2] = ld;
+    // map index of an operand: >= 0 table (stable), < 0 by value; -1000 = error, -2000 = by-value room exhausted (split
+    // the launch), -3000 = table full (fall back to the round-1 kernel)
+    struct Seen { const float* p; int64_t inner, outer, ld; int idx; };
+    Seen seen[2 * kGemmMaxSlots + kGemmMaxSeg];
+    int n_seen = 0, n_inl = 0;
+    auto map_of = [&](const float* p, int64_t inner, int64_t outer, int64_t ld, int box, int swz32) -> int {
+        for (int i = n_seen - 1; i >= 0; --i)          // slots of a batched launch mostly share one of their operands
+            if (seen[i].p == p && seen[i].inner == inner && seen[i].outer == outer && seen[i].ld == ld) return seen[i].idx;
+        int idx;
+        if (p >= g_stable_lo && p < g_stable_hi) {
+            idx = map_index(p, inner, outer, ld, box, swz32, &b.maps);
+            if (idx < 0) return idx == -2 ? -3000 : -1000;
+        } else {
+            if (n_inl >= kInline) return -2000;
+            if (host_map(p, inner, outer, ld, box, swz32, &b.inl[n_inl]) != 0) return -1000;
+            idx = -1 - n_inl++;
         }
+        seen[n_seen++] = Seen{p, inner, outer, ld, idx};
         return idx;
     };
     for (int s = 0; s < a.nseg; ++s) {
         // segment weight W[out = k][in = n]: MN-major B, rows = seg_len k, cols = N
-        const int idx = map_index(a.seg_B[s], a.N, a.seg_len, a.seg_ldb[s], 32, 1, &b.maps);
-        if (idx < 0) return idx == -2 ? 1 : -1;
+        const int idx = map_of(a.seg_B[s], a.N, a.seg_len, a.seg_ldb[s], 32, 1);
+        if (idx <= -1000) return idx == -1000 ? -1 : 1;
         b.seg_map[s] = idx;
     }
     for (int i = 0; i < a.nslots; ++i) {
@@ -687,10 +726,25 @@ int gemm_tc2_launch(const GemmArgs& a, cudaStream_t st) {
         Slot2& d = b.slot[i];
         d.bias = s.bias; d.Z = s.Z; d.C = s.C; d.C2 = s.C2; d.ldc = s.ldc; d.ldz = s.ldz; d.m = s.m;
         // A: K-major [M rows][K] (NT / NN) or MN-major [K rows][M] (TN)
-        const int ia = a_mn ? map_of(0, s.A, M, a.K, s.lda, 32, 1) : map_of(0, s.A, a.K, M, s.lda, TM, 0);
+        const int ia = a_mn ? map_of(s.A, M, a.K, s.lda, 32, 1) : map_of(s.A, a.K, M, s.lda, TM, 0);
         int ib = 0;
-        if (a.nseg == 0) ib = b_mn ? map_of(1, s.B, a.N, a.K, s.ldb, 32, 1) : map_of(1, s.B, a.K, a.N, s.ldb, TN, 0);
-        if (ia < 0 || ib < 0) return (ia == -2 || ib == -2) ? 1 : -1;
+        if (a.nseg == 0) ib = b_mn ? map_of(s.B, a.N, a.K, s.ldb, 32, 1) : map_of(s.B, a.K, a.N, s.ldb, TN, 0);
+        if (ia == -1000 || ib == -1000) return -1;
+        if (ia == -3000 || ib == -3000) return 1;
+        if (ia == -2000 || ib == -2000) {
+            // more distinct activation operands than one launch carries by value: two launches of half the slots each
+            if (a.nslots < 2) return 1;
+            const int h = a.nslots / 2;
+            GemmArgs lo = a, hi = a;
+            lo.nslots = h;
+            hi.nslots = a.nslots - h;
+            for (int j = 0; j < hi.nslots; ++j) hi.slot[j] = a.slot[h + j];
+            const int r0 = gemm_tc2_launch(lo, st);
+            if (r0 != 0) return r0 < 0 ? r0 : -1;      // (the table cannot fill up half way: by-value operands only)
+            const int r1 = gemm_tc2_launch(hi, st);
+            if (r1 == 1) set_error("gemm_tc2: tensor-map table filled up in the middle of a split launch");
+            return r1 == 0 ? 0 : -1;
+        }
         d.map_a = ia; d.map_b = ib;
     }
     PAMNET_TRY(func_smem_once(reinterpret_cast<const void*>(gemm_tc2_kernel), kSmem));

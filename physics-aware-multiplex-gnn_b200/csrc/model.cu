@@ -714,6 +714,7 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
     const Plan& pl = c.plan;
     Sched sc = make_sched(st_user, aux);
     cudaStream_t st = sc.st, s2 = sc.s2;
+    gemm_set_stable_range(params, (size_t)mp.total);          // weight operands keep their addresses: tensor maps in the device table
 
     if (st != st_user) PAMNET_TRY(sc.order(st_user, st));     // the plan and the inputs were produced on the caller's stream
     PAMNET_TRY(sc.order(st, s2));
@@ -915,6 +916,7 @@ int model_backward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const p
     const Plan& pl = c.plan;
     Sched sc = make_sched(st_user, aux);
     cudaStream_t st = sc.st, s2 = sc.s2, s3 = sc.s3;
+    gemm_set_stable_range(params, (size_t)mp.total);
 
     const bool native_comm = comm_active() && sc.dual;     // gradient all-reduce issued from here, bucket by bucket
     if (st != st_user) PAMNET_TRY(sc.order(st_user, st));

@@ -406,3 +406,32 @@ def test_second_backward_raises_clearly():
     loss.backward(retain_graph=True)
     with pytest.raises(RuntimeError, match="second time"):
         loss.backward()
+
+
+@pytest.mark.gpu
+def test_changing_batch_shapes_reuse_nothing_stale():
+    """Every batch of an epoch has its own atom / edge / triplet counts, so activation operands change address and shape
+    from step to step (by-value tensor maps) while the weights stay put (device tensor-map table): A, B, C, A again must
+    give A's outputs and gradients again (to summation-order noise: split reductions accumulate with atomics)."""
+    import torch
+    from pamnet_b200 import Config, PAMNet
+    from pamnet_b200.data import synthetic_qm9_batch
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(3)
+    model = PAMNet(Config(dataset="QM9", dim=128, n_layer=2, cutoff_l=5.0, cutoff_g=5.0)).to(dev)
+    batches = [synthetic_qm9_batch(n, seed=s).to(dev) for n, s in ((5, 1), (17, 2), (32, 3))]
+
+    def run(b):
+        model.zero_grad()
+        out = model(b)
+        (out - b.y).abs().mean().backward()
+        return out.detach().clone(), [p.grad.detach().clone() for p in model.parameters() if p.grad is not None]
+
+    first = run(batches[0])
+    for b in batches[1:]:
+        run(b)
+    again = run(batches[0])
+    assert rel_err(again[0], first[0]) < 1e-6
+    assert len(first[1]) == len(again[1]) > 0
+    for g0, g1 in zip(first[1], again[1]):
+        assert rel_err(g1, g0) < 1e-5
