@@ -200,14 +200,57 @@ def workload_config(args, sizes):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock and throttle reasons during the timed regions (B200_PROFILING.md clocks line).  In-process NVML
+    (nvidia_ml_py) from a sampling thread; falls back to an `nvidia-smi -lms` child process when NVML cannot be loaded.
+    (BENCH_SAMPLER=smi / nvml / none selects one explicitly: debugging aid for host-jitter attribution.)"""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    PERIOD_S = 0.2          # every query takes driver locks the launching threads also need: rare multi-ms stalls of a step grow with the rate
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.mode = os.environ.get("BENCH_SAMPLER", "nvml")
+        self._stop = threading.Event()
+        self._thread = None
+
+    # -- NVML in process ------------------------------------------------------------------------------------------
+    def _nvml_loop(self, nv, h):
+        bits = [("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8),
+                ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.rows.append([str(sm), str(mx)] + ["Active" if mask & b else "Not Active" for _, b in bits])
+            except Exception:
+                pass
+            self._stop.wait(self.PERIOD_S)
 
     def start(self):
+        if self.mode == "none":
+            return
+        if self.mode == "nvml":
+            try:
+                import pynvml as nv
+                nv.nvmlInit()
+                # CUDA_VISIBLE_DEVICES may renumber: resolve through the PCI bus id of the CUDA device
+                import torch
+                bus = torch.cuda.get_device_properties(self.index).pci_bus_id if hasattr(torch.cuda.get_device_properties(self.index), "pci_bus_id") else None
+                h = None
+                if bus is not None:
+                    for i in range(nv.nvmlDeviceGetCount()):
+                        hi = nv.nvmlDeviceGetHandleByIndex(i)
+                        if nv.nvmlDeviceGetPciInfo(hi).bus == bus:
+                            h = hi
+                            break
+                if h is None:
+                    h = nv.nvmlDeviceGetHandleByIndex(self.index)
+                self._thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+                self._thread.start()
+                return
+            except Exception:
+                self.mode = "smi"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -220,17 +263,25 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
+    def wait_first(self, timeout=3.0):
+        """Block until the first sample arrived (NVML / nvidia-smi start-up is over) -- called before the timed regions."""
+        t_end = time.perf_counter() + timeout
+        while self.mode != "none" and not self.rows and time.perf_counter() < t_end:
+            time.sleep(0.01)
+
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        if self.mode == "none" or (self.proc is None and self._thread is None):
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampler unavailable"], "samples": 0}
         time.sleep(0.15)
-        self.proc.terminate()
+        self._stop.set()
+        if self.proc is not None:
+            self.proc.terminate()
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvml" if self._thread is not None else "nvidia-smi"}
 
 
 def algorithmic_bytes_step(sz, D, L, s=4):
@@ -327,9 +378,15 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    warmup = max(args.warmup, 3)
+    if os.environ.get("BENCH_SWITCH"):
+        sys.setswitchinterval(float(os.environ["BENCH_SWITCH"]))
+    # at least 10 untimed steps (and one visit of every batch of --vary): allocator pools of both threads, tensor-map and
+    # plan caches, clocks; the JSON line reports the count actually run
+    warmup = max(args.warmup, 10, len(dev_pool))
     for _ in range(warmup):
         dev_step()
+    if rank == 0:
+        sampler.wait_first()            # NVML start-up is over before anything is timed
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     import gc
@@ -430,7 +487,9 @@ def run_ours(args):
         "config": workload_config(args, sizes), "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": unit, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
-        "ms_per_step_stats": {"median": sorted(per_step)[len(per_step) // 2], "min": min(per_step), "max": max(per_step)},
+        "ms_per_step_stats": {"median": sorted(per_step)[len(per_step) // 2], "min": min(per_step), "max": max(per_step),
+                              "slow_steps": [[i, round(v, 3)] for i, v in enumerate(per_step)
+                                             if v > 1.5 * sorted(per_step)[len(per_step) // 2]][:8]},
     }
     if world > 1:
         line["allreduce_ms"] = {"exposed_after_backward": sum(ar_ms) / len(ar_ms) if ar_ms else None,
