@@ -264,8 +264,8 @@ __global__ void __launch_bounds__(128) sbf_embed_fwd_kernel(const SbfTables tab,
     float y[kNumSph];
     zonal(tab, ct, y);
     st4(ysph + t * kYsphLd, make_float4(y[0], y[1], y[2], y[3]));
-    st4(ysph + t * kYsphLd + 4, make_float4(y[4], y[5], y[6], 0.f));
     const int ty = two_hop ? 0 : 1;
+    st4(ysph + t * kYsphLd + 4, make_float4(y[4], y[5], y[6], (float)ty));      // slot 7: which of the two MLPs the triplet feeds
     const float* r = radial + (size_t)p * kNumSbf;
     float acc[DT];
 #pragma unroll
@@ -324,84 +324,101 @@ int sbf_embed_forward(const SbfTables& tab, const Plan& plan, int64_t n_trip, co
 }
 
 // weight gradients of mlp_sbf2 / mlp_sbf1: g_ext[d][col] = sum_t gz[t][d] * ext_t[col] over the 86 extended columns
-// (ext_t recomputed per row), accumulated like gemm_cols_kernel: fp32 over <= 32 rows, fp64 tile per CTA, one fp32
-// atomic per output and CTA straight into the parameter-gradient buffers.
-constexpr int kSbfWgThreads = 256, kSbfWgUnroll = 2, kSbfWgFlush = 16;
+// (ext_t recomputed per row).  A warp walks rows t; lane n owns columns n, n + 32, n + 64 for all dim output rows.
+// fp32 partial sums cover at most 32 rows, then go into a PER-WARP fp64 tile in shared memory (plain read-modify-write:
+// no atomics, every lane owns its addresses); the warps' tiles meet once per CTA and one fp32 atomic per output and CTA
+// goes straight into the parameter-gradient buffers.  gz[t][:] is one coalesced load per row, its values reach the
+// lanes by shuffle; the triplet's type comes from slot 7 of its zonal row (written by the forward kernel), so the only
+// dependent load of a row is radial[t_gather[t]].
+// (History, 951 k triplets of the RNA batch: shared fp64 atomics after every window, dim broadcast loads per row and
+// lane, type looked up through t_owner -> t_ptr / t_split: 540 us.  fp64 accumulators in registers: 230 registers, one
+// CTA per SM, 900 us -- the loop is latency-bound and occupancy is what hides it.)
+constexpr int kSbfWgThreads = 128, kSbfWgUnroll = 4, kSbfWgFlush = 8;
 template <int DT>
-__global__ void __launch_bounds__(kSbfWgThreads, (DT <= 16 ? 2 : 1)) sbf_embed_wgrad_kernel(const int32_t* __restrict__ t_ptr,
-                                                                        const int32_t* __restrict__ t_split,
-                                                                        const int32_t* __restrict__ t_gather,
-                                                                        const int32_t* __restrict__ t_owner,
-                                                                        int64_t n_trip, const float* __restrict__ radial,
-                                                                        const float* __restrict__ ysph,
-                                                                        const float* __restrict__ gz, int dim,
-                                                                        float* __restrict__ gw2, float* __restrict__ gb2,
-                                                                        float* __restrict__ gw1, float* __restrict__ gb1,
-                                                                        int rows_per_cta) {
-    constexpr int NJ = 3, LDN = 96;
-    __shared__ double dacc[DT * LDN];
+__global__ void __launch_bounds__(kSbfWgThreads, (DT <= 16 ? 3 : 1)) sbf_embed_wgrad_kernel(const int32_t* __restrict__ t_gather, int64_t n_trip,
+                                                                     const float* __restrict__ radial,
+                                                                     const float* __restrict__ ysph,
+                                                                     const float* __restrict__ gz, int dim,
+                                                                     float* __restrict__ gw2, float* __restrict__ gb2,
+                                                                     float* __restrict__ gw1, float* __restrict__ gb1,
+                                                                     int rows_per_cta) {
+    // A row only touches the 42 weight columns + the bias of ITS type: lane n owns, per type, local columns n and n + 32
+    // (local column 42 = the bias; lanes 11-31 have no second column).  Tile column = 42 type + local (bias: 84 + type).
+    constexpr int NJ = 2, LDN = 96, NW = kSbfWgThreads / 32;
+    extern __shared__ double dtile[];                  // [NW][DT][LDN]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < DT * LDN; i += kSbfWgThreads) dacc[i] = 0.0;
-    __syncthreads();
-    float acc[DT][NJ];
+    double* mine = dtile + (size_t)warp * DT * LDN;
+    for (int i = lane; i < DT * LDN; i += 32) mine[i] = 0.0;
+    __syncwarp();
+    float acc[2][DT][NJ];
 #pragma unroll
-    for (int i = 0; i < DT; ++i)
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) acc[i][j] = 0.f;
-    auto flush = [&]() {
+    for (int ty = 0; ty < 2; ++ty)
 #pragma unroll
         for (int i = 0; i < DT; ++i)
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                if (acc[i][j] != 0.f) atomicAdd(&dacc[i * LDN + lane + 32 * j], (double)acc[i][j]);
-                acc[i][j] = 0.f;
+            for (int j = 0; j < NJ; ++j) acc[ty][i][j] = 0.f;
+    const bool has2 = lane + 32 <= kNumSbf;            // second local column exists (43 local columns: 0..42)
+    auto flush = [&]() {
+#pragma unroll
+        for (int ty = 0; ty < 2; ++ty)
+#pragma unroll
+            for (int i = 0; i < DT; ++i) {
+                mine[i * LDN + ty * kNumSbf + lane] += (double)acc[ty][i][0];
+                acc[ty][i][0] = 0.f;
+                if (has2) {
+                    const int lc = lane + 32;
+                    mine[i * LDN + (lc < kNumSbf ? ty * kNumSbf + lc : 2 * kNumSbf + ty)] += (double)acc[ty][i][1];
+                }
+                acc[ty][i][1] = 0.f;
             }
     };
     const int64_t k0 = (int64_t)blockIdx.x * rows_per_cta, k1 = min(n_trip, k0 + (int64_t)rows_per_cta);
-    constexpr int kStep = kSbfWgThreads / 32;
     int it = 0;
-    for (int64_t kb = k0 + warp; kb < k1; kb += kStep * kSbfWgUnroll) {
-        float bv[kSbfWgUnroll][NJ], av[kSbfWgUnroll][DT];
+    for (int64_t kb = k0 + warp; kb < k1; kb += NW * kSbfWgUnroll) {
+        float bv[kSbfWgUnroll][NJ], ao[kSbfWgUnroll];
+        int tyv[kSbfWgUnroll];
 #pragma unroll
         for (int u = 0; u < kSbfWgUnroll; ++u) {
-            const int64_t t = kb + u * kStep;
+            const int64_t t = kb + u * NW;
             const bool live = t < k1;
             const int64_t tt = live ? t : k0;
-            const int k = t_owner[tt], p = t_gather[tt];
-            const int ty = ((tt - t_ptr[k]) < t_split[k]) ? 0 : 1;
-            const float* r = radial + (size_t)p * kNumSbf;
+            const int p = t_gather[tt];
             const float* y = ysph + tt * kYsphLd;
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                const int col = lane + 32 * j;
-                float v = 0.f;
-                if (live) {
-                    if (col < 2 * kNumSbf) {
-                        const int cty = col >= kNumSbf, cc = col - cty * kNumSbf;
-                        if (cty == ty) v = r[cc] * y[cc / kNumRad];
-                    } else if (col == 2 * kNumSbf + ty) {
-                        v = 1.f;
-                    }
-                }
-                bv[u][j] = v;
-            }
-            const float* a = gz + tt * dim;
-#pragma unroll
-            for (int i = 0; i < DT; ++i) av[u][i] = (live && i < dim) ? a[i] : 0.f;
+            tyv[u] = (int)y[7];
+            const float* r = radial + (size_t)p * kNumSbf;
+            bv[u][0] = live ? r[lane] * y[lane / kNumRad] : 0.f;
+            const int lc = lane + 32;
+            bv[u][1] = (live && has2) ? (lc < kNumSbf ? r[lc] * y[lc / kNumRad] : 1.f) : 0.f;
+            ao[u] = (live && lane < dim) ? gz[tt * dim + lane] : 0.f;      // DT <= 32: one lane per gradient column
         }
 #pragma unroll
-        for (int u = 0; u < kSbfWgUnroll; ++u)
+        for (int u = 0; u < kSbfWgUnroll; ++u) {
+            if (tyv[u] == 0) {                          // warp-uniform: a row has one type
 #pragma unroll
-            for (int i = 0; i < DT; ++i)
+                for (int i = 0; i < DT; ++i) {
+                    const float ai = __shfl_sync(0xffffffffu, ao[u], i);
+                    acc[0][i][0] = fmaf(ai, bv[u][0], acc[0][i][0]);
+                    acc[0][i][1] = fmaf(ai, bv[u][1], acc[0][i][1]);
+                }
+            } else {
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) acc[i][j] = fmaf(av[u][i], bv[u][j], acc[i][j]);
+                for (int i = 0; i < DT; ++i) {
+                    const float ai = __shfl_sync(0xffffffffu, ao[u], i);
+                    acc[1][i][0] = fmaf(ai, bv[u][0], acc[1][i][0]);
+                    acc[1][i][1] = fmaf(ai, bv[u][1], acc[1][i][1]);
+                }
+            }
+        }
         if (++it == kSbfWgFlush) { flush(); it = 0; }
     }
     flush();
     __syncthreads();
     for (int i = threadIdx.x; i < dim * (2 * kNumSbf + 2); i += kSbfWgThreads) {
         const int d = i / (2 * kNumSbf + 2), col = i % (2 * kNumSbf + 2);
-        const float v = (float)dacc[d * LDN + col];
+        double tot = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) tot += dtile[((size_t)w * DT + d) * LDN + col];
+        const float v = (float)tot;
         if (v == 0.f) continue;
         if (col < kNumSbf) { if (gw2) atomicAdd(&gw2[d * kNumSbf + col], v); }
         else if (col < 2 * kNumSbf) atomicAdd(&gw1[d * kNumSbf + col - kNumSbf], v);
@@ -415,16 +432,20 @@ int sbf_embed_wgrad(const Plan& plan, int64_t n_trip, const float* radial, const
     if (n_trip == 0) return 0;
     PAMNET_CHECK_ARG(dim <= 32, "sbf_embed_wgrad: dim=%d (<= 32)", dim);
     int ctas = ceil_div(n_trip, 256);
-    if (ctas > 4 * kNumSM) ctas = 4 * kNumSM;
+    if (ctas > 8 * kNumSM) ctas = 8 * kNumSM;
     const int rows = ceil_div(n_trip, ctas);
     const dim3 grid(ceil_div(n_trip, rows));
+    const size_t smem16 = sizeof(double) * (kSbfWgThreads / 32) * 16 * 96, smem32 = 2 * smem16;
     prof_begin(KC_BASIS, 0.0, st);
-    if (dim <= 16)
-        sbf_embed_wgrad_kernel<16><<<grid, kSbfWgThreads, 0, st>>>(plan.t_ptr, plan.t_split, plan.t_gather, plan.t_owner, n_trip,
-                                                                    radial, ysph, gz, dim, gw2, gb2, gw1, gb1, rows);
-    else
-        sbf_embed_wgrad_kernel<32><<<grid, kSbfWgThreads, 0, st>>>(plan.t_ptr, plan.t_split, plan.t_gather, plan.t_owner, n_trip,
-                                                                    radial, ysph, gz, dim, gw2, gb2, gw1, gb1, rows);
+    if (dim <= 16) {
+        PAMNET_TRY(func_smem_once(reinterpret_cast<const void*>(sbf_embed_wgrad_kernel<16>), smem16));
+        sbf_embed_wgrad_kernel<16><<<grid, kSbfWgThreads, smem16, st>>>(plan.t_gather, n_trip, radial, ysph, gz, dim, gw2, gb2,
+                                                                         gw1, gb1, rows);
+    } else {
+        PAMNET_TRY(func_smem_once(reinterpret_cast<const void*>(sbf_embed_wgrad_kernel<32>), smem32));
+        sbf_embed_wgrad_kernel<32><<<grid, kSbfWgThreads, smem32, st>>>(plan.t_gather, n_trip, radial, ysph, gz, dim, gw2, gb2,
+                                                                         gw1, gb1, rows);
+    }
     prof_end(st);
     PAMNET_LAUNCH_CHECK();
     return 0;

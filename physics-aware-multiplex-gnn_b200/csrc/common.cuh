@@ -143,11 +143,15 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ---------------------------------------------------------------------------------------------
 template <int D>
 struct RowVec {
-    static constexpr int V = (D >= 128) ? 4 : (D >= 64 ? 2 : 1);   // floats per lane per chunk
-    static constexpr int C = (D + 32 * V - 1) / (32 * V);           // chunks per lane
+    // D >= 64: a warp per row (float4 / float2 per lane).  D <= 32: D / 4 lanes per row, one float4 each, so a warp
+    // carries 32 / LPR rows side by side (dim 16: 8 rows) instead of idling half its lanes on 4-byte accesses.
+    static constexpr int V = (D >= 128 || D <= 32) ? 4 : 2;        // floats per lane per chunk
+    static constexpr int LPR = (D <= 32) ? D / 4 : 32;              // lanes per row
+    static constexpr int RPW = 32 / LPR;                            // rows per warp
+    static constexpr int C = (D + LPR * V - 1) / (LPR * V);         // chunks per lane
     float v[C * V];
 
-    __device__ __forceinline__ static bool active(int lane) { return D >= 32 || lane < D; }
+    __device__ __forceinline__ static bool active(int) { return true; }
     __device__ __forceinline__ void zero() {
 #pragma unroll
         for (int i = 0; i < C * V; ++i) v[i] = 0.f;
@@ -155,7 +159,7 @@ struct RowVec {
     __device__ __forceinline__ void load(const float* __restrict__ row, int lane) {
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            const float* p = row + (c * 32 + lane) * V;
+            const float* p = row + (c * LPR + lane % LPR) * V;
             if (V == 4) {
                 float4 t = ld4(p);
                 v[c * 4 + 0] = t.x; v[c * 4 + 1] = t.y; v[c * 4 + 2] = t.z; v[c * 4 + 3] = t.w;
@@ -171,7 +175,7 @@ struct RowVec {
     __device__ __forceinline__ void atomic_add(float* __restrict__ row, int lane) const {
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            float* p = row + (c * 32 + lane) * V;
+            float* p = row + (c * LPR + lane % LPR) * V;
             if (V == 4) {
                 asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[c * 4 + 0]), "f"(v[c * 4 + 1]),
                              "f"(v[c * 4 + 2]), "f"(v[c * 4 + 3]) : "memory");
@@ -185,7 +189,7 @@ struct RowVec {
     __device__ __forceinline__ void store(float* __restrict__ row, int lane) const {
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            float* p = row + (c * 32 + lane) * V;
+            float* p = row + (c * LPR + lane % LPR) * V;
             if (V == 4) {
                 st4(p, make_float4(v[c * 4 + 0], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]));
             } else if (V == 2) {

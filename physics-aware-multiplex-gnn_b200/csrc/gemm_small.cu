@@ -4,7 +4,8 @@
 //  * NT / NN ("row kernel"): one thread per output row; the weight matrix sits in shared memory and is read by
 //    broadcast, the row is read once with 128-bit loads, bias / SiLU / SiLU' / z-output epilogues as in the other paths;
 //  * TN ("column kernel", weight gradients): a warp walks rows k, lane n owns output columns n, n + 32, ... for all
-//    M <= 32 output rows; A[k][:] is a broadcast load, B[k][:] a coalesced one; warps / CTAs combine with fp32 atomics.
+//    M <= 32 output rows; A[k][:] and B[k][:] are one coalesced load each, A's values reach the lanes by shuffle;
+//    fp64 register accumulators, CTAs combine with fp32 atomics.
 #include "gemm.cuh"
 
 namespace pamnet {
@@ -111,55 +112,72 @@ __global__ void __launch_bounds__(kSmallThreads) gemm_rows_kernel(const GemmArgs
 
 // weight gradient: C[m][n] (+)= sum_k A[k][m] B[k][n]; C2[m] += sum_k A[k][m].  Always combines with atomics: the
 // caller zero-initialises C (gemm_launch does it for plain-store launches).
-//   MT_ register rows per lane (16 or 32); NJ columns per lane (n = sub-lane + W j, W = 32 / RP lanes per row);
+//   MT_ output rows (16 or 32); NJ columns per lane (n = sub-lane + W j, W = 32 / RP lanes per row);
 //   RP rows walked side by side by the lane groups of a warp (2 when N <= 16, so that no lane idles).
-// kColsUnroll rows per lane group are loaded before any is multiplied: the loop is a stream of dependent-free loads.
+// A lane group reads its row of A and of B once, coalesced (lane sub holds A[k][sub + W r] and B[k][sub + W j]); the MT_
+// values of A[k][:] every lane multiplies with reach it by warp shuffles from the lane that loaded them.  kColsUnroll
+// rows per lane group are loaded before any is multiplied: the loop is a stream of dependent-free loads.
 // Accuracy: these reductions run over up to millions of rows with heavy cancellation (a 1185-way fp32 atomic
 // combine missed the 1e-5 parity bar on mlp_rbf_g.weight of the RNA checkpoint).  fp32 partial sums therefore cover
-// at most kColsFlush x kColsUnroll rows, are folded into a per-CTA fp64 tile in shared memory, and only
-// <= 4 x 148 per-CTA results meet in the fp32 output.
+// at most kColsFlush x kColsUnroll rows and are folded into fp64 accumulators; only <= 4 x 148 per-CTA results meet in
+// the fp32 output.
+// The fp64 accumulators live in REGISTERS and meet once per CTA (lane groups by shuffle, warps one after the other
+// through shared memory).  The first version folded every fp32 window into a shared fp64 tile with atomics -- a
+// compare-and-swap loop with 16 lanes per address: on the 775 k-edge RNA batch each weight-gradient launch took
+// 250-400 us for 99 MB of operands, ~6 % of the HBM rate (ncu launch list profiles/r02_launches_c4.csv); and every
+// lane loaded all MT_ values of A[k][:] itself (16 broadcast loads per row).
 constexpr int kColsUnroll = 4, kColsFlush = 8, kColsThreads = 256;
 template <int MT_, int NJ, int RP>
 __global__ void __launch_bounds__(kColsThreads) gemm_cols_kernel(const GemmArgs args, int rows_per_cta) {
     pdl_wait();
     pdl_trigger();
-    __shared__ double dacc[MT_ * 32 * NJ];             // [m][n], n < 32 NJ
-    __shared__ double dsum[32];
+    constexpr int W = 32 / RP, LDN = 32 * NJ;
+    constexpr int AR = (MT_ + W - 1) / W;              // registers of A per lane: rows m = sub + W r
+    constexpr bool DREG = MT_ * NJ <= 48;              // fp64 accumulators fit the register file (else: shared fp64 tile + atomics)
+    constexpr int DR_M = DREG ? MT_ : 1, DR_N = DREG ? NJ : 1;
+    __shared__ double dacc[MT_ * LDN];                 // [m][n], n < 32 NJ
+    __shared__ double dsum[W * AR];
     const GemmSlot& sl = args.slot[blockIdx.z];
     const int M = sl.m > 0 ? sl.m : args.M, N = args.N, K = args.K;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int W = 32 / RP, LDN = 32 * NJ;
     const int sub = lane % W, rp = lane / W;
-    for (int i = threadIdx.x; i < MT_ * LDN; i += kColsThreads) dacc[i] = 0.0;
-    if (threadIdx.x < 32) dsum[threadIdx.x] = 0.0;
-    __syncthreads();
+    if (!DREG) {
+        for (int i = threadIdx.x; i < MT_ * LDN; i += kColsThreads) dacc[i] = 0.0;
+        __syncthreads();
+    }
     float acc[MT_][NJ];
+    double dreg[DR_M][DR_N];
 #pragma unroll
     for (int i = 0; i < MT_; ++i)
 #pragma unroll
         for (int j = 0; j < NJ; ++j) acc[i][j] = 0.f;
-    float asum[RP];                                    // column sums of A: rows m = sub + W r of this lane group's rows
 #pragma unroll
-    for (int r = 0; r < RP; ++r) asum[r] = 0.f;
+    for (int i = 0; i < DR_M; ++i)
+#pragma unroll
+        for (int j = 0; j < DR_N; ++j) dreg[i][j] = 0.0;
+    float asum[AR];                                    // column sums of A: rows m = sub + W r of this lane group's rows
+    double dasum[AR];
+#pragma unroll
+    for (int r = 0; r < AR; ++r) { asum[r] = 0.f; dasum[r] = 0.0; }
     auto flush = [&]() {
 #pragma unroll
         for (int i = 0; i < MT_; ++i)
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
-                if (acc[i][j] != 0.f) atomicAdd(&dacc[i * LDN + sub + W * j], (double)acc[i][j]);
+                if (DREG) dreg[DREG ? i : 0][DREG ? j : 0] += (double)acc[i][j];
+                else if (acc[i][j] != 0.f) atomicAdd(&dacc[i * LDN + sub + W * j], (double)acc[i][j]);
                 acc[i][j] = 0.f;
             }
 #pragma unroll
-        for (int r = 0; r < RP; ++r) {
-            if (asum[r] != 0.f) atomicAdd(&dsum[sub + W * r], (double)asum[r]);
-            asum[r] = 0.f;
-        }
+        for (int r = 0; r < AR; ++r) { dasum[r] += (double)asum[r]; asum[r] = 0.f; }
     };
     const int k0 = blockIdx.x * rows_per_cta, k1 = min(K, k0 + rows_per_cta);
     constexpr int kStep = (kColsThreads / 32) * RP;    // rows between two consecutive rows of one lane group
     int it = 0;
-    for (int kb = k0 + warp * RP + rp; kb < k1; kb += kStep * kColsUnroll) {
-        float bv[kColsUnroll][NJ], am[kColsUnroll][RP], av[kColsUnroll][MT_];
+    // (warp-uniform trip count: the shuffles below need every lane of the warp in every iteration)
+    for (int kw = k0 + warp * RP; kw < k1; kw += kStep * kColsUnroll) {
+        const int kb = kw + rp;
+        float bv[kColsUnroll][NJ], am[kColsUnroll][AR];
 #pragma unroll
         for (int u = 0; u < kColsUnroll; ++u) {
             const int k = kb + u * kStep;
@@ -169,23 +187,53 @@ __global__ void __launch_bounds__(kColsThreads) gemm_cols_kernel(const GemmArgs 
 #pragma unroll
             for (int j = 0; j < NJ; ++j) bv[u][j] = (live && sub + W * j < N) ? b[sub + W * j] : 0.f;
 #pragma unroll
-            for (int r = 0; r < RP; ++r) am[u][r] = (live && sub + W * r < M) ? a[sub + W * r] : 0.f;
-#pragma unroll
-            for (int i = 0; i < MT_; ++i) av[u][i] = (live && i < M) ? a[i] : 0.f;      // broadcast loads
+            for (int r = 0; r < AR; ++r) am[u][r] = (live && sub + W * r < M) ? a[sub + W * r] : 0.f;
         }
 #pragma unroll
         for (int u = 0; u < kColsUnroll; ++u) {
 #pragma unroll
-            for (int r = 0; r < RP; ++r) asum[r] += am[u][r];
+            for (int r = 0; r < AR; ++r) asum[r] += am[u][r];
 #pragma unroll
-            for (int i = 0; i < MT_; ++i)
+            for (int i = 0; i < MT_; ++i) {
+                // A[k][i] of this lane group's row: loaded by its lane i % W (register i / W)
+                const float ai = __shfl_sync(0xffffffffu, am[u][i / W], i % W, W);
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) acc[i][j] = fmaf(av[u][i], bv[u][j], acc[i][j]);
+                for (int j = 0; j < NJ; ++j) acc[i][j] = fmaf(ai, bv[u][j], acc[i][j]);
+            }
         }
         if (++it == kColsFlush) { flush(); it = 0; }
     }
     flush();
-    __syncthreads();
+    // lane groups of a warp -> lane group 0
+#pragma unroll
+    for (int o = W; o < 32; o <<= 1) {
+#pragma unroll
+        for (int i = 0; i < DR_M; ++i)
+#pragma unroll
+            for (int j = 0; j < DR_N; ++j) dreg[i][j] += __shfl_xor_sync(0xffffffffu, dreg[i][j], o);
+#pragma unroll
+        for (int r = 0; r < AR; ++r) dasum[r] += __shfl_xor_sync(0xffffffffu, dasum[r], o);
+    }
+    // warps one after the other: plain read-modify-write, every lane of group 0 owns its addresses
+    for (int w = 0; w < kColsThreads / 32; ++w) {
+        if (warp == w && rp == 0) {
+            if (DREG) {
+#pragma unroll
+                for (int i = 0; i < DR_M; ++i)
+#pragma unroll
+                    for (int j = 0; j < DR_N; ++j) {
+                        double* d = &dacc[i * LDN + sub + W * j];
+                        *d = (w == 0 ? 0.0 : *d) + dreg[i][j];
+                    }
+            }
+#pragma unroll
+            for (int r = 0; r < AR; ++r) {
+                double* d = &dsum[sub + W * r];
+                *d = (w == 0 ? 0.0 : *d) + dasum[r];
+            }
+        }
+        __syncthreads();
+    }
     for (int i = threadIdx.x; i < M * N; i += kColsThreads) {
         const int m = i / N, n = i % N;
         const float v = (float)dacc[m * LDN + n];

@@ -10,6 +10,12 @@ constexpr int kUnroll = 4;       // independent row loads kept in flight per war
 
 #define ROW_FOR(i) _Pragma("unroll") for (int i = 0; i < RowVec<D>::C * RowVec<D>::V; ++i)
 
+// row (edge slot / node / work item) of this thread: a warp per row, or 32 / LPR rows per warp for dim <= 32 (common.cuh)
+template <int D>
+__device__ __forceinline__ int msg_row() {
+    return (blockIdx.x * (kMsgThreads / 32) + (threadIdx.x >> 5)) * RowVec<D>::RPW + (threadIdx.x & 31) / RowVec<D>::LPR;
+}
+
 // ---------------------------------------------------------------------------------------------
 // global layer
 // ---------------------------------------------------------------------------------------------
@@ -62,13 +68,47 @@ __global__ void __launch_bounds__(kMsgThreads) global_msg_fwd_kernel(const Globa
     }
 }
 
+// dim <= 32: one lane group (D / 4 lanes) per destination node walks its incoming edges, kUnroll in flight; large graphs
+// (the shape these dims are used on) have enough nodes to fill the GPU that way
+template <int D>
+__global__ void __launch_bounds__(kMsgThreads) global_msg_fwd_rows_kernel(const GlobalMsgArgs a) {
+    pdl_wait();
+    pdl_trigger();
+    const int lane = threadIdx.x & 31;
+    const int n = msg_row<D>();
+    if (n >= a.n_nodes) return;
+    RowVec<D> pi, acc;
+    pi.load(a.P + (size_t)n * 2 * D, lane);
+    acc.load(a.x1 + (size_t)n * D, lane);
+    const int e0 = a.ptr[n], e1 = a.ptr[n + 1];
+    for (int k = e0; k < e1; k += kUnroll) {
+        RowVec<D> pj[kUnroll], q[kUnroll], tt[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (k + u < e1) {
+                const int s = a.src[k + u];
+                pj[u].load(a.P + (size_t)s * 2 * D + D, lane);
+                q[u].load(a.QT + (size_t)(k + u) * a.ldq, lane);
+                tt[u].load(a.QT + (size_t)(k + u) * a.ldq + D, lane);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (k + u < e1) {
+                ROW_FOR(i) acc.v[i] += silu(pi.v[i] + pj[u].v[i] + q[u].v[i]) * tt[u].v[i];
+            }
+        }
+    }
+    acc.store(a.h + (size_t)n * D, lane);
+}
+
 // one warp per edge slot: every output row is per-edge, so the backward is embarrassingly edge-parallel
 template <int D>
 __global__ void __launch_bounds__(kMsgThreads) global_msg_bwd_kernel(const GlobalMsgArgs a) {
     pdl_wait();
     pdl_trigger();
     const int lane = threadIdx.x & 31;
-    const int k = blockIdx.x * (kMsgThreads / 32) + (threadIdx.x >> 5);
+    const int k = msg_row<D>();
     if (k >= a.n_edges) return;
     const int n = a.dst[k], s = a.src[k];
     RowVec<D> pi, g, pj, q, tt, gz, gt;
@@ -99,7 +139,7 @@ __global__ void __launch_bounds__(kMsgThreads) local_edge_fwd_kernel(const Local
     pdl_wait();
     pdl_trigger();
     const int lane = threadIdx.x & 31;
-    const int k = blockIdx.x * (kMsgThreads / 32) + (threadIdx.x >> 5);
+    const int k = msg_row<D>();
     if (k >= a.n_edges) return;
     const int i = a.dst[k], j = a.src[k];
     RowVec<D> pi, pj, q, r;
@@ -117,7 +157,7 @@ __global__ void __launch_bounds__(kMsgThreads) local_trip_fwd_kernel(const Local
     pdl_wait();
     pdl_trigger();
     const int lane = threadIdx.x & 31;
-    const int k = blockIdx.x * (kMsgThreads / 32) + (threadIdx.x >> 5);
+    const int k = msg_row<D>();
     if (k >= a.n_edges) return;
     const int n = a.dst[k], j = a.src[k];
     RowVec<D> pi, pj, q, ms;
@@ -151,7 +191,7 @@ __global__ void __launch_bounds__(kMsgThreads) local_msg_fwd_kernel(const LocalM
     pdl_wait();
     pdl_trigger();
     const int lane = threadIdx.x & 31;
-    const int n = blockIdx.x * (kMsgThreads / 32) + (threadIdx.x >> 5);
+    const int n = msg_row<D>();
     if (n >= a.n_nodes) return;
     RowVec<D> acc;
     acc.load(a.x1 + (size_t)n * D, lane);
@@ -181,7 +221,7 @@ __global__ void __launch_bounds__(kMsgThreads) local_msg_bwd_kernel(const LocalM
     pdl_wait();
     pdl_trigger();
     const int lane = threadIdx.x & 31;
-    const int k = blockIdx.x * (kMsgThreads / 32) + (threadIdx.x >> 5);
+    const int k = msg_row<D>();
     if (k >= a.n_edges) return;
     const int n = a.dst[k], j = a.src[k];
     RowVec<D> pi, g, ro, ms, gs, gro, pj, q, gz;
@@ -230,7 +270,7 @@ __global__ void __launch_bounds__(kMsgThreads) local_trip_bwd_kernel(const Local
     pdl_wait();
     pdl_trigger();
     const int lane = threadIdx.x & 31;
-    const int k = blockIdx.x * (kMsgThreads / 32) + (threadIdx.x >> 5);
+    const int k = msg_row<D>();
     if (k >= a.n_edges) return;
     RowVec<D> gm;
     gm.zero();
@@ -278,7 +318,7 @@ __global__ void __launch_bounds__(kMsgThreads) node_grad_gather_kernel(const Nod
     pdl_wait();
     pdl_trigger();
     const int lane = threadIdx.x & 31;
-    const int item = blockIdx.x * (kMsgThreads / 32) + (threadIdx.x >> 5);
+    const int item = msg_row<D>();
     const int ntask = 2 * a.n_blocks;
     if (item >= a.n_nodes * ntask) return;
     const int n = item / ntask, task = item % ntask, b = task >> 1;
@@ -304,13 +344,13 @@ __global__ void __launch_bounds__(kMsgThreads) node_grad_gather_kernel(const Nod
 #define DISPATCH_DIM(dim, KERNEL, rows, args, CLS, BYTES)                                             \
     do {                                                                                              \
         if ((rows) <= 0) return 0;                                                                    \
-        const int grid = ceil_div((rows), kMsgThreads / 32);                                          \
+        const int grid = ceil_div((rows), kMsgThreads / 32);            /* a warp per row */          \
         prof_begin(CLS, BYTES, st);                                                                   \
         switch (dim) {                                                                                \
             case 128: launch_pdl(KERNEL<128>, dim3(grid), dim3(kMsgThreads), 0, st, args); break;     \
             case 64:  launch_pdl(KERNEL<64>, dim3(grid), dim3(kMsgThreads), 0, st, args); break;      \
-            case 32:  launch_pdl(KERNEL<32>, dim3(grid), dim3(kMsgThreads), 0, st, args); break;      \
-            case 16:  launch_pdl(KERNEL<16>, dim3(grid), dim3(kMsgThreads), 0, st, args); break;      \
+            case 32:  launch_pdl(KERNEL<32>, dim3(ceil_div(grid, RowVec<32>::RPW)), dim3(kMsgThreads), 0, st, args); break; \
+            case 16:  launch_pdl(KERNEL<16>, dim3(ceil_div(grid, RowVec<16>::RPW)), dim3(kMsgThreads), 0, st, args); break; \
             default: set_error("unsupported dim %d (16, 32, 64, 128)", dim); return -1;               \
         }                                                                                             \
         prof_end(st);                                                                                 \
@@ -324,6 +364,19 @@ static double nbytes(int dim, double node_rows, double edge_rows, double trip_ro
 }
 
 int global_msg_fwd(int dim, const GlobalMsgArgs& a, int n_edges, cudaStream_t st) {
+    if (dim <= 32) {
+        if (a.n_nodes <= 0) return 0;
+        const double bytes = nbytes(dim, 3.0 * a.n_nodes, 3.0 * n_edges, 0, a.n_nodes + n_edges);
+        prof_begin(KC_GLOBAL_MSG_FWD, bytes, st);
+        if (dim == 32)
+            launch_pdl(global_msg_fwd_rows_kernel<32>, dim3(ceil_div(a.n_nodes, (kMsgThreads / 32) * RowVec<32>::RPW)), dim3(kMsgThreads), 0, st, a);
+        else if (dim == 16)
+            launch_pdl(global_msg_fwd_rows_kernel<16>, dim3(ceil_div(a.n_nodes, (kMsgThreads / 32) * RowVec<16>::RPW)), dim3(kMsgThreads), 0, st, a);
+        else { set_error("unsupported dim %d (16, 32, 64, 128)", dim); return -1; }
+        prof_end(st);
+        PAMNET_LAUNCH_CHECK();
+        return 0;
+    }
     // one CTA per node: rows = n_nodes * warps-per-CTA so the dispatch macro's grid = n_nodes
     DISPATCH_DIM(dim, global_msg_fwd_kernel, a.n_nodes * (kMsgThreads / 32), a, KC_GLOBAL_MSG_FWD,
                  nbytes(dim, 3.0 * a.n_nodes, 3.0 * n_edges, 0, a.n_nodes + n_edges));

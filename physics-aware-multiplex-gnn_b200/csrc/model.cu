@@ -725,8 +725,11 @@ int model_forward(const pamnet_config_t& cfg, const pamnet_sizes_t& sz, const pa
     // PAMNET_FWD_SPLIT=1 runs the local / triplet chain on a second stream and issues it after the main stream's first
     // kernels -- measured slower (1.96-2.03 vs 1.89-1.90 ms/step): the two chains then compete for the SMs the first
     // node chains need.
-    static int fwd_split = -1;
-    if (fwd_split < 0) { const char* e = getenv("PAMNET_FWD_SPLIT"); fwd_split = (e && e[0] == '1') ? 1 : 0; }
+    // Large graphs (the 775 k-edge / 951 k-triplet RNA batch): the kernels of either chain fill the GPU for 50-200 us each
+    // and the two chains are independent, so they do run side by side (auto: E_g + T >= 300 k).
+    static int fwd_split_env = -2;
+    if (fwd_split_env == -2) { const char* e = getenv("PAMNET_FWD_SPLIT"); fwd_split_env = e ? (e[0] == '1' ? 1 : 0) : -1; }
+    const int fwd_split = fwd_split_env >= 0 ? fwd_split_env : ((Eg + T >= 300000) ? 1 : 0);
     cudaStream_t sB = fwd_split ? sc.s4 : s2;
     if (sB != s2) PAMNET_TRY(sc.order(st, sB));
     auto embed_global = [&]() -> int {

@@ -154,7 +154,10 @@ def test_linear(ops, n_in, n_out, rows):
 
 @pytest.mark.parametrize("m,n,k,ksplit", [(128, 128, 599, 1), (128, 16, 5000, 4), (1, 128, 300, 1), (70, 88, 1000, 3),
                                             (300, 128, 128, 1), (1000, 256, 64, 1), (128, 384, 2000, 8), (130, 100, 16, 1),
-                                            (257, 129, 40, 2)])
+                                            (257, 129, 40, 2),
+                                            # skinny weight gradients (gemm_small.cu column kernel: register fp64 accumulators)
+                                            (16, 16, 100003, 1), (32, 16, 7777, 1), (16, 88, 5000, 1), (32, 32, 3001, 1),
+                                            (32, 96, 1000, 1), (3, 5, 17, 1)])
 def test_gemm_modes(ops, m, n, k, ksplit):
     g = torch.Generator().manual_seed(3)
     a, b = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g)

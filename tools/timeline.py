@@ -8,8 +8,14 @@ from pamnet_b200 import Config, PAMNet, _lib
 from pamnet_b200.data import synthetic_qm9_batch
 
 torch.manual_seed(0)
-model = PAMNet(Config("QM9", 128, 6, 5.0, 5.0)).cuda()
-b = synthetic_qm9_batch(32, 0).to("cuda")
+if os.environ.get("CONFIG") == "c4":        # BASELINE configs[3]: the 8-graph RNA fixture batch
+    from pamnet_b200.data import Batch
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "rna_c4.pt"), map_location="cpu", weights_only=False)
+    model = PAMNet(Config(**gold["config"])); model.load_state_dict(gold["state_dict"]); model = model.cuda()
+    b = Batch(x=gold["x"], batch=torch.repeat_interleave(torch.arange(8), torch.tensor(gold["sizes"])), y=gold["y"]).to("cuda")
+else:
+    model = PAMNet(Config("QM9", 128, 6, 5.0, 5.0)).cuda()
+    b = synthetic_qm9_batch(int(os.environ.get("BS", "32")), 0).to("cuda")
 params = list(model.parameters())
 
 def step():
@@ -37,7 +43,6 @@ for tag in sorted({t[1] for t in tl}):
         by.setdefault(t[0], [0, 0.0])
         by[t[0]][0] += 1; by[t[0]][1] += t[3] - t[2]
     print("   ", {k: (v[0], round(v[1], 3)) for k, v in sorted(by.items(), key=lambda kv: -kv[1][1])})
-# coarse main-stream trace
-ev = sorted([t for t in tl if t[1] == 0], key=lambda t: t[2])
-print("main stream trace (class, start, dur us):")
-print("  ".join(f"{t[0][:6]}@{t[2]:.2f}+{(t[3]-t[2])*1e3:.0f}" for t in ev))
+# full trace, by start time
+print("trace (stream:class @start ms +dur us):")
+print("  ".join(f"{t[1]}:{t[0][:10]}@{t[2]:.3f}+{(t[3]-t[2])*1e3:.0f}" for t in sorted(tl, key=lambda t: t[2])))
