@@ -197,22 +197,34 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_warp_kernel(const float* _
     const float inf = __int_as_float(0x7f800000);
     float ed[2] = {inf, inf};            // list entries at positions lane, 32 + lane
     int32_t ei[2] = {-1, -1};
-    float tau = inf;                     // distance at position k - 1
+    float tau = inf;                     // (distance, index) at position k - 1
+    int32_t tau_i = 0x7fffffff;
     int cnt = 0;
     const int tl = (k - 1) & 31, tr = (k - 1) >> 5;
-    for (int64_t base = s; base < e; base += 32) {
+    // Scan order: the 32-candidate block that holds the query first, then outwards (+1, -1, +2, -2, ...).  Atoms are
+    // stored along the chain, so index distance predicts spatial distance: scanned from the start of the graph every
+    // candidate before the query was a new best (~1000 list insertions per RNA query, 586 us for the batch); scanned
+    // outwards the k-th distance collapses in the first blocks.  The list is ordered by (distance, index) -- the same
+    // total order as "ties keep the lower index" of an ascending scan -- so the result is identical.
+    const int64_t nb = (e - s + 31) / 32, qb = (q - s) / 32;
+    const int64_t reach = (qb > nb - 1 - qb) ? qb : nb - 1 - qb;
+    for (int64_t stp = 0; stp <= 2 * reach; ++stp) {
+        const int64_t off = (stp + 1) / 2, blk = (stp & 1) ? qb + off : qb - off;
+        if (blk < 0 || blk >= nb) continue;
+        const int64_t base = s + blk * 32;
         const int64_t n = base + lane;
         float d2 = inf;
         if (n < e) d2 = canon_d2(qx, qy, qz, pos[3 * n], pos[3 * n + 1], pos[3 * n + 2]);
-        unsigned m = __ballot_sync(0xffffffffu, n < e && d2 < tau);
+        unsigned m = __ballot_sync(0xffffffffu, n < e && (d2 < tau || (d2 == tau && (int32_t)n < tau_i)));
         while (m) {
             const int b = __ffs(m) - 1;
             m &= m - 1;
             const float kd = __shfl_sync(0xffffffffu, d2, b);
-            if (!(kd < tau)) continue;                       // tau may have dropped since the ballot
             const int32_t ki = (int32_t)(base + b);
-            // insertion rank = number of entries <= kd (equal distances arrived earlier = lower index)
-            const int pos_ins = __popc(__ballot_sync(0xffffffffu, ed[0] <= kd)) + __popc(__ballot_sync(0xffffffffu, ed[1] <= kd));
+            if (!(kd < tau || (kd == tau && ki < tau_i))) continue;      // the k-th entry may have moved since the ballot
+            // insertion rank = number of entries before (kd, ki) in (distance, index) order (empty slots: inf)
+            const int pos_ins = __popc(__ballot_sync(0xffffffffu, ed[0] < kd || (ed[0] == kd && ei[0] < ki))) +
+                                __popc(__ballot_sync(0xffffffffu, ed[1] < kd || (ed[1] == kd && ei[1] < ki)));
             // shift positions >= pos_ins up by one and drop the key in
             const float up0 = __shfl_up_sync(0xffffffffu, ed[0], 1), up1 = __shfl_up_sync(0xffffffffu, ed[1], 1);
             const int32_t ui0 = __shfl_up_sync(0xffffffffu, ei[0], 1), ui1 = __shfl_up_sync(0xffffffffu, ei[1], 1);
@@ -224,7 +236,10 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_warp_kernel(const float* _
             if (p0 > pos_ins) { ed[0] = up0; ei[0] = ui0; }
             else if (p0 == pos_ins) { ed[0] = kd; ei[0] = ki; }
             if (cnt < k) ++cnt;
-            if (cnt == k) tau = __shfl_sync(0xffffffffu, tr ? ed[1] : ed[0], tl);
+            if (cnt == k) {
+                tau = __shfl_sync(0xffffffffu, tr ? ed[1] : ed[0], tl);
+                tau_i = __shfl_sync(0xffffffffu, tr ? ei[1] : ei[0], tl);
+            }
         }
     }
 #pragma unroll

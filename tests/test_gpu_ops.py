@@ -142,7 +142,8 @@ def test_bessel_and_spherical_basis(ops):
     assert rel_err(out, ref) < 2e-6          # the fp32 reference itself is only good to ~7e-5 here
 
 
-@pytest.mark.parametrize("n_in,n_out,rows", [(16, 128, 777), (42, 16, 100), (128, 128, 1), (384, 128, 333), (18, 32, 65)])
+@pytest.mark.parametrize("n_in,n_out,rows", [(16, 128, 777), (42, 16, 100), (128, 128, 1), (384, 128, 333), (18, 32, 65),
+                                              (16, 16, 9001), (32, 16, 4100)])
 def test_linear(ops, n_in, n_out, rows):
     g = torch.Generator().manual_seed(2)
     x, w, b = torch.randn(rows, n_in, generator=g), torch.randn(n_out, n_in, generator=g) / n_in ** 0.5, torch.randn(n_out, generator=g)
@@ -157,7 +158,9 @@ def test_linear(ops, n_in, n_out, rows):
                                             (257, 129, 40, 2),
                                             # skinny weight gradients (gemm_small.cu column kernel: register fp64 accumulators)
                                             (16, 16, 100003, 1), (32, 16, 7777, 1), (16, 88, 5000, 1), (32, 32, 3001, 1),
-                                            (32, 96, 1000, 1), (3, 5, 17, 1)])
+                                            (32, 96, 1000, 1), (3, 5, 17, 1), (9, 13, 40000, 1),
+                                            # dim-16 rows kernels on the tensor cores (N = 16, K = 16 / 32, many rows)
+                                            (5000, 16, 16, 1), (70001, 16, 32, 1)])
 def test_gemm_modes(ops, m, n, k, ksplit):
     g = torch.Generator().manual_seed(3)
     a, b = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g)
