@@ -8,6 +8,7 @@
 //    fp64 register accumulators, CTAs combine with fp32 atomics.
 #include "gemm.cuh"
 
+#include <stdio.h>
 #include <stdlib.h>
 
 namespace pamnet {
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(kColsThreads) gemm_cols_kernel(const GemmArgs 
 // operands, six products, for two 8-column tiles) instead of 16 shuffles + 16 FMAs per ROW PAIR in the kernel above (which is issue-bound:
 // ncu 50 % issue slots at 1.9 TB/s).  Fragments are loaded straight from global memory: lane (g, tq) reads
 // A[k0 + tq (+4)][g (+8)] and B[k0 + tq (+4)][8 j + g] -- every request covers whole 32-byte sectors of 8 consecutive rows.
-// Accuracy: fp32 inside one k-step only, then fp64 registers; warps meet once per CTA in shared
+// Accuracy: fp32 over the 32 rows a warp has in flight, then fp64 registers; warps meet once per CTA in shared
 // memory, CTAs with one fp32 atomic per output.  Column sums of A (bias gradient) ride along on the A fragments.
 __device__ __forceinline__ void cols_mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
     asm volatile(
@@ -312,16 +313,15 @@ __global__ void __launch_bounds__(kColsThreads) gemm_cols_mma_kernel(const GemmA
             bv[s][2] = (l0 && n_1) ? b0[g + 8] : 0.f;      // tile 1
             bv[s][3] = (l1 && n_1) ? b1[g + 8] : 0.f;
         }
+        // fp32 over the 32 rows in flight (the window of the SIMT kernel), then fp64
+        float c[2][4], cx[2][4];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { c[j][i] = 0.f; cx[j][i] = 0.f; }
         float as0 = 0.f, as1 = 0.f;
 #pragma unroll
         for (int s = 0; s < kColsMmaSteps; ++s) {
-            // fp32 only inside one k-step (8 rows x 6 products): the tensor core adds into its accumulator with
-            // truncation, so every k-step starts from zero and goes to the fp64 registers
-            float c[2][4], cx[2][4];
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { c[j][i] = 0.f; cx[j][i] = 0.f; }
             uint32_t ah[4], am[4], al[4], bh[4], bm[4], bl[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) { cols_split(av[s][i], ah[i], am[i], al[i]); cols_split(bv[s][i], bh[i], bm[i], bl[i]); }
@@ -331,18 +331,18 @@ __global__ void __launch_bounds__(kColsThreads) gemm_cols_mma_kernel(const GemmA
             for (int j = 0; j < 2; ++j) {
                 const uint32_t bhj[2] = {bh[2 * j], bh[2 * j + 1]}, bmj[2] = {bm[2 * j], bm[2 * j + 1]},
                                blj[2] = {bl[2 * j], bl[2 * j + 1]};
-                cols_mma_tf32(cx[j], al, bhj);             // small terms first, in their own accumulator
+                cols_mma_tf32(cx[j], al, bhj);             // small terms in their own accumulator
                 cols_mma_tf32(cx[j], ah, blj);
                 cols_mma_tf32(cx[j], am, bmj);
                 cols_mma_tf32(cx[j], am, bhj);
                 cols_mma_tf32(cx[j], ah, bmj);
                 cols_mma_tf32(c[j], ah, bhj);
             }
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) dc[j][i] += (double)c[j][i] + (double)cx[j][i];
         }
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dc[j][i] += (double)c[j][i] + (double)cx[j][i];
         ds[0] += (double)as0;
         ds[1] += (double)as1;
     }
@@ -389,9 +389,10 @@ __global__ void __launch_bounds__(kColsThreads) gemm_cols_mma_kernel(const GemmA
 // 2 s (slot tq) and 2 s + 1 (slot tq + 4); MMA column (tile j, c) stands for output column 4 (c / 2) + 2 j + c % 2, which
 // puts C[m][4 tq .. 4 tq + 3] of rows g and g + 8 into the lane's accumulators.  The weight fragments (all three parts)
 // follow the same maps and live in registers for the whole kernel.
-constexpr int kRowsMmaThreads = 128, kRowsMmaTiles = 4;            // row tiles in flight per warp
+constexpr int kRowsMmaThreads = 128;
 template <int EPI, int KC>                                         // KC = K / 16
 __global__ void __launch_bounds__(kRowsMmaThreads) gemm_rows_mma_kernel(const GemmArgs args) {
+    constexpr int kRowsMmaTiles = 4 / KC;                          // row tiles in flight per warp (same registers for every KC)
     pdl_wait();
     pdl_trigger();
     const GemmSlot& sl = args.slot[blockIdx.z];
@@ -486,6 +487,10 @@ __global__ void __launch_bounds__(kRowsMmaThreads) gemm_rows_mma_kernel(const Ge
                 v[0] *= dsilu(z.x); v[1] *= dsilu(z.y); v[2] *= dsilu(z.z); v[3] *= dsilu(z.w);
             }
             if (!c) continue;
+            if (EPI == EPI_NONE && args.ksplit > 1) {      // several slots / launches add into one output (gemm.cuh)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+                continue;
+            }
             if (args.accumulate) {
                 const float4 o = ld4(c);
                 v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
@@ -496,18 +501,23 @@ __global__ void __launch_bounds__(kRowsMmaThreads) gemm_rows_mma_kernel(const Ge
 }
 
 static bool al16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-// N = 16 exactly, K = 16 / 32, everything 16-byte aligned, no split-K, enough rows to matter
+// N = 16 exactly, K = 16 / 32 / 64, everything 16-byte aligned, enough rows to matter
 static bool rows_mma_ok(const GemmArgs& a) {
-    if (a.mode == GEMM_TN || a.N != 16 || (a.K != 16 && a.K != 32) || a.ksplit > 1 || a.M < 4096) return false;
-    if (a.nseg > 0 && (a.seg_len % 16 != 0 || a.mode != GEMM_NN)) return false;
+    static int dbg = -1;
+    if (dbg < 0) dbg = getenv("PAMNET_DEBUG_ROWS") ? 1 : 0;
+#define RM_NO(why) do { if (dbg && a.M >= 4096) fprintf(stderr, "rows_mma: no (%s) mode %d M %d N %d K %d epi %d ksplit %d nseg %d seg_len %d acc %d\n", why, a.mode, a.M, a.N, a.K, a.epi, a.ksplit, a.nseg, a.seg_len, a.accumulate); return false; } while (0)
+    if (a.mode == GEMM_TN) return false;
+    if (a.N != 16 || (a.K != 16 && a.K != 32 && a.K != 64) || (a.ksplit > 1 && a.epi != EPI_NONE) || a.M < 4096) RM_NO("shape");
+    if (a.nseg > 0 && (a.seg_len % 16 != 0 || a.mode != GEMM_NN)) RM_NO("segments");
     for (int i = 0; i < a.nslots; ++i) {
         const GemmSlot& s = a.slot[i];
-        if (!al16p(s.A) || s.lda % 4 != 0) return false;
-        if (s.C && (!al16p(s.C) || s.ldc % 4 != 0)) return false;
-        if (a.epi == EPI_BIAS_SILU && s.C2 && !al16p(s.C2)) return false;
-        if (a.epi == EPI_MUL_DSILU && (!s.Z || !al16p(s.Z) || s.ldz % 4 != 0)) return false;
-        if ((a.epi == EPI_BIAS || a.epi == EPI_BIAS_SILU) && s.bias && !al16p(s.bias)) return false;
+        if (!al16p(s.A) || s.lda % 4 != 0) RM_NO("A alignment");
+        if (s.C && (!al16p(s.C) || s.ldc % 4 != 0)) RM_NO("C alignment");
+        if (a.epi == EPI_BIAS_SILU && s.C2 && !al16p(s.C2)) RM_NO("C2 alignment");
+        if (a.epi == EPI_MUL_DSILU && (!s.Z || !al16p(s.Z) || s.ldz % 4 != 0)) RM_NO("Z");
+        if ((a.epi == EPI_BIAS || a.epi == EPI_BIAS_SILU) && s.bias && !al16p(s.bias)) RM_NO("bias alignment");
     }
+#undef RM_NO
     return true;
 }
 
@@ -555,11 +565,13 @@ int gemm_small_launch(const GemmArgs& a, cudaStream_t st) {
         return 0;
     }
     if (cols_mma_enabled() && rows_mma_ok(a)) {
-        dim3 grid(ceil_div(a.M, 16 * (kRowsMmaThreads / 32) * kRowsMmaTiles), 1, a.nslots);
+        const int kc = a.K / 16;
+        dim3 grid(ceil_div(a.M, 16 * (kRowsMmaThreads / 32) * (4 / kc)), 1, a.nslots);
 #define RM_CASE(EPI_) \
         do { \
-            if (a.K == 16) PAMNET_CUDA(launch_pdl(gemm_rows_mma_kernel<EPI_, 1>, grid, dim3(kRowsMmaThreads), 0, st, a)); \
-            else PAMNET_CUDA(launch_pdl(gemm_rows_mma_kernel<EPI_, 2>, grid, dim3(kRowsMmaThreads), 0, st, a)); \
+            if (kc == 1) PAMNET_CUDA(launch_pdl(gemm_rows_mma_kernel<EPI_, 1>, grid, dim3(kRowsMmaThreads), 0, st, a)); \
+            else if (kc == 2) PAMNET_CUDA(launch_pdl(gemm_rows_mma_kernel<EPI_, 2>, grid, dim3(kRowsMmaThreads), 0, st, a)); \
+            else PAMNET_CUDA(launch_pdl(gemm_rows_mma_kernel<EPI_, 4>, grid, dim3(kRowsMmaThreads), 0, st, a)); \
         } while (0)
         switch (a.epi) {
             case EPI_NONE: RM_CASE(EPI_NONE); break;
