@@ -385,6 +385,233 @@ static int chain_launch_t(const ChainArgs& a, double bytes, cudaStream_t st) {
     return 0;
 }
 
+// ---- row-group interpreter for dim <= 32 -----------------------------------------------------------------------------
+// At dim 16 / 32 a stage is a 1 - 4 KB weight matrix: the CTA-per-8-rows kernel above (k split over 8 thread groups, partial
+// sums through shared memory, three CTA barriers and a weight mbarrier per stage) spends its time on fixed per-stage
+// latencies -- 19-30 us per launch on the 15 816-node RNA batch whatever the arithmetic.  Here FOUR LANES own a row (lane
+// q of the group: columns q D/4 .. (q+1) D/4 - 1 of every stage's output): the row's slots live in shared memory as
+// [element][row] (conflict-free), only __syncwarp separates a stage's writes from the next stage's reads -- no CTA
+// barrier, no mbarrier anywhere in the stage loop -- and the weights are read straight from L1 / L2 (a warp reads one
+// 64- or 128-byte weight row per k).  Same stage table, same semantics as chain_kernel.  (One thread per row was tried
+// first: 3 warps per SM on that batch, every L1 / shared-memory latency exposed -- no faster than the CTA kernel.)
+constexpr int kRowChainThreads = 128, kRowChainTPR = 4;
+constexpr int kRowChainRows = kRowChainThreads / kRowChainTPR;      // rows per CTA
+template <int D>
+__global__ void __launch_bounds__(kRowChainThreads) chain_rows_kernel(const ChainArgs args) {
+    constexpr int NT = kRowChainThreads, NR = kRowChainRows, TPR = kRowChainTPR, CQ = D / TPR;     // CQ columns per lane
+    static_assert(CQ % 4 == 0, "128-bit column groups");
+    extern __shared__ __align__(16) float smem[];         // [(kChainSlots + 4) * D][NR]
+    __shared__ __align__(16) ChainStage s_stage[kChainMaxStages];
+    const int t = threadIdx.x, lane = t & 31;
+    {
+        const int nwords = args.n_stages * (int)(sizeof(ChainStage) / 4);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(args.st);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(s_stage);
+        for (int i = t; i < nwords; i += NT) dst[i] = src[i];
+    }
+    __syncthreads();
+    pdl_wait();
+    const int n_rows = args.n_rows, n_stages = args.n_stages;
+    const int r = t / TPR, q = t % TPR;
+    const int m = blockIdx.x * NR + r;
+    const bool live = m < n_rows;
+    const size_t mr = (size_t)(live ? m : 0);
+    float* mine = smem + r;                               // element e of slot s of this row: mine[(s * D + e) * NR]
+    const int c0 = q * CQ;                                // this lane's columns of a D-wide row
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+
+    for (int si = 0; si < n_stages; ++si) {
+        const ChainStage& st = s_stage[si];
+        if (si == n_stages - 1) pdl_trigger();
+        if (st.op == CH_LOAD) {
+            float* d = mine + (size_t)st.dst * D * NR;
+            const float* g0 = st.g0 + mr * st.ld_g;
+            const float* g1 = st.g1 ? st.g1 + mr * st.ld_g : nullptr;
+            const float* as = st.add_slot >= 0 ? mine + (size_t)st.add_slot * D * NR : nullptr;
+            float* oa = st.out_a ? st.out_a + mr * st.ld_out : nullptr;
+            const bool v4 = al16(g0) && (!g1 || al16(g1)) && (!oa || al16(oa));
+            for (int c = 4 * q; c < st.width; c += 4 * TPR) {        // lanes interleave 16-byte groups: coalesced rows
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                if (live) {
+                    if (v4) {
+                        const float4 a = ld4(g0 + c);
+                        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+                        if (g1) { const float4 b = ld4(g1 + c); v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w; }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) v[j] = g0[c + j] + (g1 ? g1[c + j] : 0.f);
+                    }
+                    if (as) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) v[j] += as[(size_t)(c + j) * NR];
+                    }
+                    if (oa) {
+                        if (v4) st4(oa + c, make_float4(v[0], v[1], v[2], v[3]));
+                        else { for (int j = 0; j < 4; ++j) oa[c + j] = v[j]; }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) d[(size_t)(c + j) * NR] = v[j];
+            }
+            __syncwarp();
+        } else if (st.op == CH_HEADS_BWD) {
+            float* d = mine + (size_t)st.dst * D * NR;
+            const float ga = live ? st.g0[m] : 0.f, go = live ? st.g1[m] : 0.f;
+            const float* W = st.W; const float* Wo = st.bias; const float* o3 = st.zmul;
+            float* gW = st.out_z; float* gWo = st.out_a; float* gbo = st.save_src;
+#pragma unroll
+            for (int cc = 0; cc < CQ; ++cc) {
+                const int c = c0 + cc;
+                d[(size_t)c * NR] = ga * W[c] + go * Wo[c];
+                if (o3) {
+                    const float a = live ? o3[mr * D + c] : 0.f;
+                    float pa = ga * a, po = go * a;
+#pragma unroll
+                    for (int o = 16; o >= TPR; o >>= 1) {            // the 8 rows of the warp (lanes with the same q)
+                        pa += __shfl_xor_sync(0xffffffffu, pa, o);
+                        po += __shfl_xor_sync(0xffffffffu, po, o);
+                    }
+                    if (lane < TPR) { atomicAdd(gW + c, pa); atomicAdd(gWo + c, po); }
+                }
+            }
+            if (o3 && gbo) {
+                float sgo = go;
+#pragma unroll
+                for (int o = 16; o >= TPR; o >>= 1) sgo += __shfl_xor_sync(0xffffffffu, sgo, o);
+                if (lane == 0) atomicAdd(gbo, sgo);
+            }
+            __syncwarp();
+        } else if (st.op == CH_DOT2) {
+            const float* x = mine + (size_t)st.src * D * NR;
+            float a = 0.f, o = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < CQ; ++cc) {
+                const float xv = x[(size_t)(c0 + cc) * NR];
+                a = fmaf(xv, st.W[c0 + cc], a);
+                o = fmaf(xv, st.bias[c0 + cc], o);
+            }
+#pragma unroll
+            for (int s2 = 1; s2 < TPR; s2 <<= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, s2);
+                o += __shfl_xor_sync(0xffffffffu, o, s2);
+            }
+            if (live && q == 0) { st.out_z[m] = a; st.out_a[m] = o + st.g0[0]; }
+        } else {  // CH_GEMM
+            const float* in = mine + ((size_t)st.src * D + st.src_off) * NR;
+            if (st.psrc >= 0) {       // prologue: src * SiLU'(zmul) -> psrc (and to global, for the weight gradients)
+                float* p = mine + (size_t)st.psrc * D * NR;
+                const float* zr = st.zmul + mr * D;
+                float* sv = st.save_src ? st.save_src + mr * D : nullptr;
+#pragma unroll
+                for (int cc = 0; cc < CQ; cc += 4) {
+                    const int c = c0 + cc;
+                    float v[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (live) {
+                        const float4 dz = dsilu4(ld4(zr + c));
+                        v[0] = in[(size_t)c * NR] * dz.x; v[1] = in[(size_t)(c + 1) * NR] * dz.y;
+                        v[2] = in[(size_t)(c + 2) * NR] * dz.z; v[3] = in[(size_t)(c + 3) * NR] * dz.w;
+                        if (sv) st4(sv + c, make_float4(v[0], v[1], v[2], v[3]));
+                    }
+                    // (psrc == src is allowed: every lane rewrites exactly the elements it read)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) p[(size_t)(c + j) * NR] = v[j];
+                }
+                in = p;
+                __syncwarp();
+            }
+            float acc[CQ];
+#pragma unroll
+            for (int n = 0; n < CQ; ++n) acc[n] = 0.f;
+            const float* W = st.W + c0;
+            const int ldw = st.ldw;
+#pragma unroll 8
+            for (int k = 0; k < D; ++k) {
+                const float xk = in[(size_t)k * NR];
+                const float* wr = W + (size_t)k * ldw;
+#pragma unroll
+                for (int n = 0; n < CQ; n += 4) {
+                    const float4 w = ld4(wr + n);
+                    acc[n] = fmaf(xk, w.x, acc[n]); acc[n + 1] = fmaf(xk, w.y, acc[n + 1]);
+                    acc[n + 2] = fmaf(xk, w.z, acc[n + 2]); acc[n + 3] = fmaf(xk, w.w, acc[n + 3]);
+                }
+            }
+            __syncwarp();             // the row's four lanes are done reading `in` (post_dst may be that very slot)
+            const float* bias = st.bias;
+            float* oz = st.out_z ? st.out_z + mr * st.ld_out : nullptr;
+            float* oa = st.out_a ? st.out_a + mr * st.ld_out : nullptr;
+            const float* ag = st.add_g ? st.add_g + mr * st.ld_add : nullptr;
+            const float* as = st.add_slot >= 0 ? mine + (size_t)st.add_slot * D * NR : nullptr;
+            float* dd = (st.dst >= 0 && st.dst != st.post_dst) ? mine + (size_t)st.dst * D * NR : nullptr;
+            float* pd = st.post_dst >= 0 ? mine + (size_t)st.post_dst * D * NR : nullptr;
+            const float* pz = st.post_dst >= 0 ? st.post_zmul + mr * D : nullptr;
+            float* ps = (st.post_dst >= 0 && st.post_save) ? st.post_save + mr * D : nullptr;
+            const bool v4 = (!oz || al16(oz)) && (!oa || al16(oa)) && (!ag || al16(ag));
+            const int act = st.act;
+#pragma unroll
+            for (int nn = 0; nn < CQ; nn += 4) {
+                const int n = c0 + nn;
+                float x[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[j] = acc[nn + j] + (bias ? bias[n + j] : 0.f);
+                if (live && oz) {
+                    if (v4) st4(oz + n, make_float4(x[0], x[1], x[2], x[3]));
+                    else { for (int j = 0; j < 4; ++j) oz[n + j] = x[j]; }
+                }
+                if (act) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) x[j] = silu(x[j]);
+                }
+                if (as) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) x[j] += as[(size_t)(n + j) * NR];
+                }
+                if (live && ag) {
+                    if (v4) { const float4 a = ld4(ag + n); x[0] += a.x; x[1] += a.y; x[2] += a.z; x[3] += a.w; }
+                    else { for (int j = 0; j < 4; ++j) x[j] += ag[n + j]; }
+                }
+                if (!live) { x[0] = 0.f; x[1] = 0.f; x[2] = 0.f; x[3] = 0.f; }
+                if (live && oa) {
+                    if (v4) st4(oa + n, make_float4(x[0], x[1], x[2], x[3]));
+                    else { for (int j = 0; j < 4; ++j) oa[n + j] = x[j]; }
+                }
+                if (dd) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dd[(size_t)(n + j) * NR] = x[j];
+                }
+                if (pd) {            // the next stage's prologue, on register values
+                    float y[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (live) {
+                        const float4 dz = dsilu4(ld4(pz + n));
+                        y[0] = x[0] * dz.x; y[1] = x[1] * dz.y; y[2] = x[2] * dz.z; y[3] = x[3] * dz.w;
+                        if (ps) st4(ps + n, make_float4(y[0], y[1], y[2], y[3]));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) pd[(size_t)(n + j) * NR] = y[j];
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// PAMNET_CHAIN_ROWS=0: the CTA-per-8-rows interpreter also at dim <= 32
+static bool chain_rows_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("PAMNET_CHAIN_ROWS"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on == 1;
+}
+
+template <int D>
+static int chain_rows_launch_t(const ChainArgs& a, double bytes, cudaStream_t st) {
+    const size_t smem = sizeof(float) * (kChainSlots + 4) * D * kRowChainRows;
+    PAMNET_TRY(func_smem_once(reinterpret_cast<const void*>(chain_rows_kernel<D>), smem));
+    prof_begin(KC_CHAIN, bytes, st);
+    launch_pdl(chain_rows_kernel<D>, dim3(ceil_div(a.n_rows, kRowChainRows)), dim3(kRowChainThreads), smem, st, a);
+    prof_end(st);
+    PAMNET_LAUNCH_CHECK();
+    return 0;
+}
+
 // stage-table preprocessing shared by both interpreters: algorithmic bytes, prologue fusion, next-GEMM links
 static double chain_prepare(int D, const ChainArgs& args, ChainArgs* out) {
     double bytes = 0.0;
@@ -435,6 +662,10 @@ int chain_launch(int dim, const ChainArgs& args, cudaStream_t st) {
     if (node_mlp < 0) { const char* e = getenv("PAMNET_NODE_MLP"); node_mlp = (e && strcmp(e, "tf32") == 0) ? 1 : 0; }
     a.precision = node_mlp;
     if (chain_mma_enabled(dim)) return chain_mma_launch(dim, a, bytes, st);
+    if (dim <= 32 && chain_rows_enabled()) {
+        if (dim == 32) return chain_rows_launch_t<32>(a, bytes, st);
+        if (dim == 16) return chain_rows_launch_t<16>(a, bytes, st);
+    }
     switch (dim) {
         case 128: return chain_launch_t<128>(a, bytes, st);
         case 64:  return chain_launch_t<64>(a, bytes, st);
