@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--torch-loss", action="store_true", help="F.l1_loss instead of the fused loss + gradient launch")
     ap.add_argument("--no-prefetch", action="store_true",
                     help="build every step's graph plan inline instead of on a side stream behind the previous backward")
+    ap.add_argument("--loss-readback", default="early", choices=["early", "late"],
+                    help="e2e arm: early = the step's loss is read back through a copy stream right after the loss kernel "
+                         "(default); late = loss.item() after backward, as the reference loop does")
     ap.add_argument("--vary", type=int, default=1,
                     help="visit K distinct synthetic batches round-robin (different atom / edge / triplet counts every step, as "
                          "an epoch does) instead of re-running one batch")
@@ -183,10 +186,12 @@ def workload_config(args, sizes):
                          "buckets": "bucketed gradient all-reduce issued from Python, overlapped with backward",
                          "native": "bucketed ncclAllReduce issued by the library inside backward (two-layer buckets, head last)"}[
                          getattr(args, "allreduce", "native")]) if args.gpus > 1 else "single GPU",
-         "l2": "flushed (256 MiB write) before every timed step",
+         "l2": "flushed (256 MiB write) before every timed step of the device-resident arm; e2e arm: no flush, a step's working set (~0.5 GB of workspace at bs=32) is larger than the 126 MB L2",
          "node_mlp": "single-pass TF32 tensor-core node MLPs (reduced precision, PAMNET_NODE_MLP=tf32)" if args.node_mlp == "tf32"
                      else "3xTF32 tensor-core node MLPs (fp32-accurate)",
          "loss": "F.l1_loss" if getattr(args, "torch_loss", False) else "pamnet_b200.ops.l1_loss (value + gradient in one launch)",
+         "e2e_loss_readback": "every step, from pinned memory, copied on a copy stream right after the step's loss kernel" if getattr(args, "loss_readback", "early") == "early"
+                              else "loss.item() after backward, every step",
          "front_end": "inline" if getattr(args, "no_prefetch", False)
                       else "next step's H2D copy + graph plan on a side stream from a prefetch worker thread (model.prefetch_async), overlapping this step's backward; one plan and one H2D copy per step"}
     if getattr(args, "vary", 1) > 1:
@@ -200,32 +205,24 @@ def workload_config(args, sizes):
 
 
 class ClockSampler:
-    """SM clock and throttle reasons during the timed regions (B200_PROFILING.md clocks line).  In-process NVML
-    (nvidia_ml_py) from a sampling thread; falls back to an `nvidia-smi -lms` child process when NVML cannot be loaded.
-    (BENCH_SAMPLER=smi / nvml / none selects one explicitly: debugging aid for host-jitter attribution.)"""
+    """SM clock and throttle reasons during the timed regions (B200_PROFILING.md clocks line), from NVML (the source
+    `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` reads), queried from the TIMING thread between two steps
+    -- after a step's closing event, before the next step's opening one -- while the GPU still works through what is
+    queued.  Why not a background `nvidia-smi -lms` / NVML thread: a query normally takes ~10 us, but every few seconds
+    the driver refreshes its cached values and the call takes 10-40 ms while holding a lock the launching threads need;
+    with a 1.5 ms step that showed up as a 10-80 ms stall of one step in about every second 300-step run
+    (`tools/nvml_cost.py`, profiles/README.md).  Between the event brackets the same refresh delays the next step's
+    launch but is not attributed to a step.  BENCH_SAMPLER=smi keeps the recipe's background child for comparison;
+    BENCH_SAMPLER=none disables sampling."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-    PERIOD_S = 0.2          # every query takes driver locks the launching threads also need: rare multi-ms stalls of a step grow with the rate
+    BITS = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
         self.mode = os.environ.get("BENCH_SAMPLER", "nvml")
-        self._stop = threading.Event()
-        self._thread = None
-
-    # -- NVML in process ------------------------------------------------------------------------------------------
-    def _nvml_loop(self, nv, h):
-        bits = [("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8),
-                ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
-        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-        while not self._stop.is_set():
-            try:
-                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
-                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                self.rows.append([str(sm), str(mx)] + ["Active" if mask & b else "Not Active" for _, b in bits])
-            except Exception:
-                pass
-            self._stop.wait(self.PERIOD_S)
+        self.nv = self.h = None
+        self.mx = None
 
     def start(self):
         if self.mode == "none":
@@ -233,27 +230,27 @@ class ClockSampler:
         if self.mode == "nvml":
             try:
                 import pynvml as nv
+                import torch
                 nv.nvmlInit()
                 # CUDA_VISIBLE_DEVICES may renumber: resolve through the PCI bus id of the CUDA device
-                import torch
-                bus = torch.cuda.get_device_properties(self.index).pci_bus_id if hasattr(torch.cuda.get_device_properties(self.index), "pci_bus_id") else None
+                props = torch.cuda.get_device_properties(self.index)
                 h = None
-                if bus is not None:
+                if hasattr(props, "pci_bus_id"):
                     for i in range(nv.nvmlDeviceGetCount()):
                         hi = nv.nvmlDeviceGetHandleByIndex(i)
-                        if nv.nvmlDeviceGetPciInfo(hi).bus == bus:
+                        if nv.nvmlDeviceGetPciInfo(hi).bus == props.pci_bus_id:
                             h = hi
                             break
                 if h is None:
                     h = nv.nvmlDeviceGetHandleByIndex(self.index)
-                self._thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
-                self._thread.start()
+                self.mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)      # (slow call: once, before anything is timed)
+                self.nv, self.h = nv, h
                 return
             except Exception:
                 self.mode = "smi"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -263,25 +260,37 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
+    def sample_now(self):
+        """One NVML sample from the calling thread (no-op in the other modes)."""
+        if self.nv is None:
+            return
+        try:
+            sm = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+            mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            self.rows.append([str(sm), str(self.mx)] + ["Active" if mask & b else "Not Active" for _, b in self.BITS])
+        except Exception:
+            pass
+
     def wait_first(self, timeout=3.0):
-        """Block until the first sample arrived (NVML / nvidia-smi start-up is over) -- called before the timed regions."""
+        """nvidia-smi mode: block until the first sample arrived (its start-up is over) -- before the timed regions."""
         t_end = time.perf_counter() + timeout
-        while self.mode != "none" and not self.rows and time.perf_counter() < t_end:
+        while self.proc is not None and not self.rows and time.perf_counter() < t_end:
             time.sleep(0.01)
 
     def stop(self):
-        if self.mode == "none" or (self.proc is None and self._thread is None):
+        if self.mode == "none" or (self.proc is None and self.nv is None):
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampler unavailable"], "samples": 0}
-        time.sleep(0.15)
-        self._stop.set()
         if self.proc is not None:
+            time.sleep(0.15)
             self.proc.terminate()
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        names = [n for n, _ in self.BITS]
         reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm), "source": "nvml" if self._thread is not None else "nvidia-smi"}
+                "reasons": reasons, "samples": len(sm),
+                "source": "NVML, queried between steps of the timed regions (GPU busy with the queued step)" if self.nv is not None
+                          else "nvidia-smi -lms 200 child"}
 
 
 def algorithmic_bytes_step(sz, D, L, s=4):
@@ -337,7 +346,16 @@ def run_ours(args):
     sync = OverlappedGradSync(model) if (world > 1 and args.allreduce == "buckets") else None
     native = NativeGradSync(model) if (world > 1 and args.allreduce == "native") else None
 
-    def step(batch, sync_grads=True, next_batch=None):
+    # --loss-readback early (default): the step's loss is complete when its own kernel is, long before backward ends -- it
+    # is copied to pinned host memory on a copy stream behind an event recorded right after the loss launch, and the host
+    # reads it there.  `late` = loss.item() after backward (the reference loop, main_qm9.py:109): the host then cannot
+    # enqueue the next forward before the whole step has drained.
+    early = args.loss_readback == "early"
+    copy_stream = torch.cuda.Stream(device=dev) if early else None
+    host_loss = torch.zeros(1, dtype=torch.float32).pin_memory() if early else None
+    loss_ready = {"ev": None}
+
+    def step(batch, sync_grads=True, next_batch=None, read_loss=False):
         if sync is not None:
             sync.wait()                     # the previous step's collectives read the gradient buffer backward is about to zero
         model.zero_grad()                   # optimizer.zero_grad() of main_qm9.py:106 (the module's O(1) form: grads stay attached, backward overwrites)
@@ -345,6 +363,16 @@ def run_ours(args):
         if next_batch is not None:          # the next step's front end: started on the prefetch worker while this thread
             next_batch()                    # enqueues the loss and the backward pass
         loss = l1(out, batch.y)             # main_qm9.py:108
+        if read_loss and early:             # D2H of this step's loss: ordered after the loss kernel only
+            ev = torch.cuda.Event()
+            ev.record()
+            copy_stream.wait_event(ev)
+            with torch.cuda.stream(copy_stream):
+                host_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(copy_stream)
+            loss.record_stream(copy_stream)
+            loss_ready["ev"] = done
         loss.backward()
         if world > 1 and sync_grads:        # enqueue the collectives first: they overlap what backward still has queued
             if sync is not None:
@@ -395,13 +423,16 @@ def run_ours(args):
     launches0 = _lib.launch_count()
     ar_ms = []
     barrier()
-    for s0, s1 in ev:
+    every = max(10, args.steps // 4)       # clock samples: ~4 per region, each right after a step's closing event
+    for i, (s0, s1) in enumerate(ev):
         flush.fill_(1)
         s0.record()
         dev_step()
         if sync is not None:
             sync.wait()                     # the step ends when its gradients are reduced
         s1.record()
+        if rank == 0 and i % every == every // 2:
+            sampler.sample_now()
         if sync is not None and len(ar_ms) < 8:
             ar_ms.append(sync.allreduce_ms())       # (synchronises: only for a few steps)
     barrier()
@@ -424,17 +455,22 @@ def run_ours(args):
         if prefetch:            # this step's batch was copied and planned during the previous step; copy + plan the next
             if not pending:
                 h2d_and_plan()
-            loss = step(pending.pop(0).result(), next_batch=h2d_and_plan)
+            loss = step(pending.pop(0).result(), next_batch=h2d_and_plan, read_loss=True)
         else:
             b = host_pool[turn["e2e"] % len(host_pool)].to(dev, non_blocking=True)      # H2D from pinned memory, inside the timed region
             turn["e2e"] += 1
-            loss = step(b)
+            loss = step(b, read_loss=True)
         if sync is not None:
             sync.wait()
-        return loss.item()                                  # D2H read of the step's result
+        if early:                                           # D2H read of the step's result (host waits for the copy only)
+            loss_ready["ev"].synchronize()
+            return float(host_loss[0])
+        return loss.item()
 
     for _ in range(3):
         e2e_step()
+    if rank == 0:
+        sampler.sample_now()        # under load (the warm-up steps are still running), outside the wall-clock region below
     barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
